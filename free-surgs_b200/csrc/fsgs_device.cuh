@@ -1,0 +1,157 @@
+// fsgs_device.cuh -- sm_100a device helpers: mbarrier + 1-D bulk TMA (cp.async.bulk), warp
+// reduce-scatter, the pinned-order alpha evaluation shared by the forward and backward
+// compositors, and the buffer layouts shared between kernels and host code.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fsgs_math.cuh"
+
+namespace fsgs {
+
+constexpr int CTA = 256;              // threads per compositor / sort CTA (one 16x16 tile)
+constexpr int BATCH = 256;            // tile-list entries staged per bulk copy
+constexpr int REC_F4 = 3;             // float4 per splat record (48 B)
+constexpr int ACC_F = 12;             // floats per Gaussian in the gradient accumulator (48 B)
+constexpr uint32_t FULL = 0xffffffffu;
+
+// ---- splat record (48 B, 16-B aligned; one per Gaussian, and one per sorted tile instance) ----
+//   q0 = (x, y, conic.x, conic.y)   q1 = (conic.z, opacity, r, g)   q2 = (b, depth, radius, tiles)
+// radius / tiles are int bit patterns.
+//
+// ---- gradient accumulator row (48 B) written by the backward compositor ----
+//   [0..3]  = d(mean2D.x), d(mean2D.y), d(conic.x), d(conic.y)
+//   [4..7]  = d(conic.z), d(opacity), d(r), d(g)
+//   [8..11] = d(b), d(depth), d(mean2D.x | RGB planes only), d(mean2D.y | RGB planes only)
+
+struct ImgLayout {
+    size_t final_T, n_contrib, tile_count, tile_offset, cursor, counters, total;
+    int tiles;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__host__ inline ImgLayout img_layout(int W, int H) {
+    ImgLayout L;
+    const size_t HW = (size_t)W * H;
+    L.tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+    size_t o = 0;
+    L.final_T = o; o = align_up(o + HW * 4, 256);
+    L.n_contrib = o; o = align_up(o + HW * 4, 256);
+    L.tile_count = o; o = align_up(o + (size_t)L.tiles * 4, 256);
+    L.tile_offset = o; o = align_up(o + ((size_t)L.tiles + 1) * 4, 256);
+    L.cursor = o; o = align_up(o + (size_t)L.tiles * 4, 256);
+    L.counters = o; o = align_up(o + 64, 256);
+    L.total = o;
+    return L;
+}
+
+// counters[] (uint64): 0 = instances after culling (R), 1 = instances of the reference's
+// rectangles, 2 = longest tile list, 3 = device error / watchdog flag
+enum { CNT_R = 0, CNT_RECT = 1, CNT_MAXLIST = 2, CNT_ERR = 3 };
+
+struct GeomLayout {
+    size_t records, clamped, total;
+};
+__host__ inline GeomLayout geom_layout(int P) {
+    GeomLayout L;
+    const size_t n = P > 0 ? P : 1;
+    size_t o = 0;
+    L.records = o; o = align_up(o + n * 48, 256);
+    L.clamped = o; o = align_up(o + n, 256);
+    L.total = o;
+    return L;
+}
+
+struct BinLayout {
+    size_t keys, records, total;
+};
+__host__ inline BinLayout bin_layout(int64_t R) {
+    BinLayout L;
+    const size_t n = R > 0 ? (size_t)R : 1;
+    size_t o = 0;
+    L.keys = o; o = align_up(o + n * 8, 256);
+    L.records = o; o = align_up(o + n * 48, 256);
+    L.total = o;
+    return L;
+}
+
+#if defined(__CUDACC__)
+
+// ---- mbarrier / bulk-copy PTX (sm_90+; SASS: SYNCS.*, UBLKCP) ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    // make the initialised barrier visible to the async proxy before the first bulk copy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a stuck barrier sets the error flag instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, unsigned long long *err) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) {
+            if (err) atomicExch(err, 1ull);
+            break;
+        }
+    }
+}
+// global -> shared 1-D bulk copy through the TMA engine; bytes % 16 == 0, both sides 16-B aligned
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// gauss_power (pinned operation order) lives in fsgs_math.cuh so the CPU emulation shares it.
+__device__ __forceinline__ float gauss_weight(float power) {
+#ifdef FSGS_PRECISE_EXP
+    return expf(power);
+#else
+    return __expf(power);
+#endif
+}
+
+// ---- warp reduce-scatter of 16 values ----------------------------------------------------------
+// After the call lane L holds in v[0] the warp-wide sum of input index (L >> 1) & 15.
+// 16 shuffles instead of 16 * 5.
+__device__ __forceinline__ void warp_reduce_scatter16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, mask = 16; half >= 1; half >>= 1, mask >>= 1) {
+        const bool upper = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = upper ? v[i + half] : v[i];
+            const float send = upper ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(FULL, send, mask);
+        }
+    }
+    v[0] += __shfl_xor_sync(FULL, v[0], 1);
+}
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+#endif  // __CUDACC__
+
+}  // namespace fsgs

@@ -1,0 +1,125 @@
+// fsgs_kernels_bwd.cuh -- per-Gaussian backward (K8 + K9): conic/mean2D/colour/depth gradients
+// from the compositor's accumulator -> gradients of the rasteriser inputs; the fused flavour
+// continues through the activations, the SH evaluation and transform_to_frame and reduces the
+// pose gradient dL/dRt = sum_i g_i [p_i;1]^T on the fly (warp reduce-scatter -> shared memory ->
+// 12 atomics per CTA).
+#pragma once
+
+#include "fsgs_device.cuh"
+#include "fsgs_kernels_pre.cuh"
+
+namespace fsgs {
+
+__device__ __forceinline__ void load_acc(const float *__restrict__ grad_acc, int i, float *a) {
+    const float4 *r = reinterpret_cast<const float4 *>(grad_acc + (size_t)i * ACC_F);
+    const float4 x = r[0], y = r[1], z = r[2];
+    a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w;
+    a[8] = z.x; a[9] = z.y; a[10] = z.z; a[11] = z.w;
+}
+
+__global__ void __launch_bounds__(CTA)
+k_preprocess_api_bwd(CamConst cc, int P, const float *__restrict__ means3D, const float *__restrict__ shs,
+                     const float *__restrict__ scales, const float *__restrict__ rotations,
+                     const float *__restrict__ cov3D_precomp, const float *__restrict__ viewmatrix,
+                     const float *__restrict__ projmatrix, const float *__restrict__ campos,
+                     const float4 *__restrict__ records, const uint8_t *__restrict__ clamped,
+                     const float *__restrict__ grad_acc, float *__restrict__ dL_dmeans2D,
+                     float *__restrict__ dL_dcolors, float *__restrict__ dL_dopacity, float *__restrict__ dL_dmeans3D,
+                     float *__restrict__ dL_dcov3D, float *__restrict__ dL_dsh, float *__restrict__ dL_dscales,
+                     float *__restrict__ dL_drot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const size_t n = (size_t)i;
+    const int radius = __float_as_int(records[n * 3 + 2].z);
+    float a[ACC_F];
+    float dmean[3] = {0.f, 0.f, 0.f}, dc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < ACC_F; ++k) a[k] = 0.f;
+    const int nsh = cc.n_coeffs * 3;
+    float *dsh_i = (shs && dL_dsh) ? dL_dsh + n * nsh : nullptr;
+    if (radius > 0) {
+        load_acc(grad_acc, i, a);
+        float V[16], PM[16], cp[3] = {0.f, 0.f, 0.f};
+        load16(viewmatrix, V);
+        load16(projmatrix, PM);
+        if (shs) { cp[0] = __ldg(campos); cp[1] = __ldg(campos + 1); cp[2] = __ldg(campos + 2); }
+        const float mean[3] = {means3D[3 * n], means3D[3 * n + 1], means3D[3 * n + 2]};
+        api_backward_one(cc, V, PM, cp, mean, shs ? shs + n * nsh : nullptr, scales ? scales + 3 * n : nullptr,
+                         rotations ? rotations + 4 * n : nullptr, cov3D_precomp ? cov3D_precomp + 6 * n : nullptr,
+                         clamped[i], a, dmean, dc6, dsh_i, ds, dq);
+    } else if (dsh_i) {
+        for (int k = 0; k < nsh; ++k) dsh_i[k] = 0.f;
+    }
+    if (dL_dmeans2D) { dL_dmeans2D[3 * n] = a[0]; dL_dmeans2D[3 * n + 1] = a[1]; dL_dmeans2D[3 * n + 2] = 0.f; }
+    if (dL_dcolors) { dL_dcolors[3 * n] = a[6]; dL_dcolors[3 * n + 1] = a[7]; dL_dcolors[3 * n + 2] = a[8]; }
+    if (dL_dopacity) dL_dopacity[i] = a[5];
+    if (dL_dmeans3D) { dL_dmeans3D[3 * n] = dmean[0]; dL_dmeans3D[3 * n + 1] = dmean[1]; dL_dmeans3D[3 * n + 2] = dmean[2]; }
+    if (dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * n + k] = dc6[k];
+    }
+    if (dL_dscales) { dL_dscales[3 * n] = ds[0]; dL_dscales[3 * n + 1] = ds[1]; dL_dscales[3 * n + 2] = ds[2]; }
+    if (dL_drot) *reinterpret_cast<float4 *>(dL_drot + 4 * n) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+}
+
+__global__ void __launch_bounds__(CTA)
+k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const float *__restrict__ f_dc,
+                       const float *__restrict__ f_rest, const float *__restrict__ opacity_raw,
+                       const float *__restrict__ scaling_raw, const float *__restrict__ rotation_raw,
+                       const float *__restrict__ pose, const float *__restrict__ cam_center,
+                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
+                       const float4 *__restrict__ records, const uint8_t *__restrict__ clamped,
+                       const float *__restrict__ grad_acc, int gs_grad, int cam_grad, float *__restrict__ dL_dxyz,
+                       float *__restrict__ dL_dfdc, float *__restrict__ dL_dfrest, float *__restrict__ dL_dopacity_raw,
+                       float *__restrict__ dL_dscaling_raw, float *__restrict__ dL_drotation_raw,
+                       float *__restrict__ dL_dpose, float *__restrict__ dL_dmeans2D) {
+    __shared__ float s_pose[16];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 16) s_pose[threadIdx.x] = 0.f;
+    __syncthreads();
+    float pg[16];   // pose-gradient contributions of this Gaussian: g_r * [x y z 1]_c at [4r + c]
+#pragma unroll
+    for (int k = 0; k < 16; ++k) pg[k] = 0.f;
+    if (i < P) {
+        const size_t n = (size_t)i;
+        const int radius = __float_as_int(records[n * 3 + 2].z);
+        float dxyz[3] = {0.f, 0.f, 0.f}, ds_raw[3] = {0.f, 0.f, 0.f}, dq_raw[4] = {0.f, 0.f, 0.f, 0.f};
+        float dop_raw = 0.f, dfdc[3] = {0.f, 0.f, 0.f}, m2d[2] = {0.f, 0.f};
+        float *drest = dL_dfrest ? dL_dfrest + 45 * n : nullptr;
+        if (radius > 0) {
+            float a[ACC_F];
+            load_acc(grad_acc, i, a);
+            float V[16], PM[16], Rt[12], cp[3];
+            load16(viewmatrix, V);
+            load16(projmatrix, PM);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose + k);
+            cp[0] = __ldg(cam_center); cp[1] = __ldg(cam_center + 1); cp[2] = __ldg(cam_center + 2);
+            const float w[3] = {xyz[3 * n], xyz[3 * n + 1], xyz[3 * n + 2]};
+            const float sc[3] = {scaling_raw[3 * n], scaling_raw[3 * n + 1], scaling_raw[3 * n + 2]};
+            const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
+            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+            fused_backward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, f_rest + 45 * n, opacity_raw[i], sc, q, clamped[i], a,
+                               gs_grad, cam_grad, dxyz, dfdc, drest, dop_raw, ds_raw, dq_raw, pg, m2d);
+        } else if (drest) {
+            for (int k = 0; k < 45; ++k) drest[k] = 0.f;
+        }
+        if (dL_dxyz) { dL_dxyz[3 * n] = dxyz[0]; dL_dxyz[3 * n + 1] = dxyz[1]; dL_dxyz[3 * n + 2] = dxyz[2]; }
+        if (dL_dfdc) { dL_dfdc[3 * n] = dfdc[0]; dL_dfdc[3 * n + 1] = dfdc[1]; dL_dfdc[3 * n + 2] = dfdc[2]; }
+        if (dL_dopacity_raw) dL_dopacity_raw[i] = dop_raw;
+        if (dL_dscaling_raw) { dL_dscaling_raw[3 * n] = ds_raw[0]; dL_dscaling_raw[3 * n + 1] = ds_raw[1]; dL_dscaling_raw[3 * n + 2] = ds_raw[2]; }
+        if (dL_drotation_raw) *reinterpret_cast<float4 *>(dL_drotation_raw + 4 * n) = make_float4(dq_raw[0], dq_raw[1], dq_raw[2], dq_raw[3]);
+        if (dL_dmeans2D) { dL_dmeans2D[3 * n] = m2d[0]; dL_dmeans2D[3 * n + 1] = m2d[1]; dL_dmeans2D[3 * n + 2] = 0.f; }
+    }
+    if (cam_grad && dL_dpose) {
+        warp_reduce_scatter16(pg, lane);
+        const int idx = lane >> 1;
+        if ((lane & 1) == 0 && idx < 12 && pg[0] != 0.f) atomicAdd(&s_pose[idx], pg[0]);
+        __syncthreads();
+        if (threadIdx.x < 12 && s_pose[threadIdx.x] != 0.f) atomicAdd(&dL_dpose[threadIdx.x], s_pose[threadIdx.x]);
+    }
+}
+
+}  // namespace fsgs

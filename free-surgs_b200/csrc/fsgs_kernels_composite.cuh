@@ -1,0 +1,274 @@
+// fsgs_kernels_composite.cuh -- tile-order alpha compositing, forward and backward (K6, K7).
+//
+// One CTA per 16x16 tile, 8 warps, each warp owning an 8x4 pixel block.  The tile's depth-sorted
+// splat records (48 B each, written contiguously by k_tile_sort) are streamed into shared memory
+// in batches of 256 by 1-D bulk TMA copies (cp.async.bulk + mbarrier, double buffered); every
+// thread then walks the batch from shared memory (broadcast reads).
+//
+//   FUSED = false : one GaussianRasterizer pass -- 3 colour planes + the package's depth plane.
+//   FUSED = true  : Free-SurGS' two passes at once -- RGB | depth, silhouette, depth^2, all six
+//                   planes with "+ T_final * bg" exactly as the reference's second pass produces
+//                   them (gaussian_renderer/__init__.py:68-74, bg = 1 quirk iv in SURVEY.md 8a).
+#pragma once
+
+#include "fsgs_device.cuh"
+
+namespace fsgs {
+
+struct TilePix {
+    int px, py;
+    bool inside;
+};
+__device__ __forceinline__ TilePix tile_pixel(const CamConst &cc, int tile) {
+    const int tx = tile % cc.gx, ty = tile / cc.gx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TilePix p;
+    p.px = tx * TILE + (warp & 1) * 8 + (lane & 7);
+    p.py = ty * TILE + (warp >> 1) * 4 + (lane >> 3);
+    p.inside = p.px < cc.W && p.py < cc.H;
+    return p;
+}
+
+// Stage `cnt` records starting at `src` into `dst`: bulk TMA (thread 0) or cooperative loads.
+__device__ __forceinline__ void stage_issue_tma(float4 *dst, const float4 *src, int cnt, uint64_t *bar) {
+    const uint32_t bytes = (uint32_t)cnt * 48u;
+    mbar_arrive_expect_tx(bar, bytes);
+    tma_load_1d(dst, src, bytes, bar);
+}
+__device__ __forceinline__ void stage_plain(float4 *dst, const float4 *src, int cnt) {
+    for (int p = threadIdx.x; p < cnt * REC_F4; p += CTA) dst[p] = ldg4(src + p);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(CTA)
+k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const float4 *__restrict__ sorted_rec,
+                const float *__restrict__ bg, float *__restrict__ out_planes, float *__restrict__ out_depth,
+                float *__restrict__ final_T, unsigned int *__restrict__ n_contrib, unsigned int flags,
+                unsigned long long *__restrict__ err) {
+    __shared__ __align__(128) float4 s_rec[2][BATCH * REC_F4];
+    __shared__ __align__(8) uint64_t s_full[2];
+    const int tile = blockIdx.x;
+    const unsigned int start = tile_offset[tile];
+    const int n = (int)(tile_offset[tile + 1] - start);
+    const int nb = (n + BATCH - 1) / BATCH;
+    const bool use_tma = (flags & 1u) == 0;
+    const TilePix pix = tile_pixel(cc, tile);
+    const float pxf = (float)pix.px, pyf = (float)pix.py;
+    const float4 *src = sorted_rec + (size_t)start * REC_F4;
+
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_full[0], 1);
+            mbar_init(&s_full[1], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && nb > 0) stage_issue_tma(s_rec[0], src, min(BATCH, n), &s_full[0]);
+    }
+
+    bool done = !pix.inside;
+    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, S = 0.f, D2 = 0.f;
+    unsigned int last = 0;
+
+    for (int k = 0; k < nb; ++k) {
+        const int all_done = __syncthreads_and(done ? 1 : 0);   // everyone is also past batch k-1
+        const int buf = k & 1;
+        const int cnt = min(BATCH, n - k * BATCH);
+        if (use_tma) {
+            if (threadIdx.x == 0 && !all_done && k + 1 < nb)
+                stage_issue_tma(s_rec[buf ^ 1], src + (size_t)(k + 1) * BATCH * REC_F4, min(BATCH, n - (k + 1) * BATCH),
+                                &s_full[buf ^ 1]);
+            mbar_wait(&s_full[buf], (uint32_t)(k >> 1) & 1u, err);   // drain even when leaving
+            if (all_done) break;
+        } else {
+            if (all_done) break;
+            stage_plain(s_rec[buf], src + (size_t)k * BATCH * REC_F4, cnt);
+            __syncthreads();
+        }
+        const float4 *sb = s_rec[buf];
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            if (__all_sync(FULL, done)) break;
+            const int jend = min(cnt, j0 + 32);
+            for (int j = j0; j < jend && !done; ++j) {
+                const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
+                const float dx = q0.x - pxf, dy = q0.y - pyf;
+                const float power = gauss_power(q0.z, q0.w, q1.x, dx, dy);
+                if (power > 0.f) continue;
+                const float alpha = fminf(ALPHA_MAX, q1.y * gauss_weight(power));
+                if (alpha < ALPHA_MIN) continue;
+                const float test_T = T * (1.f - alpha);
+                if (test_T < T_MIN) { done = true; break; }
+                const float4 q2 = sb[j * 3 + 2];
+                const float w = alpha * T;
+                C0 += q1.z * w; C1 += q1.w * w; C2 += q2.x * w; D += q2.y * w;
+                if (FUSED) { S += w; D2 += q2.y * q2.y * w; }
+                T = test_T;
+                last = (unsigned int)(k * BATCH + j + 1);
+            }
+        }
+    }
+
+    if (pix.inside) {
+        const size_t HW = (size_t)cc.W * cc.H, p = (size_t)pix.py * cc.W + pix.px;
+        const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
+        final_T[p] = T;
+        n_contrib[p] = last;
+        out_planes[p] = C0 + T * b0;
+        out_planes[HW + p] = C1 + T * b1;
+        out_planes[2 * HW + p] = C2 + T * b2;
+        if (FUSED) {
+            out_planes[3 * HW + p] = D + T * b0;
+            out_planes[4 * HW + p] = S + T * b1;
+            out_planes[5 * HW + p] = D2 + T * b2;
+        } else {
+            out_depth[p] = D;
+        }
+    }
+}
+
+// ---- backward -----------------------------------------------------------------------------------
+// Back-to-front replay over the first max(n_contrib) entries of the tile list.  Per (warp, entry)
+// the 32 per-pixel partial gradients are combined with a 16-shuffle reduce-scatter and added to a
+// per-batch shared-memory accumulator; after each batch one thread per entry flushes its 12
+// floats to the per-Gaussian accumulator with three vector atomics.
+template <bool FUSED>
+__global__ void __launch_bounds__(CTA)
+k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
+                const unsigned long long *__restrict__ keys, const float4 *__restrict__ sorted_rec,
+                const float *__restrict__ bg, const float *__restrict__ final_T,
+                const unsigned int *__restrict__ n_contrib, const float *__restrict__ dL_dplanes,
+                const float *__restrict__ dL_ddepth, float *__restrict__ grad_acc, unsigned int flags,
+                unsigned long long *__restrict__ err) {
+    __shared__ __align__(128) float4 s_rec[2][BATCH * REC_F4];
+    __shared__ __align__(16) float s_acc[BATCH * ACC_F];
+    __shared__ unsigned int s_id[2][BATCH];
+    __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ unsigned int s_maxlast;
+    const int tile = blockIdx.x;
+    const unsigned int start = tile_offset[tile];
+    const int n = (int)(tile_offset[tile + 1] - start);
+    if (n == 0) return;
+    const bool use_tma = (flags & 1u) == 0;
+    const int lane = threadIdx.x & 31;
+    const TilePix pix = tile_pixel(cc, tile);
+    const float pxf = (float)pix.px, pyf = (float)pix.py;
+    const size_t HW = (size_t)cc.W * cc.H, p = (size_t)pix.py * cc.W + pix.px;
+
+    if (threadIdx.x == 0) {
+        s_maxlast = 0;
+        if (use_tma) {
+            mbar_init(&s_full[0], 1);
+            mbar_init(&s_full[1], 1);
+            mbar_fence_init();
+        }
+    }
+    for (int q = threadIdx.x; q < BATCH * ACC_F; q += CTA) s_acc[q] = 0.f;
+    __syncthreads();
+
+    const int last = pix.inside ? (int)n_contrib[p] : 0;
+    {
+        const unsigned int wmax = __reduce_max_sync(FULL, (unsigned int)last);
+        if (lane == 0 && wmax) atomicMax(&s_maxlast, wmax);
+    }
+    __syncthreads();
+    const int maxlast = min((int)s_maxlast, n);
+    if (maxlast == 0) return;
+    const int nb = (maxlast + BATCH - 1) / BATCH;
+
+    constexpr int NG = FUSED ? 6 : 4;   // pixel gradients: planes (+ depth plane for the API flavour)
+    float g[NG];
+    const float T_final = pix.inside ? final_T[p] : 0.f;
+    float bgdot_rgb = 0.f, bgdot_dep = 0.f;
+    {
+        const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
+#pragma unroll
+        for (int ch = 0; ch < NG; ++ch) g[ch] = 0.f;
+        if (pix.inside) {
+            g[0] = dL_dplanes[p]; g[1] = dL_dplanes[HW + p]; g[2] = dL_dplanes[2 * HW + p];
+            if (FUSED) {
+                g[3] = dL_dplanes[3 * HW + p]; g[4] = dL_dplanes[4 * HW + p]; g[5] = dL_dplanes[5 * HW + p];
+                bgdot_dep = b0 * g[3] + b1 * g[4] + b2 * g[5];
+            } else {
+                g[3] = dL_ddepth ? dL_ddepth[p] : 0.f;
+            }
+            bgdot_rgb = b0 * g[0] + b1 * g[1] + b2 * g[2];
+        }
+    }
+    const float ddelx_dx = 0.5f * cc.W, ddely_dy = 0.5f * cc.H;
+
+    BwdPixel ps;
+    ps.T = T_final; ps.last_alpha = 0.f;
+    ps.acc_r = ps.acc_g = ps.acc_b = ps.acc_d = ps.acc_s = ps.acc_d2 = 0.f;
+    ps.lc_r = ps.lc_g = ps.lc_b = ps.lc_d = 0.f;
+
+    const float4 *src = sorted_rec + (size_t)start * REC_F4;
+    const unsigned long long *kp = keys + start;
+    auto batch_cnt = [&](int k) { return min(BATCH, maxlast - k * BATCH); };
+
+    // prologue: stage the LAST batch
+    {
+        const int k = nb - 1;
+        if (use_tma && threadIdx.x == 0) stage_issue_tma(s_rec[0], src + (size_t)k * BATCH * REC_F4, batch_cnt(k), &s_full[0]);
+        if (threadIdx.x < batch_cnt(k)) s_id[0][threadIdx.x] = (unsigned int)kp[(size_t)k * BATCH + threadIdx.x];
+    }
+
+    for (int it = 0; it < nb; ++it) {
+        const int k = nb - 1 - it;
+        const int buf = it & 1;
+        const int cnt = batch_cnt(k);
+        __syncthreads();   // batch it-1 fully consumed and flushed; s_id[buf] written
+        if (it + 1 < nb) {
+            const int kn = k - 1;
+            if (use_tma && threadIdx.x == 0)
+                stage_issue_tma(s_rec[buf ^ 1], src + (size_t)kn * BATCH * REC_F4, batch_cnt(kn), &s_full[buf ^ 1]);
+            if (threadIdx.x < batch_cnt(kn)) s_id[buf ^ 1][threadIdx.x] = (unsigned int)kp[(size_t)kn * BATCH + threadIdx.x];
+        }
+        if (use_tma) {
+            mbar_wait(&s_full[buf], (uint32_t)(it >> 1) & 1u, err);
+        } else {
+            stage_plain(s_rec[buf], src + (size_t)k * BATCH * REC_F4, cnt);
+            __syncthreads();
+        }
+        const float4 *sb = s_rec[buf];
+
+        for (int j = cnt - 1; j >= 0; --j) {
+            const int gidx = k * BATCH + j;
+            const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
+            const float dx = q0.x - pxf, dy = q0.y - pyf;
+            const float power = gauss_power(q0.z, q0.w, q1.x, dx, dy);
+            const float G = gauss_weight(power);
+            const float alpha = fminf(ALPHA_MAX, q1.y * G);
+            const bool valid = (gidx < last) && (power <= 0.f) && (alpha >= ALPHA_MIN);
+            if (!__any_sync(FULL, valid)) continue;
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = 0.f;
+            if (valid) {
+                const float4 q2 = sb[j * 3 + 2];
+                bwd_pair<FUSED>(ps, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final,
+                                bgdot_rgb, bgdot_dep, ddelx_dx, ddely_dy, v);
+            }
+            warp_reduce_scatter16(v, lane);
+            const int idx = lane >> 1;
+            if ((lane & 1) == 0 && idx < ACC_F && v[0] != 0.f) atomicAdd(&s_acc[j * ACC_F + idx], v[0]);
+        }
+
+        __syncthreads();   // all warps' shared-memory adds for this batch are in
+        if (threadIdx.x < cnt) {
+            float4 *row = reinterpret_cast<float4 *>(&s_acc[threadIdx.x * ACC_F]);
+            const float4 a = row[0], b = row[1], c = row[2];
+            const bool nz = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) |
+                            (b.z != 0.f) | (b.w != 0.f) | (c.x != 0.f) | (c.y != 0.f) | (c.z != 0.f) | (c.w != 0.f);
+            if (nz) {
+                float4 *dst = reinterpret_cast<float4 *>(grad_acc + (size_t)s_id[buf][threadIdx.x] * ACC_F);
+                atomicAdd(dst, a);
+                atomicAdd(dst + 1, b);
+                atomicAdd(dst + 2, c);
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                row[0] = z4; row[1] = z4; row[2] = z4;
+            }
+        }
+    }
+}
+
+}  // namespace fsgs

@@ -1,0 +1,311 @@
+// fsgs_kernels_pre.cuh -- per-Gaussian kernels: projection (API + fused), per-tile counting,
+// tile scan, instance scatter, per-tile sort.  sm_100a.
+#pragma once
+
+#include "fsgs_device.cuh"
+
+namespace fsgs {
+
+// One compiled copy of the tile test, so the counting pass (inside the projection kernels) and
+// the scatter pass take bit-identical keep/drop decisions.
+__device__ __noinline__ bool tile_hit_ni(float px, float py, float A, float B, float C, float tau, int tx, int ty) {
+    CullEllipse e;
+    e.px = px; e.py = py; e.A = A; e.B = B; e.C = C; e.tau = tau; e.hx = 0.f; e.hy = 0.f;
+    return tile_hit(e, tx, ty);
+}
+
+// Tile range + padded threshold of one Gaussian; also a single compiled copy (it contains
+// mul+add chains that the compiler could otherwise contract differently per call site).
+struct TileRange {
+    int x0, y0, x1, y1;
+    float tau;
+};
+__device__ __noinline__ TileRange tile_range_ni(int gx, int gy, float px, float py, float A, float B, float C,
+                                                float opacity, int radius, int no_cull) {
+    const float rad = (float)radius;
+    const int rminx = clampi((int)((px - rad) / TILE), 0, gx);
+    const int rminy = clampi((int)((py - rad) / TILE), 0, gy);
+    const int rmaxx = clampi((int)((px + rad + TILE - 1) / TILE), 0, gx);
+    const int rmaxy = clampi((int)((py + rad + TILE - 1) / TILE), 0, gy);
+    TileRange r;
+    if (no_cull) {
+        r.x0 = rminx; r.y0 = rminy; r.x1 = rmaxx; r.y1 = rmaxy; r.tau = 3.0e38f;
+        return r;
+    }
+    const CullEllipse e = make_cull_ellipse(px, py, A, B, C, opacity);
+    cull_rect(e, rminx, rminy, rmaxx, rmaxy, r.x0, r.y0, r.x1, r.y1);
+    r.tau = e.tau;
+    return r;
+}
+
+// Visit every kept tile of one Gaussian.  f(tile_index) is called for each; returns the count.
+template <typename F>
+__device__ __forceinline__ int for_each_tile(const CamConst &cc, float px, float py, float A, float B, float C,
+                                             float opacity, int radius, bool no_cull, F &&f) {
+    const TileRange tr = tile_range_ni(cc.gx, cc.gy, px, py, A, B, C, opacity, radius, no_cull ? 1 : 0);
+    int n = 0;
+    for (int ty = tr.y0; ty < tr.y1; ++ty)
+        for (int tx = tr.x0; tx < tr.x1; ++tx)
+            if (tile_hit_ni(px, py, A, B, C, tr.tau, tx, ty)) { f(ty * cc.gx + tx); ++n; }
+    return n;
+}
+
+__device__ __forceinline__ void load16(const float *__restrict__ p, float *o) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __ldg(p + i);
+}
+
+__device__ __forceinline__ void store_record(float4 *rec, int i, const Splat &s, float opacity, float r, float g,
+                                             float b, int tiles) {
+    rec[(size_t)i * 3 + 0] = make_float4(s.px, s.py, s.conx, s.cony);
+    rec[(size_t)i * 3 + 1] = make_float4(s.conz, opacity, r, g);
+    rec[(size_t)i * 3 + 2] = make_float4(b, s.depth, __int_as_float(s.radius), __int_as_float(tiles));
+}
+__device__ __forceinline__ void store_empty_record(float4 *rec, int i) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec[(size_t)i * 3 + 0] = z; rec[(size_t)i * 3 + 1] = z; rec[(size_t)i * 3 + 2] = z;
+}
+
+// block-wide sum of a small integer, one atomic per CTA
+__device__ __forceinline__ void block_add_u64(unsigned long long *dst, unsigned int v) {
+    __shared__ unsigned int s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const unsigned int w = __reduce_add_sync(FULL, v);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_sum, w);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum) atomicAdd(dst, (unsigned long long)s_sum);
+}
+
+// ---- K1, API flavour: one GaussianRasterizer call -----------------------------------------------
+__global__ void __launch_bounds__(CTA)
+k_preprocess_api(CamConst cc, int P, const float *__restrict__ means3D, const float *__restrict__ colors_precomp,
+                 const float *__restrict__ shs, const float *__restrict__ opacities,
+                 const float *__restrict__ scales, const float *__restrict__ rotations,
+                 const float *__restrict__ cov3D_precomp, const float *__restrict__ viewmatrix,
+                 const float *__restrict__ projmatrix, const float *__restrict__ campos, float4 *__restrict__ records,
+                 uint8_t *__restrict__ clamped, int *__restrict__ radii, unsigned int *__restrict__ tile_count,
+                 unsigned long long *__restrict__ counters, unsigned int flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int rect_tiles = 0;
+    if (i < P) {
+        float V[16], PM[16], cp[3] = {0.f, 0.f, 0.f};
+        load16(viewmatrix, V);
+        load16(projmatrix, PM);
+        if (shs) { cp[0] = __ldg(campos); cp[1] = __ldg(campos + 1); cp[2] = __ldg(campos + 2); }
+        const size_t n = (size_t)i;
+        const float mean[3] = {means3D[3 * n], means3D[3 * n + 1], means3D[3 * n + 2]};
+        Splat sp;
+        float rgb[3];
+        uint8_t cl = 0;
+        int radius = 0;
+        if (api_forward_one(cc, V, PM, cp, mean, colors_precomp ? colors_precomp + 3 * n : nullptr,
+                            shs ? shs + n * cc.n_coeffs * 3 : nullptr, scales ? scales + 3 * n : nullptr,
+                            rotations ? rotations + 4 * n : nullptr, cov3D_precomp ? cov3D_precomp + 6 * n : nullptr, sp,
+                            rgb, cl)) {
+            radius = sp.radius;
+            const float opacity = opacities[i];
+            rect_tiles = (unsigned int)((sp.rmaxx - sp.rminx) * (sp.rmaxy - sp.rminy));
+            const int tiles = for_each_tile(cc, sp.px, sp.py, sp.conx, sp.cony, sp.conz, opacity, sp.radius,
+                                            (flags & 2u) != 0, [&](int t) { atomicAdd(&tile_count[t], 1u); });
+            store_record(records, i, sp, opacity, rgb[0], rgb[1], rgb[2], tiles);
+        } else {
+            store_empty_record(records, i);
+        }
+        clamped[i] = cl;
+        radii[i] = radius;
+    }
+    block_add_u64(&counters[CNT_RECT], rect_tiles);
+}
+
+// ---- K1, fused flavour: gaussian_renderer.render's pre-processing folded in -----------------------
+// pose is ROW-major [4,4] (LearnPose.forward output); features_dc [P,1,3], features_rest [P,15,3].
+__global__ void __launch_bounds__(CTA)
+k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const float *__restrict__ f_dc,
+                   const float *__restrict__ f_rest, const float *__restrict__ opacity_raw,
+                   const float *__restrict__ scaling_raw, const float *__restrict__ rotation_raw,
+                   const float *__restrict__ pose, const float *__restrict__ cam_center,
+                   const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
+                   float4 *__restrict__ records, uint8_t *__restrict__ clamped, int *__restrict__ radii,
+                   unsigned int *__restrict__ tile_count, unsigned long long *__restrict__ counters,
+                   unsigned int flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int rect_tiles = 0;
+    if (i < P) {
+        float V[16], PM[16], Rt[12], cp[3];
+        load16(viewmatrix, V);
+        load16(projmatrix, PM);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose + k);
+        cp[0] = __ldg(cam_center); cp[1] = __ldg(cam_center + 1); cp[2] = __ldg(cam_center + 2);
+        const size_t n = (size_t)i;
+        const float w[3] = {xyz[3 * n], xyz[3 * n + 1], xyz[3 * n + 2]};
+        const float sc[3] = {scaling_raw[3 * n], scaling_raw[3 * n + 1], scaling_raw[3 * n + 2]};
+        const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+        Splat sp;
+        float rgb[3], opacity = 0.f;
+        uint8_t cl = 0;
+        int radius = 0;
+        if (fused_forward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, f_rest + 45 * n, opacity_raw[i], sc, q, sp, opacity,
+                              rgb, cl)) {
+            radius = sp.radius;
+            rect_tiles = (unsigned int)((sp.rmaxx - sp.rminx) * (sp.rmaxy - sp.rminy));
+            const int tiles = for_each_tile(cc, sp.px, sp.py, sp.conx, sp.cony, sp.conz, opacity, sp.radius,
+                                            (flags & 2u) != 0, [&](int t) { atomicAdd(&tile_count[t], 1u); });
+            store_record(records, i, sp, opacity, rgb[0], rgb[1], rgb[2], tiles);
+        } else {
+            store_empty_record(records, i);
+        }
+        clamped[i] = cl;
+        radii[i] = radius;
+    }
+    block_add_u64(&counters[CNT_RECT], rect_tiles);
+}
+
+// ---- K2: exclusive scan of the per-tile counts (single CTA; a few thousand tiles) ------------------
+__global__ void __launch_bounds__(1024)
+k_tile_scan(int tiles, const unsigned int *__restrict__ tile_count, unsigned int *__restrict__ tile_offset,
+            unsigned int *__restrict__ cursor, unsigned long long *__restrict__ counters) {
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_max[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (tiles + 1023) / 1024;
+    const int b = tid * per, e = min(tiles, b + per);
+    unsigned int sum = 0, mx = 0;
+    for (int t = b; t < e; ++t) { const unsigned int c = tile_count[t]; sum += c; mx = max(mx, c); }
+    // inclusive scan of per-thread sums
+    unsigned int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int n = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += n;
+    }
+    mx = __reduce_max_sync(FULL, mx);
+    if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) s_max[warp] = mx;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int n = __shfl_up_sync(FULL, w, d);
+            if (lane >= d) w += n;
+        }
+        s_warp[lane] = w;   // inclusive over warps
+        const unsigned int m = __reduce_max_sync(FULL, s_max[lane]);
+        if (lane == 0) s_max[0] = m;
+    }
+    __syncthreads();
+    unsigned int run = incl - sum + (warp > 0 ? s_warp[warp - 1] : 0u);
+    for (int t = b; t < e; ++t) {
+        tile_offset[t] = run;
+        cursor[t] = 0;
+        run += tile_count[t];
+    }
+    if (tid == 1023) {
+        tile_offset[tiles] = s_warp[31];
+        counters[CNT_R] = s_warp[31];
+        counters[CNT_MAXLIST] = s_max[0];
+    }
+}
+
+// ---- K3: scatter (depth, id) keys into the per-tile segments ----------------------------------------
+__global__ void __launch_bounds__(CTA)
+k_scatter(CamConst cc, int P, const float4 *__restrict__ records, const unsigned int *__restrict__ tile_offset,
+          unsigned int *__restrict__ cursor, unsigned long long *__restrict__ keys, unsigned int flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float4 q2 = records[(size_t)i * 3 + 2];
+    if (__float_as_int(q2.w) <= 0) return;
+    const float4 q0 = records[(size_t)i * 3 + 0];
+    const float4 q1 = records[(size_t)i * 3 + 1];
+    const unsigned long long key_hi = ((unsigned long long)__float_as_uint(q2.y)) << 32;
+    for_each_tile(cc, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_int(q2.z), (flags & 2u) != 0, [&](int t) {
+        const unsigned int slot = atomicAdd(&cursor[t], 1u);
+        keys[(size_t)tile_offset[t] + slot] = key_hi | (unsigned int)i;
+    });
+}
+
+// ---- K4+K5: per-tile sort by (depth bits, Gaussian id) and gather of the splat records -------------
+// A data-independent compare-exchange network whose comparators all point the same way, so a list
+// of arbitrary length n behaves as if padded with +inf to the next power of two.
+template <typename KeyPtr>
+__device__ __forceinline__ void tile_sort_network(KeyPtr a, int n) {
+    int N = 1;
+    while (N < n) N <<= 1;
+    const int half = N >> 1;
+    for (int k = 2; k <= N; k <<= 1) {
+        const int hk = k >> 1;
+        for (int p = threadIdx.x; p < half; p += blockDim.x) {
+            const int blk = p / hk, r = p - blk * hk;
+            const int lo = blk * k + r, hi = blk * k + (k - 1 - r);
+            if (hi < n) {
+                const unsigned long long x = a[lo], y = a[hi];
+                if (x > y) { a[lo] = y; a[hi] = x; }
+            }
+        }
+        __syncthreads();
+        for (int j = k >> 2; j > 0; j >>= 1) {
+            for (int p = threadIdx.x; p < half; p += blockDim.x) {
+                const int blk = p / j, r = p - blk * j;
+                const int lo = blk * 2 * j + r, hi = lo + j;
+                if (hi < n) {
+                    const unsigned long long x = a[lo], y = a[hi];
+                    if (x > y) { a[lo] = y; a[hi] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+constexpr int SORT_SMEM_KEYS = 8192;   // 64 KB of dynamic shared memory
+
+__global__ void __launch_bounds__(CTA)
+k_tile_sort(const unsigned int *__restrict__ tile_offset, unsigned long long *__restrict__ keys,
+            const float4 *__restrict__ records, float4 *__restrict__ sorted_rec) {
+    extern __shared__ __align__(16) unsigned long long s_keys[];
+    const unsigned int start = tile_offset[blockIdx.x];
+    const int n = (int)(tile_offset[blockIdx.x + 1] - start);
+    if (n == 0) return;
+    unsigned long long *g = keys + start;
+    if (n <= SORT_SMEM_KEYS) {
+        for (int p = threadIdx.x; p < n; p += blockDim.x) s_keys[p] = g[p];
+        __syncthreads();
+        if (n > 1) tile_sort_network(s_keys, n);
+        for (int p = threadIdx.x; p < n; p += blockDim.x) {
+            const unsigned long long k = s_keys[p];
+            g[p] = k;
+            const unsigned int id = (unsigned int)k;
+            const float4 a = ldg4(records + (size_t)id * 3), b = ldg4(records + (size_t)id * 3 + 1),
+                         c = ldg4(records + (size_t)id * 3 + 2);
+            float4 *dst = sorted_rec + ((size_t)start + p) * 3;
+            dst[0] = a; dst[1] = b; dst[2] = c;
+        }
+    } else {
+        // rare: list longer than the shared-memory window -> same network in global memory (L2)
+        tile_sort_network(g, n);
+        for (int p = threadIdx.x; p < n; p += blockDim.x) {
+            const unsigned int id = (unsigned int)g[p];
+            const float4 a = ldg4(records + (size_t)id * 3), b = ldg4(records + (size_t)id * 3 + 1),
+                         c = ldg4(records + (size_t)id * 3 + 2);
+            float4 *dst = sorted_rec + ((size_t)start + p) * 3;
+            dst[0] = a; dst[1] = b; dst[2] = c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CTA)
+k_mark_visible(int P, const float *__restrict__ means3D, const float *__restrict__ viewmatrix,
+               uint8_t *__restrict__ visible) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float V[16];
+    load16(viewmatrix, V);
+    float x, y, z;
+    xf43(V, means3D[3 * (size_t)i], means3D[3 * (size_t)i + 1], means3D[3 * (size_t)i + 2], x, y, z);
+    visible[i] = z > NEAR_CULL ? 1 : 0;
+}
+
+}  // namespace fsgs

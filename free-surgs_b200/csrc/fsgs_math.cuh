@@ -1,0 +1,602 @@
+// fsgs_math.cuh -- per-Gaussian arithmetic of the rasteriser (projection, EWA covariance, SH,
+// and their closed-form backward), written as host/device inline functions so that the CUDA
+// kernels use them on the GPU and tests/cpu_emul can compile the very same code with g++ to
+// check it against the oracle in the build container (which has no GPU).
+//
+// Behavioural spec: SURVEY.md Appendix A (kernels K1, K8, K9), i.e. the arithmetic of the
+// `diff_gaussian_rasterization` package that Free-SurGS calls at
+// gaussian_renderer/__init__.py:68,69,131, plus the Python pre-processing of
+// scene/gaussian_model.py:118-138,260-333, utils/sh_utils.py:57-112 and
+// scene/pose_optimizer.py:960-989 that the fused path folds in.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FSGS_HD __host__ __device__ __forceinline__
+#else
+#define FSGS_HD inline
+#endif
+
+namespace fsgs {
+
+constexpr int TILE = 16;
+constexpr float NEAR_CULL = 0.2f;
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr float ALPHA_MAX = 0.99f;
+constexpr float T_MIN = 0.0001f;
+constexpr float COV_DILATION = 0.3f;
+
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+constexpr float SH_C2_0 = 1.0925484305920792f, SH_C2_1 = -1.0925484305920792f, SH_C2_2 = 0.31539156525252005f,
+                SH_C2_3 = -1.0925484305920792f, SH_C2_4 = 0.5462742152960396f;
+constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH_C3_2 = -0.4570457994644658f,
+                SH_C3_3 = 0.3731763325901154f, SH_C3_4 = -0.4570457994644658f, SH_C3_5 = 1.445305721320277f,
+                SH_C3_6 = -0.5900435899266435f;
+
+// Camera constants one launch needs, derived on the host from fsgs_settings.
+struct CamConst {
+    int W, H, gx, gy;
+    float fx, fy;          // focal lengths in pixels: W/(2 tanfovx), H/(2 tanfovy)
+    float limx, limy;      // 1.3 * tanfov
+    float mod;             // scale modifier
+    int sh_deg, n_coeffs;
+};
+
+// Result of projecting one Gaussian (K1).
+struct Splat {
+    float px, py;          // pixel-space centre
+    float depth;           // view-space z
+    float a, b, c;         // 2D covariance (with the +0.3 dilation)
+    float conx, cony, conz;
+    int radius;            // ceil(3 sqrt(lambda_max)), the reference's screen radius
+    int rminx, rminy, rmaxx, rmaxy;   // the reference's tile rectangle [min,max)
+};
+
+FSGS_HD void xf43(const float *M, float x, float y, float z, float &ox, float &oy, float &oz) {
+    ox = M[0] * x + M[4] * y + M[8] * z + M[12];
+    oy = M[1] * x + M[5] * y + M[9] * z + M[13];
+    oz = M[2] * x + M[6] * y + M[10] * z + M[14];
+}
+
+// Rotation matrix (row-major) of a quaternion (w,x,y,z) used as given.
+FSGS_HD void quat_to_R(const float *q, float *R) {
+    const float r = q[0], x = q[1], y = q[2], z = q[3];
+    R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - r * z); R[2] = 2.f * (x * z + r * y);
+    R[3] = 2.f * (x * y + r * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - r * x);
+    R[6] = 2.f * (x * z - r * y); R[7] = 2.f * (y * z + r * x); R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+// Sigma = R diag(s^2) R^T as (xx,xy,xz,yy,yz,zz); s already includes the scale modifier.
+FSGS_HD void cov3d_from_scale_rot(const float *s, const float *q, float *c6) {
+    float R[9];
+    quat_to_R(q, R);
+    const float s0 = s[0] * s[0], s1 = s[1] * s[1], s2 = s[2] * s[2];
+    c6[0] = R[0] * R[0] * s0 + R[1] * R[1] * s1 + R[2] * R[2] * s2;
+    c6[1] = R[0] * R[3] * s0 + R[1] * R[4] * s1 + R[2] * R[5] * s2;
+    c6[2] = R[0] * R[6] * s0 + R[1] * R[7] * s1 + R[2] * R[8] * s2;
+    c6[3] = R[3] * R[3] * s0 + R[4] * R[4] * s1 + R[5] * R[5] * s2;
+    c6[4] = R[3] * R[6] * s0 + R[4] * R[7] * s1 + R[5] * R[8] * s2;
+    c6[5] = R[6] * R[6] * s0 + R[7] * R[7] * s1 + R[8] * R[8] * s2;
+}
+
+// View-space point with the reference's +-1.3 tanfov clamp, and M = J * W3 (2x3, row-major),
+// W3[r][c] = V[4c + r].  xmask/ymask are 0 where the clamp is active.
+FSGS_HD void ewa_M(const CamConst &cc, const float *V, const float *mean, float *t, float *M, float &xmask,
+                   float &ymask) {
+    xf43(V, mean[0], mean[1], mean[2], t[0], t[1], t[2]);
+    const float txtz = t[0] / t[2], tytz = t[1] / t[2];
+    xmask = (txtz < -cc.limx || txtz > cc.limx) ? 0.f : 1.f;
+    ymask = (tytz < -cc.limy || tytz > cc.limy) ? 0.f : 1.f;
+    t[0] = fminf(cc.limx, fmaxf(-cc.limx, txtz)) * t[2];
+    t[1] = fminf(cc.limy, fmaxf(-cc.limy, tytz)) * t[2];
+    const float J00 = cc.fx / t[2], J02 = -(cc.fx * t[0]) / (t[2] * t[2]);
+    const float J11 = cc.fy / t[2], J12 = -(cc.fy * t[1]) / (t[2] * t[2]);
+    M[0] = J00 * V[0] + J02 * V[2]; M[1] = J00 * V[4] + J02 * V[6]; M[2] = J00 * V[8] + J02 * V[10];
+    M[3] = J11 * V[1] + J12 * V[2]; M[4] = J11 * V[5] + J12 * V[6]; M[5] = J11 * V[9] + J12 * V[10];
+}
+
+// (S M0, S M1) and a,b,c of M S M^T + 0.3 I.
+FSGS_HD void ewa_abc(const float *M, const float *c6, float *SM0, float *SM1, float &a, float &b, float &c) {
+    SM0[0] = c6[0] * M[0] + c6[1] * M[1] + c6[2] * M[2];
+    SM0[1] = c6[1] * M[0] + c6[3] * M[1] + c6[4] * M[2];
+    SM0[2] = c6[2] * M[0] + c6[4] * M[1] + c6[5] * M[2];
+    SM1[0] = c6[0] * M[3] + c6[1] * M[4] + c6[2] * M[5];
+    SM1[1] = c6[1] * M[3] + c6[3] * M[4] + c6[4] * M[5];
+    SM1[2] = c6[2] * M[3] + c6[4] * M[4] + c6[5] * M[5];
+    a = M[0] * SM0[0] + M[1] * SM0[1] + M[2] * SM0[2] + COV_DILATION;
+    b = M[0] * SM1[0] + M[1] * SM1[1] + M[2] * SM1[2];
+    c = M[3] * SM1[0] + M[4] * SM1[1] + M[5] * SM1[2] + COV_DILATION;
+}
+
+FSGS_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// K1 geometry of one Gaussian.  Returns false when the reference would skip it (radius 0).
+FSGS_HD bool project_gaussian(const CamConst &cc, const float *V, const float *PM, const float *mean,
+                              const float *c6, Splat &o) {
+    float vx, vy, vz;
+    xf43(V, mean[0], mean[1], mean[2], vx, vy, vz);
+    if (vz <= NEAR_CULL) return false;
+    const float hx = PM[0] * mean[0] + PM[4] * mean[1] + PM[8] * mean[2] + PM[12];
+    const float hy = PM[1] * mean[0] + PM[5] * mean[1] + PM[9] * mean[2] + PM[13];
+    const float hw = PM[3] * mean[0] + PM[7] * mean[1] + PM[11] * mean[2] + PM[15];
+    const float pw = 1.0f / (hw + 0.0000001f);
+    float t[3], M[6], xm, ym, SM0[3], SM1[3];
+    ewa_M(cc, V, mean, t, M, xm, ym);
+    ewa_abc(M, c6, SM0, SM1, o.a, o.b, o.c);
+    const float det = o.a * o.c - o.b * o.b;
+    if (det == 0.0f) return false;
+    const float det_inv = 1.f / det;
+    o.conx = o.c * det_inv; o.cony = -o.b * det_inv; o.conz = o.a * det_inv;
+    const float mid = 0.5f * (o.a + o.c);
+    const float lam = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+    const float rad = ceilf(3.f * sqrtf(lam));
+    o.px = ((hx * pw + 1.0f) * cc.W - 1.0f) * 0.5f;
+    o.py = ((hy * pw + 1.0f) * cc.H - 1.0f) * 0.5f;
+    o.rminx = clampi((int)((o.px - rad) / TILE), 0, cc.gx);
+    o.rminy = clampi((int)((o.py - rad) / TILE), 0, cc.gy);
+    o.rmaxx = clampi((int)((o.px + rad + TILE - 1) / TILE), 0, cc.gx);
+    o.rmaxy = clampi((int)((o.py + rad + TILE - 1) / TILE), 0, cc.gy);
+    if ((o.rmaxx - o.rminx) * (o.rmaxy - o.rminy) == 0) return false;
+    o.depth = vz;
+    o.radius = (int)rad;
+    return true;
+}
+
+// ---- exact tile culling ---------------------------------------------------------------------
+// A Gaussian can only change a pixel if alpha = opacity*exp(-q(d)) >= 1/255, i.e.
+// q(d) = 0.5*(A dx^2 + C dy^2) + B dx dy <= tau = ln(255*opacity).  A tile of the reference's
+// rectangle whose pixel square lies entirely outside that ellipse contributes nothing (every
+// pixel takes the reference's `alpha < 1/255 -> continue` branch), so dropping the
+// (tile, Gaussian) instance leaves the image and all gradients unchanged.  The test below is the
+// exact minimum of the convex quadratic q over the (continuous) pixel square, padded so that
+// float rounding can only keep extra tiles, never drop a contributing one.
+struct CullEllipse {
+    float px, py, A, B, C, tau;   // tau already padded; tau < 0 => Gaussian can never contribute
+    float hx, hy;                 // half extents of the ellipse's axis-aligned bounding box
+};
+
+FSGS_HD CullEllipse make_cull_ellipse(float px, float py, float conx, float cony, float conz, float opacity) {
+    CullEllipse e;
+    e.px = px; e.py = py; e.A = conx; e.B = cony; e.C = conz;
+    const float t = logf(255.0f * opacity);
+    e.tau = (opacity * 255.0f >= 0.999f) ? (t * 1.0005f + 0.01f) : -1.0f;
+    // bbox of {q <= tau}: |dx| <= sqrt(2 tau * C / det(conic)), |dy| <= sqrt(2 tau * A / det(conic))
+    const float det = fmaxf(conx * conz - cony * cony, 1e-30f);
+    const float tt = fmaxf(e.tau, 0.f) * 2.0f;
+    e.hx = sqrtf(tt * conz / det) * 1.0005f + 0.01f;
+    e.hy = sqrtf(tt * conx / det) * 1.0005f + 0.01f;
+    return e;
+}
+
+// min over dy in [lo,hi] of 0.5*(A dx^2 + C dy^2) + B dx dy for fixed dx
+FSGS_HD float edge_min(float A, float B, float C, float dx, float lo, float hi) {
+    float dy = -B * dx / C;
+    dy = fminf(hi, fmaxf(lo, dy));
+    return 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
+}
+
+// Does tile (tx,ty) contain a pixel centre (integer coordinates, as the compositor uses) with
+// q <= tau?  Conservative (continuous relaxation + padding).
+FSGS_HD bool tile_hit(const CullEllipse &e, int tx, int ty) {
+    const float x0 = (float)(tx * TILE), x1 = x0 + (float)(TILE - 1);
+    const float y0 = (float)(ty * TILE), y1 = y0 + (float)(TILE - 1);
+    // d = centre - pixel, so dx ranges over [px - x1, px - x0]
+    const float dxl = e.px - x1, dxh = e.px - x0, dyl = e.py - y1, dyh = e.py - y0;
+    if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return true;   // centre inside the square
+    float q = edge_min(e.A, e.B, e.C, dxl, dyl, dyh);
+    q = fminf(q, edge_min(e.A, e.B, e.C, dxh, dyl, dyh));
+    q = fminf(q, edge_min(e.C, e.B, e.A, dyl, dxl, dxh));
+    q = fminf(q, edge_min(e.C, e.B, e.A, dyh, dxl, dxh));
+    return q <= e.tau;
+}
+
+// Tile range = reference rectangle intersected with the ellipse's bounding box.
+FSGS_HD void cull_rect(const CullEllipse &e, int rminx, int rminy, int rmaxx, int rmaxy, int &x0, int &y0,
+                       int &x1, int &y1) {
+    if (e.tau < 0.f) { x0 = x1 = y0 = y1 = 0; return; }
+    // tile tx covers pixels [16 tx, 16 tx + 15]
+    const int bx0 = (int)floorf((e.px - e.hx) / TILE), bx1 = (int)floorf((e.px + e.hx) / TILE) + 1;
+    const int by0 = (int)floorf((e.py - e.hy) / TILE), by1 = (int)floorf((e.py + e.hy) / TILE) + 1;
+    x0 = rminx > bx0 ? rminx : bx0; x1 = rmaxx < bx1 ? rmaxx : bx1;
+    y0 = rminy > by0 ? rminy : by0; y1 = rmaxy < by1 ? rmaxy : by1;
+    if (x1 < x0) x1 = x0;
+    if (y1 < y0) y1 = y0;
+}
+
+// ---- spherical harmonics ----------------------------------------------------------------------
+// basis values B[0..(deg+1)^2) at unit direction d (utils/sh_utils.py:74-100)
+FSGS_HD void sh_basis(int deg, float x, float y, float z, float *B) {
+    B[0] = SH_C0;
+    if (deg > 0) {
+        B[1] = -SH_C1 * y; B[2] = SH_C1 * z; B[3] = -SH_C1 * x;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            B[4] = SH_C2_0 * xy; B[5] = SH_C2_1 * yz; B[6] = SH_C2_2 * (2.f * zz - xx - yy);
+            B[7] = SH_C2_3 * xz; B[8] = SH_C2_4 * (xx - yy);
+            if (deg > 2) {
+                B[9] = SH_C3_0 * y * (3.f * xx - yy); B[10] = SH_C3_1 * xy * z;
+                B[11] = SH_C3_2 * y * (4.f * zz - xx - yy); B[12] = SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                B[13] = SH_C3_4 * x * (4.f * zz - xx - yy); B[14] = SH_C3_5 * z * (xx - yy);
+                B[15] = SH_C3_6 * x * (xx - 3.f * yy);
+            }
+        }
+    }
+}
+
+// d(B[k])/d(dir) for k >= 1 (k = 0 is constant); dB is [16][3], entries not listed stay 0.
+FSGS_HD void sh_basis_grad(int deg, float x, float y, float z, float (*dB)[3]) {
+    for (int k = 0; k < 16; ++k) { dB[k][0] = 0.f; dB[k][1] = 0.f; dB[k][2] = 0.f; }
+    if (deg > 0) {
+        dB[1][1] = -SH_C1; dB[2][2] = SH_C1; dB[3][0] = -SH_C1;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            dB[4][0] = SH_C2_0 * y; dB[4][1] = SH_C2_0 * x;
+            dB[5][1] = SH_C2_1 * z; dB[5][2] = SH_C2_1 * y;
+            dB[6][0] = SH_C2_2 * -2.f * x; dB[6][1] = SH_C2_2 * -2.f * y; dB[6][2] = SH_C2_2 * 4.f * z;
+            dB[7][0] = SH_C2_3 * z; dB[7][2] = SH_C2_3 * x;
+            dB[8][0] = SH_C2_4 * 2.f * x; dB[8][1] = SH_C2_4 * -2.f * y;
+            if (deg > 2) {
+                dB[9][0] = SH_C3_0 * 6.f * xy; dB[9][1] = SH_C3_0 * (3.f * xx - 3.f * yy);
+                dB[10][0] = SH_C3_1 * yz; dB[10][1] = SH_C3_1 * xz; dB[10][2] = SH_C3_1 * xy;
+                dB[11][0] = SH_C3_2 * -2.f * xy; dB[11][1] = SH_C3_2 * (4.f * zz - xx - 3.f * yy);
+                dB[11][2] = SH_C3_2 * 8.f * yz;
+                dB[12][0] = SH_C3_3 * -6.f * xz; dB[12][1] = SH_C3_3 * -6.f * yz;
+                dB[12][2] = SH_C3_3 * (6.f * zz - 3.f * xx - 3.f * yy);
+                dB[13][0] = SH_C3_4 * (4.f * zz - 3.f * xx - yy); dB[13][1] = SH_C3_4 * -2.f * xy;
+                dB[13][2] = SH_C3_4 * 8.f * xz;
+                dB[14][0] = SH_C3_5 * 2.f * xz; dB[14][1] = SH_C3_5 * -2.f * yz; dB[14][2] = SH_C3_5 * (xx - yy);
+                dB[15][0] = SH_C3_6 * (3.f * xx - 3.f * yy); dB[15][1] = SH_C3_6 * -6.f * xy;
+            }
+        }
+    }
+}
+
+// ---- backward of the projection (K8 + the mean part of K9) ---------------------------------------
+// In : dconic = dL/d(conic.x, conic.y [half], conic.z) as accumulated by the compositor,
+//      dmean2D = dL/d(NDC x,y) (already scaled by 0.5W / 0.5H), ddepth = dL/d(view z).
+// Out: dmean[3] (gradient w.r.t. the point fed to the rasteriser), dc6[6] (w.r.t. Sigma entries).
+FSGS_HD void project_backward(const CamConst &cc, const float *V, const float *PM, const float *mean,
+                              const float *c6, float gconx, float gcony, float gconz, float g2x, float g2y,
+                              float gdepth, float *dmean, float *dc6) {
+    float t[3], M[6], xm, ym, SM0[3], SM1[3], a, b, c;
+    ewa_M(cc, V, mean, t, M, xm, ym);
+    ewa_abc(M, c6, SM0, SM1, a, b, c);
+    const float denom = a * c - b * b;
+    const float d2inv = 1.f / (denom * denom + 0.0000001f);
+    float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+    if (d2inv != 0.f) {
+        dL_da = d2inv * (-c * c * gconx + 2.f * b * c * gcony + (denom - a * c) * gconz);
+        dL_dc = d2inv * (-a * a * gconz + 2.f * a * b * gcony + (denom - a * c) * gconx);
+        dL_db = d2inv * 2.f * (b * c * gconx - (denom + 2.f * b * b) * gcony + a * b * gconz);
+    }
+    dc6[0] = M[0] * M[0] * dL_da + M[0] * M[3] * dL_db + M[3] * M[3] * dL_dc;
+    dc6[3] = M[1] * M[1] * dL_da + M[1] * M[4] * dL_db + M[4] * M[4] * dL_dc;
+    dc6[5] = M[2] * M[2] * dL_da + M[2] * M[5] * dL_db + M[5] * M[5] * dL_dc;
+    dc6[1] = 2.f * M[0] * M[1] * dL_da + (M[0] * M[4] + M[1] * M[3]) * dL_db + 2.f * M[3] * M[4] * dL_dc;
+    dc6[2] = 2.f * M[0] * M[2] * dL_da + (M[0] * M[5] + M[2] * M[3]) * dL_db + 2.f * M[3] * M[5] * dL_dc;
+    dc6[4] = 2.f * M[2] * M[1] * dL_da + (M[1] * M[5] + M[2] * M[4]) * dL_db + 2.f * M[4] * M[5] * dL_dc;
+    float dM[6];
+    for (int j = 0; j < 3; ++j) {
+        dM[j] = 2.f * SM0[j] * dL_da + SM1[j] * dL_db;
+        dM[3 + j] = 2.f * SM1[j] * dL_dc + SM0[j] * dL_db;
+    }
+    const float dJ00 = V[0] * dM[0] + V[4] * dM[1] + V[8] * dM[2];
+    const float dJ02 = V[2] * dM[0] + V[6] * dM[1] + V[10] * dM[2];
+    const float dJ11 = V[1] * dM[3] + V[5] * dM[4] + V[9] * dM[5];
+    const float dJ12 = V[2] * dM[3] + V[6] * dM[4] + V[10] * dM[5];
+    const float tz = 1.f / t[2], tz2 = tz * tz, tz3 = tz2 * tz;
+    const float dtx = xm * -cc.fx * tz2 * dJ02;
+    const float dty = ym * -cc.fy * tz2 * dJ12;
+    const float dtz = -cc.fx * tz2 * dJ00 - cc.fy * tz2 * dJ11 + (2.f * cc.fx * t[0]) * tz3 * dJ02 +
+                      (2.f * cc.fy * t[1]) * tz3 * dJ12;
+    dmean[0] = V[0] * dtx + V[1] * dty + V[2] * dtz;
+    dmean[1] = V[4] * dtx + V[5] * dty + V[6] * dtz;
+    dmean[2] = V[8] * dtx + V[9] * dty + V[10] * dtz;
+    // projected centre (K9)
+    const float hw = PM[3] * mean[0] + PM[7] * mean[1] + PM[11] * mean[2] + PM[15];
+    const float mw = 1.0f / (hw + 0.0000001f);
+    const float mul1 = (PM[0] * mean[0] + PM[4] * mean[1] + PM[8] * mean[2] + PM[12]) * mw * mw;
+    const float mul2 = (PM[1] * mean[0] + PM[5] * mean[1] + PM[9] * mean[2] + PM[13]) * mw * mw;
+    dmean[0] += (PM[0] * mw - PM[3] * mul1) * g2x + (PM[1] * mw - PM[3] * mul2) * g2y;
+    dmean[1] += (PM[4] * mw - PM[7] * mul1) * g2x + (PM[5] * mw - PM[7] * mul2) * g2y;
+    dmean[2] += (PM[8] * mw - PM[11] * mul1) * g2x + (PM[9] * mw - PM[11] * mul2) * g2y;
+    // view-space depth
+    dmean[0] += V[2] * gdepth; dmean[1] += V[6] * gdepth; dmean[2] += V[10] * gdepth;
+}
+
+// dSigma(6) -> d(scale) (w.r.t. the s fed to cov3d_from_scale_rot) and d(quaternion as given).
+FSGS_HD void cov3d_backward(const float *s, const float *q, const float *dc6, float *ds, float *dq) {
+    float R[9];
+    quat_to_R(q, R);
+    const float G[9] = {dc6[0], 0.5f * dc6[1], 0.5f * dc6[2], 0.5f * dc6[1], dc6[3],
+                        0.5f * dc6[4], 0.5f * dc6[2], 0.5f * dc6[4], dc6[5]};
+    float GR[9], dR[9];
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k)
+            GR[r * 3 + k] = G[r * 3] * R[k] + G[r * 3 + 1] * R[3 + k] + G[r * 3 + 2] * R[6 + k];
+    for (int k = 0; k < 3; ++k) {
+        const float rgr = R[k] * GR[k] + R[3 + k] * GR[3 + k] + R[6 + k] * GR[6 + k];
+        ds[k] = 2.f * s[k] * rgr;
+        const float s2 = 2.f * s[k] * s[k];
+        dR[k] = GR[k] * s2; dR[3 + k] = GR[3 + k] * s2; dR[6 + k] = GR[6 + k] * s2;
+    }
+    const float r = q[0], x = q[1], y = q[2], z = q[3];
+    dq[0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+    dq[1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] -
+                   2.f * x * dR[8]);
+    dq[2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] -
+                   2.f * y * dR[8]);
+    dq[3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] +
+                   x * dR[6] + y * dR[7]);
+}
+
+// backward of v -> v/|v| : given dL/d(unit), unit vector n and 1/|v|, returns dL/dv
+FSGS_HD void normalize_backward(const float *n, float inv_len, const float *dn, float *dv) {
+    const float dot = n[0] * dn[0] + n[1] * dn[1] + n[2] * dn[2];
+    dv[0] = (dn[0] - n[0] * dot) * inv_len;
+    dv[1] = (dn[1] - n[1] * dot) * inv_len;
+    dv[2] = (dn[2] - n[2] * dot) * inv_len;
+}
+
+// ---- per-(pixel, Gaussian) arithmetic of the compositor -----------------------------------------
+// Exponent with a pinned operation order: the backward must reproduce the forward's per-pair
+// decisions bit for bit, so no compiler re-association / contraction is allowed here.
+FSGS_HD float gauss_power(float A, float B, float C, float dx, float dy) {
+#if defined(__CUDA_ARCH__)
+    const float s = __fmaf_rn(__fmul_rn(C, dy), dy, __fmul_rn(__fmul_rn(A, dx), dx));
+    return __fmaf_rn(-0.5f, s, -__fmul_rn(__fmul_rn(B, dx), dy));
+#else
+    const float s = fmaf(C * dy, dy, (A * dx) * dx);
+    return fmaf(-0.5f, s, -((B * dx) * dy));
+#endif
+}
+
+// Per-pixel state of the back-to-front replay (K7).
+struct BwdPixel {
+    float T, last_alpha;
+    float acc_r, acc_g, acc_b, acc_d, acc_s, acc_d2;   // "accum_rec" per plane
+    float lc_r, lc_g, lc_b, lc_d;                      // colour / depth of the previously replayed entry
+};
+
+// One contributing (pixel, Gaussian) pair of the backward compositor.
+//   record: (x, y | conA, conB, conC | opacity | r, g, b | z);  dx,dy = centre - pixel; G = exp(power)
+//   g[]   : dL/d(plane) at this pixel -- FUSED: 6 planes (RGB | depth, silhouette, depth^2);
+//           otherwise 3 colour planes + the package's depth plane in g[3]
+//   v[12] : this pair's contribution to the Gaussian's accumulator row (layout in fsgs_device.cuh)
+template <bool FUSED>
+FSGS_HD void bwd_pair(BwdPixel &s, float conA, float conB, float conC, float opacity, float cr, float cg, float cb,
+                      float z, float dx, float dy, float G, float alpha, const float *g, float T_final,
+                      float bgdot_rgb, float bgdot_dep, float ddelx_dx, float ddely_dy, float *v) {
+    const float one_m = 1.f - alpha;
+    s.T = s.T / one_m;
+    const float w = alpha * s.T;
+    const float la = s.last_alpha, lb = 1.f - s.last_alpha;
+    s.acc_r = la * s.lc_r + lb * s.acc_r; s.lc_r = cr;
+    s.acc_g = la * s.lc_g + lb * s.acc_g; s.lc_g = cg;
+    s.acc_b = la * s.lc_b + lb * s.acc_b; s.lc_b = cb;
+    float da_rgb = (cr - s.acc_r) * g[0] + (cg - s.acc_g) * g[1] + (cb - s.acc_b) * g[2];
+    // The fused flavour's extra planes carry the colours (z, 1, z^2); their recurrences read the
+    // previously replayed entry's colour, so they are advanced before lc_d is overwritten.
+    float dz = w * g[3];
+    if (FUSED) {
+        s.acc_s = la + lb * s.acc_s;
+        s.acc_d2 = la * (s.lc_d * s.lc_d) + lb * s.acc_d2;
+    }
+    s.acc_d = la * s.lc_d + lb * s.acc_d; s.lc_d = z;
+    float da_dep = (z - s.acc_d) * g[3];
+    if (FUSED) {
+        da_dep += (1.f - s.acc_s) * g[4] + (z * z - s.acc_d2) * g[5];
+        dz += w * 2.f * z * g[5];
+    }
+    da_rgb *= s.T; da_dep *= s.T;
+    const float tf = -T_final / one_m;
+    da_rgb += tf * bgdot_rgb;
+    if (FUSED) da_dep += tf * bgdot_dep;
+    s.last_alpha = alpha;
+    const float dL_dalpha = da_rgb + da_dep;
+    const float dL_dG = opacity * dL_dalpha;
+    const float gdx = G * dx, gdy = G * dy;
+    const float dG_ddelx = -gdx * conA - gdy * conB;
+    const float dG_ddely = -gdy * conC - gdx * conB;
+    v[0] = dL_dG * dG_ddelx * ddelx_dx;
+    v[1] = dL_dG * dG_ddely * ddely_dy;
+    v[2] = -0.5f * gdx * dx * dL_dG;
+    v[3] = -0.5f * gdx * dy * dL_dG;
+    v[4] = -0.5f * gdy * dy * dL_dG;
+    v[5] = G * dL_dalpha;
+    v[6] = w * g[0]; v[7] = w * g[1]; v[8] = w * g[2];
+    v[9] = dz;
+    if (FUSED) {
+        const float dG_rgb = opacity * da_rgb;
+        v[10] = dG_rgb * dG_ddelx * ddelx_dx;
+        v[11] = dG_rgb * dG_ddely * ddely_dy;
+    } else {
+        v[10] = v[0]; v[11] = v[1];
+    }
+}
+
+// ---- whole-Gaussian forward / backward bodies (shared by the CUDA kernels and the CPU emulation) --
+// SH -> RGB (+0.5, clamp at 0, remember which channels were clamped).  coef(k, ch) returns the
+// k-th coefficient of channel ch.
+template <typename Coef>
+FSGS_HD void sh_to_rgb(int deg, const float *dir, Coef coef, float *rgb, uint8_t &clamp) {
+    float B[16];
+    sh_basis(deg, dir[0], dir[1], dir[2], B);
+    const int nb = (deg + 1) * (deg + 1);
+    rgb[0] = rgb[1] = rgb[2] = 0.f;
+    for (int k = 0; k < nb; ++k) {
+        rgb[0] += B[k] * coef(k, 0); rgb[1] += B[k] * coef(k, 1); rgb[2] += B[k] * coef(k, 2);
+    }
+    clamp = 0;
+    for (int ch = 0; ch < 3; ++ch) {
+        rgb[ch] += 0.5f;
+        if (rgb[ch] < 0.f) { clamp |= (uint8_t)(1u << ch); rgb[ch] = 0.f; }
+    }
+}
+
+// Backward of sh_to_rgb + the direction normalisation: writes dcoef(k, ch, value) for every stored
+// coefficient (zeros beyond the active degree) and returns dL/d(un-normalised direction) in dv.
+template <typename Coef, typename DCoef>
+FSGS_HD void sh_to_rgb_backward(int deg, int n_coeffs, const float *dir, float inv_len, Coef coef, uint8_t clamp,
+                                const float *grgb, DCoef dcoef, float *dv) {
+    float B[16], dB[16][3];
+    sh_basis(deg, dir[0], dir[1], dir[2], B);
+    sh_basis_grad(deg, dir[0], dir[1], dir[2], dB);
+    const int nb = (deg + 1) * (deg + 1);
+    const float gc[3] = {(clamp & 1) ? 0.f : grgb[0], (clamp & 2) ? 0.f : grgb[1], (clamp & 4) ? 0.f : grgb[2]};
+    float ddir[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < n_coeffs; ++k) {
+        if (k < nb) {
+            dcoef(k, 0, B[k] * gc[0]); dcoef(k, 1, B[k] * gc[1]); dcoef(k, 2, B[k] * gc[2]);
+            const float t = coef(k, 0) * gc[0] + coef(k, 1) * gc[1] + coef(k, 2) * gc[2];
+            ddir[0] += dB[k][0] * t; ddir[1] += dB[k][1] * t; ddir[2] += dB[k][2] * t;
+        } else {
+            dcoef(k, 0, 0.f); dcoef(k, 1, 0.f); dcoef(k, 2, 0.f);
+        }
+    }
+    normalize_backward(dir, inv_len, ddir, dv);
+}
+
+FSGS_HD float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Fused flavour, forward: transform_to_frame + activations + projection + SH for Gaussian i.
+// pose: row-major 3x4 (first 12 floats of LearnPose.forward's output).  Returns false if skipped.
+FSGS_HD bool fused_forward_one(const CamConst &cc, const float *V, const float *PM, const float *pose,
+                               const float *cam_center, const float *xyz, const float *dc, const float *rest,
+                               float op_raw, const float *sc_raw, const float *rot_raw, Splat &sp, float &opacity,
+                               float *rgb, uint8_t &clamp) {
+    float mean[3];
+    for (int r = 0; r < 3; ++r)
+        mean[r] = pose[4 * r] * xyz[0] + pose[4 * r + 1] * xyz[1] + pose[4 * r + 2] * xyz[2] + pose[4 * r + 3];
+    const float s[3] = {cc.mod * expf(sc_raw[0]), cc.mod * expf(sc_raw[1]), cc.mod * expf(sc_raw[2])};
+    const float qn = fmaxf(sqrtf(rot_raw[0] * rot_raw[0] + rot_raw[1] * rot_raw[1] + rot_raw[2] * rot_raw[2] +
+                                 rot_raw[3] * rot_raw[3]), 1e-12f);
+    const float qi = 1.0f / qn;
+    const float q[4] = {rot_raw[0] * qi, rot_raw[1] * qi, rot_raw[2] * qi, rot_raw[3] * qi};
+    float c6[6];
+    cov3d_from_scale_rot(s, q, c6);
+    if (!project_gaussian(cc, V, PM, mean, c6, sp)) return false;
+    opacity = sigmoidf(op_raw);
+    // SH view direction: WORLD position minus the frozen camera centre (reference quirk iii)
+    float d[3] = {xyz[0] - cam_center[0], xyz[1] - cam_center[1], xyz[2] - cam_center[2]};
+    const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    d[0] *= inv; d[1] *= inv; d[2] *= inv;
+    sh_to_rgb(cc.sh_deg, d, [&](int k, int ch) { return k == 0 ? dc[ch] : rest[3 * (k - 1) + ch]; }, rgb, clamp);
+    return true;
+}
+
+// Fused flavour, backward for Gaussian i (radius > 0).  acc = the compositor's 12-float row.
+// Outputs: dxyz[3], dfdc[3], drest[45] (may be null), dop_raw, ds_raw[3], dq_raw[4],
+// pg[12] = this Gaussian's contribution to dL/d(pose[:3,:]) (zeros unless cam_grad), m2d[2].
+FSGS_HD void fused_backward_one(const CamConst &cc, const float *V, const float *PM, const float *pose,
+                                const float *cam_center, const float *xyz, const float *dc, const float *rest,
+                                float op_raw, const float *sc_raw, const float *rot_raw, uint8_t clamp,
+                                const float *acc, int gs_grad, int cam_grad, float *dxyz, float *dfdc, float *drest,
+                                float &dop_raw, float *ds_raw, float *dq_raw, float *pg, float *m2d) {
+    float mean[3];
+    for (int r = 0; r < 3; ++r)
+        mean[r] = pose[4 * r] * xyz[0] + pose[4 * r + 1] * xyz[1] + pose[4 * r + 2] * xyz[2] + pose[4 * r + 3];
+    const float s[3] = {cc.mod * expf(sc_raw[0]), cc.mod * expf(sc_raw[1]), cc.mod * expf(sc_raw[2])};
+    const float qn = fmaxf(sqrtf(rot_raw[0] * rot_raw[0] + rot_raw[1] * rot_raw[1] + rot_raw[2] * rot_raw[2] +
+                                 rot_raw[3] * rot_raw[3]), 1e-12f);
+    const float qi = 1.0f / qn;
+    const float q[4] = {rot_raw[0] * qi, rot_raw[1] * qi, rot_raw[2] * qi, rot_raw[3] * qi};
+    float c6[6], dmean[3], dc6[6], ds[3], dq[4];
+    cov3d_from_scale_rot(s, q, c6);
+    // acc[9] = dL/d(view z) through the depth / depth^2 colour planes
+    project_backward(cc, V, PM, mean, c6, acc[2], acc[3], acc[4], acc[0], acc[1], acc[9], dmean, dc6);
+    cov3d_backward(s, q, dc6, ds, dq);
+    // exp / normalize / sigmoid
+    ds_raw[0] = ds[0] * s[0]; ds_raw[1] = ds[1] * s[1]; ds_raw[2] = ds[2] * s[2];
+    const float qdot = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2] + q[3] * dq[3];
+    for (int k = 0; k < 4; ++k) dq_raw[k] = (dq[k] - q[k] * qdot) * qi;
+    const float o = sigmoidf(op_raw);
+    dop_raw = acc[5] * o * (1.f - o);
+    // SH (world position, frozen camera centre): gradient goes straight to xyz, not through the pose
+    float d[3] = {xyz[0] - cam_center[0], xyz[1] - cam_center[1], xyz[2] - cam_center[2]};
+    const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    d[0] *= inv; d[1] *= inv; d[2] *= inv;
+    const float grgb[3] = {acc[6], acc[7], acc[8]};
+    sh_to_rgb_backward(
+        cc.sh_deg, 16, d, inv, [&](int k, int ch) { return k == 0 ? dc[ch] : rest[3 * (k - 1) + ch]; }, clamp, grgb,
+        [&](int k, int ch, float v) {
+            if (k == 0) dfdc[ch] = v;
+            else if (drest) drest[3 * (k - 1) + ch] = v;
+        },
+        dxyz);
+    // transform_to_frame backward
+    if (gs_grad) {
+        dxyz[0] += pose[0] * dmean[0] + pose[4] * dmean[1] + pose[8] * dmean[2];
+        dxyz[1] += pose[1] * dmean[0] + pose[5] * dmean[1] + pose[9] * dmean[2];
+        dxyz[2] += pose[2] * dmean[0] + pose[6] * dmean[1] + pose[10] * dmean[2];
+    }
+    for (int k = 0; k < 12; ++k) pg[k] = 0.f;
+    if (cam_grad) {
+        for (int r = 0; r < 3; ++r) {
+            pg[4 * r] = dmean[r] * xyz[0]; pg[4 * r + 1] = dmean[r] * xyz[1]; pg[4 * r + 2] = dmean[r] * xyz[2];
+            pg[4 * r + 3] = dmean[r];
+        }
+    }
+    m2d[0] = acc[10]; m2d[1] = acc[11];
+}
+
+// API flavour, forward.  Exactly one of (colors_precomp | shs) and one of (scales+rots | cov3D).
+FSGS_HD bool api_forward_one(const CamConst &cc, const float *V, const float *PM, const float *campos,
+                             const float *mean, const float *color_i, const float *sh_i, const float *scale_i,
+                             const float *rot_i, const float *cov_i, Splat &sp, float *rgb, uint8_t &clamp) {
+    float c6[6];
+    if (cov_i) {
+        for (int k = 0; k < 6; ++k) c6[k] = cov_i[k];
+    } else {
+        const float s[3] = {cc.mod * scale_i[0], cc.mod * scale_i[1], cc.mod * scale_i[2]};
+        cov3d_from_scale_rot(s, rot_i, c6);
+    }
+    if (!project_gaussian(cc, V, PM, mean, c6, sp)) return false;
+    clamp = 0;
+    if (sh_i) {
+        float d[3] = {mean[0] - campos[0], mean[1] - campos[1], mean[2] - campos[2]};
+        const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        d[0] *= inv; d[1] *= inv; d[2] *= inv;
+        sh_to_rgb(cc.sh_deg, d, [&](int k, int ch) { return sh_i[3 * k + ch]; }, rgb, clamp);
+    } else {
+        rgb[0] = color_i[0]; rgb[1] = color_i[1]; rgb[2] = color_i[2];
+    }
+    return true;
+}
+
+// API flavour, backward (radius > 0).  dsh_i may be null.
+FSGS_HD void api_backward_one(const CamConst &cc, const float *V, const float *PM, const float *campos,
+                              const float *mean, const float *sh_i, const float *scale_i, const float *rot_i,
+                              const float *cov_i, uint8_t clamp, const float *acc, float *dmean, float *dc6,
+                              float *dsh_i, float *ds, float *dq) {
+    float c6[6], s[3] = {0.f, 0.f, 0.f};
+    if (cov_i) {
+        for (int k = 0; k < 6; ++k) c6[k] = cov_i[k];
+    } else {
+        s[0] = cc.mod * scale_i[0]; s[1] = cc.mod * scale_i[1]; s[2] = cc.mod * scale_i[2];
+        cov3d_from_scale_rot(s, rot_i, c6);
+    }
+    project_backward(cc, V, PM, mean, c6, acc[2], acc[3], acc[4], acc[0], acc[1], acc[9], dmean, dc6);
+    if (sh_i && dsh_i) {
+        float d[3] = {mean[0] - campos[0], mean[1] - campos[1], mean[2] - campos[2]};
+        const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        d[0] *= inv; d[1] *= inv; d[2] *= inv;
+        const float grgb[3] = {acc[6], acc[7], acc[8]};
+        float dv[3];
+        sh_to_rgb_backward(
+            cc.sh_deg, cc.n_coeffs, d, inv, [&](int k, int ch) { return sh_i[3 * k + ch]; }, clamp, grgb,
+            [&](int k, int ch, float v) { dsh_i[3 * k + ch] = v; }, dv);
+        dmean[0] += dv[0]; dmean[1] += dv[1]; dmean[2] += dv[2];
+    }
+    ds[0] = ds[1] = ds[2] = 0.f;
+    dq[0] = dq[1] = dq[2] = dq[3] = 0.f;
+    if (!cov_i) {
+        cov3d_backward(s, rot_i, dc6, ds, dq);
+        ds[0] *= cc.mod; ds[1] *= cc.mod; ds[2] *= cc.mod;
+    }
+}
+
+}  // namespace fsgs

@@ -1,0 +1,371 @@
+// fsgs_raster.cu -- host side of the C ABI declared in include/fsgs_raster.h.
+// Builds into libfsgs_raster.so with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// No torch, no Python: raw pointers, a stream, allocation callbacks.
+#include "../../include/fsgs_raster.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "fsgs_kernels_bwd.cuh"
+#include "fsgs_kernels_composite.cuh"
+#include "fsgs_kernels_pre.cuh"
+
+using namespace fsgs;
+
+namespace {
+
+thread_local char g_cuda_msg[256] = {0};
+
+#define FSGS_CUDA(call)                                                                             \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            snprintf(g_cuda_msg, sizeof(g_cuda_msg), "%s failed: %s (%s:%d)", #call,                \
+                     cudaGetErrorString(e__), __FILE__, __LINE__);                                  \
+            return FSGS_E_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+inline int check_launch(const fsgs_settings *st, cudaStream_t s, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && st->debug) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        snprintf(g_cuda_msg, sizeof(g_cuda_msg), "kernel %s failed: %s", what, cudaGetErrorString(e));
+        return FSGS_E_CUDA;
+    }
+    return FSGS_OK;
+}
+#define FSGS_LAUNCH_OK(what)                                  \
+    do {                                                      \
+        int r__ = check_launch(st, stream, what);             \
+        if (r__ != FSGS_OK) return r__;                       \
+    } while (0)
+
+int make_cam(const fsgs_settings *st, CamConst &cc) {
+    if (!st || st->image_width <= 0 || st->image_height <= 0 || st->tanfovx <= 0.f || st->tanfovy <= 0.f)
+        return FSGS_E_INVALID;
+    if (st->sh_degree < 0 || st->sh_degree > 3) return FSGS_E_INVALID;
+    cc.W = st->image_width; cc.H = st->image_height;
+    cc.gx = (cc.W + TILE - 1) / TILE; cc.gy = (cc.H + TILE - 1) / TILE;
+    cc.fx = cc.W / (2.0f * st->tanfovx); cc.fy = cc.H / (2.0f * st->tanfovy);
+    cc.limx = 1.3f * st->tanfovx; cc.limy = 1.3f * st->tanfovy;
+    cc.mod = st->scale_modifier;
+    cc.sh_deg = st->sh_degree; cc.n_coeffs = st->n_coeffs;
+    return FSGS_OK;
+}
+
+int check_arch() {
+    static int cached = 0;   // 0 unknown, 1 ok, -1 bad
+    if (cached == 0) {
+        int dev = 0, major = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return FSGS_E_CUDA;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return FSGS_E_CUDA;
+        cached = (major == 10) ? 1 : -1;
+    }
+    return cached == 1 ? FSGS_OK : FSGS_E_ARCH;
+}
+
+inline int blocks(int n) { return (n + CTA - 1) / CTA; }
+
+struct Buffers {
+    char *geom, *img, *bin;
+    GeomLayout gl;
+    ImgLayout il;
+    BinLayout bl;
+};
+
+// Shared tail of both forward flavours: scan -> R read-back -> scatter -> sort -> composite.
+template <bool FUSED>
+int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float *bg, Buffers &B,
+                 fsgs_alloc_fn binning_alloc, void *binning_user, float *out_planes, float *out_depth,
+                 int64_t *num_rendered_host, int64_t *num_rect_host, cudaStream_t stream) {
+    const int tiles = B.il.tiles;
+    unsigned int *tile_count = reinterpret_cast<unsigned int *>(B.img + B.il.tile_count);
+    unsigned int *tile_offset = reinterpret_cast<unsigned int *>(B.img + B.il.tile_offset);
+    unsigned int *cursor = reinterpret_cast<unsigned int *>(B.img + B.il.cursor);
+    unsigned long long *counters = reinterpret_cast<unsigned long long *>(B.img + B.il.counters);
+    float4 *records = reinterpret_cast<float4 *>(B.geom + B.gl.records);
+
+    k_tile_scan<<<1, 1024, 0, stream>>>(tiles, tile_count, tile_offset, cursor, counters);
+    FSGS_LAUNCH_OK("k_tile_scan");
+    unsigned long long h_cnt[4] = {0, 0, 0, 0};
+    FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
+    FSGS_CUDA(cudaStreamSynchronize(stream));
+    const int64_t R = (int64_t)h_cnt[CNT_R];
+    if (num_rendered_host) *num_rendered_host = R;
+    if (num_rect_host) *num_rect_host = (int64_t)h_cnt[CNT_RECT];
+    if (R >= (int64_t)1 << 32) return FSGS_E_INVALID;
+
+    B.bl = bin_layout(R);
+    B.bin = static_cast<char *>(binning_alloc(binning_user, B.bl.total));
+    if (!B.bin) return FSGS_E_ALLOC;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(B.bin + B.bl.keys);
+    float4 *sorted_rec = reinterpret_cast<float4 *>(B.bin + B.bl.records);
+
+    if (R > 0) {
+        k_scatter<<<blocks(P), CTA, 0, stream>>>(cc, P, records, tile_offset, cursor, keys, (unsigned)st->flags);
+        FSGS_LAUNCH_OK("k_scatter");
+        k_tile_sort<<<tiles, CTA, SORT_SMEM_KEYS * sizeof(unsigned long long), stream>>>(tile_offset, keys, records,
+                                                                                           sorted_rec);
+        FSGS_LAUNCH_OK("k_tile_sort");
+    }
+    k_composite_fwd<FUSED><<<tiles, CTA, 0, stream>>>(
+        cc, tile_offset, sorted_rec, bg, out_planes, out_depth, reinterpret_cast<float *>(B.img + B.il.final_T),
+        reinterpret_cast<unsigned int *>(B.img + B.il.n_contrib), (unsigned)st->flags, counters + CNT_ERR);
+    FSGS_LAUNCH_OK("k_composite_fwd");
+    if (st->debug) {
+        FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
+        FSGS_CUDA(cudaStreamSynchronize(stream));
+        if (h_cnt[CNT_ERR]) return FSGS_E_WATCHDOG;
+    }
+    return FSGS_OK;
+}
+
+int alloc_fixed(int P, const CamConst &cc, fsgs_alloc_fn geom_alloc, void *geom_user, fsgs_alloc_fn img_alloc,
+                void *img_user, Buffers &B, cudaStream_t stream) {
+    B.gl = geom_layout(P);
+    B.il = img_layout(cc.W, cc.H);
+    B.geom = static_cast<char *>(geom_alloc(geom_user, B.gl.total));
+    B.img = static_cast<char *>(img_alloc(img_user, B.il.total));
+    B.bin = nullptr;
+    if (!B.geom || !B.img) return FSGS_E_ALLOC;
+    // tile_count .. counters are contiguous: one memset
+    FSGS_CUDA(cudaMemsetAsync(B.img + B.il.tile_count, 0, B.il.total - B.il.tile_count, stream));
+    return FSGS_OK;
+}
+
+int one_time_setup() {
+    static int done = 0;
+    if (!done) {
+        FSGS_CUDA(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(SORT_SMEM_KEYS * sizeof(unsigned long long))));
+        done = 1;
+    }
+    return FSGS_OK;
+}
+
+// fills the whole image with the background (P == 0 or nothing visible is handled by the kernels,
+// this is only for P == 0 where no kernel runs)
+__global__ void k_fill_bg(int HW, int planes, const float *__restrict__ bg, float *__restrict__ out,
+                          float *__restrict__ depth) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    for (int c = 0; c < planes; ++c) out[(size_t)c * HW + i] = __ldg(bg + (c % 3));
+    if (depth) depth[i] = 0.f;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fsgs_abi_version(void) { return FSGS_ABI_VERSION; }
+
+const char *fsgs_error_string(int code) {
+    switch (code) {
+        case FSGS_OK: return "ok";
+        case FSGS_E_INVALID: return "invalid argument";
+        case FSGS_E_CUDA: return g_cuda_msg[0] ? g_cuda_msg : "CUDA error";
+        case FSGS_E_ALLOC: return "allocation callback returned NULL";
+        case FSGS_E_ARCH: return "device is not compute capability 10.x (this library is sm_100a only)";
+        case FSGS_E_WATCHDOG: return "device-side wait exceeded its spin budget (mbarrier never completed)";
+        default: return "unknown error";
+    }
+}
+
+const char *fsgs_kernel_names(void) {
+    return "k_preprocess_api,k_preprocess_fused,k_tile_scan,k_scatter,k_tile_sort,k_composite_fwd,"
+           "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible";
+}
+
+size_t fsgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
+size_t fsgs_img_bytes(int32_t W, int32_t H) { return img_layout(W, H).total; }
+size_t fsgs_binning_bytes(int64_t R) { return bin_layout(R).total; }
+size_t fsgs_grad_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * ACC_F * 4, 256); }
+size_t fsgs_geom_record_offset(int32_t P) { return geom_layout(P).records; }
+
+int fsgs_rasterize_forward(const fsgs_settings *st, int32_t P, const float *bg, const float *means3D,
+                           const float *colors_precomp, const float *shs, const float *opacities,
+                           const float *scales, const float *rotations, const float *cov3D_precomp,
+                           const float *viewmatrix, const float *projmatrix, const float *campos,
+                           fsgs_alloc_fn geom_alloc, void *geom_user, fsgs_alloc_fn binning_alloc,
+                           void *binning_user, fsgs_alloc_fn img_alloc, void *img_user, float *out_color,
+                           float *out_depth, int32_t *radii, int64_t *num_rendered_host, int64_t *num_rect_host,
+                           void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CamConst cc;
+    int rc = make_cam(st, cc);
+    if (rc) return rc;
+    if (P < 0 || !bg || !out_color || !out_depth || !viewmatrix || !projmatrix || !geom_alloc || !binning_alloc ||
+        !img_alloc)
+        return FSGS_E_INVALID;
+    if ((colors_precomp == nullptr) == (shs == nullptr) && P > 0) return FSGS_E_INVALID;
+    if (P > 0 && (!means3D || !opacities || !radii)) return FSGS_E_INVALID;
+    if (P > 0 && ((cov3D_precomp != nullptr) == (scales != nullptr && rotations != nullptr))) return FSGS_E_INVALID;
+    if (shs && (!campos || st->n_coeffs < (st->sh_degree + 1) * (st->sh_degree + 1) || st->n_coeffs > 16))
+        return FSGS_E_INVALID;
+    if ((rc = check_arch())) return rc;
+    if ((rc = one_time_setup())) return rc;
+    if (num_rendered_host) *num_rendered_host = 0;
+    if (num_rect_host) *num_rect_host = 0;
+    const int HW = cc.W * cc.H;
+    if (P == 0) {
+        k_fill_bg<<<blocks(HW), CTA, 0, stream>>>(HW, 3, bg, out_color, out_depth);
+        FSGS_LAUNCH_OK("k_fill_bg");
+        return FSGS_OK;
+    }
+    Buffers B;
+    if ((rc = alloc_fixed(P, cc, geom_alloc, geom_user, img_alloc, img_user, B, stream))) return rc;
+    k_preprocess_api<<<blocks(P), CTA, 0, stream>>>(
+        cc, P, means3D, colors_precomp, shs, opacities, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, campos,
+        reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped), radii,
+        reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
+        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags);
+    FSGS_LAUNCH_OK("k_preprocess_api");
+    return forward_tail<false>(st, cc, P, bg, B, binning_alloc, binning_user, out_color, out_depth, num_rendered_host,
+                               num_rect_host, stream);
+}
+
+int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg,
+                            const float *means3D, const float *colors_precomp, const float *shs,
+                            const float *opacities, const float *scales, const float *rotations,
+                            const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+                            const float *campos, const void *geom, const void *binning, const void *img,
+                            const float *dL_dout_color, const float *dL_dout_depth, void *grad_scratch,
+                            float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D,
+                            float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CamConst cc;
+    int rc = make_cam(st, cc);
+    if (rc) return rc;
+    if (P <= 0) return P == 0 ? FSGS_OK : FSGS_E_INVALID;
+    if (!geom || !img || !binning || !dL_dout_color || !grad_scratch || !means3D || !viewmatrix || !projmatrix || !bg)
+        return FSGS_E_INVALID;
+    if ((rc = check_arch())) return rc;
+    const GeomLayout gl = geom_layout(P);
+    const ImgLayout il = img_layout(cc.W, cc.H);
+    const BinLayout bl = bin_layout(num_rendered);
+    const char *g = static_cast<const char *>(geom), *im = static_cast<const char *>(img),
+               *bn = static_cast<const char *>(binning);
+    float *acc = static_cast<float *>(grad_scratch);
+    FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
+    if (num_rendered > 0) {
+        k_composite_bwd<false><<<il.tiles, CTA, 0, stream>>>(
+            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
+            reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
+            bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
+            dL_dout_color, dL_dout_depth, acc, (unsigned)st->flags,
+            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
+        FSGS_LAUNCH_OK("k_composite_bwd");
+    }
+    k_preprocess_api_bwd<<<blocks(P), CTA, 0, stream>>>(
+        cc, P, means3D, shs, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, campos,
+        reinterpret_cast<const float4 *>(g + gl.records), reinterpret_cast<const uint8_t *>(g + gl.clamped), acc,
+        dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations);
+    FSGS_LAUNCH_OK("k_preprocess_api_bwd");
+    (void)colors_precomp; (void)opacities;
+    return FSGS_OK;
+}
+
+int fsgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                      uint8_t *visible, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    (void)projmatrix;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !visible))) return FSGS_E_INVALID;
+    if (P == 0) return FSGS_OK;
+    int rc = check_arch();
+    if (rc) return rc;
+    k_mark_visible<<<blocks(P), CTA, 0, stream>>>(P, means3D, viewmatrix, visible);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_cuda_msg, sizeof(g_cuda_msg), "kernel k_mark_visible failed: %s", cudaGetErrorString(e));
+        return FSGS_E_CUDA;
+    }
+    return FSGS_OK;
+}
+
+int fsgs_render_forward(const fsgs_settings *st, int32_t P, const float *bg, const float *xyz,
+                        const float *features_dc, const float *features_rest, const float *opacity_raw,
+                        const float *scaling_raw, const float *rotation_raw, const float *pose,
+                        const float *cam_center, const float *viewmatrix, const float *projmatrix,
+                        fsgs_alloc_fn geom_alloc, void *geom_user, fsgs_alloc_fn binning_alloc, void *binning_user,
+                        fsgs_alloc_fn img_alloc, void *img_user, float *out_planes, int32_t *radii,
+                        int64_t *num_rendered_host, int64_t *num_rect_host, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CamConst cc;
+    int rc = make_cam(st, cc);
+    if (rc) return rc;
+    if (P < 0 || !bg || !out_planes || !viewmatrix || !projmatrix || !pose || !cam_center || !geom_alloc ||
+        !binning_alloc || !img_alloc)
+        return FSGS_E_INVALID;
+    if (P > 0 && (!xyz || !features_dc || !features_rest || !opacity_raw || !scaling_raw || !rotation_raw || !radii))
+        return FSGS_E_INVALID;
+    if ((rc = check_arch())) return rc;
+    if ((rc = one_time_setup())) return rc;
+    cc.n_coeffs = 16;
+    if (num_rendered_host) *num_rendered_host = 0;
+    if (num_rect_host) *num_rect_host = 0;
+    const int HW = cc.W * cc.H;
+    if (P == 0) {
+        k_fill_bg<<<blocks(HW), CTA, 0, stream>>>(HW, 6, bg, out_planes, nullptr);
+        FSGS_LAUNCH_OK("k_fill_bg");
+        return FSGS_OK;
+    }
+    Buffers B;
+    if ((rc = alloc_fixed(P, cc, geom_alloc, geom_user, img_alloc, img_user, B, stream))) return rc;
+    k_preprocess_fused<<<blocks(P), CTA, 0, stream>>>(
+        cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
+        projmatrix, reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped),
+        radii, reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
+        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags);
+    FSGS_LAUNCH_OK("k_preprocess_fused");
+    return forward_tail<true>(st, cc, P, bg, B, binning_alloc, binning_user, out_planes, nullptr, num_rendered_host,
+                              num_rect_host, stream);
+}
+
+int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg, const float *xyz,
+                         const float *features_dc, const float *features_rest, const float *opacity_raw,
+                         const float *scaling_raw, const float *rotation_raw, const float *pose,
+                         const float *cam_center, const float *viewmatrix, const float *projmatrix, const void *geom,
+                         const void *binning, const void *img, const float *dL_dplanes, void *grad_scratch,
+                         int32_t gs_grad, int32_t cam_grad, float *dL_dxyz, float *dL_dfeatures_dc,
+                         float *dL_dfeatures_rest, float *dL_dopacity_raw, float *dL_dscaling_raw,
+                         float *dL_drotation_raw, float *dL_dpose, float *dL_dmeans2D, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CamConst cc;
+    int rc = make_cam(st, cc);
+    if (rc) return rc;
+    cc.n_coeffs = 16;
+    if (dL_dpose) FSGS_CUDA(cudaMemsetAsync(dL_dpose, 0, 16 * sizeof(float), stream));
+    if (P <= 0) return P == 0 ? FSGS_OK : FSGS_E_INVALID;
+    if (!geom || !img || !binning || !dL_dplanes || !grad_scratch || !xyz || !features_dc || !features_rest ||
+        !opacity_raw || !scaling_raw || !rotation_raw || !pose || !cam_center || !viewmatrix || !projmatrix || !bg)
+        return FSGS_E_INVALID;
+    if ((rc = check_arch())) return rc;
+    const GeomLayout gl = geom_layout(P);
+    const ImgLayout il = img_layout(cc.W, cc.H);
+    const BinLayout bl = bin_layout(num_rendered);
+    const char *g = static_cast<const char *>(geom), *im = static_cast<const char *>(img),
+               *bn = static_cast<const char *>(binning);
+    float *acc = static_cast<float *>(grad_scratch);
+    FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
+    if (num_rendered > 0) {
+        k_composite_bwd<true><<<il.tiles, CTA, 0, stream>>>(
+            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
+            reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
+            bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
+            dL_dplanes, nullptr, acc, (unsigned)st->flags,
+            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
+        FSGS_LAUNCH_OK("k_composite_bwd");
+    }
+    k_preprocess_fused_bwd<<<blocks(P), CTA, 0, stream>>>(
+        cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
+        projmatrix, reinterpret_cast<const float4 *>(g + gl.records), reinterpret_cast<const uint8_t *>(g + gl.clamped),
+        acc, gs_grad, cam_grad, dL_dxyz, dL_dfeatures_dc, dL_dfeatures_rest, dL_dopacity_raw, dL_dscaling_raw,
+        dL_drotation_raw, dL_dpose, dL_dmeans2D);
+    FSGS_LAUNCH_OK("k_preprocess_fused_bwd");
+    return FSGS_OK;
+}
+
+}  // extern "C"

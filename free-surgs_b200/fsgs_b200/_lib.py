@@ -1,0 +1,100 @@
+"""ctypes binding of ``libfsgs_raster.so`` (the C ABI declared in ``include/fsgs_raster.h``).
+
+There is NO fallback: if the shared library is missing, or the device is not a B200-class
+(sm_100) GPU, every entry point raises.  PyTorch is only used by the callers for device memory
+and streams; nothing torch-typed crosses this boundary.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfsgs_raster.so")
+CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
+
+FLAG_NO_TMA = 1
+FLAG_NO_TILE_CULL = 2
+
+
+class FsgsError(RuntimeError):
+    pass
+
+
+class Settings(ctypes.Structure):
+    _fields_ = [("image_height", ctypes.c_int32), ("image_width", ctypes.c_int32),
+                ("tanfovx", ctypes.c_float), ("tanfovy", ctypes.c_float),
+                ("scale_modifier", ctypes.c_float), ("sh_degree", ctypes.c_int32),
+                ("n_coeffs", ctypes.c_int32), ("debug", ctypes.c_int32), ("flags", ctypes.c_int32)]
+
+
+ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+_vp, _i32, _i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "fsgs_abi_version": (ctypes.c_int, []),
+    "fsgs_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    "fsgs_kernel_names": (ctypes.c_char_p, []),
+    "fsgs_geom_bytes": (ctypes.c_size_t, [_i32]),
+    "fsgs_img_bytes": (ctypes.c_size_t, [_i32, _i32]),
+    "fsgs_binning_bytes": (ctypes.c_size_t, [_i64]),
+    "fsgs_grad_scratch_bytes": (ctypes.c_size_t, [_i32]),
+    "fsgs_geom_record_offset": (ctypes.c_size_t, [_i32]),
+    "fsgs_rasterize_forward": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 11 +
+                               [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp] + [_vp] * 3 +
+                               [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
+    "fsgs_rasterize_backward": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 26),
+    "fsgs_mark_visible": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp]),
+    "fsgs_render_forward": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 11 +
+                            [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp] + [_vp] * 2 +
+                            [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
+    "fsgs_render_backward": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 16 +
+                             [_i32, _i32] + [_vp] * 9),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lock = threading.Lock()
+_lib = None
+
+
+def build(force: bool = False, extra: str = "") -> str:
+    """Compile the library in-tree with nvcc for sm_100a (works without a GPU)."""
+    cmd = ["make", "-C", CSRC]
+    if force:
+        cmd.append("-B")
+    if extra:
+        cmd.append(f"EXTRA={extra}")
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and type the shared library.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise FsgsError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; "
+                                    f"g.build()'` (or `make -C {CSRC}`); there is no CPU / PyTorch fallback")
+                L = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(L, name)
+                    fn.restype, fn.argtypes = res, args
+                if L.fsgs_abi_version() != 1:
+                    raise FsgsError("libfsgs_raster.so ABI version mismatch; rebuild")
+                _lib = L
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        msg = lib().fsgs_error_string(code)
+        raise FsgsError(f"fsgs_raster error {code}: {msg.decode() if msg else '?'}")
+
+
+def kernel_names():
+    return lib().fsgs_kernel_names().decode().split(",")

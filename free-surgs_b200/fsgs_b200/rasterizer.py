@@ -1,0 +1,248 @@
+"""Drop-in ``diff_gaussian_rasterization`` API on top of the sm_100a C-ABI library.
+
+Mirrors the third-party package Free-SurGS imports (``requirements.txt:26``; call sites
+``gaussian_renderer/__init__.py:15,68,69,131``, ``scene/pose_optimizer.py:5,619-632``,
+``scene/gaussian_model.py:18``): same class names, same 12-field settings tuple, same keyword
+call convention, same 3-tuple return ``(color[3,H,W], radii[P] int32, depth[1,H,W])``, same error
+messages, same gradient slots.  All arithmetic runs in ``libfsgs_raster.so``; there is no
+PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+# process-wide switches used by tests / profiling (never needed in production)
+_FLAGS = {"flags": 0}
+
+
+def set_debug_flags(no_tma: bool = False, no_tile_cull: bool = False) -> None:
+    _FLAGS["flags"] = (_lib.FLAG_NO_TMA if no_tma else 0) | (_lib.FLAG_NO_TILE_CULL if no_tile_cull else 0)
+
+
+class _Arena:
+    """Owns the scratch tensors the library requests through its allocation callbacks."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensors = {}
+        self._cbs = []
+
+    def callback(self, name: str):
+        def cb(_user, nbytes):
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self.tensors[name] = t
+            return t.data_ptr()
+        fn = _lib.ALLOC_FN(cb)
+        self._cbs.append(fn)
+        return fn
+
+
+def _f32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
+    if t is None or t.numel() == 0:
+        return None
+    if t.device != device:
+        raise ValueError(f"tensor on {t.device}, expected {device}")
+    return t.detach().contiguous().float()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.FsgsError("fsgs_b200 runs on a CUDA (sm_100a) device only: there is no CPU fallback")
+
+
+def make_settings(rs, n_coeffs: int = 0, sh_degree: Optional[int] = None) -> _lib.Settings:
+    return _lib.Settings(int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
+                         float(rs.scale_modifier), int(rs.sh_degree if sh_degree is None else sh_degree),
+                         int(n_coeffs), 1 if rs.debug else 0, _FLAGS["flags"])
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------
+# `_C`-level functions (what the reference's pybind module exposes)
+# ------------------------------------------------------------------------------------------------
+def rasterize_gaussians(bg, means3D, colors_precomp, opacities, scales, rotations, scale_modifier, cov3D_precomp,
+                        viewmatrix, projmatrix, tanfovx, tanfovy, image_height, image_width, sh, degree, campos,
+                        prefiltered, debug):
+    """-> (num_rendered, color, depth, radii, geomBuffer, binningBuffer, imgBuffer)"""
+    _require_cuda(means3D)
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    dev = means3D.device
+    P = means3D.shape[0]
+    H, W = int(image_height), int(image_width)
+    sh_t = _f32(sh, dev)
+    n_coeffs = 0 if sh_t is None else sh_t.shape[1]
+    st = _lib.Settings(H, W, float(tanfovx), float(tanfovy), float(scale_modifier), int(degree), int(n_coeffs),
+                       1 if debug else 0, _FLAGS["flags"])
+    t = dict(bg=_f32(bg, dev), means3D=_f32(means3D, dev), colors=_f32(colors_precomp, dev), sh=sh_t,
+             opac=_f32(opacities, dev), scales=_f32(scales, dev), rots=_f32(rotations, dev),
+             cov=_f32(cov3D_precomp, dev), view=_f32(viewmatrix, dev), proj=_f32(projmatrix, dev),
+             campos=_f32(campos, dev))
+    color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+    depth = torch.empty(1, H, W, dtype=torch.float32, device=dev)
+    radii = torch.zeros(P, dtype=torch.int32, device=dev)
+    arena = _Arena(dev)
+    nr, nrect = ctypes.c_int64(0), ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().fsgs_rasterize_forward(
+            ctypes.byref(st), P, _ptr(t["bg"]), _ptr(t["means3D"]), _ptr(t["colors"]), _ptr(t["sh"]), _ptr(t["opac"]),
+            _ptr(t["scales"]), _ptr(t["rots"]), _ptr(t["cov"]), _ptr(t["view"]), _ptr(t["proj"]), _ptr(t["campos"]),
+            arena.callback("geom"), None, arena.callback("binning"), None, arena.callback("img"), None,
+            _ptr(color), _ptr(depth), _ptr(radii), ctypes.byref(nr), ctypes.byref(nrect), _stream(dev))
+    _lib.check(rc)
+    empty = torch.empty(0, dtype=torch.uint8, device=dev)
+    bufs = [arena.tensors.get(k, empty) for k in ("geom", "binning", "img")]
+    rasterize_gaussians.last_num_rect = int(nrect.value)
+    return int(nr.value), color, depth, radii, bufs[0], bufs[1], bufs[2]
+
+
+rasterize_gaussians.last_num_rect = 0
+
+
+def rasterize_gaussians_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale_modifier, cov3D_precomp,
+                                 viewmatrix, projmatrix, tanfovx, tanfovy, grad_out_color, grad_out_depth, sh, degree,
+                                 campos, geomBuffer, num_rendered, binningBuffer, imgBuffer, debug, opacities=None,
+                                 image_height=None, image_width=None):
+    """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)"""
+    _require_cuda(means3D)
+    dev = means3D.device
+    P = means3D.shape[0]
+    H = int(grad_out_color.shape[1]) if image_height is None else int(image_height)
+    W = int(grad_out_color.shape[2]) if image_width is None else int(image_width)
+    sh_t = _f32(sh, dev)
+    n_coeffs = 0 if sh_t is None else sh_t.shape[1]
+    st = _lib.Settings(H, W, float(tanfovx), float(tanfovy), float(scale_modifier), int(degree), int(n_coeffs),
+                       1 if debug else 0, _FLAGS["flags"])
+    z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+    g = dict(means2D=z(P, 3), colors=z(P, 3), opacity=z(P, 1), means3D=z(P, 3), cov3D=z(P, 6),
+             sh=z(P, max(n_coeffs, 0), 3), scales=z(P, 3), rots=z(P, 4))
+    if P == 0:
+        return tuple(g[k] for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rots"))
+    t = dict(bg=_f32(bg, dev), means3D=_f32(means3D, dev), colors=_f32(colors_precomp, dev), sh=sh_t,
+             opac=_f32(opacities, dev), scales=_f32(scales, dev), rots=_f32(rotations, dev),
+             cov=_f32(cov3D_precomp, dev), view=_f32(viewmatrix, dev), proj=_f32(projmatrix, dev),
+             campos=_f32(campos, dev), gc=_f32(grad_out_color, dev), gd=_f32(grad_out_depth, dev))
+    scratch = torch.empty(_lib.lib().fsgs_grad_scratch_bytes(P), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().fsgs_rasterize_backward(
+            ctypes.byref(st), P, int(num_rendered), _ptr(t["bg"]), _ptr(t["means3D"]), _ptr(t["colors"]), _ptr(t["sh"]),
+            _ptr(t["opac"]), _ptr(t["scales"]), _ptr(t["rots"]), _ptr(t["cov"]), _ptr(t["view"]), _ptr(t["proj"]),
+            _ptr(t["campos"]), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), _ptr(t["gc"]), _ptr(t["gd"]),
+            _ptr(scratch), _ptr(g["means2D"]), _ptr(g["colors"]), _ptr(g["opacity"]), _ptr(g["means3D"]),
+            _ptr(g["cov3D"]), _ptr(g["sh"]) if n_coeffs > 0 else None, _ptr(g["scales"]), _ptr(g["rots"]), _stream(dev))
+    _lib.check(rc)
+    return tuple(g[k] for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rots"))
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    _require_cuda(means3D)
+    dev = means3D.device
+    P = means3D.shape[0]
+    vis = torch.zeros(P, dtype=torch.uint8, device=dev)
+    m, v, p = _f32(means3D, dev), _f32(viewmatrix, dev), _f32(projmatrix, dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().fsgs_mark_visible(P, _ptr(m), _ptr(v), _ptr(p), _ptr(vis), _stream(dev))
+    _lib.check(rc)
+    return vis.bool()
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd function + module (the Python layer of the reference package)
+# ------------------------------------------------------------------------------------------------
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        rs = raster_settings
+        num_rendered, color, depth, radii, geomBuffer, binningBuffer, imgBuffer = rasterize_gaussians(
+            rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+            rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh, rs.sh_degree,
+            rs.campos, rs.prefiltered, rs.debug)
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.num_rect = rasterize_gaussians.last_num_rect
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, opacities,
+                              geomBuffer, binningBuffer, imgBuffer)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii, grad_out_depth):
+        rs = ctx.raster_settings
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, opacities, geomBuffer, binningBuffer,
+         imgBuffer) = ctx.saved_tensors
+        if grad_out_color is None:
+            grad_out_color = torch.zeros(3, rs.image_height, rs.image_width, device=means3D.device)
+        (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
+         grad_rotations) = rasterize_gaussians_backward(
+            rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix,
+            rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color, grad_out_depth, sh, rs.sh_degree, rs.campos,
+            geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer, rs.debug, opacities=opacities,
+            image_height=rs.image_height, image_width=rs.image_width)
+        none_if_empty = lambda g, src: g if src.numel() > 0 else None
+        return (grad_means3D, grad_means2D, none_if_empty(grad_sh, sh), none_if_empty(grad_colors_precomp, colors_precomp),
+                grad_opacities, none_if_empty(grad_scales, scales), none_if_empty(grad_rotations, rotations),
+                none_if_empty(grad_cov3Ds_precomp, cov3Ds_precomp), None)
+
+
+def rasterize_gaussians_autograd(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                 raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            return mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        empty = torch.Tensor([]).to(means3D.device)
+        shs = empty if shs is None else shs
+        colors_precomp = empty if colors_precomp is None else colors_precomp
+        scales = empty if scales is None else scales
+        rotations = empty if rotations is None else rotations
+        cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
+        return rasterize_gaussians_autograd(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                            cov3D_precomp, rs)

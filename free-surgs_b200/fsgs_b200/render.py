@@ -1,0 +1,163 @@
+"""Fused, drop-in replacement for ``gaussian_renderer.render`` (reference
+``gaussian_renderer/__init__.py:49-92``).
+
+``render(viewpoint_camera, index, pc, gs_grad=True, cam_grad=True)`` takes the reference's own
+objects (``PoseModel`` / ``GaussianModel``, or the light-weight mirrors in ``fsgs_b200.model``) and
+returns the same dict with the same side effects, but performs the whole per-frame path in one
+library call: pose transform + activations + SH + projection, ONE tile binning / sort, a six-plane
+composite (RGB | depth, silhouette, depth^2) and a backward that emits the parameter gradients
+and dL/d(pose) directly (``fsgs_render_forward`` / ``fsgs_render_backward`` in
+``include/fsgs_raster.h``).
+
+``render_two_pass`` is the literal two-rasteriser-call formulation of the reference on top of
+``GaussianRasterizer`` (same library, un-fused) -- it is what an unmodified
+``gaussian_renderer.render`` executes when it imports our ``diff_gaussian_rasterization``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict
+
+import torch
+
+from . import _lib
+from .rasterizer import GaussianRasterizer, _Arena, _f32, _ptr, _require_cuda, _stream, make_settings
+
+_IDENTITY_OK: Dict[tuple, bool] = {}
+
+
+def _check_identity_view(rs) -> None:
+    """The fused path composites the depth planes from the view-space z of the (single) projection,
+    which equals the reference's ``get_depth_and_silhouette`` only for the identity rasteriser view
+    Free-SurGS always uses (train.py:41, gaussian_model.py:245-246).  Checked once per tensor."""
+    vm = rs.viewmatrix
+    key = (vm.data_ptr(), vm._version, str(vm.device))
+    ok = _IDENTITY_OK.get(key)
+    if ok is None:
+        ok = bool(torch.equal(vm.reshape(4, 4).float().cpu(), torch.eye(4)))
+        _IDENTITY_OK[key] = ok
+    if not ok:
+        raise NotImplementedError("fused render requires the identity rasteriser view Free-SurGS uses; "
+                                  "use render_two_pass / GaussianRasterizer for a general view matrix")
+
+
+class _RenderFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, rs, cam_center,
+                active_sh_degree, gs_grad, cam_grad):
+        _require_cuda(xyz)
+        dev = xyz.device
+        P = xyz.shape[0]
+        H, W = int(rs.image_height), int(rs.image_width)
+        st = make_settings(rs, n_coeffs=16, sh_degree=int(active_sh_degree))
+        t = [_f32(x, dev) for x in (rs.bg, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center,
+                                    rs.viewmatrix, rs.projmatrix)]
+        planes = torch.empty(6, H, W, dtype=torch.float32, device=dev)
+        radii = torch.zeros(P, dtype=torch.int32, device=dev)
+        arena = _Arena(dev)
+        nr, nrect = ctypes.c_int64(0), ctypes.c_int64(0)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().fsgs_render_forward(
+                ctypes.byref(st), P, *[_ptr(x) for x in t], arena.callback("geom"), None, arena.callback("binning"),
+                None, arena.callback("img"), None, _ptr(planes), _ptr(radii), ctypes.byref(nr), ctypes.byref(nrect),
+                _stream(dev))
+        _lib.check(rc)
+        empty = torch.empty(0, dtype=torch.uint8, device=dev)
+        ctx.save_for_backward(*t, *[arena.tensors.get(k, empty) for k in ("geom", "binning", "img")])
+        ctx.st, ctx.P, ctx.num_rendered, ctx.num_rect = st, P, int(nr.value), int(nrect.value)
+        ctx.flags = (bool(gs_grad), bool(cam_grad))
+        ctx.mark_non_differentiable(radii)
+        stats = torch.tensor([nr.value, nrect.value], dtype=torch.int64)
+        ctx.mark_non_differentiable(stats)
+        return planes, radii, stats
+
+    @staticmethod
+    def backward(ctx, g_planes, _g_radii, _g_stats):
+        *t, geom, binning, img = ctx.saved_tensors
+        dev = t[1].device
+        P = ctx.P
+        gs_grad, cam_grad = ctx.flags
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        g = dict(xyz=z(P, 3), f_dc=z(P, 1, 3), f_rest=z(P, 15, 3), opacity=z(P, 1), scaling=z(P, 3), rotation=z(P, 4),
+                 pose=z(4, 4), means2D=z(P, 3))
+        if P > 0:
+            gp = _f32(g_planes, dev)
+            scratch = torch.empty(_lib.lib().fsgs_grad_scratch_bytes(P), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                rc = _lib.lib().fsgs_render_backward(
+                    ctypes.byref(ctx.st), P, ctx.num_rendered, *[_ptr(x) for x in t], _ptr(geom), _ptr(binning),
+                    _ptr(img), _ptr(gp), _ptr(scratch), int(gs_grad), int(cam_grad), _ptr(g["xyz"]), _ptr(g["f_dc"]),
+                    _ptr(g["f_rest"]), _ptr(g["opacity"]), _ptr(g["scaling"]), _ptr(g["rotation"]), _ptr(g["pose"]),
+                    _ptr(g["means2D"]), _stream(dev))
+            _lib.check(rc)
+        return (g["xyz"], g["f_dc"], g["f_rest"], g["opacity"], g["scaling"], g["rotation"],
+                g["pose"] if cam_grad else None, g["means2D"], None, None, None, None, None)
+
+
+def render_planes(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, raster_settings,
+                  cam_center, active_sh_degree, gs_grad=True, cam_grad=True):
+    """Tensor-level entry: -> (planes[6,H,W], radii[P] int32, stats[2] = (instances, rect instances))."""
+    _check_identity_view(raster_settings)
+    return _RenderFused.apply(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D,
+                              raster_settings, cam_center, active_sh_degree, gs_grad, cam_grad)
+
+
+def _pack(pc, viewmatrix_cur, im, depth_sil, radius, means2D):
+    depth = depth_sil[0, :, :]
+    silhouette = depth_sil[1, :, :]
+    presence_sil_mask = (silhouette > 0.3)
+    depth_sq = depth_sil[2, :, :].unsqueeze(0)
+    uncertainty = (depth_sq - depth ** 2).detach()
+    pc.variables['means2D'] = means2D
+    seen = radius > 0
+    pc.variables['max_radii2D'][seen] = torch.max(radius[seen], pc.variables['max_radii2D'][seen])
+    pc.variables['seen'] = seen
+    nan_mask = (~torch.isnan(depth)) & (~torch.isnan(uncertainty))
+    return {"render": im, "render_dep": depth, "render_w2c": viewmatrix_cur, "render_opacity": silhouette,
+            "nan_mask": nan_mask, "presence_mask": presence_sil_mask, "uncertainty": uncertainty,
+            "viewspace_points": means2D, "visibility_filter": radius > 0, "radii": radius}
+
+
+def render(viewpoint_camera, index, pc, gs_grad=True, cam_grad=True):
+    """Same signature, return dict and side effects as the reference's ``render``."""
+    xyz = pc.params['_xyz']
+    means2D = torch.zeros_like(xyz, requires_grad=True, device=xyz.device) + 0
+    if gs_grad:
+        means2D.retain_grad()
+    viewmatrix_cur = viewpoint_camera.get_pose(index)
+    pose = viewmatrix_cur if cam_grad else viewmatrix_cur.detach()
+    planes, radius, stats = render_planes(
+        xyz, pc.params['_features_dc'], pc.params['_features_rest'], pc.params['_opacity'], pc.params['_scaling'],
+        pc.params['_rotation'], pose, means2D, pc.cam, viewpoint_camera.cam_center, pc.active_sh_degree,
+        gs_grad=gs_grad, cam_grad=cam_grad)
+    out = _pack(pc, viewmatrix_cur, planes[0:3], planes[3:6], radius, means2D)
+    out["num_rendered"] = stats
+    return out
+
+
+def render_two_pass(viewpoint_camera, index, pc, gs_grad=True, cam_grad=True):
+    """The reference's own formulation (PyTorch pre-processing + two GaussianRasterizer calls),
+    restated here so that tests/bench can run the un-fused drop-in path without /root/reference."""
+    from .model import eval_sh, transform_to_frame
+    xyz = pc.params['_xyz']
+    means2D = torch.zeros_like(xyz, requires_grad=True, device=xyz.device) + 0
+    if gs_grad:
+        means2D.retain_grad()
+    viewmatrix_cur = viewpoint_camera.get_pose(index)
+    means_cam = transform_to_frame(xyz, viewmatrix_cur, gs_grad, cam_grad)
+    opacity, scales, rots = pc.get_opacity, pc.get_scaling, pc.get_rotation
+    feats = pc.get_features
+    shs_view = feats.transpose(1, 2).view(-1, 3, (pc.max_sh_degree + 1) ** 2)
+    dir_pp = xyz - viewpoint_camera.cam_center.repeat(feats.shape[0], 1)
+    dir_pp = dir_pp / dir_pp.norm(dim=1, keepdim=True)
+    colors = torch.clamp_min(eval_sh(pc.active_sh_degree, shs_view, dir_pp) + 0.5, 0.0)
+    pts4 = torch.cat((means_cam, torch.ones_like(means_cam[:, :1])), dim=-1)
+    z = (pc.cam.viewmatrix[0] @ pts4.transpose(0, 1)).transpose(0, 1)[:, 2]
+    dcol = torch.stack([z, torch.ones_like(z), z * z], dim=1)
+    means2D_b = torch.zeros_like(xyz, requires_grad=True, device=xyz.device) + 0
+    im, radius, _ = GaussianRasterizer(raster_settings=pc.cam)(
+        means3D=means_cam, shs=None, colors_precomp=colors, rotations=rots, opacities=opacity, scales=scales,
+        cov3D_precomp=None, means2D=means2D)
+    depth_sil, _, _ = GaussianRasterizer(raster_settings=pc.cam)(
+        means3D=means_cam, colors_precomp=dcol, rotations=rots, opacities=opacity, scales=scales, means2D=means2D_b)
+    return _pack(pc, viewmatrix_cur, im, depth_sil, radius, means2D)

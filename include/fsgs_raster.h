@@ -1,0 +1,164 @@
+/*
+ * fsgs_raster.h -- C ABI of the B200-native differentiable Gaussian rasteriser for Free-SurGS.
+ *
+ * Plain `extern "C"`, raw device pointers + sizes + a CUDA stream handle; no torch types.
+ * Every entry point returns 0 on success or a negative FSGS_E_* code (fsgs_error_string()).
+ * All pointers are DEVICE pointers unless the parameter name ends in `_host`; tensors are
+ * contiguous float32 unless stated.  Work is enqueued on `stream` (a cudaStream_t passed as
+ * void*); the only host synchronisation is the one read-back of the tile-instance count in the
+ * forward calls (the reference rasteriser has the same one).
+ *
+ * What each entry point replaces in the reference (wrld/Free-SurGS):
+ *
+ *   fsgs_rasterize_forward / _backward / fsgs_mark_visible
+ *       the pybind functions `_C.rasterize_gaussians`, `_C.rasterize_gaussians_backward`,
+ *       `_C.mark_visible` of the un-vendored package `diff_gaussian_rasterization`
+ *       (requirements.txt:26, .gitmodules:4-6) that `GaussianRasterizer.forward` calls; reference
+ *       call sites gaussian_renderer/__init__.py:68,69,131 and scene/pose_optimizer.py:619-632.
+ *
+ *   fsgs_render_forward / _backward
+ *       the whole per-frame body of `gaussian_renderer.render` (gaussian_renderer/__init__.py:49-92):
+ *       transform_to_frame (scene/pose_optimizer.py:960-989), the activations
+ *       (scene/gaussian_model.py:118-138), SH->RGB (scene/gaussian_model.py:308-333 +
+ *       utils/sh_utils.py:57-112), the depth/silhouette colours (scene/gaussian_model.py:260-291)
+ *       and BOTH rasteriser passes (one projection / binning / sort, six composited planes), with
+ *       the backward additionally reducing dL/d(pose) = sum_i g_i [p_i;1]^T, i.e. the backward of
+ *       the matmul at scene/pose_optimizer.py:987.
+ *
+ * Scratch memory is requested through caller-supplied allocation callbacks (the analogue of the
+ * `resizeFunctional` lambdas the reference's binding passes to its C++ rasteriser) so that the
+ * host framework's caching allocator owns every byte; the three buffers must be kept alive by
+ * the caller until the matching backward has run.
+ */
+#ifndef FSGS_RASTER_H_
+#define FSGS_RASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSGS_ABI_VERSION 1
+
+enum {
+    FSGS_OK = 0,
+    FSGS_E_INVALID = -1,   /* bad argument (null pointer, negative size, unsupported degree ...) */
+    FSGS_E_CUDA = -2,      /* a CUDA runtime call failed; see fsgs_error_string(code)            */
+    FSGS_E_ALLOC = -3,     /* an allocation callback returned NULL                               */
+    FSGS_E_ARCH = -4,      /* device is not sm_100                                               */
+    FSGS_E_WATCHDOG = -5   /* debug builds only: a device-side wait exceeded its spin budget      */
+};
+
+/* Returns a device pointer to at least `bytes` bytes, 256-byte aligned, valid until the caller
+ * releases it (after backward).  Called on the calling host thread, synchronously. */
+typedef void *(*fsgs_alloc_fn)(void *user, size_t bytes);
+
+/* Static per-call configuration: the scalar fields of GaussianRasterizationSettings
+ * (scene/pose_optimizer.py:619-632) plus the SH layout. */
+typedef struct fsgs_settings {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    float scale_modifier;
+    int32_t sh_degree;   /* active SH degree 0..3 (only read when SH coefficients are given)     */
+    int32_t n_coeffs;    /* coefficients per channel stored in `shs` (M of [P,M,3]); 16 for fused */
+    int32_t debug;       /* !=0: synchronise + check after every kernel, enable device watchdog   */
+    int32_t flags;       /* FSGS_FLAG_*                                                           */
+} fsgs_settings;
+
+#define FSGS_FLAG_NO_TMA 1u        /* stage tile batches with plain loads instead of bulk TMA     */
+#define FSGS_FLAG_NO_TILE_CULL 2u  /* keep every tile of the reference's 3-sigma rectangle        */
+
+/* ------------------------------------------------------------------------------------------
+ * API-level rasteriser (one GaussianRasterizer call).
+ *   bg[3], viewmatrix[16], projmatrix[16] (column-major, i.e. the transposed row-major matrices the
+ *   reference passes), campos[3]: device pointers.
+ *   Exactly one of {colors_precomp[P,3], shs[P,n_coeffs,3]} and exactly one of
+ *   {(scales[P,3], rotations[P,4]), cov3D_precomp[P,6]} must be non-NULL.
+ *   out_color[3,H,W], out_depth[1,H,W], radii[P] (int32).  *num_rendered_host receives the
+ *   number of (tile, Gaussian) instances actually composited (after exact tile culling);
+ *   *num_rect_host (optional) the reference's 3-sigma-rectangle count.
+ * ------------------------------------------------------------------------------------------ */
+int fsgs_rasterize_forward(const fsgs_settings *st, int32_t P, const float *bg, const float *means3D,
+                           const float *colors_precomp, const float *shs, const float *opacities,
+                           const float *scales, const float *rotations, const float *cov3D_precomp,
+                           const float *viewmatrix, const float *projmatrix, const float *campos,
+                           fsgs_alloc_fn geom_alloc, void *geom_user, fsgs_alloc_fn binning_alloc,
+                           void *binning_user, fsgs_alloc_fn img_alloc, void *img_user, float *out_color,
+                           float *out_depth, int32_t *radii, int64_t *num_rendered_host,
+                           int64_t *num_rect_host, void *stream);
+
+/* Backward of the call above.  geom/binning/img are the buffers the forward obtained from the
+ * callbacks.  dL_dout_depth may be NULL (treated as zero).  Outputs (all overwritten; a NULL
+ * output is skipped): dL_dmeans2D[P,3] (z = 0), dL_dcolors[P,3], dL_dopacity[P,1],
+ * dL_dmeans3D[P,3], dL_dcov3D[P,6], dL_dsh[P,n_coeffs,3], dL_dscales[P,3], dL_drotations[P,4].
+ * `grad_scratch` is a caller-provided device buffer of fsgs_grad_scratch_bytes(P) bytes. */
+int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg,
+                            const float *means3D, const float *colors_precomp, const float *shs,
+                            const float *opacities, const float *scales, const float *rotations,
+                            const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+                            const float *campos, const void *geom, const void *binning, const void *img,
+                            const float *dL_dout_color, const float *dL_dout_depth, void *grad_scratch,
+                            float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D,
+                            float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
+                            void *stream);
+
+/* visible[P] (uint8): view-space z > 0.2 (the reference's frustum test). */
+int fsgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                      uint8_t *visible, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused per-frame render (gaussian_renderer.render).  Raw (pre-activation) parameters:
+ *   xyz[P,3] world, features_dc[P,1,3], features_rest[P,15,3], opacity_raw[P,1] (sigmoid),
+ *   scaling_raw[P,3] (exp), rotation_raw[P,4] (L2-normalised), pose[4,4] ROW-major world->camera
+ *   (LearnPose.forward output), cam_center[3] (SH view origin; the reference keeps it at the
+ *   first frame's centre).  viewmatrix/projmatrix/bg as above (identity view in Free-SurGS).
+ *   out_planes[6,H,W] = RGB | depth, silhouette, depth^2 (each + T_final * bg as the reference's
+ *   second pass does).  radii[P] int32.
+ * ------------------------------------------------------------------------------------------ */
+int fsgs_render_forward(const fsgs_settings *st, int32_t P, const float *bg, const float *xyz,
+                        const float *features_dc, const float *features_rest, const float *opacity_raw,
+                        const float *scaling_raw, const float *rotation_raw, const float *pose,
+                        const float *cam_center, const float *viewmatrix, const float *projmatrix,
+                        fsgs_alloc_fn geom_alloc, void *geom_user, fsgs_alloc_fn binning_alloc,
+                        void *binning_user, fsgs_alloc_fn img_alloc, void *img_user, float *out_planes,
+                        int32_t *radii, int64_t *num_rendered_host, int64_t *num_rect_host, void *stream);
+
+/* Backward of the fused render.  dL_dplanes[6,H,W].  Outputs (overwritten; NULL = skip):
+ * dL_dxyz[P,3], dL_dfeatures_dc[P,1,3], dL_dfeatures_rest[P,15,3], dL_dopacity_raw[P,1],
+ * dL_dscaling_raw[P,3], dL_drotation_raw[P,4], dL_dpose[4,4] (row 3 = 0),
+ * dL_dmeans2D[P,3] (screen-space gradient of the RGB planes only, as the reference's
+ * `viewspace_points.grad`).  gs_grad / cam_grad mirror transform_to_frame's detach flags:
+ * gs_grad=0 drops the pose path from dL_dxyz (the SH view-direction path stays, as in the
+ * reference); cam_grad=0 leaves dL_dpose zero. */
+int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg,
+                         const float *xyz, const float *features_dc, const float *features_rest,
+                         const float *opacity_raw, const float *scaling_raw, const float *rotation_raw,
+                         const float *pose, const float *cam_center, const float *viewmatrix,
+                         const float *projmatrix, const void *geom, const void *binning, const void *img,
+                         const float *dL_dplanes, void *grad_scratch, int32_t gs_grad, int32_t cam_grad,
+                         float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
+                         float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw,
+                         float *dL_dpose, float *dL_dmeans2D, void *stream);
+
+/* Sizes / layout helpers (host only, no CUDA calls). */
+size_t fsgs_geom_bytes(int32_t P);
+size_t fsgs_img_bytes(int32_t image_width, int32_t image_height);
+size_t fsgs_binning_bytes(int64_t num_rendered);
+size_t fsgs_grad_scratch_bytes(int32_t P);
+/* Byte offset of the packed per-Gaussian splat records (48 B each: x, y, conic.xyz, opacity,
+ * r, g, b, depth, radius-as-int, tiles-touched-as-int) inside the geometry buffer. */
+size_t fsgs_geom_record_offset(int32_t P);
+
+int fsgs_abi_version(void);
+const char *fsgs_error_string(int code);
+/* Name of the kernels a forward+backward launches, comma separated (for launch accounting). */
+const char *fsgs_kernel_names(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSGS_RASTER_H_ */

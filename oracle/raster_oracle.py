@@ -359,16 +359,25 @@ def rasterize(means3D, means2D, opacities, st, colors_precomp=None, shs=None, sc
 
 
 def fragile_pixel_mask(aux, H: int, W: int, eps_pix: float = 1e-4, eps_gauss: float = 1e-5) -> torch.Tensor:
-    """Pixels where a float32 implementation may legitimately flip a threshold decision
-    (alpha<1/255, T<1e-4, integer radius / rect edge / near cull) relative to this oracle.
-    Needs ``want_aux=True``.  ``eps_*`` are relative distances to the threshold."""
+    """Pixels where a float32 implementation may legitimately flip a threshold decision relative to
+    this oracle.  Needs ``want_aux=True``.  ``eps_*`` are relative distances to the threshold.
+      * per pixel: some evaluated entry has alpha within eps_pix of 1/255, or T within eps_pix of 1e-4;
+      * per Gaussian: integer radius / tile-rectangle edge / near-plane decision within eps_gauss --
+        this can only add or remove the OUTER RING of tiles of its rectangle, so only that ring (one
+        tile either side of each rectangle edge) is marked.
+    """
     mask = aux["pix_margin"] < eps_pix
     pre = aux["pre"]
     frag = (pre["visible"] & (pre["margin"] < eps_gauss)).nonzero().flatten()
     gx, gy = (W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK
+    tile_mask = torch.zeros(gy, gx, dtype=torch.bool)
     for i in frag.tolist():
         x0, y0, x1, y1 = pre["rect"][i].tolist()
-        x0, y0 = max(0, x0 - 1), max(0, y0 - 1)
-        x1, y1 = min(gx, x1 + 1), min(gy, y1 + 1)
-        mask[y0 * BLOCK:y1 * BLOCK, x0 * BLOCK:x1 * BLOCK] = True
+        ox0, oy0, ox1, oy1 = max(0, x0 - 1), max(0, y0 - 1), min(gx, x1 + 1), min(gy, y1 + 1)
+        ring = torch.zeros(gy, gx, dtype=torch.bool)
+        ring[oy0:oy1, ox0:ox1] = True
+        ring[y0 + 1:y1 - 1, x0 + 1:x1 - 1] = False
+        tile_mask |= ring
+    if frag.numel():
+        mask = mask | tile_mask.repeat_interleave(BLOCK, 0).repeat_interleave(BLOCK, 1)[:H, :W]
     return mask
