@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Free-SurGS hot path (BASELINE.json):
+Gaussians*frames/s, forward+backward, 1280x1024, 500k splats, SH degree 3 (configs[1]).
+
+A "step" is one frame: the fused ``render`` (pose transform + activations + SH + projection, tile
+binning/sort, six-plane composite) and its backward (parameter gradients + dL/d(pose)) under the
+linear loss  sum(G_rgb*render) + sum(G_dep*render_dep)  of SURVEY.md 8d, on the synthetic
+"endo-synth" scene (seed 0, size multiplier m=2).
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--m 2] [--P 500000]
+
+N>1: launched by torchrun, one process per GPU; rank g renders frame g of the synthetic sequence
+against the shared Gaussian model and the Gaussian gradients are sum-all-reduced over NCCL
+(weak scaling: one frame per GPU per step).  ``--impl reference`` times the CPU port of the
+reference path (oracle/, float32 C + torch CPU pre-processing, all host threads) on rank 0.
+Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "free-surgs_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "gaussians_frames_per_s_fwd_bwd_1280x1024_500k"
+UNIT = "Gaussians*frames/s"
+W, H = 1280, 1024
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(P, R, HW):
+    """SURVEY.md 8d, fused render(): B_min = 724 P + 48 HW, B_model = B_min + 168 R (R = tile instances
+    actually composited).  Per kernel: composite_bwd reads 48 B record + 4 B id and
+    writes one 48 B partial gradient per instance, plus 24 B/px dL/dplanes + 8 B/px pixel state."""
+    b_min = 724 * P + 48 * HW
+    return {"frame_min": b_min, "frame_model": b_min + 168 * R,
+            "k_composite_bwd": 100 * R + 32 * HW, "k_composite_fwd": 48 * R + 32 * HW,
+            "k_tile_sort": (8 + 8 + 48 + 48) * R, "k_scatter": 48 * P + 8 * R,
+            "k_preprocess_fused": 236 * P + 48 * P + 4 * P, "k_preprocess_fused_bwd": (236 + 48 + 48) * P + 248 * P}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_port_step(sc, dtype=torch.float32):
+    """One frame of the reference path on the CPU: torch CPU pre-processing (the reference's Python
+    half, oracle/render_oracle.py) + the plain-C rasteriser port for both passes, fwd + bwd."""
+    from oracle import render_oracle as R
+    params = {k: v.to(dtype).requires_grad_(True) for k, v in sc.params.items()}
+    r, t = sc.pose_q.to(dtype).requires_grad_(True), sc.pose_t.to(dtype).requires_grad_(True)
+    out = R.render(params, r, t, sc.camera, 3, sc.camera.campos, True, True, backend="c")
+    loss = (out["render"] * sc.grads_out["G_rgb"].to(dtype)).sum() + (out["render_dep"] * sc.grads_out["G_dep"].to(dtype)).sum()
+    loss.backward()
+    return float(loss)
+
+
+def cpu_sample(args, budget_s, steps):
+    """Pick the largest area fraction f in {1, 1/4, 1/16, 1/64} of the workload whose `steps` CPU frames fit
+    the budget.  The fractional sample is the same generator at P*f Gaussians and (W*sqrt f)x(H*sqrt f)
+    pixels: identical splat density and footprint per pixel, so Gaussians*frames/s is comparable."""
+    from fsgs_b200.synth import make_scene
+    probe = make_scene(args.P // 64, W // 8, H // 8, size_mult=args.m, seed=0)
+    cpu_port_step(probe)                                  # warm (library load, thread pool)
+    t0 = time.perf_counter()
+    cpu_port_step(probe)
+    t64 = time.perf_counter() - t0
+    frac = 64
+    for f in (1, 4, 16, 64):
+        if steps * t64 * (64 / f) <= budget_s:
+            frac = f
+            break
+    k = int(round(frac ** 0.5))
+    sc = make_scene(args.P // frac, W // k, H // k, size_mult=args.m, seed=0)
+    desc = (f"endo-synth at 1/{frac} of the frame area: P={args.P // frac}, {W // k}x{H // k}, same density/footprint "
+            f"(m={args.m}), fwd+bwd, torch CPU pre-processing + plain-C float32 rasteriser port (both passes)")
+    return sc, desc
+
+
+def run_reference(args):
+    from oracle import c_oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c_oracle.build()
+    cores = c_oracle.num_threads()
+    sc, desc = cpu_sample(args, budget_s=150.0, steps=args.steps + args.warmup)
+    for _ in range(args.warmup):
+        cpu_port_step(sc)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_step(sc)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = sc.P / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"endo-synth P={args.P} {W}x{H} SH3 m={args.m} seed0, fused render fwd+bwd, 1 frame/GPU/step",
+                   "note": "CPU port of the reference path (oracle/); the reference's own CUDA rasteriser is not on disk "
+                           "(third-party, un-vendored: parity unpinned) and the reference has no CPU path of its own"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"per step: {desc}"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from fsgs_b200 import _lib, model, render
+    from fsgs_b200.synth import frame_pose_params, make_scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    sc = make_scene(args.P, W, H, size_mult=args.m, seed=0)
+    poses, pc = model.scene_to_device(sc, dev)
+    q, t = frame_pose_params(rank)            # rank g renders frame g of the sequence
+    poses.set_pose(0, q, t)
+    HW = W * H
+    # per-step host inputs (the reference copies the GT image to the GPU every iteration, train.py:174)
+    G_host = torch.empty(4, H, W).pin_memory()
+    G_host[:3] = sc.grads_out["G_rgb"]
+    G_host[3] = sc.grads_out["G_dep"]
+    G_dev = G_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    grads = [pc.params[k] for k in ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation")]
+    last = {}
+
+    def step(G, lean=False):
+        pc.zero_grad()
+        poses.pose_param_net.zero_grad(set_to_none=True)
+        out = render.render(poses, 0, pc, gs_grad=True, cam_grad=True)
+        loss = (out["render"] * G[:3]).sum() + (out["render_dep"] * G[3]).sum()
+        loss.backward()
+        if world > 1:
+            hs = [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True) for p in grads]
+            for h in hs:
+                h.wait()
+        last["stats"] = out["num_rendered"]
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(G_dev)
+    barrier()
+
+    # ---- timed region: K steps, device time, L2 flushed between steps (flush outside the events) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step(G_dev)
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    ms = [a.elapsed_time(b) for a, b in ev]
+    ms_step = sum(ms) / len(ms)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: per-step H2D of the step's host inputs + D2H of the loss, through render() ----
+    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    G_in = torch.empty_like(G_dev)
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        e2e_ev[k][0].record()
+        G_in.copy_(G_host, non_blocking=True)
+        loss = step(G_in)
+        loss_host = loss.item()                                   # D2H read of the step's result (+ sync)
+        pg = poses.pose_param_net.r.grad.cpu(), poses.pose_param_net.t.grad.cpu()
+        e2e_ev[k][1].record()
+    barrier()
+    ms_e2e = sum(a.elapsed_time(b) for a, b in e2e_ev) / args.steps
+
+    # ---- pose-gradient latency: tracking-mode step (gs_grad=False, cam_grad=True), RGB loss only ----
+    def track_step():
+        pc.zero_grad()
+        poses.pose_param_net.zero_grad(set_to_none=True)
+        out = render.render(poses, 0, pc, gs_grad=False, cam_grad=True)
+        (out["render"] * G_dev[:3]).sum().backward()
+    for _ in range(3):
+        track_step()
+    barrier()
+    tr = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.zero_()
+        tr[k][0].record(); track_step(); tr[k][1].record()
+    barrier()
+    ms_track = sum(a.elapsed_time(b) for a, b in tr) / args.steps
+
+    # ---- per-kernel durations (separate pass; events inside the library on the launching stream) ----
+    _lib.profile_enable(True)
+    nprof = min(args.steps, 10)
+    for _ in range(nprof):
+        flush.zero_()
+        step(G_dev)
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+
+    # max over ranks
+    t = torch.tensor([ms_step, ms_e2e, ms_track], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_e2e, ms_track = t.tolist()
+
+    if rank == 0:
+        R_inst, R_rect = int(last["stats"][0]), int(last["stats"][1])
+        bytes_ = algorithmic_bytes(args.P, R_inst, HW)
+        peak, peak_kind = measured_peak()
+        kern = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()}
+        top = max(kern, key=lambda k: kern[k])
+        achieved = bytes_.get(top, 0) / (kern[top] * 1e-3) / 1e9 if kern[top] > 0 else 0.0
+        value = args.P * world / (ms_step * 1e-3)
+        e2e_value = args.P * world / (ms_e2e * 1e-3)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import c_oracle
+            c_oracle.build()
+            sc_cpu, desc = cpu_sample(args, budget_s=25.0, steps=1)
+            t0 = time.perf_counter()
+            cpu_port_step(sc_cpu)
+            dt_cpu = time.perf_counter() - t0
+            cpu = {"value": sc_cpu.P / dt_cpu, "unit": UNIT, "cores": c_oracle.num_threads(), "kind": "port",
+                   "sample": f"{desc}; {dt_cpu:.1f} s"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"endo-synth P={args.P} {W}x{H} SH3 m={args.m} seed0, fused render fwd+bwd, "
+                                   f"1 frame/GPU/step", "l2": "256 MiB flush before every timed step (outside the events)",
+                       "tile_instances": R_inst, "tile_instances_reference_rect": R_rect,
+                       "parallelism": f"frame-dp{world}" + ("+nccl allreduce(grads)" if world > 1 else "")},
+            "pose_grad_ms_per_frame": ms_track,
+            "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "algorithmic_bytes_per_launch": bytes_.get(top), "launch_ms": kern[top]},
+            "roofline_frame": {"B_model": bytes_["frame_model"], "B_min": bytes_["frame_min"],
+                               "achieved_model_GBs": bytes_["frame_model"] / (ms_step * 1e-3) / 1e9,
+                               "frac_model": bytes_["frame_model"] / (ms_step * 1e-3) / 1e9 / peak,
+                               "frac_min": bytes_["frame_min"] / (ms_step * 1e-3) / 1e9 / peak},
+            "kernel_ms": {k: round(v, 4) for k, v in kern.items() if v > 0},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(G_host.numel() * 4),
+                    "d2h_bytes_per_step": 4 + 7 * 4, "ms_per_step": ms_e2e},
+            "gpu_launches": 7 * args.steps,
+            "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--m", type=float, default=2.0, help="splat size multiplier of the synthetic scene")
+    ap.add_argument("--P", type=int, default=500_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 3 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        run_reference(args)
+    else:
+        args.steps = 20 if args.steps is None else args.steps
+        args.warmup = 5 if args.warmup is None else args.warmup
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,37 @@ int check_arch() {
 
 inline int blocks(int n) { return (n + CTA - 1) / CTA; }
 
+// ---- optional per-kernel timing (CUDA events on the launching stream) ---------------------------
+// Off by default.  bench.py switches it on for a separate profiling pass (never for the timed
+// steps) to obtain the per-launch duration of each kernel for the roofline line.
+enum KernelId { K_PRE_API = 0, K_PRE_FUSED, K_SCAN, K_SCATTER, K_SORT, K_COMP_FWD, K_COMP_BWD, K_PRE_API_BWD,
+                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_COUNT };
+struct Profiler {
+    bool on = false;
+    static constexpr int MAXREC = 8192;
+    cudaEvent_t ev[MAXREC][2];
+    int kid[MAXREC];
+    int created = 0, used = 0;
+};
+Profiler g_prof;
+
+inline void prof_begin(int id, cudaStream_t s) {
+    if (!g_prof.on || g_prof.used >= Profiler::MAXREC) return;
+    if (g_prof.used >= g_prof.created) {
+        cudaEventCreate(&g_prof.ev[g_prof.created][0]);
+        cudaEventCreate(&g_prof.ev[g_prof.created][1]);
+        g_prof.created++;
+    }
+    g_prof.kid[g_prof.used] = id;
+    cudaEventRecord(g_prof.ev[g_prof.used][0], s);
+}
+inline void prof_end(int id, cudaStream_t s) {
+    if (!g_prof.on || g_prof.used >= Profiler::MAXREC) return;
+    (void)id;
+    cudaEventRecord(g_prof.ev[g_prof.used][1], s);
+    g_prof.used++;
+}
+
 struct Buffers {
     char *geom, *img, *bin;
     GeomLayout gl;
@@ -88,7 +119,9 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
     unsigned long long *counters = reinterpret_cast<unsigned long long *>(B.img + B.il.counters);
     float4 *records = reinterpret_cast<float4 *>(B.geom + B.gl.records);
 
+    prof_begin(K_SCAN, stream);
     k_tile_scan<<<1, 1024, 0, stream>>>(tiles, tile_count, tile_offset, cursor, counters);
+    prof_end(K_SCAN, stream);
     FSGS_LAUNCH_OK("k_tile_scan");
     unsigned long long h_cnt[4] = {0, 0, 0, 0};
     FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
@@ -105,15 +138,21 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
     float4 *sorted_rec = reinterpret_cast<float4 *>(B.bin + B.bl.records);
 
     if (R > 0) {
+        prof_begin(K_SCATTER, stream);
         k_scatter<<<blocks(P), CTA, 0, stream>>>(cc, P, records, tile_offset, cursor, keys, (unsigned)st->flags);
+        prof_end(K_SCATTER, stream);
         FSGS_LAUNCH_OK("k_scatter");
+        prof_begin(K_SORT, stream);
         k_tile_sort<<<tiles, CTA, SORT_SMEM_KEYS * sizeof(unsigned long long), stream>>>(tile_offset, keys, records,
                                                                                            sorted_rec);
+        prof_end(K_SORT, stream);
         FSGS_LAUNCH_OK("k_tile_sort");
     }
+    prof_begin(K_COMP_FWD, stream);
     k_composite_fwd<FUSED><<<tiles, CTA, 0, stream>>>(
         cc, tile_offset, sorted_rec, bg, out_planes, out_depth, reinterpret_cast<float *>(B.img + B.il.final_T),
         reinterpret_cast<unsigned int *>(B.img + B.il.n_contrib), (unsigned)st->flags, counters + CNT_ERR);
+    prof_end(K_COMP_FWD, stream);
     FSGS_LAUNCH_OK("k_composite_fwd");
     if (st->debug) {
         FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
@@ -162,6 +201,26 @@ extern "C" {
 
 int fsgs_abi_version(void) { return FSGS_ABI_VERSION; }
 
+int fsgs_profile_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.used = 0;
+    return FSGS_OK;
+}
+
+int fsgs_profile_collect(double *ms_sum, int64_t *count, int n) {
+    if (!ms_sum || !count || n < K_COUNT) return FSGS_E_INVALID;
+    for (int k = 0; k < n; ++k) { ms_sum[k] = 0.0; count[k] = 0; }
+    FSGS_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < g_prof.used; ++i) {
+        float ms = 0.f;
+        FSGS_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[i][0], g_prof.ev[i][1]));
+        ms_sum[g_prof.kid[i]] += ms;
+        count[g_prof.kid[i]] += 1;
+    }
+    g_prof.used = 0;
+    return FSGS_OK;
+}
+
 const char *fsgs_error_string(int code) {
     switch (code) {
         case FSGS_OK: return "ok";
@@ -184,6 +243,15 @@ size_t fsgs_img_bytes(int32_t W, int32_t H) { return img_layout(W, H).total; }
 size_t fsgs_binning_bytes(int64_t R) { return bin_layout(R).total; }
 size_t fsgs_grad_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * ACC_F * 4, 256); }
 size_t fsgs_geom_record_offset(int32_t P) { return geom_layout(P).records; }
+void fsgs_img_offsets(int32_t W, int32_t H, size_t *out6) {
+    const ImgLayout L = img_layout(W, H);
+    out6[0] = L.final_T; out6[1] = L.n_contrib; out6[2] = L.tile_count; out6[3] = L.tile_offset; out6[4] = L.cursor;
+    out6[5] = L.counters;
+}
+void fsgs_binning_offsets(int64_t R, size_t *out2) {
+    const BinLayout L = bin_layout(R);
+    out2[0] = L.keys; out2[1] = L.records;
+}
 
 int fsgs_rasterize_forward(const fsgs_settings *st, int32_t P, const float *bg, const float *means3D,
                            const float *colors_precomp, const float *shs, const float *opacities,
@@ -217,11 +285,13 @@ int fsgs_rasterize_forward(const fsgs_settings *st, int32_t P, const float *bg, 
     }
     Buffers B;
     if ((rc = alloc_fixed(P, cc, geom_alloc, geom_user, img_alloc, img_user, B, stream))) return rc;
+    prof_begin(K_PRE_API, stream);
     k_preprocess_api<<<blocks(P), CTA, 0, stream>>>(
         cc, P, means3D, colors_precomp, shs, opacities, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, campos,
         reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped), radii,
         reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
         reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags);
+    prof_end(K_PRE_API, stream);
     FSGS_LAUNCH_OK("k_preprocess_api");
     return forward_tail<false>(st, cc, P, bg, B, binning_alloc, binning_user, out_color, out_depth, num_rendered_host,
                                num_rect_host, stream);
@@ -251,18 +321,22 @@ int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rend
     float *acc = static_cast<float *>(grad_scratch);
     FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
     if (num_rendered > 0) {
+        prof_begin(K_COMP_BWD, stream);
         k_composite_bwd<false><<<il.tiles, CTA, 0, stream>>>(
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
             reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_dout_color, dL_dout_depth, acc, (unsigned)st->flags,
             const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
+        prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");
     }
+    prof_begin(K_PRE_API_BWD, stream);
     k_preprocess_api_bwd<<<blocks(P), CTA, 0, stream>>>(
         cc, P, means3D, shs, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, campos,
         reinterpret_cast<const float4 *>(g + gl.records), reinterpret_cast<const uint8_t *>(g + gl.clamped), acc,
         dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations);
+    prof_end(K_PRE_API_BWD, stream);
     FSGS_LAUNCH_OK("k_preprocess_api_bwd");
     (void)colors_precomp; (void)opacities;
     return FSGS_OK;
@@ -276,7 +350,9 @@ int fsgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, 
     if (P == 0) return FSGS_OK;
     int rc = check_arch();
     if (rc) return rc;
+    prof_begin(K_MARK_VISIBLE, stream);
     k_mark_visible<<<blocks(P), CTA, 0, stream>>>(P, means3D, viewmatrix, visible);
+    prof_end(K_MARK_VISIBLE, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_cuda_msg, sizeof(g_cuda_msg), "kernel k_mark_visible failed: %s", cudaGetErrorString(e));
@@ -314,11 +390,13 @@ int fsgs_render_forward(const fsgs_settings *st, int32_t P, const float *bg, con
     }
     Buffers B;
     if ((rc = alloc_fixed(P, cc, geom_alloc, geom_user, img_alloc, img_user, B, stream))) return rc;
+    prof_begin(K_PRE_FUSED, stream);
     k_preprocess_fused<<<blocks(P), CTA, 0, stream>>>(
         cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
         projmatrix, reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped),
         radii, reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
         reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags);
+    prof_end(K_PRE_FUSED, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused");
     return forward_tail<true>(st, cc, P, bg, B, binning_alloc, binning_user, out_planes, nullptr, num_rendered_host,
                               num_rect_host, stream);
@@ -351,19 +429,23 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
     float *acc = static_cast<float *>(grad_scratch);
     FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
     if (num_rendered > 0) {
+        prof_begin(K_COMP_BWD, stream);
         k_composite_bwd<true><<<il.tiles, CTA, 0, stream>>>(
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
             reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_dplanes, nullptr, acc, (unsigned)st->flags,
             const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
+        prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");
     }
+    prof_begin(K_PRE_FUSED_BWD, stream);
     k_preprocess_fused_bwd<<<blocks(P), CTA, 0, stream>>>(
         cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
         projmatrix, reinterpret_cast<const float4 *>(g + gl.records), reinterpret_cast<const uint8_t *>(g + gl.clamped),
         acc, gs_grad, cam_grad, dL_dxyz, dL_dfeatures_dc, dL_dfeatures_rest, dL_dopacity_raw, dL_dscaling_raw,
         dL_drotation_raw, dL_dpose, dL_dmeans2D);
+    prof_end(K_PRE_FUSED_BWD, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused_bwd");
     return FSGS_OK;
 }

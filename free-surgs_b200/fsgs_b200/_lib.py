@@ -38,11 +38,15 @@ _SIGNATURES = {
     "fsgs_abi_version": (ctypes.c_int, []),
     "fsgs_error_string": (ctypes.c_char_p, [ctypes.c_int]),
     "fsgs_kernel_names": (ctypes.c_char_p, []),
+    "fsgs_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "fsgs_profile_collect": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i64), ctypes.c_int]),
     "fsgs_geom_bytes": (ctypes.c_size_t, [_i32]),
     "fsgs_img_bytes": (ctypes.c_size_t, [_i32, _i32]),
     "fsgs_binning_bytes": (ctypes.c_size_t, [_i64]),
     "fsgs_grad_scratch_bytes": (ctypes.c_size_t, [_i32]),
     "fsgs_geom_record_offset": (ctypes.c_size_t, [_i32]),
+    "fsgs_img_offsets": (None, [_i32, _i32, ctypes.POINTER(ctypes.c_size_t)]),
+    "fsgs_binning_offsets": (None, [_i64, ctypes.POINTER(ctypes.c_size_t)]),
     "fsgs_rasterize_forward": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 11 +
                                [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp] + [_vp] * 3 +
                                [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
@@ -94,6 +98,31 @@ def check(code: int) -> None:
     if code != 0:
         msg = lib().fsgs_error_string(code)
         raise FsgsError(f"fsgs_raster error {code}: {msg.decode() if msg else '?'}")
+
+
+def img_offsets(W: int, H: int):
+    out = (ctypes.c_size_t * 6)()
+    lib().fsgs_img_offsets(W, H, out)
+    return dict(zip(("final_T", "n_contrib", "tile_count", "tile_offset", "cursor", "counters"), map(int, out)))
+
+
+def binning_offsets(R: int):
+    out = (ctypes.c_size_t * 2)()
+    lib().fsgs_binning_offsets(R, out)
+    return {"keys": int(out[0]), "records": int(out[1])}
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().fsgs_profile_enable(1 if on else 0))
+
+
+def profile_collect():
+    """-> {kernel name: (total ms, launches)} since profile_enable(True)."""
+    names = kernel_names()
+    ms = (ctypes.c_double * len(names))()
+    cnt = (_i64 * len(names))()
+    check(lib().fsgs_profile_collect(ms, cnt, len(names)))
+    return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(names)}
 
 
 def kernel_names():

@@ -152,6 +152,20 @@ size_t fsgs_grad_scratch_bytes(int32_t P);
 /* Byte offset of the packed per-Gaussian splat records (48 B each: x, y, conic.xyz, opacity,
  * r, g, b, depth, radius-as-int, tiles-touched-as-int) inside the geometry buffer. */
 size_t fsgs_geom_record_offset(int32_t P);
+/* Documented buffer layouts (for debugging / tests that read the scratch buffers back):
+ *   img     : out[0] final_T f32[HW], out[1] n_contrib u32[HW], out[2] tile_count u32[T],
+ *             out[3] tile_offset u32[T+1] (exclusive scan; [T] = instance count), out[4] cursor u32[T],
+ *             out[5] counters u64[4] (instances, rect instances, longest list, error flag)
+ *   binning : out[0] keys u64[R] ((depth float bits << 32) | Gaussian id, sorted inside each tile's
+ *             [tile_offset[t], tile_offset[t+1]) segment), out[1] sorted splat records 48 B x R */
+void fsgs_img_offsets(int32_t image_width, int32_t image_height, size_t *out6);
+void fsgs_binning_offsets(int64_t num_rendered, size_t *out2);
+
+/* Optional per-kernel timing with CUDA events on the launching stream (single-threaded use; off
+ * by default).  fsgs_profile_collect synchronises the device and returns, per kernel in the
+ * order of fsgs_kernel_names(), the summed duration in ms and the launch count since enable. */
+int fsgs_profile_enable(int on);
+int fsgs_profile_collect(double *ms_sum, int64_t *count, int n);
 
 int fsgs_abi_version(void);
 const char *fsgs_error_string(int code);

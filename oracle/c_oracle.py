@@ -42,7 +42,7 @@ def _lib(dtype: torch.dtype):
         fwd = getattr(lib, f"fsgs_oracle_forward_{sfx}")
         fwd.restype = ctypes.c_void_p
         fwd.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, p, p, p, p, p, real, p, p, p, p, p,
-                        ctypes.c_int, ctypes.c_int, real, real, p, p, p, p, p]
+                        ctypes.c_int, ctypes.c_int, real, real, p, p, p, p, p, p]
         bwd = getattr(lib, f"fsgs_oracle_backward_{sfx}")
         bwd.restype = None
         bwd.argtypes = [p] * 11
@@ -74,7 +74,7 @@ class _Handle:
 
 
 def forward(means3D, opacities, st, colors_precomp=None, shs=None, scales=None, rotations=None,
-            cov3D_precomp=None):
+            cov3D_precomp=None, want_margin=False):
     """Raw forward.  ``st`` is anything with the GaussianRasterizationSettings fields.
     Returns (color[3,H,W], radii[P] int32, depth[1,H,W], handle, num_rendered)."""
     dt = means3D.dtype
@@ -92,13 +92,18 @@ def forward(means3D, opacities, st, colors_precomp=None, shs=None, scales=None, 
     depth = torch.empty(1, H, W, dtype=dt)
     radii = torch.zeros(max(P, 1), dtype=torch.int32)
     nr = ctypes.c_int64(0)
+    margin = torch.empty(H, W, dtype=dt) if want_margin else None
     n_coeffs = 0 if shs is None else shs.shape[1]
     ptr = fwd(P, int(st.sh_degree), n_coeffs, _ptr(means3D), _ptr(shs), _ptr(colors_precomp),
               _ptr(opacities), _ptr(scales), float(st.scale_modifier), _ptr(rotations),
               _ptr(cov3D_precomp), _ptr(view), _ptr(proj), _ptr(campos), W, H, float(st.tanfovx),
-              float(st.tanfovy), _ptr(bg), _ptr(color), _ptr(depth), _ptr(radii), ctypes.byref(nr))
+              float(st.tanfovy), _ptr(bg), _ptr(color), _ptr(depth), _ptr(radii), ctypes.byref(nr),
+              _ptr(margin))
     keep = (means3D, opacities, colors_precomp, shs, scales, rotations, cov3D_precomp)
-    return color, radii[:P], depth, _Handle(ptr, fr, keep), int(nr.value)
+    h = _Handle(ptr, fr, keep)
+    h.pix_margin = margin
+    h.num_rendered = int(nr.value)
+    return color, radii[:P], depth, h, int(nr.value)
 
 
 def backward(handle: _Handle, dL_dcolor, dL_ddepth, P: int, n_coeffs: int, dt):
@@ -117,10 +122,14 @@ def backward(handle: _Handle, dL_dcolor, dL_ddepth, P: int, n_coeffs: int, dt):
 
 
 class _RasterizeC(torch.autograd.Function):
+    want_margin = False     # tests flip this to also get the per-pixel threshold margins
+    last_handle = None
+
     @staticmethod
     def forward(ctx, means3D, means2D, opacities, colors_precomp, shs, scales, rotations, cov3D_precomp, st):
         color, radii, depth, h, nr = forward(means3D, opacities, st, colors_precomp, shs, scales,
-                                             rotations, cov3D_precomp)
+                                             rotations, cov3D_precomp, want_margin=_RasterizeC.want_margin)
+        _RasterizeC.last_handle = h
         ctx.h, ctx.P, ctx.dt = h, means3D.shape[0], means3D.dtype
         ctx.n_coeffs = 0 if shs is None else shs.shape[1]
         ctx.flags = (colors_precomp is not None, shs is not None, scales is not None, cov3D_precomp is not None)
@@ -138,7 +147,26 @@ class _RasterizeC(torch.autograd.Function):
 
 
 def rasterize(means3D, means2D, opacities, st, colors_precomp=None, shs=None, scales=None,
-              rotations=None, cov3D_precomp=None):
-    """Differentiable ``GaussianRasterizer(st)(...)`` on the CPU through the C oracle."""
-    return _RasterizeC.apply(means3D, means2D, opacities, colors_precomp, shs, scales, rotations,
-                             cov3D_precomp, st)
+              rotations=None, cov3D_precomp=None, want_aux=False):
+    """Differentiable ``GaussianRasterizer(st)(...)`` on the CPU through the C oracle.
+    Returns (color, radii, depth, aux) like ``raster_oracle.rasterize``; with ``want_aux`` the aux
+    dict carries what ``raster_oracle.fragile_pixel_mask`` needs."""
+    _RasterizeC.want_margin = bool(want_aux)
+    try:
+        color, radii, depth = _RasterizeC.apply(means3D, means2D, opacities, colors_precomp, shs, scales,
+                                                rotations, cov3D_precomp, st)
+    finally:
+        _RasterizeC.want_margin = False
+    h = _RasterizeC.last_handle
+    aux = {"num_rendered": getattr(h, "num_rendered", None)}
+    if want_aux:
+        from . import raster_oracle as ro
+        dt = means3D.dtype
+        with torch.no_grad():
+            pre = ro.preprocess(means3D.detach(), torch.zeros_like(means3D), opacities.detach(),
+                                None if scales is None else scales.detach(),
+                                None if rotations is None else rotations.detach(),
+                                None if cov3D_precomp is None else cov3D_precomp.detach(),
+                                ro.RasterSettings.from_any(st, dt), colors_precomp=torch.zeros_like(means3D))
+        aux.update(pix_margin=h.pix_margin.double(), pre=pre)
+    return color, radii, depth, aux

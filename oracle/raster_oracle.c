@@ -219,7 +219,7 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
                               real scale_modifier, const real *rotations, const real *cov3D_precomp,
                               const real *viewmatrix, const real *projmatrix, const real *campos, int W,
                               int H, real tanfovx, real tanfovy, const real *bg, real *out_color,
-                              real *out_depth, int *radii_out, int64_t *num_rendered) {
+                              real *out_depth, int *radii_out, int64_t *num_rendered, real *pix_margin) {
     Ctx *c = (Ctx *)calloc(1, sizeof(Ctx));
     c->P = P; c->sh_deg = sh_deg; c->n_coeffs = n_coeffs; c->W = W; c->H = H;
     c->means3D = means3D; c->shs = shs; c->colors_precomp = colors_precomp; c->opacities = opacities;
@@ -342,6 +342,7 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
         for (int py = ty0; py < ty0 + BLOCK && py < H; ++py)
             for (int px = tx0; px < tx0 + BLOCK && px < W; ++px) {
                 real T = 1, C[NCH] = {0, 0, 0}, D = 0;
+                real margin = (real)1e30;   /* relative distance of the closest threshold decision */
                 int contributor = 0, last = 0;
                 for (int64_t k = s; k < e; ++k) {
                     contributor++;
@@ -349,10 +350,13 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
                     real dx = c->xy[2 * id] - (real)px, dy = c->xy[2 * id + 1] - (real)py;
                     const real *con = c->conic + 3 * id;
                     real power = (real)-0.5 * (con[0] * dx * dx + con[2] * dy * dy) - con[1] * dx * dy;
+                    if (fabs(power) < (real)1e-12) margin = 0;
                     if (power > 0) continue;
                     real alpha = fmin((real)0.99, opacities[id] * R_EXP(power));
+                    margin = fmin(margin, fabs(alpha - (real)(1.0 / 255.0)) * 255);
                     if (alpha < (real)(1.0 / 255.0)) continue;
                     real test_T = T * (1 - alpha);
+                    margin = fmin(margin, fabs(test_T - (real)0.0001) * 10000);
                     if (test_T < (real)0.0001) break;
                     for (int ch = 0; ch < NCH; ++ch) C[ch] += c->rgb[3 * id + ch] * alpha * T;
                     D += c->depth[id] * alpha * T;
@@ -362,6 +366,7 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
                 int64_t pix = (int64_t)py * W + px;
                 c->final_T[pix] = T;
                 c->n_contrib[pix] = last;
+                if (pix_margin) pix_margin[pix] = margin;
                 for (int ch = 0; ch < NCH; ++ch) out_color[(int64_t)ch * H * W + pix] = C[ch] + T * c->bg[ch];
                 out_depth[pix] = D;
             }

@@ -1,0 +1,301 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box): the CUDA path, called through the C-ABI
+library, against the oracle on the same seeded inputs.
+
+  * small scenes   -> float64 torch.autograd oracle (independent formulation), live
+  * config 1       -> plain-C float64 oracle, live (validated against the autograd oracle on CPU)
+                      and the committed golden fixture tests/golden/config1_golden.npz
+  * full size      -> size-independent properties (determinism, linearity of the backward,
+                      sortedness of the tile lists, silhouette == 1, culling / TMA invariance)
+Tolerances: <= 1e-5 abs on RGB/depth planes (pixels sitting on a flipped alpha<1/255 or T<1e-4
+decision are counted and bounded, see tests/parity.py), <= 1e-4 rel on every gradient.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(__file__))
+from parity import check_grad, check_image, rel_err  # noqa: E402
+
+from fsgs_b200 import _lib  # noqa: E402
+from fsgs_b200.synth import make_camera, make_scene, pose_matrix  # noqa: E402
+from oracle import raster_oracle as ro  # noqa: E402
+from oracle import render_oracle as R  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _gpu_modules():
+    import fsgs_b200
+    from fsgs_b200 import model, rasterizer, render
+    return fsgs_b200, model, rasterizer, render
+
+
+def _settings_to_cuda(cam, rasterizer):
+    return rasterizer.GaussianRasterizationSettings(
+        image_height=cam.image_height, image_width=cam.image_width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=cam.bg.to(DEV), scale_modifier=cam.scale_modifier, viewmatrix=cam.viewmatrix.to(DEV),
+        projmatrix=cam.projmatrix.to(DEV), sh_degree=cam.sh_degree, campos=cam.campos.to(DEV), prefiltered=False,
+        debug=True)
+
+
+def _run_fused(sc, G6, gs_grad=True, cam_grad=True, sh_deg=3, which="fused"):
+    _, model, _, render = _gpu_modules()
+    poses, pc = model.scene_to_device(sc, DEV)
+    pc.active_sh_degree = sh_deg
+    pc.cam = pc.cam._replace(debug=True)
+    fn = render.render if which == "fused" else render.render_two_pass
+    out = fn(poses, 0, pc, gs_grad=gs_grad, cam_grad=cam_grad)
+    planes = torch.stack([out["render"][0], out["render"][1], out["render"][2], out["render_dep"],
+                          out["render_opacity"], out["uncertainty"][0] + out["render_dep"].detach() ** 2])
+    loss = (out["render"] * G6[:3].to(DEV)).sum() + (out["render_dep"] * G6[3].to(DEV)).sum() + \
+           (out["render_opacity"] * G6[4].to(DEV)).sum()
+    out["render_w2c"].retain_grad()
+    loss.backward()
+    g = {k: v.grad.detach().cpu() if v.grad is not None else None for k, v in pc.params.items()}
+    g["pose"] = None if out["render_w2c"].grad is None else out["render_w2c"].grad.detach().cpu()
+    g["r"] = None if poses.pose_param_net.r.grad is None else poses.pose_param_net.r.grad.detach().cpu()
+    g["t"] = None if poses.pose_param_net.t.grad is None else poses.pose_param_net.t.grad.detach().cpu()
+    g["means2D"] = None if out["viewspace_points"].grad is None else out["viewspace_points"].grad.detach().cpu()
+    return out, planes.detach().cpu(), g
+
+
+def _oracle_fused(sc, G6, gs_grad, cam_grad, sh_deg, backend):
+    dt = torch.float64
+    params = {k: v.to(dt).requires_grad_(True) for k, v in sc.params.items()}
+    r, t = sc.pose_q.to(dt).requires_grad_(True), sc.pose_t.to(dt).requires_grad_(True)
+    out = R.render(params, r, t, sc.camera, sh_deg, sc.camera.campos, gs_grad, cam_grad, want_aux=True, backend=backend)
+    # depth^2 plane is detached in the reference (uncertainty), so it takes no gradient here either
+    loss = (out["render"] * G6[:3].to(dt)).sum() + (out["render_dep"] * G6[3].to(dt)).sum() + \
+           (out["render_opacity"] * G6[4].to(dt)).sum()
+    out["render_w2c"].retain_grad()
+    loss.backward()
+    planes = torch.cat([out["render"], out["_depth_sil"]], 0).detach()
+    g = {k: v.grad for k, v in params.items()}
+    g.update(pose=out["render_w2c"].grad, r=r.grad, t=t.grad, means2D=out["viewspace_points"].grad)
+    return out, planes, g
+
+
+def _compare_fused(sc, got_out, got_planes, got_g, ref_out, ref_planes, ref_g, gs_grad, cam_grad):
+    assert (got_out["radii"].cpu() != ref_out["radii"]).sum().item() <= max(1, sc.P // 2000)
+    check_image("rgb", got_planes[:3], ref_planes[:3], ref_out["_aux"])
+    check_image("depth_sil", got_planes[3:5], ref_planes[3:5], ref_out["_aux"], scale=2.0)
+    check_image("depth_sq", got_planes[5:6], ref_planes[5:6], ref_out["_aux"], scale=4.0)
+    for k in ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation", "means2D"):
+        if ref_g[k] is None or ref_g[k].abs().max() == 0:
+            assert got_g[k] is None or got_g[k].abs().max().item() == 0, k
+            continue
+        check_grad(k, got_g[k].reshape(ref_g[k].shape), ref_g[k])
+    if cam_grad:
+        check_grad("pose", got_g["pose"][:3], ref_g["pose"][:3])
+        check_grad("dL/dr", got_g["r"][0, :, 0], ref_g["r"])
+        check_grad("dL/dt", got_g["t"][:, 0], ref_g["t"])
+
+
+# ------------------------------------------------------------------------------------------------
+def test_library_loaded_and_arch():
+    L = _lib.lib()
+    assert L.fsgs_abi_version() == 1
+    assert torch.cuda.get_device_capability(0)[0] == 10, "these kernels are sm_100a only"
+
+
+@pytest.mark.parametrize("gs_grad,cam_grad,sh_deg,which", [(True, True, 3, "fused"), (False, True, 3, "fused"),
+                                                          (True, False, 1, "fused"), (True, True, 3, "two_pass")])
+def test_fused_render_small_vs_autograd_oracle(gs_grad, cam_grad, sh_deg, which):
+    sc = make_scene(1200, 200, 152, size_mult=2.0, seed=4)
+    G6 = torch.randn(6, sc.height, sc.width, generator=torch.Generator().manual_seed(1))
+    got = _run_fused(sc, G6, gs_grad, cam_grad, sh_deg, which)
+    ref = _oracle_fused(sc, G6, gs_grad, cam_grad, sh_deg, "py")
+    _compare_fused(sc, *got, *ref, gs_grad, cam_grad)
+
+
+@pytest.mark.parametrize("mode,sh_deg", [("sh", 3), ("sh", 1), ("precomp", 0), ("cov", 0)])
+def test_api_rasterizer_small_vs_autograd_oracle(mode, sh_deg):
+    _, _, rasterizer, _ = _gpu_modules()
+    P, W, H = 900, 150, 100          # ragged image: not multiples of 16
+    dt = torch.float64
+    sc = make_scene(P, W, H, size_mult=2.0, seed=3)
+    cam = make_camera(W, H, pose_matrix((1, 0.05, -0.03, 0.02), (0.02, 0.01, -0.03)))
+    cam.bg = torch.tensor([0.2, 0.7, 1.0])
+    cam.sh_degree = sh_deg
+    xyz = (sc.Rt(dt) @ torch.cat([sc.params["_xyz"].to(dt), torch.ones(P, 1, dtype=dt)], 1).T).T[:, :3]
+    xyz = xyz * torch.tensor([1.6, 1.6, 1.0], dtype=dt)     # some splats hit the +-1.3 tanfov clamp
+    d = dict(means3D=xyz, means2D=torch.zeros(P, 3, dtype=dt), opacities=torch.sigmoid(sc.params["_opacity"].to(dt)))
+    if mode == "cov":
+        S = ro.build_cov3d(torch.exp(sc.params["_scaling"].to(dt)),
+                           torch.nn.functional.normalize(sc.params["_rotation"].to(dt)), 1.0)
+        d["cov3D_precomp"] = torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1)
+    else:
+        d["scales"] = torch.exp(sc.params["_scaling"].to(dt))
+        d["rotations"] = torch.nn.functional.normalize(sc.params["_rotation"].to(dt)) * 1.1
+    if mode == "sh":
+        d["shs"] = torch.cat([sc.params["_features_dc"], sc.params["_features_rest"]], 1).to(dt)
+    else:
+        d["colors_precomp"] = torch.rand(P, 3, generator=torch.Generator().manual_seed(1)).to(dt)
+    ref_in = {k: v.detach().clone().requires_grad_(True) for k, v in d.items()}
+    gen = torch.Generator().manual_seed(5)
+    Gc, Gd = torch.randn(3, H, W, generator=gen), torch.randn(1, H, W, generator=gen)
+    color, radii, depth, aux = ro.rasterize(st=cam, want_aux=True, **ref_in)
+    ((color * Gc.to(dt)).sum() + (depth * Gd.to(dt)).sum()).backward()
+
+    gpu_in = {k: v.detach().float().to(DEV).requires_grad_(True) for k, v in d.items()}
+    rs = _settings_to_cuda(cam, rasterizer)
+    c2, r2, d2 = rasterizer.GaussianRasterizer(raster_settings=rs)(**gpu_in)
+    ((c2 * Gc.to(DEV)).sum() + (d2 * Gd.to(DEV)).sum()).backward()
+    assert r2.dtype == torch.int32 and c2.shape == (3, H, W) and d2.shape == (1, H, W)
+    assert (r2.cpu() != radii).sum().item() == 0
+    check_image("color", c2, color, aux)
+    check_image("depth", d2, depth, aux, scale=2.0)
+    for k, v in ref_in.items():
+        check_grad(k, gpu_in[k].grad.reshape(v.shape), v.grad)
+
+
+def test_config1_vs_c_oracle_and_golden():
+    """BASELINE.json configs[0]: 10k Gaussians, 640x512, m=2, SH degree 3, fwd+bwd incl. dL/d(pose)."""
+    sc = make_scene(10000, 640, 512, size_mult=2.0, seed=0)
+    G6 = torch.zeros(6, 512, 640)
+    G6[:3] = sc.grads_out["G_rgb"]
+    G6[3] = sc.grads_out["G_dep"]
+    got = _run_fused(sc, G6, True, True, 3, "fused")
+    ref = _oracle_fused(sc, G6, True, True, 3, "c")
+    _compare_fused(sc, *got, *ref, True, True)
+    # committed golden fixture (generated in the build container by tests/golden/make_config1_golden.py)
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "config1_golden.npz"))
+    planes = got[1]
+    sub = planes[:, ::4, ::4].double()
+    err = (sub - torch.from_numpy(gold["planes_sub4"])).abs()
+    assert (err.amax(0) > 1e-5 * 4).double().mean().item() < 2e-3 and err.max().item() < 2e-2
+    for k in ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation", "pose", "means2D"):
+        gk = got[2][k] if k != "pose" else got[2]["pose"][:3]
+        rk = torch.from_numpy(gold["g_" + k])
+        check_grad("golden " + k, gk.reshape(rk.shape), rk)
+    assert int(got[0]["num_rendered"][1]) == int(gold["num_rendered_rect"])
+
+
+def test_tma_and_culling_do_not_change_results():
+    _, _, rasterizer, _ = _gpu_modules()
+    sc = make_scene(6000, 320, 256, size_mult=2.0, seed=2)
+    G6 = torch.randn(6, sc.height, sc.width, generator=torch.Generator().manual_seed(1))
+    res = {}
+    try:
+        for name, kw in (("default", {}), ("no_tma", dict(no_tma=True)), ("no_cull", dict(no_tile_cull=True))):
+            rasterizer.set_debug_flags(**kw)
+            out, planes, g = _run_fused(sc, G6)
+            res[name] = (planes, g, out["num_rendered"].clone())
+    finally:
+        rasterizer.set_debug_flags()
+    p0, g0, n0 = res["default"]
+    assert torch.equal(p0, res["no_tma"][0]), "bulk-TMA staging must be a pure data-movement change"
+    assert torch.equal(p0, res["no_cull"][0]), "exact tile culling must not change any pixel"
+    assert int(res["no_cull"][2][0]) == int(n0[1]) and int(n0[0]) < int(n0[1])
+    for name in ("no_tma", "no_cull"):
+        for k, v in g0.items():
+            if v is not None:
+                assert rel_err(res[name][1][k], v) < 2e-6, (name, k)   # float atomics order only
+
+
+def test_edge_cases():
+    _, _, rasterizer, _ = _gpu_modules()
+    cam = make_camera(70, 50)
+    rs = _settings_to_cuda(cam, rasterizer)
+    z = lambda *s: torch.zeros(*s, device=DEV)
+    # empty
+    c, r, d = rasterizer.GaussianRasterizer(rs)(means3D=z(0, 3), means2D=z(0, 3), opacities=z(0, 1), colors_precomp=z(0, 3),
+                                               scales=z(0, 3), rotations=z(0, 4))
+    assert torch.allclose(c, torch.ones_like(c)) and d.abs().max().item() == 0 and r.numel() == 0
+    # everything behind the camera / near plane
+    m = torch.tensor([[0.0, 0.0, -1.0], [0.0, 0.0, 0.1]], device=DEV, requires_grad=True)
+    c, r, d = rasterizer.GaussianRasterizer(rs)(means3D=m, means2D=z(2, 3), opacities=torch.ones(2, 1, device=DEV),
+                                               colors_precomp=torch.rand(2, 3, device=DEV), scales=torch.ones(2, 3, device=DEV) * 0.01,
+                                               rotations=torch.tensor([[1.0, 0, 0, 0]] * 2, device=DEV))
+    assert (r == 0).all() and torch.allclose(c, torch.ones_like(c))
+    c.sum().backward()
+    assert m.grad.abs().max().item() == 0
+    # XOR argument checks keep the reference's messages
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rasterizer.GaussianRasterizer(rs)(means3D=m, means2D=z(2, 3), opacities=z(2, 1), scales=z(2, 3), rotations=z(2, 4))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        rasterizer.GaussianRasterizer(rs)(means3D=m, means2D=z(2, 3), opacities=z(2, 1), colors_precomp=z(2, 3))
+    assert rasterizer.GaussianRasterizer(rs).markVisible(m.detach()).tolist() == [False, False]
+
+
+@pytest.mark.parametrize("n_stack", [300, 9000])
+def test_long_tile_lists_and_depth_ties(n_stack):
+    """One tile with a very long list (multi-batch staging; > 8192 entries takes the global-memory
+    sort path) and many exactly equal depths (order must fall back to the Gaussian id)."""
+    _, _, rasterizer, _ = _gpu_modules()
+    from oracle import c_oracle as co
+    W = H = 32
+    cam = make_camera(W, H)
+    g = torch.Generator().manual_seed(n_stack)
+    P = n_stack
+    means = torch.zeros(P, 3)
+    means[:, 0] = (torch.rand(P, generator=g) - 0.5) * 0.01
+    means[:, 1] = (torch.rand(P, generator=g) - 0.5) * 0.01
+    means[:, 2] = 1.0 + 0.25 * torch.randint(0, 4, (P,), generator=g).float()     # only 4 distinct depths
+    d = dict(means3D=means, opacities=torch.full((P, 1), 0.005) + 0.007 * torch.rand(P, 1, generator=g),
+             colors_precomp=torch.rand(P, 3, generator=g), scales=torch.full((P, 3), 0.05),
+             rotations=torch.tensor([[1.0, 0, 0, 0]]).repeat(P, 1))
+    rs = _settings_to_cuda(cam, rasterizer)
+    gpu = {k: v.to(DEV).requires_grad_(True) for k, v in d.items()}
+    c, r, dep = rasterizer.GaussianRasterizer(rs)(means2D=torch.zeros(P, 3, device=DEV), **gpu)
+    Gc = torch.randn(3, H, W, generator=g)
+    (c * Gc.to(DEV)).sum().backward()
+    ref = {k: v.double().requires_grad_(True) for k, v in d.items()}
+    c_ref, r_ref, dep_ref, aux = co.rasterize(means2D=torch.zeros(P, 3, dtype=torch.float64), st=cam, want_aux=True, **ref)
+    (c_ref * Gc.double()).sum().backward()
+    assert (r.cpu() != r_ref).sum().item() == 0
+    check_image("color", c, c_ref, aux)
+    check_image("depth", dep, dep_ref, aux, scale=2.0)
+    for k in ("means3D", "opacities", "colors_precomp", "scales"):
+        check_grad(k, gpu[k].grad, ref[k].grad, tol=2e-4)
+
+
+def test_full_size_properties():
+    """Config 2 size (500k Gaussians, 1280x1024): properties that need no oracle."""
+    sc = make_scene(500_000, 1280, 1024, size_mult=2.0, seed=0)
+    G6 = torch.zeros(6, 1024, 1280)
+    G6[:3] = sc.grads_out["G_rgb"]
+    G6[3] = sc.grads_out["G_dep"]
+    out1, p1, g1 = _run_fused(sc, G6)
+    out2, p2, g2 = _run_fused(sc, G6)
+    assert torch.isfinite(p1).all()
+    assert torch.equal(p1, p2), "forward must be deterministic (sorted order fixes the scatter order)"
+    assert (p1[4] - 1.0).abs().max().item() < 1e-4, "silhouette + T_final == 1 (white background, quirk iv)"
+    assert int(out1["num_rendered"][1]) == 3_637_628 or abs(int(out1["num_rendered"][1]) - 3_640_000) < 40_000
+    for k, v in g1.items():
+        if v is not None:
+            assert torch.isfinite(v).all(), k
+            assert rel_err(g2[k], v) < 1e-5, k               # atomics order only
+    # linearity of the backward in the upstream gradient
+    _, _, g3 = _run_fused(sc, 2.0 * G6)
+    for k, v in g1.items():
+        if v is not None:
+            assert rel_err(g3[k], 2.0 * v) < 1e-5, k
+    # sortedness of every tile list, read back through the documented buffer layout
+    _, model, rasterizer, _ = _gpu_modules()
+    poses, pc = model.scene_to_device(sc, DEV)
+    with torch.no_grad():
+        means_cam = model.transform_to_frame(pc.params["_xyz"], poses.get_pose(0))
+        rs = pc.cam
+        nr, color, depth, radii, geom, binning, img = rasterizer.rasterize_gaussians(
+            rs.bg, means_cam, torch.rand(sc.P, 3, device=DEV), pc.get_opacity, pc.get_scaling, pc.get_rotation, 1.0,
+            torch.empty(0, device=DEV), rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+            rs.image_width, torch.empty(0, device=DEV), 0, rs.campos, False, True)
+    assert nr == int(out1["num_rendered"][0])
+    T = (1280 // 16) * (1024 // 16)
+    io, bo = _lib.img_offsets(1280, 1024), _lib.binning_offsets(nr)
+    tile_offset = img[io["tile_offset"]:io["tile_offset"] + 4 * (T + 1)].view(torch.int32).long()
+    keys = binning[bo["keys"]:bo["keys"] + 8 * nr].view(torch.int64)
+    assert int(tile_offset[-1]) == nr and (tile_offset[1:] >= tile_offset[:-1]).all()
+    asc = keys[1:] >= keys[:-1]                       # depth bits are positive floats -> signed compare is fine
+    boundary = torch.zeros(nr - 1, dtype=torch.bool, device=DEV)
+    inner = tile_offset[1:-1]
+    boundary[(inner[(inner > 0) & (inner < nr)] - 1)] = True
+    assert bool((asc | boundary).all()), "every tile list must be sorted by (depth bits, Gaussian id)"
+    ids = keys & 0xFFFFFFFF
+    assert int(ids.max()) < sc.P and int((radii[ids] > 0).all())
+    assert int((radii > 0).sum()) > 400_000

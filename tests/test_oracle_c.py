@@ -41,7 +41,7 @@ def test_c_oracle_matches_autograd_oracle(mode, W, H, spread, sh_deg):
     Gc = torch.randn(3, H, W, dtype=dt, generator=gen)
     Gd = torch.randn(1, H, W, dtype=dt, generator=gen)
     res = {}
-    for name, fn in (("py", lambda **kw: ro.rasterize(st=cam, **kw)[:3]), ("c", lambda **kw: co.rasterize(st=cam, **kw))):
+    for name, fn in (("py", lambda **kw: ro.rasterize(st=cam, **kw)[:3]), ("c", lambda **kw: co.rasterize(st=cam, **kw)[:3])):
         inp = _inputs(sc, dt, mode, spread)
         color, radii, depth = fn(**inp)
         ((color * Gc).sum() + (depth * Gd).sum()).backward()
@@ -69,7 +69,7 @@ def test_c_oracle_float32_close_to_float64():
     out = {}
     for dt in (torch.float32, torch.float64):
         inp = _inputs(sc, dt, "precomp")
-        color, radii, depth = co.rasterize(st=cam, **inp)
+        color, radii, depth, _ = co.rasterize(st=cam, **inp)
         out[dt] = (color.detach().double(), depth.detach().double())
     assert (out[torch.float32][0] - out[torch.float64][0]).abs().max().item() < 5e-3   # decision flips bound
     assert (out[torch.float32][0] - out[torch.float64][0]).abs().median().item() < 1e-6
