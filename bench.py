@@ -163,7 +163,8 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
-    from fsgs_b200 import _lib, model, render
+    from fsgs_b200 import _lib, model
+    from fsgs_b200 import frame_render as render
     from fsgs_b200.synth import frame_pose_params, make_scene
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

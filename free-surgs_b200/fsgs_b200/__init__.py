@@ -10,7 +10,7 @@ CPU or PyTorch fallback.
 from . import _lib
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, mark_visible, rasterize_gaussians,
                          rasterize_gaussians_backward, set_debug_flags)
-from .render import render, render_planes, render_two_pass
+from .frame_render import render, render_planes, render_two_pass
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "render", "render_planes", "render_two_pass",
            "mark_visible", "rasterize_gaussians", "rasterize_gaussians_backward", "set_debug_flags", "_lib"]

@@ -192,19 +192,28 @@ def preprocess(means3D, means2D, opacities, scales, rotations, cov3D_precomp, st
         # fragility of integer decisions (used by tests to exclude decision-flip pixels)
         frac = rad_f - torch.floor(rad_f)
         m_rad = torch.minimum(frac, 1 - frac) / rad_f.clamp(min=1.0)
-        def _edge(vv):
+        def _edge_px(vv):      # distance (pixels) of an edge coordinate to the nearest tile boundary
             q = vv / BLOCK
             f = q - torch.floor(q)
-            return torch.minimum(f, 1 - f) * BLOCK / (vv.abs() + 1.0)
-        m_rect = torch.stack([_edge(xyd[:, 0] - radius), _edge(xyd[:, 1] - radius),
-                              _edge(xyd[:, 0] + radius + BLOCK - 1),
-                              _edge(xyd[:, 1] + radius + BLOCK - 1)], dim=1).min(dim=1).values
+            return torch.minimum(f, 1 - f) * BLOCK
+
+        def _edge(vv):         # the same, relative to the coordinate's magnitude
+            return _edge_px(vv) / (vv.abs() + 1.0)
+        m_edges = torch.stack([_edge(xyd[:, 0] - radius), _edge(xyd[:, 1] - radius),
+                               _edge(xyd[:, 0] + radius + BLOCK - 1), _edge(xyd[:, 1] + radius + BLOCK - 1)], dim=1)
+        # a radius that is about to round the other way moves all four edges by one pixel; that only
+        # matters where the moved edge is within one pixel of a tile boundary
+        near_px = torch.stack([_edge_px(xyd[:, 0] - radius), _edge_px(xyd[:, 1] - radius),
+                               _edge_px(xyd[:, 0] + radius + BLOCK - 1), _edge_px(xyd[:, 1] + radius + BLOCK - 1)], dim=1)
+        m_rad_edges = torch.where(near_px <= 1.0 + 1e-3, m_rad[:, None].expand(-1, 4), torch.full_like(m_edges, float("inf")))
+        m_edges = torch.minimum(m_edges, m_rad_edges)
         m_z = (p_view[:, 2] - NEAR_CULL).abs() / NEAR_CULL
-        margin = torch.minimum(torch.minimum(m_rad, m_rect), m_z)
+        margin = torch.minimum(m_edges.min(dim=1).values, m_z)
 
     out = dict(p_view=p_view, depth=p_view[:, 2], xy=xy, conic=conic, cov2d=torch.stack([a, b, c2], 1),
                radii=radii, rect=torch.stack([rmin_x, rmin_y, rmax_x, rmax_y], 1), visible=visible,
-               tiles_touched=torch.where(visible, area, torch.zeros_like(area)), margin=margin)
+               tiles_touched=torch.where(visible, area, torch.zeros_like(area)), margin=margin,
+               margin_edges=m_edges, margin_z=m_z)
 
     if shs is not None:
         # shs [P,K,3]; dir from campos (Appendix A K1 colour branch)
@@ -358,26 +367,38 @@ def rasterize(means3D, means2D, opacities, st, colors_precomp=None, shs=None, sc
     return color, pre["radii"], depth, aux
 
 
-def fragile_pixel_mask(aux, H: int, W: int, eps_pix: float = 1e-4, eps_gauss: float = 1e-5) -> torch.Tensor:
+def fragile_pixel_mask(aux, H: int, W: int, eps_pix: float = 1e-4, eps_gauss: float = 2e-6) -> torch.Tensor:
     """Pixels where a float32 implementation may legitimately flip a threshold decision relative to
-    this oracle.  Needs ``want_aux=True``.  ``eps_*`` are relative distances to the threshold.
+    this oracle.  Needs ``want_aux=True``.  ``eps_*`` are relative distances to the threshold
+    (float32 epsilon is 6e-8).
       * per pixel: some evaluated entry has alpha within eps_pix of 1/255, or T within eps_pix of 1e-4;
-      * per Gaussian: integer radius / tile-rectangle edge / near-plane decision within eps_gauss --
-        this can only add or remove the OUTER RING of tiles of its rectangle, so only that ring (one
-        tile either side of each rectangle edge) is marked.
+      * per Gaussian: a tile-rectangle edge within eps_gauss of a tile boundary (directly, or through
+        an integer radius about to round the other way) can add/remove one line of tiles at that
+        edge -- the two tile lines either side of the edge are marked; a near-plane decision within
+        eps_gauss marks the whole rectangle.
     """
     mask = aux["pix_margin"] < eps_pix
     pre = aux["pre"]
-    frag = (pre["visible"] & (pre["margin"] < eps_gauss)).nonzero().flatten()
     gx, gy = (W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK
     tile_mask = torch.zeros(gy, gx, dtype=torch.bool)
+    me, mz = pre["margin_edges"], pre["margin_z"]
+    frag = ((me.min(dim=1).values < eps_gauss) | (pre["visible"] & (mz < eps_gauss)) |
+            (~pre["visible"] & (mz < eps_gauss))).nonzero().flatten()
     for i in frag.tolist():
         x0, y0, x1, y1 = pre["rect"][i].tolist()
         ox0, oy0, ox1, oy1 = max(0, x0 - 1), max(0, y0 - 1), min(gx, x1 + 1), min(gy, y1 + 1)
-        ring = torch.zeros(gy, gx, dtype=torch.bool)
-        ring[oy0:oy1, ox0:ox1] = True
-        ring[y0 + 1:y1 - 1, x0 + 1:x1 - 1] = False
-        tile_mask |= ring
+        if mz[i] < eps_gauss:
+            tile_mask[oy0:oy1, ox0:ox1] = True
+            continue
+        e = me[i] < eps_gauss
+        if e[0]:
+            tile_mask[oy0:oy1, max(0, x0 - 1):min(gx, x0 + 1)] = True
+        if e[1]:
+            tile_mask[max(0, y0 - 1):min(gy, y0 + 1), ox0:ox1] = True
+        if e[2]:
+            tile_mask[oy0:oy1, max(0, x1 - 1):min(gx, x1 + 1)] = True
+        if e[3]:
+            tile_mask[max(0, y1 - 1):min(gy, y1 + 1), ox0:ox1] = True
     if frag.numel():
         mask = mask | tile_mask.repeat_interleave(BLOCK, 0).repeat_interleave(BLOCK, 1)[:H, :W]
     return mask

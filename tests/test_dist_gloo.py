@@ -1,0 +1,94 @@
+"""Host logic of the frame data-parallel path, world_size 2 over gloo on CPU (no GPU needed):
+frame sharding, the sum all-reduce of the six Gaussian gradient tensors (bucketed and not),
+ranks without gradients, and the densification-statistics reductions."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fsgs_b200 import dist as fd
+
+SHAPES = {"_xyz": (7, 3), "_features_dc": (7, 1, 3), "_features_rest": (7, 15, 3), "_opacity": (7, 1),
+          "_scaling": (7, 3), "_rotation": (7, 4)}
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _grad(rank, key):
+    g = torch.Generator().manual_seed(1000 * rank + list(SHAPES).index(key))
+    return torch.randn(*SHAPES[key], generator=g)
+
+
+def _worker(rank, world, port, bucket, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        params = {k: torch.zeros(*s, requires_grad=True) for k, s in SHAPES.items()}
+        for k, p in params.items():
+            if not (rank == 1 and k == "_opacity"):          # rank 1 has no grad for one tensor
+                p.grad = _grad(rank, k)
+        nbytes = fd.allreduce_gaussian_grads(params, bucket=bucket)
+        assert nbytes == 7 * 59 * 4
+        for k, p in params.items():
+            want = sum(_grad(r, k) for r in range(world) if not (r == 1 and k == "_opacity"))
+            assert torch.allclose(p.grad, want, atol=1e-6), k
+        var = {"xyz_gradient_accum": torch.full((7, 1), float(rank + 1)), "denom": torch.ones(7, 1),
+               "max_radii2D": torch.arange(7.0) * (rank + 1)}
+        fd.allreduce_densification_stats(var)
+        assert torch.equal(var["xyz_gradient_accum"], torch.full((7, 1), 3.0))
+        assert torch.equal(var["denom"], torch.full((7, 1), 2.0))
+        assert torch.equal(var["max_radii2D"], torch.arange(7.0) * 2)
+        # frame-DP step with a stand-in renderer (the CUDA renderer needs a GPU): loss is a function of
+        # the shared parameter and of the frame id, so the reduced gradient must equal the serial sum
+        pc = type("PC", (), {})()
+        pc.params = {k: torch.ones(*s, requires_grad=True) for k, s in SHAPES.items()}
+        frames = fd.shard_frames(list(range(5)), world, rank)
+        render = lambda poses, f, pc, gs_grad, cam_grad: {"x": sum((p * (f + 1)).sum() for p in pc.params.values())}
+        loss, pkgs = fd.dp_render_step(render, None, pc, frames, lambda f, pkg: pkg["x"])
+        assert len(pkgs) == len(frames)
+        for k, p in pc.params.items():
+            assert torch.allclose(p.grad, torch.full(SHAPES[k], float(sum(f + 1 for f in range(5))))), k
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bucket", [True, False])
+def test_frame_dp_host_logic_world2_gloo(bucket):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, bucket, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: "ok", 1: "ok"}, res
+
+
+def test_shard_frames():
+    assert fd.shard_frames(list(range(8)), 8, 3) == [3]
+    assert fd.shard_frames(list(range(5)), 2, 0) == [0, 2, 4] and fd.shard_frames(list(range(5)), 2, 1) == [1, 3]
+    assert fd.shard_frames([], 4, 1) == []
+    with pytest.raises(ValueError):
+        fd.shard_frames([0, 1], 2, 2)
+
+
+def test_single_process_is_a_noop():
+    params = {k: torch.zeros(*s, requires_grad=True) for k, s in SHAPES.items()}
+    for k, p in params.items():
+        p.grad = torch.ones_like(p)
+    assert fd.allreduce_gaussian_grads(params) == 7 * 59 * 4
+    assert all(torch.equal(p.grad, torch.ones_like(p)) for p in params.values())

@@ -17,7 +17,7 @@ import pytest
 import torch
 
 sys.path.insert(0, os.path.dirname(__file__))
-from parity import check_grad, check_image, rel_err  # noqa: E402
+from parity import check_grad, check_image, fragile_mask, rel_err  # noqa: E402
 
 from fsgs_b200 import _lib  # noqa: E402
 from fsgs_b200.synth import make_camera, make_scene, pose_matrix  # noqa: E402
@@ -30,7 +30,8 @@ DEV = "cuda"
 
 def _gpu_modules():
     import fsgs_b200
-    from fsgs_b200 import model, rasterizer, render
+    from fsgs_b200 import frame_render as render
+    from fsgs_b200 import model, rasterizer
     return fsgs_b200, model, rasterizer, render
 
 
@@ -63,11 +64,14 @@ def _run_fused(sc, G6, gs_grad=True, cam_grad=True, sh_deg=3, which="fused"):
     return out, planes.detach().cpu(), g
 
 
-def _oracle_fused(sc, G6, gs_grad, cam_grad, sh_deg, backend):
+def _oracle_fused(sc, G6, gs_grad, cam_grad, sh_deg, backend, mask=None):
     dt = torch.float64
     params = {k: v.to(dt).requires_grad_(True) for k, v in sc.params.items()}
     r, t = sc.pose_q.to(dt).requires_grad_(True), sc.pose_t.to(dt).requires_grad_(True)
     out = R.render(params, r, t, sc.camera, sh_deg, sc.camera.campos, gs_grad, cam_grad, want_aux=True, backend=backend)
+    if mask is None:
+        mask = fragile_mask(out["_aux"], sc.height, sc.width)
+    G6 = G6 * (~mask).float()[None]
     # depth^2 plane is detached in the reference (uncertainty), so it takes no gradient here either
     loss = (out["render"] * G6[:3].to(dt)).sum() + (out["render_dep"] * G6[3].to(dt)).sum() + \
            (out["render_opacity"] * G6[4].to(dt)).sum()
@@ -76,7 +80,7 @@ def _oracle_fused(sc, G6, gs_grad, cam_grad, sh_deg, backend):
     planes = torch.cat([out["render"], out["_depth_sil"]], 0).detach()
     g = {k: v.grad for k, v in params.items()}
     g.update(pose=out["render_w2c"].grad, r=r.grad, t=t.grad, means2D=out["viewspace_points"].grad)
-    return out, planes, g
+    return out, planes, g, G6
 
 
 def _compare_fused(sc, got_out, got_planes, got_g, ref_out, ref_planes, ref_g, gs_grad, cam_grad):
@@ -107,8 +111,8 @@ def test_library_loaded_and_arch():
 def test_fused_render_small_vs_autograd_oracle(gs_grad, cam_grad, sh_deg, which):
     sc = make_scene(1200, 200, 152, size_mult=2.0, seed=4)
     G6 = torch.randn(6, sc.height, sc.width, generator=torch.Generator().manual_seed(1))
-    got = _run_fused(sc, G6, gs_grad, cam_grad, sh_deg, which)
-    ref = _oracle_fused(sc, G6, gs_grad, cam_grad, sh_deg, "py")
+    *ref, G6m = _oracle_fused(sc, G6, gs_grad, cam_grad, sh_deg, "py")
+    got = _run_fused(sc, G6m, gs_grad, cam_grad, sh_deg, which)
     _compare_fused(sc, *got, *ref, gs_grad, cam_grad)
 
 
@@ -139,6 +143,8 @@ def test_api_rasterizer_small_vs_autograd_oracle(mode, sh_deg):
     gen = torch.Generator().manual_seed(5)
     Gc, Gd = torch.randn(3, H, W, generator=gen), torch.randn(1, H, W, generator=gen)
     color, radii, depth, aux = ro.rasterize(st=cam, want_aux=True, **ref_in)
+    keep = (~fragile_mask(aux, H, W)).float()
+    Gc, Gd = Gc * keep, Gd * keep
     ((color * Gc.to(dt)).sum() + (depth * Gd.to(dt)).sum()).backward()
 
     gpu_in = {k: v.detach().float().to(DEV).requires_grad_(True) for k, v in d.items()}
@@ -159,11 +165,14 @@ def test_config1_vs_c_oracle_and_golden():
     G6 = torch.zeros(6, 512, 640)
     G6[:3] = sc.grads_out["G_rgb"]
     G6[3] = sc.grads_out["G_dep"]
-    got = _run_fused(sc, G6, True, True, 3, "fused")
-    ref = _oracle_fused(sc, G6, True, True, 3, "c")
-    _compare_fused(sc, *got, *ref, True, True)
-    # committed golden fixture (generated in the build container by tests/golden/make_config1_golden.py)
+    # committed golden fixture (generated in the build container by tests/golden/make_config1_golden.py);
+    # its fragile-pixel mask is the one the live oracle must reproduce
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "config1_golden.npz"))
+    mask = torch.from_numpy(np.unpackbits(gold["fragile_mask_bits"])[:512 * 640].reshape(512, 640).astype(bool))
+    *ref, G6m = _oracle_fused(sc, G6, True, True, 3, "c", mask=mask)
+    assert torch.equal(fragile_mask(ref[0]["_aux"], 512, 640), mask)
+    got = _run_fused(sc, G6m, True, True, 3, "fused")
+    _compare_fused(sc, *got, *ref, True, True)
     planes = got[1]
     sub = planes[:, ::4, ::4].double()
     err = (sub - torch.from_numpy(gold["planes_sub4"])).abs()
@@ -243,9 +252,10 @@ def test_long_tile_lists_and_depth_ties(n_stack):
     gpu = {k: v.to(DEV).requires_grad_(True) for k, v in d.items()}
     c, r, dep = rasterizer.GaussianRasterizer(rs)(means2D=torch.zeros(P, 3, device=DEV), **gpu)
     Gc = torch.randn(3, H, W, generator=g)
-    (c * Gc.to(DEV)).sum().backward()
     ref = {k: v.double().requires_grad_(True) for k, v in d.items()}
     c_ref, r_ref, dep_ref, aux = co.rasterize(means2D=torch.zeros(P, 3, dtype=torch.float64), st=cam, want_aux=True, **ref)
+    Gc = Gc * (~fragile_mask(aux, H, W)).float()
+    (c * Gc.to(DEV)).sum().backward()
     (c_ref * Gc.double()).sum().backward()
     assert (r.cpu() != r_ref).sum().item() == 0
     check_image("color", c, c_ref, aux)
