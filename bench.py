@@ -307,6 +307,7 @@ def run_ours(args):
                        "tile_instances": R_inst, "tile_instances_reference_rect": R_rect,
                        "parallelism": f"frame-dp{world}" + ("+nccl allreduce(grads)" if world > 1 else "")},
             "pose_grad_ms_per_frame": ms_track,
+            "ms_steps": [round(x, 3) for x in ms],
             "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,

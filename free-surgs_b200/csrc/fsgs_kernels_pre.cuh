@@ -296,6 +296,30 @@ k_tile_sort(const unsigned int *__restrict__ tile_offset, unsigned long long *__
     }
 }
 
+// LearnPose.forward / its backward for one frame: a single thread each (7 parameters).
+// r is the [1,4,N] quaternion tensor, t the [3,N] translation tensor of the reference; `cam`
+// selects the column, `n_cams` is N.
+__global__ void k_pose_forward(const float *__restrict__ r, const float *__restrict__ t, int cam, int n_cams,
+                               float *__restrict__ Rt) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float q[4] = {r[cam], r[n_cams + cam], r[2 * n_cams + cam], r[3 * n_cams + cam]};
+    const float tt[3] = {t[cam], t[n_cams + cam], t[2 * n_cams + cam]};
+    float out[16];
+    pose_forward(q, tt, out);
+    for (int k = 0; k < 16; ++k) Rt[k] = out[k];
+}
+__global__ void k_pose_backward(const float *__restrict__ r, int cam, int n_cams, const float *__restrict__ dRt,
+                                float *__restrict__ dr, float *__restrict__ dt) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float q[4] = {r[cam], r[n_cams + cam], r[2 * n_cams + cam], r[3 * n_cams + cam]};
+    float g[16], gq[4], gt[3];
+    for (int k = 0; k < 16; ++k) g[k] = dRt[k];
+    pose_backward(q, g, gq, gt);
+    // dr [1,4,N], dt [3,N]: only column `cam` is non-zero (the caller zero-fills)
+    for (int k = 0; k < 4; ++k) dr[k * n_cams + cam] = gq[k];
+    for (int k = 0; k < 3; ++k) dt[k * n_cams + cam] = gt[k];
+}
+
 __global__ void __launch_bounds__(CTA)
 k_mark_visible(int P, const float *__restrict__ means3D, const float *__restrict__ viewmatrix,
                uint8_t *__restrict__ visible) {

@@ -307,6 +307,18 @@ FSGS_HD void project_backward(const CamConst &cc, const float *V, const float *P
     dmean[0] += V[2] * gdepth; dmean[1] += V[6] * gdepth; dmean[2] += V[10] * gdepth;
 }
 
+// dL/dR (row-major 3x3) -> dL/dq for R = quat_to_R(q), q = (w,x,y,z) used as given.
+FSGS_HD void quat_R_backward(const float *q, const float *dR, float *dq) {
+    const float r = q[0], x = q[1], y = q[2], z = q[3];
+    dq[0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+    dq[1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] -
+                   2.f * x * dR[8]);
+    dq[2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] -
+                   2.f * y * dR[8]);
+    dq[3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] +
+                   x * dR[6] + y * dR[7]);
+}
+
 // dSigma(6) -> d(scale) (w.r.t. the s fed to cov3d_from_scale_rot) and d(quaternion as given).
 FSGS_HD void cov3d_backward(const float *s, const float *q, const float *dc6, float *ds, float *dq) {
     float R[9];
@@ -323,14 +335,7 @@ FSGS_HD void cov3d_backward(const float *s, const float *q, const float *dc6, fl
         const float s2 = 2.f * s[k] * s[k];
         dR[k] = GR[k] * s2; dR[3 + k] = GR[3 + k] * s2; dR[6 + k] = GR[6 + k] * s2;
     }
-    const float r = q[0], x = q[1], y = q[2], z = q[3];
-    dq[0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
-    dq[1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] -
-                   2.f * x * dR[8]);
-    dq[2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] -
-                   2.f * y * dR[8]);
-    dq[3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] +
-                   x * dR[6] + y * dR[7]);
+    quat_R_backward(q, dR, dq);
 }
 
 // backward of v -> v/|v| : given dL/d(unit), unit vector n and 1/|v|, returns dL/dv
@@ -597,6 +602,37 @@ FSGS_HD void api_backward_one(const CamConst &cc, const float *V, const float *P
         cov3d_backward(s, rot_i, dc6, ds, dq);
         ds[0] *= cc.mod; ds[1] *= cc.mod; ds[2] *= cc.mod;
     }
+}
+
+// ---- per-frame pose: LearnPose.forward (scene/pose_optimizer.py:822-877) -------------------------
+// r_raw (w,x,y,z) -> F.normalize (eps 1e-12) -> q2rot (normalises once more) -> Rt = [[R, t],[0 0 0 1]]
+FSGS_HD void pose_forward(const float *r_raw, const float *t, float *Rt) {
+    const float n1 = fmaxf(sqrtf(r_raw[0] * r_raw[0] + r_raw[1] * r_raw[1] + r_raw[2] * r_raw[2] + r_raw[3] * r_raw[3]), 1e-12f);
+    const float q1[4] = {r_raw[0] / n1, r_raw[1] / n1, r_raw[2] / n1, r_raw[3] / n1};
+    const float n2 = sqrtf(q1[0] * q1[0] + q1[1] * q1[1] + q1[2] * q1[2] + q1[3] * q1[3]);
+    const float q2[4] = {q1[0] / n2, q1[1] / n2, q1[2] / n2, q1[3] / n2};
+    float R[9];
+    quat_to_R(q2, R);
+    for (int r = 0; r < 3; ++r) {
+        Rt[4 * r] = R[3 * r]; Rt[4 * r + 1] = R[3 * r + 1]; Rt[4 * r + 2] = R[3 * r + 2]; Rt[4 * r + 3] = t[r];
+    }
+    Rt[12] = 0.f; Rt[13] = 0.f; Rt[14] = 0.f; Rt[15] = 1.f;
+}
+
+// dL/dRt [4,4] -> dL/dr_raw [4], dL/dt [3]
+FSGS_HD void pose_backward(const float *r_raw, const float *dRt, float *dr, float *dt) {
+    const float n1 = fmaxf(sqrtf(r_raw[0] * r_raw[0] + r_raw[1] * r_raw[1] + r_raw[2] * r_raw[2] + r_raw[3] * r_raw[3]), 1e-12f);
+    const float q1[4] = {r_raw[0] / n1, r_raw[1] / n1, r_raw[2] / n1, r_raw[3] / n1};
+    const float n2 = sqrtf(q1[0] * q1[0] + q1[1] * q1[1] + q1[2] * q1[2] + q1[3] * q1[3]);
+    const float q2[4] = {q1[0] / n2, q1[1] / n2, q1[2] / n2, q1[3] / n2};
+    const float dR[9] = {dRt[0], dRt[1], dRt[2], dRt[4], dRt[5], dRt[6], dRt[8], dRt[9], dRt[10]};
+    float dq2[4], dq1[4];
+    quat_R_backward(q2, dR, dq2);
+    float dot = q2[0] * dq2[0] + q2[1] * dq2[1] + q2[2] * dq2[2] + q2[3] * dq2[3];
+    for (int k = 0; k < 4; ++k) dq1[k] = (dq2[k] - q2[k] * dot) / n2;
+    dot = q1[0] * dq1[0] + q1[1] * dq1[1] + q1[2] * dq1[2] + q1[3] * dq1[3];
+    for (int k = 0; k < 4; ++k) dr[k] = (dq1[k] - q1[k] * dot) / n1;
+    dt[0] = dRt[3]; dt[1] = dRt[7]; dt[2] = dRt[11];
 }
 
 }  // namespace fsgs

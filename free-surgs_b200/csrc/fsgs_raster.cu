@@ -73,7 +73,7 @@ inline int blocks(int n) { return (n + CTA - 1) / CTA; }
 // Off by default.  bench.py switches it on for a separate profiling pass (never for the timed
 // steps) to obtain the per-launch duration of each kernel for the roofline line.
 enum KernelId { K_PRE_API = 0, K_PRE_FUSED, K_SCAN, K_SCATTER, K_SORT, K_COMP_FWD, K_COMP_BWD, K_PRE_API_BWD,
-                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_COUNT };
+                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_COUNT };
 struct Profiler {
     bool on = false;
     static constexpr int MAXREC = 8192;
@@ -235,7 +235,7 @@ const char *fsgs_error_string(int code) {
 
 const char *fsgs_kernel_names(void) {
     return "k_preprocess_api,k_preprocess_fused,k_tile_scan,k_scatter,k_tile_sort,k_composite_fwd,"
-           "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible";
+           "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible,k_pose_forward,k_pose_backward";
 }
 
 size_t fsgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
@@ -358,6 +358,25 @@ int fsgs_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, 
         snprintf(g_cuda_msg, sizeof(g_cuda_msg), "kernel k_mark_visible failed: %s", cudaGetErrorString(e));
         return FSGS_E_CUDA;
     }
+    return FSGS_OK;
+}
+
+int fsgs_pose_forward(const float *r, const float *t, int32_t cam, int32_t n_cams, float *Rt, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!r || !t || !Rt || n_cams <= 0 || cam < 0 || cam >= n_cams) return FSGS_E_INVALID;
+    k_pose_forward<<<1, 32, 0, stream>>>(r, t, cam, n_cams, Rt);
+    if (cudaGetLastError() != cudaSuccess) return FSGS_E_CUDA;
+    return FSGS_OK;
+}
+
+int fsgs_pose_backward(const float *r, int32_t cam, int32_t n_cams, const float *dRt, float *dr, float *dt,
+                       void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!r || !dRt || !dr || !dt || n_cams <= 0 || cam < 0 || cam >= n_cams) return FSGS_E_INVALID;
+    FSGS_CUDA(cudaMemsetAsync(dr, 0, sizeof(float) * 4 * n_cams, stream));
+    FSGS_CUDA(cudaMemsetAsync(dt, 0, sizeof(float) * 3 * n_cams, stream));
+    k_pose_backward<<<1, 32, 0, stream>>>(r, cam, n_cams, dRt, dr, dt);
+    if (cudaGetLastError() != cudaSuccess) return FSGS_E_CUDA;
     return FSGS_OK;
 }
 

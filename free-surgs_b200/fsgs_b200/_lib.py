@@ -52,6 +52,8 @@ _SIGNATURES = {
                                [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
     "fsgs_rasterize_backward": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 26),
     "fsgs_mark_visible": (ctypes.c_int, [_i32, _vp, _vp, _vp, _vp, _vp]),
+    "fsgs_pose_forward": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
+    "fsgs_pose_backward": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "fsgs_render_forward": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 11 +
                             [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp] + [_vp] * 2 +
                             [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),

@@ -42,6 +42,8 @@ def _check_identity_view(rs) -> None:
 
 
 class _RenderFused(torch.autograd.Function):
+    last_stats = (0, 0)
+
     @staticmethod
     def forward(ctx, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, rs, cam_center,
                 active_sh_degree, gs_grad, cam_grad):
@@ -53,7 +55,7 @@ class _RenderFused(torch.autograd.Function):
         t = [_f32(x, dev) for x in (rs.bg, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center,
                                     rs.viewmatrix, rs.projmatrix)]
         planes = torch.empty(6, H, W, dtype=torch.float32, device=dev)
-        radii = torch.zeros(P, dtype=torch.int32, device=dev)
+        radii = torch.empty(P, dtype=torch.int32, device=dev)     # the projection kernel writes every entry
         arena = _Arena(dev)
         nr, nrect = ctypes.c_int64(0), ctypes.c_int64(0)
         with torch.cuda.device(dev):
@@ -67,19 +69,21 @@ class _RenderFused(torch.autograd.Function):
         ctx.st, ctx.P, ctx.num_rendered, ctx.num_rect = st, P, int(nr.value), int(nrect.value)
         ctx.flags = (bool(gs_grad), bool(cam_grad))
         ctx.mark_non_differentiable(radii)
-        stats = torch.tensor([nr.value, nrect.value], dtype=torch.int64)
-        ctx.mark_non_differentiable(stats)
-        return planes, radii, stats
+        _RenderFused.last_stats = (int(nr.value), int(nrect.value))
+        return planes, radii
 
     @staticmethod
-    def backward(ctx, g_planes, _g_radii, _g_stats):
+    def backward(ctx, g_planes, _g_radii):
         *t, geom, binning, img = ctx.saved_tensors
         dev = t[1].device
         P = ctx.P
         gs_grad, cam_grad = ctx.flags
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        # every output is fully overwritten by the library (zeros where a Gaussian is not visible)
+        z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         g = dict(xyz=z(P, 3), f_dc=z(P, 1, 3), f_rest=z(P, 15, 3), opacity=z(P, 1), scaling=z(P, 3), rotation=z(P, 4),
                  pose=z(4, 4), means2D=z(P, 3))
+        if P == 0:
+            g["pose"].zero_()
         if P > 0:
             gp = _f32(g_planes, dev)
             scratch = torch.empty(_lib.lib().fsgs_grad_scratch_bytes(P), dtype=torch.uint8, device=dev)
@@ -96,10 +100,11 @@ class _RenderFused(torch.autograd.Function):
 
 def render_planes(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, raster_settings,
                   cam_center, active_sh_degree, gs_grad=True, cam_grad=True):
-    """Tensor-level entry: -> (planes[6,H,W], radii[P] int32, stats[2] = (instances, rect instances))."""
+    """Tensor-level entry: -> (planes[6,H,W], radii[P] int32, (instances, reference-rectangle instances))."""
     _check_identity_view(raster_settings)
-    return _RenderFused.apply(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D,
-                              raster_settings, cam_center, active_sh_degree, gs_grad, cam_grad)
+    planes, radii = _RenderFused.apply(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D,
+                                       raster_settings, cam_center, active_sh_degree, gs_grad, cam_grad)
+    return planes, radii, _RenderFused.last_stats
 
 
 def _pack(pc, viewmatrix_cur, im, depth_sil, radius, means2D):
@@ -110,7 +115,11 @@ def _pack(pc, viewmatrix_cur, im, depth_sil, radius, means2D):
     uncertainty = (depth_sq - depth ** 2).detach()
     pc.variables['means2D'] = means2D
     seen = radius > 0
-    pc.variables['max_radii2D'][seen] = torch.max(radius[seen], pc.variables['max_radii2D'][seen])
+    # reference: max_radii2D[seen] = max(radius[seen], max_radii2D[seen]) (__init__.py:77-80).  radii are 0
+    # where not seen and max_radii2D >= 0, so an in-place element-wise maximum is the same update without
+    # the boolean-index gather/scatter (and its host sync).
+    mr = pc.variables['max_radii2D']
+    torch.maximum(mr, radius.to(mr.dtype), out=mr)
     pc.variables['seen'] = seen
     nan_mask = (~torch.isnan(depth)) & (~torch.isnan(uncertainty))
     return {"render": im, "render_dep": depth, "render_w2c": viewmatrix_cur, "render_opacity": silhouette,

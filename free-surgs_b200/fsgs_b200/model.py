@@ -61,6 +61,41 @@ def transform_to_frame(means3D, viewmatrix, gaussians_grad=True, camera_grad=Tru
     return (rel_w2c @ pts4.T).T[:, :3]
 
 
+class _PoseFn(torch.autograd.Function):
+    """LearnPose.forward as two one-thread library kernels (fsgs_pose_forward / _backward) instead of
+    the ~150 element-wise PyTorch launches the reference's q2rot + autograd take per frame."""
+
+    @staticmethod
+    def forward(ctx, r, t, cam_id):
+        import ctypes
+        from . import _lib
+        rc_, tc_ = r.detach().contiguous(), t.detach().contiguous()
+        n = rc_.shape[-1]
+        Rt = torch.empty(4, 4, dtype=torch.float32, device=r.device)
+        s = ctypes.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
+        with torch.cuda.device(r.device):
+            _lib.check(_lib.lib().fsgs_pose_forward(ctypes.c_void_p(rc_.data_ptr()), ctypes.c_void_p(tc_.data_ptr()),
+                                                    int(cam_id), int(n), ctypes.c_void_p(Rt.data_ptr()), s))
+        ctx.save_for_backward(rc_)
+        ctx.cam_id, ctx.n, ctx.shapes = int(cam_id), int(n), (r.shape, t.shape)
+        return Rt
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes
+        from . import _lib
+        (rc_,) = ctx.saved_tensors
+        g = g.contiguous().float()
+        dr = torch.empty(ctx.shapes[0], dtype=torch.float32, device=g.device)
+        dt = torch.empty(ctx.shapes[1], dtype=torch.float32, device=g.device)
+        s = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().fsgs_pose_backward(ctypes.c_void_p(rc_.data_ptr()), ctx.cam_id, ctx.n,
+                                                     ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(dr.data_ptr()),
+                                                     ctypes.c_void_p(dt.data_ptr()), s))
+        return dr, dt, None
+
+
 class LearnPose(nn.Module):
     """Per-frame learnable pose: quaternion ``r[1,4,N]`` (w,x,y,z) + translation ``t[3,N]``."""
 
@@ -85,6 +120,9 @@ class LearnPose(nn.Module):
 
     def forward(self, cam_id: int) -> torch.Tensor:
         cam_id = int(cam_id)
+        if self.r.is_cuda:
+            return _PoseFn.apply(self.r, self.t, cam_id)
+        # CPU tensors (host-logic tests only): the reference's own formulation
         r = F.normalize(self.r[..., cam_id])
         t = self.t[..., cam_id]
         R = self.q2rot(r)[0]

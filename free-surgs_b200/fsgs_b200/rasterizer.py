@@ -109,7 +109,7 @@ def rasterize_gaussians(bg, means3D, colors_precomp, opacities, scales, rotation
              campos=_f32(campos, dev))
     color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
     depth = torch.empty(1, H, W, dtype=torch.float32, device=dev)
-    radii = torch.zeros(P, dtype=torch.int32, device=dev)
+    radii = torch.empty(P, dtype=torch.int32, device=dev)       # every entry is written by the projection kernel
     arena = _Arena(dev)
     nr, nrect = ctypes.c_int64(0), ctypes.c_int64(0)
     with torch.cuda.device(dev):
@@ -142,7 +142,8 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors_precomp, scales, rot
     n_coeffs = 0 if sh_t is None else sh_t.shape[1]
     st = _lib.Settings(H, W, float(tanfovx), float(tanfovy), float(scale_modifier), int(degree), int(n_coeffs),
                        1 if debug else 0, _FLAGS["flags"])
-    z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+    z = (lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)) if P > 0 else \
+        (lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev))     # the library overwrites every output
     g = dict(means2D=z(P, 3), colors=z(P, 3), opacity=z(P, 1), means3D=z(P, 3), cov3D=z(P, 6),
              sh=z(P, max(n_coeffs, 0), 3), scales=z(P, 3), rots=z(P, 4))
     if P == 0:

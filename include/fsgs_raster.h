@@ -144,6 +144,14 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
                          float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw,
                          float *dL_dpose, float *dL_dmeans2D, void *stream);
 
+/* Per-frame pose, LearnPose.forward (scene/pose_optimizer.py:822-877): r[1,4,N] raw quaternion
+ * (w,x,y,z) and t[3,N] as the reference stores them; column `cam` -> Rt[4,4] row-major
+ * (F.normalize, q2rot with its own normalisation, [[R,t],[0,0,0,1]]).  The backward turns dL/dRt
+ * into dL/dr[1,4,N], dL/dt[3,N] (zero outside column `cam`). */
+int fsgs_pose_forward(const float *r, const float *t, int32_t cam, int32_t n_cams, float *Rt, void *stream);
+int fsgs_pose_backward(const float *r, int32_t cam, int32_t n_cams, const float *dRt, float *dr, float *dt,
+                       void *stream);
+
 /* Sizes / layout helpers (host only, no CUDA calls). */
 size_t fsgs_geom_bytes(int32_t P);
 size_t fsgs_img_bytes(int32_t image_width, int32_t image_height);

@@ -255,3 +255,8 @@ int emul_rasterize_api(int P, int W, int H, float tanfovx, float tanfovy, float 
 }
 
 }  // extern "C"
+
+extern "C" void emul_pose(const float *r_raw, const float *t, float *Rt, const float *dRt, float *dr, float *dt) {
+    fsgs::pose_forward(r_raw, t, Rt);
+    if (dRt) fsgs::pose_backward(r_raw, dRt, dr, dt);
+}

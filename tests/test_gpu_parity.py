@@ -193,7 +193,7 @@ def test_tma_and_culling_do_not_change_results():
         for name, kw in (("default", {}), ("no_tma", dict(no_tma=True)), ("no_cull", dict(no_tile_cull=True))):
             rasterizer.set_debug_flags(**kw)
             out, planes, g = _run_fused(sc, G6)
-            res[name] = (planes, g, out["num_rendered"].clone())
+            res[name] = (planes, g, tuple(out["num_rendered"]))
     finally:
         rasterizer.set_debug_flags()
     p0, g0, n0 = res["default"]

@@ -97,3 +97,22 @@ def test_api_emulation_matches_oracle(mode, sh_deg):
              "shs": "sh", "colors_precomp": "colors", "cov3D_precomp": "cov3D"}
     for k, v in d.items():
         check_grad(k, g[names[k]].reshape(v.shape), v.grad)
+
+
+def test_pose_kernel_math_matches_reference_golden():
+    """pose_forward / pose_backward (the bodies of k_pose_forward / k_pose_backward) against the
+    reference's own LearnPose outputs and autograd gradients (tests/golden/ref_python_half.npz)."""
+    import ctypes
+    import numpy as np
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_python_half.npz"))
+    L = cpu_emul.lib()
+    for k in (0, 1):
+        r = torch.from_numpy(G["in_r"])[0, :, k].contiguous()
+        t = torch.from_numpy(G["in_t"])[:, k].contiguous()
+        dRt = torch.from_numpy(G["learnpose_G"]).contiguous()
+        Rt, dr, dt = torch.zeros(16), torch.zeros(4), torch.zeros(3)
+        p = lambda x: ctypes.c_void_p(x.data_ptr())
+        L.emul_pose(p(r), p(t), p(Rt), p(dRt), p(dr), p(dt))
+        assert (Rt.view(4, 4) - torch.from_numpy(G[f"learnpose_Rt{k}"])).abs().max().item() < 2e-7
+        assert (dr - torch.from_numpy(G[f"learnpose_dr{k}"])[0, :, k]).abs().max().item() < 2e-5
+        assert (dt - torch.from_numpy(G[f"learnpose_dt{k}"])[:, k]).abs().max().item() < 1e-6
