@@ -5,6 +5,12 @@
 // in batches of 256 by 1-D bulk TMA copies (cp.async.bulk + mbarrier, double buffered); every
 // thread then walks the batch from shared memory (broadcast reads).
 //
+// Sorted record: q0 = (x, y, a2, b2)  q1 = (c2, opacity, r, g)  q2 = (b, depth, block mask, -)
+// with the conic pre-scaled for a base-2 exponent (fsgs_math.cuh) and an 8-bit mask saying which
+// of the tile's eight 8x4 blocks the splat can reach with alpha >= 1/255 -- a warp whose bit is
+// clear skips the entry after one shared-memory word (exact: every lane would have taken the
+// reference's `alpha < 1/255 -> continue`).
+//
 //   FUSED = false : one GaussianRasterizer pass -- 3 colour planes + the package's depth plane.
 //   FUSED = true  : Free-SurGS' two passes at once -- RGB | depth, silhouette, depth^2, all six
 //                   planes with "+ T_final * bg" exactly as the reference's second pass produces
@@ -52,6 +58,7 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
     const int n = (int)(tile_offset[tile + 1] - start);
     const int nb = (n + BATCH - 1) / BATCH;
     const bool use_tma = (flags & 1u) == 0;
+    const unsigned int warp_bit = 1u << (threadIdx.x >> 5);
     const TilePix pix = tile_pixel(cc, tile);
     const float pxf = (float)pix.px, pyf = (float)pix.py;
     const float4 *src = sorted_rec + (size_t)start * REC_F4;
@@ -89,21 +96,26 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
         for (int j0 = 0; j0 < cnt; j0 += 32) {
             if (__all_sync(FULL, done)) break;
             const int jend = min(cnt, j0 + 32);
-            for (int j = j0; j < jend && !done; ++j) {
+            for (int j = j0; j < jend; ++j) {
+                const float4 q2 = sb[j * 3 + 2];
+                if (!(__float_as_uint(q2.z) & warp_bit)) continue;      // warp-uniform: block not reached
+                if (done) continue;
                 const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
                 const float dx = q0.x - pxf, dy = q0.y - pyf;
-                const float power = gauss_power(q0.z, q0.w, q1.x, dx, dy);
-                if (power > 0.f) continue;
-                const float alpha = fminf(ALPHA_MAX, q1.y * gauss_weight(power));
-                if (alpha < ALPHA_MIN) continue;
-                const float test_T = T * (1.f - alpha);
-                if (test_T < T_MIN) { done = true; break; }
-                const float4 q2 = sb[j * 3 + 2];
-                const float w = alpha * T;
-                C0 += q1.z * w; C1 += q1.w * w; C2 += q2.x * w; D += q2.y * w;
-                if (FUSED) { S += w; D2 += q2.y * q2.y * w; }
-                T = test_T;
-                last = (unsigned int)(k * BATCH + j + 1);
+                const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
+                const float alpha = fminf(ALPHA_MAX, q1.y * fast_exp2(p2));
+                if (p2 <= 0.f && alpha >= ALPHA_MIN) {
+                    const float test_T = T * (1.f - alpha);
+                    if (test_T < T_MIN) {
+                        done = true;
+                    } else {
+                        const float w = alpha * T;
+                        C0 += q1.z * w; C1 += q1.w * w; C2 += q2.x * w; D += q2.y * w;
+                        if (FUSED) { S += w; D2 += q2.y * q2.y * w; }
+                        T = test_T;
+                        last = (unsigned int)(k * BATCH + j + 1);
+                    }
+                }
             }
         }
     }
@@ -127,10 +139,12 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 }
 
 // ---- backward -----------------------------------------------------------------------------------
-// Back-to-front replay over the first max(n_contrib) entries of the tile list.  Per (warp, entry)
-// the 32 per-pixel partial gradients are combined with a 16-shuffle reduce-scatter and added to a
-// per-batch shared-memory accumulator; after each batch one thread per entry flushes its 12
-// floats to the per-Gaussian accumulator with three vector atomics.
+// Back-to-front replay over the first max(n_contrib) entries of the tile list.  Each contributing
+// (pixel, Gaussian) pair produces 12 moments (bwd_pair2); per (warp, entry) the 32 lanes' moments
+// are combined with a 16-shuffle reduce-scatter and added to a per-batch shared-memory
+// accumulator; after each batch one thread per entry turns its summed moments into the final
+// gradient row (bwd_finalize) and flushes it to the per-Gaussian accumulator with three vector
+// atomics (red.global.add.v4.f32).
 template <bool FUSED>
 __global__ void __launch_bounds__(CTA)
 k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
@@ -150,6 +164,7 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
     if (n == 0) return;
     const bool use_tma = (flags & 1u) == 0;
     const int lane = threadIdx.x & 31;
+    const unsigned int warp_bit = 1u << (threadIdx.x >> 5);
     const TilePix pix = tile_pixel(cc, tile);
     const float pxf = (float)pix.px, pyf = (float)pix.py;
     const size_t HW = (size_t)cc.W * cc.H, p = (size_t)pix.py * cc.W + pix.px;
@@ -194,7 +209,7 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
             bgdot_rgb = b0 * g[0] + b1 * g[1] + b2 * g[2];
         }
     }
-    const float ddelx_dx = 0.5f * cc.W, ddely_dy = 0.5f * cc.H;
+    const float kx = 0.5f * cc.W, ky = 0.5f * cc.H;
 
     BwdPixel ps;
     ps.T = T_final; ps.last_alpha = 0.f;
@@ -232,22 +247,21 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
         const float4 *sb = s_rec[buf];
 
         for (int j = cnt - 1; j >= 0; --j) {
+            const float4 q2 = sb[j * 3 + 2];
+            if (!(__float_as_uint(q2.z) & warp_bit)) continue;          // warp-uniform: block not reached
             const int gidx = k * BATCH + j;
             const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
             const float dx = q0.x - pxf, dy = q0.y - pyf;
-            const float power = gauss_power(q0.z, q0.w, q1.x, dx, dy);
-            const float G = gauss_weight(power);
+            const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
+            const float G = fast_exp2(p2);
             const float alpha = fminf(ALPHA_MAX, q1.y * G);
-            const bool valid = (gidx < last) && (power <= 0.f) && (alpha >= ALPHA_MIN);
+            const bool valid = (gidx < last) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
             if (!__any_sync(FULL, valid)) continue;
             float v[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = 0.f;
-            if (valid) {
-                const float4 q2 = sb[j * 3 + 2];
-                bwd_pair<FUSED>(ps, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final,
-                                bgdot_rgb, bgdot_dep, ddelx_dx, ddely_dy, v);
-            }
+            if (valid)
+                bwd_pair2<FUSED>(ps, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final, bgdot_rgb, bgdot_dep, v);
             warp_reduce_scatter16(v, lane);
             const int idx = lane >> 1;
             if ((lane & 1) == 0 && idx < ACC_F && v[0] != 0.f) atomicAdd(&s_acc[j * ACC_F + idx], v[0]);
@@ -260,10 +274,14 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
             const bool nz = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) |
                             (b.z != 0.f) | (b.w != 0.f) | (c.x != 0.f) | (c.y != 0.f) | (c.z != 0.f) | (c.w != 0.f);
             if (nz) {
+                const float m[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+                const float4 r0 = sb[threadIdx.x * 3], r1 = sb[threadIdx.x * 3 + 1];
+                float o[12];
+                bwd_finalize(m, r0.z, r0.w, r1.x, r1.y, kx, ky, FUSED, o);
                 float4 *dst = reinterpret_cast<float4 *>(grad_acc + (size_t)s_id[buf][threadIdx.x] * ACC_F);
-                atomicAdd(dst, a);
-                atomicAdd(dst + 1, b);
-                atomicAdd(dst + 2, c);
+                atomicAdd(dst, make_float4(o[0], o[1], o[2], o[3]));
+                atomicAdd(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
+                atomicAdd(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 row[0] = z4; row[1] = z4; row[2] = z4;
             }

@@ -262,13 +262,29 @@ __device__ __forceinline__ void tile_sort_network(KeyPtr a, int n) {
 
 constexpr int SORT_SMEM_KEYS = 8192;   // 64 KB of dynamic shared memory
 
+// Gather one sorted instance: per-Gaussian record -> compositor record (conic pre-scaled for the
+// base-2 exponent, 8x4-block reach mask of this tile in q2.z).
+__device__ __forceinline__ void emit_sorted_record(const float4 *__restrict__ records, unsigned int id,
+                                                   float4 *__restrict__ dst, int tile_x0, int tile_y0, bool no_cull) {
+    const float4 a = ldg4(records + (size_t)id * 3), b = ldg4(records + (size_t)id * 3 + 1),
+                 c = ldg4(records + (size_t)id * 3 + 2);
+    float a2, b2, c2;
+    scale_conic(a.z, a.w, b.x, a2, b2, c2);
+    const unsigned mask = no_cull ? 0xffu : block_mask(a.x, a.y, a.z, a.w, b.x, b.y, tile_x0, tile_y0);
+    dst[0] = make_float4(a.x, a.y, a2, b2);
+    dst[1] = make_float4(c2, b.y, b.z, b.w);
+    dst[2] = make_float4(c.x, c.y, __uint_as_float(mask), 0.f);
+}
+
 __global__ void __launch_bounds__(CTA)
-k_tile_sort(const unsigned int *__restrict__ tile_offset, unsigned long long *__restrict__ keys,
-            const float4 *__restrict__ records, float4 *__restrict__ sorted_rec) {
+k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long long *__restrict__ keys,
+            const float4 *__restrict__ records, float4 *__restrict__ sorted_rec, unsigned int flags) {
     extern __shared__ __align__(16) unsigned long long s_keys[];
     const unsigned int start = tile_offset[blockIdx.x];
     const int n = (int)(tile_offset[blockIdx.x + 1] - start);
     if (n == 0) return;
+    const int tile_x0 = (int)(blockIdx.x % gx) * TILE, tile_y0 = (int)(blockIdx.x / gx) * TILE;
+    const bool no_cull = (flags & 2u) != 0;
     unsigned long long *g = keys + start;
     if (n <= SORT_SMEM_KEYS) {
         for (int p = threadIdx.x; p < n; p += blockDim.x) s_keys[p] = g[p];
@@ -277,22 +293,13 @@ k_tile_sort(const unsigned int *__restrict__ tile_offset, unsigned long long *__
         for (int p = threadIdx.x; p < n; p += blockDim.x) {
             const unsigned long long k = s_keys[p];
             g[p] = k;
-            const unsigned int id = (unsigned int)k;
-            const float4 a = ldg4(records + (size_t)id * 3), b = ldg4(records + (size_t)id * 3 + 1),
-                         c = ldg4(records + (size_t)id * 3 + 2);
-            float4 *dst = sorted_rec + ((size_t)start + p) * 3;
-            dst[0] = a; dst[1] = b; dst[2] = c;
+            emit_sorted_record(records, (unsigned int)k, sorted_rec + ((size_t)start + p) * 3, tile_x0, tile_y0, no_cull);
         }
     } else {
         // rare: list longer than the shared-memory window -> same network in global memory (L2)
         tile_sort_network(g, n);
-        for (int p = threadIdx.x; p < n; p += blockDim.x) {
-            const unsigned int id = (unsigned int)g[p];
-            const float4 a = ldg4(records + (size_t)id * 3), b = ldg4(records + (size_t)id * 3 + 1),
-                         c = ldg4(records + (size_t)id * 3 + 2);
-            float4 *dst = sorted_rec + ((size_t)start + p) * 3;
-            dst[0] = a; dst[1] = b; dst[2] = c;
-        }
+        for (int p = threadIdx.x; p < n; p += blockDim.x)
+            emit_sorted_record(records, (unsigned int)g[p], sorted_rec + ((size_t)start + p) * 3, tile_x0, tile_y0, no_cull);
     }
 }
 

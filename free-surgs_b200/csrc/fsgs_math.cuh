@@ -635,4 +635,135 @@ FSGS_HD void pose_backward(const float *r_raw, const float *dRt, float *dr, floa
     dt[0] = dRt[3]; dt[1] = dRt[7]; dt[2] = dRt[11];
 }
 
+// ---- compositor arithmetic, second generation ---------------------------------------------------
+// The depth-sorted per-instance records carry the conic pre-scaled for a base-2 exponent:
+//   a2 = -0.5*log2(e)*A,  b2 = -log2(e)*B,  c2 = -0.5*log2(e)*C
+// so that  log2(G) = dx*(a2*dx + b2*dy) + c2*dy*dy  is 2 FMUL + ... 5 instructions, and
+// G = ex2(log2 G) is one MUFU.  Forward and backward evaluate the SAME pinned expression on the
+// SAME records, so their per-pair decisions agree bit for bit.
+constexpr float LOG2E = 1.4426950408889634f;
+
+FSGS_HD void scale_conic(float A, float B, float C, float &a2, float &b2, float &c2) {
+    a2 = A * (-0.5f * LOG2E); b2 = B * (-LOG2E); c2 = C * (-0.5f * LOG2E);
+}
+FSGS_HD void unscale_conic(float a2, float b2, float c2, float &A, float &B, float &C) {
+    A = a2 * (-2.0f / LOG2E); B = b2 * (-1.0f / LOG2E); C = c2 * (-2.0f / LOG2E);
+}
+FSGS_HD float gauss_power2(float a2, float b2, float c2, float dx, float dy) {
+#if defined(__CUDA_ARCH__)
+    const float t = __fmaf_rn(b2, dy, __fmul_rn(a2, dx));
+    return __fmaf_rn(dx, t, __fmul_rn(__fmul_rn(c2, dy), dy));
+#else
+    const float t = fmaf(b2, dy, a2 * dx);
+    return fmaf(dx, t, (c2 * dy) * dy);
+#endif
+}
+FSGS_HD float fast_exp2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return exp2f(x);
+#endif
+}
+// 1/x: MUFU.RCP + one Newton step (avoids the ~10-instruction IEEE division in the hot loop)
+FSGS_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return __fmaf_rn(r, __fmaf_rn(-x, r, 1.0f), r);
+#else
+    return 1.0f / x;
+#endif
+}
+
+// Conservative test: can the rectangle of pixel centres [x0,x1]x[y0,y1] contain a pixel with
+// q <= tau?  (tile_hit generalised; used for the per-instance 8x4-block masks.)
+FSGS_HD bool rect_hit(float px, float py, float A, float B, float C, float tau, float x0, float x1, float y0,
+                      float y1) {
+    const float dxl = px - x1, dxh = px - x0, dyl = py - y1, dyh = py - y0;
+    if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return true;
+    float q = edge_min(A, B, C, dxl, dyl, dyh);
+    q = fminf(q, edge_min(A, B, C, dxh, dyl, dyh));
+    q = fminf(q, edge_min(C, B, A, dyl, dxl, dxh));
+    q = fminf(q, edge_min(C, B, A, dyh, dxl, dxh));
+    return q <= tau;
+}
+// Bit w of the mask = the 8x4 pixel block of warp w ((w&1)*8, (w>>1)*4 inside the 16x16 tile) may
+// hold a pixel this splat changes.  tile_x0/tile_y0 = pixel coordinates of the tile's corner.
+FSGS_HD unsigned block_mask(float px, float py, float A, float B, float C, float opacity, int tile_x0, int tile_y0) {
+    const CullEllipse e = make_cull_ellipse(px, py, A, B, C, opacity);
+    unsigned m = 0;
+    for (int w = 0; w < 8; ++w) {
+        const float x0 = (float)(tile_x0 + (w & 1) * 8), y0 = (float)(tile_y0 + (w >> 1) * 4);
+        if (rect_hit(px, py, A, B, C, e.tau, x0, x0 + 7.f, y0, y0 + 3.f)) m |= 1u << w;
+    }
+    return m;
+}
+
+// One contributing pair of the backward compositor, "moment" form: instead of the final
+// per-Gaussian gradients each pixel adds the moments of q = G*o*dL/dalpha over d = centre - pixel;
+// bwd_finalize turns the summed moments into the accumulator row once per (tile, Gaussian).
+//   v = [Sx, Sy, Sxx, Sxy, Syy, S0 | d r, d g, d b, d z | Sx_rgb, Sy_rgb]
+template <bool FUSED>
+FSGS_HD void bwd_pair2(BwdPixel &s, float opacity, float cr, float cg, float cb, float z, float dx, float dy,
+                       float G, float alpha, const float *g, float T_final, float bgdot_rgb, float bgdot_dep,
+                       float *v) {
+    const float inv = fast_rcp(1.f - alpha);
+    s.T = s.T * inv;
+    const float w = alpha * s.T;
+    const float la = s.last_alpha, lb = 1.f - s.last_alpha;
+    s.acc_r = la * s.lc_r + lb * s.acc_r; s.lc_r = cr;
+    s.acc_g = la * s.lc_g + lb * s.acc_g; s.lc_g = cg;
+    s.acc_b = la * s.lc_b + lb * s.acc_b; s.lc_b = cb;
+    float da_rgb = (cr - s.acc_r) * g[0] + (cg - s.acc_g) * g[1] + (cb - s.acc_b) * g[2];
+    float dz = w * g[3];
+    if (FUSED) {
+        s.acc_s = la + lb * s.acc_s;
+        s.acc_d2 = la * (s.lc_d * s.lc_d) + lb * s.acc_d2;
+    }
+    s.acc_d = la * s.lc_d + lb * s.acc_d; s.lc_d = z;
+    float da_dep = (z - s.acc_d) * g[3];
+    if (FUSED) {
+        da_dep += (1.f - s.acc_s) * g[4] + (z * z - s.acc_d2) * g[5];
+        dz += w * 2.f * z * g[5];
+    }
+    const float tf = -T_final * inv;
+    da_rgb = da_rgb * s.T + tf * bgdot_rgb;
+    da_dep = da_dep * s.T;
+    if (FUSED) da_dep += tf * bgdot_dep;
+    s.last_alpha = alpha;
+    const float Go = G * opacity;
+    const float q = Go * (da_rgb + da_dep);
+    const float qx = q * dx, qy = q * dy;
+    v[0] = qx; v[1] = qy; v[2] = qx * dx; v[3] = qx * dy; v[4] = qy * dy; v[5] = q;
+    v[6] = w * g[0]; v[7] = w * g[1]; v[8] = w * g[2]; v[9] = dz;
+    if (FUSED) {
+        const float q_rgb = Go * da_rgb;
+        v[10] = q_rgb * dx; v[11] = q_rgb * dy;
+    } else {
+        v[10] = 0.f; v[11] = 0.f;
+    }
+}
+
+// Summed moments of one (tile, Gaussian) -> accumulator row (layout in fsgs_device.cuh).
+// kx = 0.5 W, ky = 0.5 H (the reference returns the mean2D gradient in NDC units).
+FSGS_HD void bwd_finalize(const float *m, float a2, float b2, float c2, float opacity, float kx, float ky, bool fused,
+                          float *out) {
+    float A, B, C;
+    unscale_conic(a2, b2, c2, A, B, C);
+    out[0] = -kx * (A * m[0] + B * m[1]);
+    out[1] = -ky * (C * m[1] + B * m[0]);
+    out[2] = -0.5f * m[2]; out[3] = -0.5f * m[3]; out[4] = -0.5f * m[4];
+    out[5] = m[5] / opacity;
+    out[6] = m[6]; out[7] = m[7]; out[8] = m[8]; out[9] = m[9];
+    if (fused) {
+        out[10] = -kx * (A * m[10] + B * m[11]);
+        out[11] = -ky * (C * m[11] + B * m[10]);
+    } else {
+        out[10] = out[0]; out[11] = out[1];
+    }
+}
+
 }  // namespace fsgs

@@ -143,8 +143,8 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
         prof_end(K_SCATTER, stream);
         FSGS_LAUNCH_OK("k_scatter");
         prof_begin(K_SORT, stream);
-        k_tile_sort<<<tiles, CTA, SORT_SMEM_KEYS * sizeof(unsigned long long), stream>>>(tile_offset, keys, records,
-                                                                                           sorted_rec);
+        k_tile_sort<<<tiles, CTA, SORT_SMEM_KEYS * sizeof(unsigned long long), stream>>>(
+            cc.gx, tile_offset, keys, records, sorted_rec, (unsigned)st->flags);
         prof_end(K_SORT, stream);
         FSGS_LAUNCH_OK("k_tile_sort");
     }

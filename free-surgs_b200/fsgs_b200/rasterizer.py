@@ -41,19 +41,94 @@ def set_debug_flags(no_tma: bool = False, no_tile_cull: bool = False) -> None:
     _FLAGS["flags"] = (_lib.FLAG_NO_TMA if no_tma else 0) | (_lib.FLAG_NO_TILE_CULL if no_tile_cull else 0)
 
 
+class _WorkspacePool:
+    """Grow-only cache of the library's scratch buffers (geometry / binning / image state / gradient
+    accumulator), keyed by (device, stream, kind).  Leased at forward, handed back when the autograd
+    node dies (after backward) -- so the ~300 MB of per-frame scratch never goes through the framework
+    allocator's split/merge machinery, which otherwise fragments under the mixed lifetimes and ends
+    up in a cudaMalloc per frame.  Reuse is stream-ordered: a buffer is only handed to work enqueued
+    on the stream that used it last."""
+    MAX_PER_KEY = 6
+
+    def __init__(self):
+        import threading
+        self._lock = threading.Lock()
+        self._free = {}
+
+    def acquire(self, key, nbytes: int, device, headroom: float = 1.0) -> torch.Tensor:
+        with self._lock:
+            lst = self._free.get(key)
+            if lst:
+                best = None
+                for i, t in enumerate(lst):
+                    if t.numel() >= nbytes and (best is None or t.numel() < lst[best].numel()):
+                        best = i
+                if best is not None:
+                    return lst.pop(best)
+        want = max(int(nbytes * headroom), 256)
+        want = (want + (1 << 20) - 1) >> 20 << 20 if want > (1 << 20) else want
+        return torch.empty(want, dtype=torch.uint8, device=device)
+
+    def release(self, key, t: torch.Tensor) -> None:
+        with self._lock:
+            lst = self._free.setdefault(key, [])
+            lst.append(t)
+            if len(lst) > self.MAX_PER_KEY:
+                lst.sort(key=lambda x: x.numel())
+                lst.pop(0)
+
+    def clear(self) -> None:
+        with self._lock:
+            self._free.clear()
+
+
+_POOL = _WorkspacePool()
+
+
+class _Lease:
+    """Buffers checked out of the pool for one forward; returned when this object is collected."""
+
+    def __init__(self):
+        self.items = []
+
+    def add(self, key, t):
+        self.items.append((key, t))
+
+    def release(self):
+        items, self.items = self.items, []
+        for key, t in items:
+            _POOL.release(key, t)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:  # interpreter shutdown
+            pass
+
+
 class _Arena:
-    """Owns the scratch tensors the library requests through its allocation callbacks."""
+    """Serves the library's allocation callbacks from the workspace pool."""
+    HEADROOM = {"binning": 1.25}
 
     def __init__(self, device):
         self.device = device
+        self.stream = torch.cuda.current_stream(device).cuda_stream
         self.tensors = {}
+        self.lease = _Lease()
         self._cbs = []
+
+    def key(self, name):
+        return (self.device.index, self.stream, name)
+
+    def take(self, name: str, nbytes: int) -> torch.Tensor:
+        t = _POOL.acquire(self.key(name), int(nbytes), self.device, self.HEADROOM.get(name, 1.0))
+        self.lease.add(self.key(name), t)
+        self.tensors[name] = t
+        return t
 
     def callback(self, name: str):
         def cb(_user, nbytes):
-            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
-            self.tensors[name] = t
-            return t.data_ptr()
+            return self.take(name, nbytes).data_ptr()
         fn = _lib.ALLOC_FN(cb)
         self._cbs.append(fn)
         return fn
@@ -122,6 +197,8 @@ def rasterize_gaussians(bg, means3D, colors_precomp, opacities, scales, rotation
     empty = torch.empty(0, dtype=torch.uint8, device=dev)
     bufs = [arena.tensors.get(k, empty) for k in ("geom", "binning", "img")]
     rasterize_gaussians.last_num_rect = int(nrect.value)
+    for b in bufs:                  # the buffers return to the workspace pool once the caller drops all three
+        b._fsgs_lease = arena.lease
     return int(nr.value), color, depth, radii, bufs[0], bufs[1], bufs[2]
 
 
@@ -152,7 +229,8 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors_precomp, scales, rot
              opac=_f32(opacities, dev), scales=_f32(scales, dev), rots=_f32(rotations, dev),
              cov=_f32(cov3D_precomp, dev), view=_f32(viewmatrix, dev), proj=_f32(projmatrix, dev),
              campos=_f32(campos, dev), gc=_f32(grad_out_color, dev), gd=_f32(grad_out_depth, dev))
-    scratch = torch.empty(_lib.lib().fsgs_grad_scratch_bytes(P), dtype=torch.uint8, device=dev)
+    arena = _Arena(dev)
+    scratch = arena.take("grad_scratch", _lib.lib().fsgs_grad_scratch_bytes(P))
     with torch.cuda.device(dev):
         rc = _lib.lib().fsgs_rasterize_backward(
             ctypes.byref(st), P, int(num_rendered), _ptr(t["bg"]), _ptr(t["means3D"]), _ptr(t["colors"]), _ptr(t["sh"]),
@@ -160,6 +238,7 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors_precomp, scales, rot
             _ptr(t["campos"]), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), _ptr(t["gc"]), _ptr(t["gd"]),
             _ptr(scratch), _ptr(g["means2D"]), _ptr(g["colors"]), _ptr(g["opacity"]), _ptr(g["means3D"]),
             _ptr(g["cov3D"]), _ptr(g["sh"]) if n_coeffs > 0 else None, _ptr(g["scales"]), _ptr(g["rots"]), _stream(dev))
+    arena.lease.release()                 # kernels are enqueued; reuse is ordered on this stream
     _lib.check(rc)
     return tuple(g[k] for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rots"))
 
@@ -189,6 +268,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh, rs.sh_degree,
             rs.campos, rs.prefiltered, rs.debug)
         ctx.raster_settings = rs
+        ctx.lease = getattr(geomBuffer, "_fsgs_lease", None)
         ctx.num_rendered = num_rendered
         ctx.num_rect = rasterize_gaussians.last_num_rect
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, opacities,

@@ -71,25 +71,49 @@ Lists bin_and_sort(const CamConst &cc, const std::vector<Rec> &recs, bool no_cul
     return L;
 }
 
+// What k_tile_sort's epilogue writes per (tile, Gaussian) instance.
+struct SRec {
+    float x, y, a2, b2, c2, o, r, g, b, z;
+    unsigned mask;
+    uint32_t id;
+};
+std::vector<std::vector<SRec>> sorted_records(const CamConst &cc, const std::vector<Rec> &recs, const Lists &L, bool no_cull) {
+    std::vector<std::vector<SRec>> out(L.per_tile.size());
+    for (size_t t = 0; t < L.per_tile.size(); ++t) {
+        const int tx0 = (int)(t % cc.gx) * TILE, ty0 = (int)(t / cc.gx) * TILE;
+        for (uint64_t key : L.per_tile[t]) {
+            const Rec &r = recs[(uint32_t)key];
+            SRec s;
+            s.x = r.x; s.y = r.y; s.o = r.o; s.r = r.r; s.g = r.g; s.b = r.b; s.z = r.z; s.id = (uint32_t)key;
+            scale_conic(r.A, r.B, r.C, s.a2, s.b2, s.c2);
+            s.mask = no_cull ? 0xffu : block_mask(r.x, r.y, r.A, r.B, r.C, r.o, tx0, ty0);
+            out[t].push_back(s);
+        }
+    }
+    return out;
+}
+inline unsigned warp_bit_of(int px, int py) { return 1u << ((((py % TILE) / 4) << 1) | ((px % TILE) / 8)); }
+
 // composite forward for all pixels; planes = FUSED ? 6 : 3 (+ depth plane for the API flavour)
 template <bool FUSED>
-void composite_fwd(const CamConst &cc, const std::vector<Rec> &recs, const Lists &L, const float *bg, float *planes,
+void composite_fwd(const CamConst &cc, const std::vector<std::vector<SRec>> &SR, const float *bg, float *planes,
                    float *depth, std::vector<float> &final_T, std::vector<int> &n_contrib) {
     const size_t HW = (size_t)cc.W * cc.H;
     final_T.assign(HW, 1.f);
     n_contrib.assign(HW, 0);
     for (int py = 0; py < cc.H; ++py)
         for (int px = 0; px < cc.W; ++px) {
-            const auto &lst = L.per_tile[(size_t)(py / TILE) * cc.gx + px / TILE];
+            const auto &lst = SR[(size_t)(py / TILE) * cc.gx + px / TILE];
+            const unsigned wb = warp_bit_of(px, py);
             float T = 1.f, C0 = 0, C1 = 0, C2 = 0, D = 0, S = 0, D2 = 0;
             int last = 0;
             for (size_t j = 0; j < lst.size(); ++j) {
-                const Rec &r = recs[(uint32_t)lst[j]];
+                const SRec &r = lst[j];
+                if (!(r.mask & wb)) continue;
                 const float dx = r.x - (float)px, dy = r.y - (float)py;
-                const float power = gauss_power(r.A, r.B, r.C, dx, dy);
-                if (power > 0.f) continue;
-                const float alpha = fminf(ALPHA_MAX, r.o * expf(power));
-                if (alpha < ALPHA_MIN) continue;
+                const float p2 = gauss_power2(r.a2, r.b2, r.c2, dx, dy);
+                const float alpha = fminf(ALPHA_MAX, r.o * fast_exp2(p2));
+                if (!(p2 <= 0.f && alpha >= ALPHA_MIN)) continue;
                 const float test_T = T * (1.f - alpha);
                 if (test_T < T_MIN) break;
                 const float w = alpha * T;
@@ -110,43 +134,56 @@ void composite_fwd(const CamConst &cc, const std::vector<Rec> &recs, const Lists
 }
 
 template <bool FUSED>
-void composite_bwd(const CamConst &cc, const std::vector<Rec> &recs, const Lists &L, const float *bg,
+void composite_bwd(const CamConst &cc, size_t P, const std::vector<std::vector<SRec>> &SR, const float *bg,
                    const std::vector<float> &final_T, const std::vector<int> &n_contrib, const float *dplanes,
                    const float *ddepth, std::vector<float> &acc) {
     const size_t HW = (size_t)cc.W * cc.H;
-    acc.assign(recs.size() * 12, 0.f);
-    std::vector<double> acc64(recs.size() * 12, 0.0);   // order-independent accumulation
-    const float ddelx_dx = 0.5f * cc.W, ddely_dy = 0.5f * cc.H;
-    for (int py = 0; py < cc.H; ++py)
-        for (int px = 0; px < cc.W; ++px) {
-            const size_t p = (size_t)py * cc.W + px;
-            const auto &lst = L.per_tile[(size_t)(py / TILE) * cc.gx + px / TILE];
-            float g[6] = {dplanes[p], dplanes[HW + p], dplanes[2 * HW + p], 0, 0, 0};
-            float bgdot_dep = 0.f;
-            if (FUSED) {
-                g[3] = dplanes[3 * HW + p]; g[4] = dplanes[4 * HW + p]; g[5] = dplanes[5 * HW + p];
-                bgdot_dep = bg[0] * g[3] + bg[1] * g[4] + bg[2] * g[5];
-            } else {
-                g[3] = ddepth ? ddepth[p] : 0.f;
+    acc.assign(P * 12, 0.f);
+    std::vector<double> acc64(P * 12, 0.0);   // order-independent accumulation of the finalised rows
+    const float kx = 0.5f * cc.W, ky = 0.5f * cc.H;
+    for (size_t t = 0; t < SR.size(); ++t) {
+        const auto &lst = SR[t];
+        if (lst.empty()) continue;
+        std::vector<double> mom(lst.size() * 12, 0.0);      // per (tile, entry) moments, as s_acc
+        const int tx0 = (int)(t % cc.gx) * TILE, ty0 = (int)(t / cc.gx) * TILE;
+        for (int py = ty0; py < ty0 + TILE && py < cc.H; ++py)
+            for (int px = tx0; px < tx0 + TILE && px < cc.W; ++px) {
+                const size_t p = (size_t)py * cc.W + px;
+                const unsigned wb = warp_bit_of(px, py);
+                float g[6] = {dplanes[p], dplanes[HW + p], dplanes[2 * HW + p], 0, 0, 0};
+                float bgdot_dep = 0.f;
+                if (FUSED) {
+                    g[3] = dplanes[3 * HW + p]; g[4] = dplanes[4 * HW + p]; g[5] = dplanes[5 * HW + p];
+                    bgdot_dep = bg[0] * g[3] + bg[1] * g[4] + bg[2] * g[5];
+                } else {
+                    g[3] = ddepth ? ddepth[p] : 0.f;
+                }
+                const float bgdot_rgb = bg[0] * g[0] + bg[1] * g[1] + bg[2] * g[2];
+                BwdPixel s;
+                std::memset(&s, 0, sizeof(s));
+                s.T = final_T[p];
+                for (int j = n_contrib[p] - 1; j >= 0; --j) {
+                    const SRec &r = lst[j];
+                    if (!(r.mask & wb)) continue;
+                    const float dx = r.x - (float)px, dy = r.y - (float)py;
+                    const float p2 = gauss_power2(r.a2, r.b2, r.c2, dx, dy);
+                    const float G = fast_exp2(p2);
+                    const float alpha = fminf(ALPHA_MAX, r.o * G);
+                    if (!(p2 <= 0.f && alpha >= ALPHA_MIN)) continue;
+                    float v[12];
+                    bwd_pair2<FUSED>(s, r.o, r.r, r.g, r.b, r.z, dx, dy, G, alpha, g, final_T[p], bgdot_rgb, bgdot_dep, v);
+                    for (int k = 0; k < 12; ++k) mom[(size_t)j * 12 + k] += v[k];
+                }
             }
-            const float bgdot_rgb = bg[0] * g[0] + bg[1] * g[1] + bg[2] * g[2];
-            BwdPixel s;
-            std::memset(&s, 0, sizeof(s));
-            s.T = final_T[p];
-            for (int j = n_contrib[p] - 1; j >= 0; --j) {
-                const uint32_t id = (uint32_t)lst[j];
-                const Rec &r = recs[id];
-                const float dx = r.x - (float)px, dy = r.y - (float)py;
-                const float power = gauss_power(r.A, r.B, r.C, dx, dy);
-                const float G = expf(power);
-                const float alpha = fminf(ALPHA_MAX, r.o * G);
-                if (!(power <= 0.f && alpha >= ALPHA_MIN)) continue;
-                float v[12];
-                bwd_pair<FUSED>(s, r.A, r.B, r.C, r.o, r.r, r.g, r.b, r.z, dx, dy, G, alpha, g, final_T[p], bgdot_rgb,
-                                bgdot_dep, ddelx_dx, ddely_dy, v);
-                for (int k = 0; k < 12; ++k) acc64[(size_t)id * 12 + k] += v[k];
-            }
+        for (size_t j = 0; j < lst.size(); ++j) {
+            float m[12], o[12];
+            bool nz = false;
+            for (int k = 0; k < 12; ++k) { m[k] = (float)mom[j * 12 + k]; nz |= m[k] != 0.f; }
+            if (!nz) continue;
+            bwd_finalize(m, lst[j].a2, lst[j].b2, lst[j].c2, lst[j].o, kx, ky, FUSED, o);
+            for (int k = 0; k < 12; ++k) acc64[(size_t)lst[j].id * 12 + k] += o[k];
         }
+    }
     for (size_t k = 0; k < acc.size(); ++k) acc[k] = (float)acc64[k];
 }
 
@@ -179,10 +216,11 @@ int emul_render_fused(int P, int W, int H, float tanfovx, float tanfovy, float m
     *R = L.R; *Rrect = L.Rrect;
     std::vector<float> final_T;
     std::vector<int> n_contrib;
-    composite_fwd<true>(cc, recs, L, bg, planes, nullptr, final_T, n_contrib);
+    const auto SR = sorted_records(cc, recs, L, no_cull != 0);
+    composite_fwd<true>(cc, SR, bg, planes, nullptr, final_T, n_contrib);
     if (!dplanes) return 0;
     std::vector<float> acc;
-    composite_bwd<true>(cc, recs, L, bg, final_T, n_contrib, dplanes, nullptr, acc);
+    composite_bwd<true>(cc, (size_t)P, SR, bg, final_T, n_contrib, dplanes, nullptr, acc);
     double pose_acc[12] = {0};
     for (int i = 0; i < P; ++i) {
         float dx3[3] = {0, 0, 0}, dd[3] = {0, 0, 0}, ds3[3] = {0, 0, 0}, dq4[4] = {0, 0, 0, 0}, pg[12] = {0}, m2[2] = {0, 0};
@@ -231,10 +269,11 @@ int emul_rasterize_api(int P, int W, int H, float tanfovx, float tanfovy, float 
     *R = L.R; *Rrect = L.Rrect;
     std::vector<float> final_T;
     std::vector<int> n_contrib;
-    composite_fwd<false>(cc, recs, L, bg, out_color, out_depth, final_T, n_contrib);
+    const auto SR = sorted_records(cc, recs, L, no_cull != 0);
+    composite_fwd<false>(cc, SR, bg, out_color, out_depth, final_T, n_contrib);
     if (!dcolor) return 0;
     std::vector<float> acc;
-    composite_bwd<false>(cc, recs, L, bg, final_T, n_contrib, dcolor, ddepth, acc);
+    composite_bwd<false>(cc, (size_t)P, SR, bg, final_T, n_contrib, dcolor, ddepth, acc);
     for (int i = 0; i < P; ++i) {
         float dmean[3] = {0, 0, 0}, dc6[6] = {0, 0, 0, 0, 0, 0}, ds[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 0};
         const float *a = acc.data() + 12 * (size_t)i;

@@ -92,6 +92,8 @@ def _compare_fused(sc, got_out, got_planes, got_g, ref_out, ref_planes, ref_g, g
         if ref_g[k] is None or ref_g[k].abs().max() == 0:
             assert got_g[k] is None or got_g[k].abs().max().item() == 0, k
             continue
+        if k == "means2D" and not gs_grad:
+            continue      # the reference only retains viewspace_points.grad when gs_grad (__init__.py:57-58)
         check_grad(k, got_g[k].reshape(ref_g[k].shape), ref_g[k])
     if cam_grad:
         check_grad("pose", got_g["pose"][:3], ref_g["pose"][:3])
