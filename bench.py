@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -211,14 +211,21 @@ def run_ours(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step(G_dev)
-    barrier()
-
-    # ---- timed region: K steps, device time, L2 flushed between steps (flush outside the events) ----
+    # clocks sampler: started BEFORE the warm-up so that nvidia-smi's own start-up (NVML init stalls kernel
+    # launches for tens of ms) is over when the timed region begins; it keeps sampling through it
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        t_wait = time.perf_counter()
+        while not sampler.lines and sampler.proc is not None and time.perf_counter() - t_wait < 10.0:
+            time.sleep(0.05)
+    for _ in range(max(args.warmup, 3)):
+        step(G_dev)
+    barrier()
+    if rank == 0:
+        sampler.lines.clear()
+
+    # ---- timed region: K steps, device time, L2 flushed between steps (flush outside the events) ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall = time.perf_counter()
@@ -307,6 +314,7 @@ def run_ours(args):
                        "tile_instances": R_inst, "tile_instances_reference_rect": R_rect,
                        "parallelism": f"frame-dp{world}" + ("+nccl allreduce(grads)" if world > 1 else "")},
             "pose_grad_ms_per_frame": ms_track,
+            "ms_per_step_median": sorted(ms)[len(ms) // 2],
             "ms_steps": [round(x, 3) for x in ms],
             "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -320,7 +328,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(G_host.numel() * 4),
                     "d2h_bytes_per_step": 4 + 7 * 4, "ms_per_step": ms_e2e},
-            "gpu_launches": 7 * args.steps,
+            "gpu_launches": 9 * args.steps,     # pose fwd, 5 forward kernels, 2 backward kernels, pose bwd
             "clocks": clocks,
         }
         print(json.dumps(out))
