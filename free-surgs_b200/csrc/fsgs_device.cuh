@@ -150,6 +150,44 @@ __device__ __forceinline__ void warp_reduce_scatter16(float (&v)[16], int lane) 
     v[0] += __shfl_xor_sync(FULL, v[0], 1);
 }
 
+// ---- warp reduce-scatter of 12 values (13 shuffles) -------------------------------------------
+// Halving tree 12 -> 6 -> 3 -> (2 + pad) -> 1.  Returns the index of the input whose warp-wide sum
+// this lane now holds in v[0], or -1 (odd lanes duplicate their neighbour, and the lanes with bits
+// 2 and 1 both set hold the padding slot).  idx = 6*bit4 + 3*bit3 + 2*bit2 + bit1.
+__device__ __forceinline__ int warp_reduce_scatter12(float (&v)[12], int lane) {
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const float keep = up ? v[i + 6] : v[i], send = up ? v[i] : v[i + 6];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+    }
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float keep = up ? v[i + 3] : v[i], send = up ? v[i] : v[i + 3];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
+        }
+    }
+    {
+        const bool up = (lane & 4) != 0;
+        const float keep0 = up ? v[2] : v[0], send0 = up ? v[0] : v[2];
+        const float keep1 = up ? 0.f : v[1], send1 = up ? v[1] : 0.f;
+        v[0] = keep0 + __shfl_xor_sync(FULL, send0, 4);
+        v[1] = keep1 + __shfl_xor_sync(FULL, send1, 4);
+    }
+    {
+        const bool up = (lane & 2) != 0;
+        const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+        v[0] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+    v[0] += __shfl_xor_sync(FULL, v[0], 1);
+    if ((lane & 1) || ((lane & 6) == 6)) return -1;
+    return ((lane >> 4) & 1) * 6 + ((lane >> 3) & 1) * 3 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 
 #endif  // __CUDACC__

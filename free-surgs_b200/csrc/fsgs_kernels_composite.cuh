@@ -2,14 +2,14 @@
 //
 // One CTA per 16x16 tile, 8 warps, each warp owning an 8x4 pixel block.  The tile's depth-sorted
 // splat records (48 B each, written contiguously by k_tile_sort) are streamed into shared memory
-// in batches of 256 by 1-D bulk TMA copies (cp.async.bulk + mbarrier, double buffered); every
-// thread then walks the batch from shared memory (broadcast reads).
+// in batches of 256 by 1-D bulk TMA copies (cp.async.bulk + mbarrier, double buffered).
 //
 // Sorted record: q0 = (x, y, a2, b2)  q1 = (c2, opacity, r, g)  q2 = (b, depth, block mask, -)
 // with the conic pre-scaled for a base-2 exponent (fsgs_math.cuh) and an 8-bit mask saying which
-// of the tile's eight 8x4 blocks the splat can reach with alpha >= 1/255 -- a warp whose bit is
-// clear skips the entry after one shared-memory word (exact: every lane would have taken the
-// reference's `alpha < 1/255 -> continue`).
+// of the tile's eight 8x4 blocks the splat can reach with alpha >= 1/255.  For every staged batch
+// each warp first compacts, with ballots, the indices of the entries whose mask names its block
+// into a private shared-memory list and then walks only that list -- exact, because for the
+// skipped entries every lane would have taken the reference's `alpha < 1/255 -> continue`.
 //
 //   FUSED = false : one GaussianRasterizer pass -- 3 colour planes + the package's depth plane.
 //   FUSED = true  : Free-SurGS' two passes at once -- RGB | depth, silhouette, depth^2, all six
@@ -45,6 +45,22 @@ __device__ __forceinline__ void stage_plain(float4 *dst, const float4 *src, int 
     for (int p = threadIdx.x; p < cnt * REC_F4; p += CTA) dst[p] = ldg4(src + p);
 }
 
+// Ballot-compact the indices j in [0, limit) of the staged batch whose block mask contains
+// `warp_bit` into `list` (ascending).  Returns the count.  One call per warp per batch.
+__device__ __forceinline__ int compact_entries(const float4 *sb, int limit, unsigned int warp_bit, int lane,
+                                               unsigned char *list) {
+    int n = 0;
+    for (int c = 0; c < limit; c += 32) {
+        const int j = c + lane;
+        const bool rel = j < limit && (__float_as_uint(sb[j * 3 + 2].z) & warp_bit) != 0;
+        const unsigned int b = __ballot_sync(FULL, rel);
+        if (rel) list[n + __popc(b & ((1u << lane) - 1u))] = (unsigned char)j;
+        n += __popc(b);
+    }
+    __syncwarp();
+    return n;
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(CTA)
 k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const float4 *__restrict__ sorted_rec,
@@ -53,12 +69,14 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
                 unsigned long long *__restrict__ err) {
     __shared__ __align__(128) float4 s_rec[2][BATCH * REC_F4];
     __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ unsigned char s_list[CTA / 32][BATCH];
     const int tile = blockIdx.x;
     const unsigned int start = tile_offset[tile];
     const int n = (int)(tile_offset[tile + 1] - start);
     const int nb = (n + BATCH - 1) / BATCH;
     const bool use_tma = (flags & 1u) == 0;
-    const unsigned int warp_bit = 1u << (threadIdx.x >> 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int warp_bit = 1u << warp;
     const TilePix pix = tile_pixel(cc, tile);
     const float pxf = (float)pix.px, pyf = (float)pix.py;
     const float4 *src = sorted_rec + (size_t)start * REC_F4;
@@ -92,29 +110,28 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
             stage_plain(s_rec[buf], src + (size_t)k * BATCH * REC_F4, cnt);
             __syncthreads();
         }
+        if (__all_sync(FULL, done)) continue;                       // this warp's pixels are finished
         const float4 *sb = s_rec[buf];
-        for (int j0 = 0; j0 < cnt; j0 += 32) {
-            if (__all_sync(FULL, done)) break;
-            const int jend = min(cnt, j0 + 32);
-            for (int j = j0; j < jend; ++j) {
-                const float4 q2 = sb[j * 3 + 2];
-                if (!(__float_as_uint(q2.z) & warp_bit)) continue;      // warp-uniform: block not reached
-                if (done) continue;
-                const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
-                const float dx = q0.x - pxf, dy = q0.y - pyf;
-                const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
-                const float alpha = fminf(ALPHA_MAX, q1.y * fast_exp2(p2));
-                if (p2 <= 0.f && alpha >= ALPHA_MIN) {
-                    const float test_T = T * (1.f - alpha);
-                    if (test_T < T_MIN) {
-                        done = true;
-                    } else {
-                        const float w = alpha * T;
-                        C0 += q1.z * w; C1 += q1.w * w; C2 += q2.x * w; D += q2.y * w;
-                        if (FUSED) { S += w; D2 += q2.y * q2.y * w; }
-                        T = test_T;
-                        last = (unsigned int)(k * BATCH + j + 1);
-                    }
+        const int nrel = compact_entries(sb, cnt, warp_bit, lane, s_list[warp]);
+        for (int i = 0; i < nrel; ++i) {
+            if ((i & 7) == 0 && __all_sync(FULL, done)) break;
+            if (done) continue;
+            const int j = s_list[warp][i];
+            const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
+            const float dx = q0.x - pxf, dy = q0.y - pyf;
+            const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
+            const float alpha = fminf(ALPHA_MAX, q1.y * fast_exp2(p2));
+            if (p2 <= 0.f && alpha >= ALPHA_MIN) {
+                const float test_T = T * (1.f - alpha);
+                if (test_T < T_MIN) {
+                    done = true;
+                } else {
+                    const float4 q2 = sb[j * 3 + 2];
+                    const float w = alpha * T;
+                    C0 += q1.z * w; C1 += q1.w * w; C2 += q2.x * w; D += q2.y * w;
+                    if (FUSED) { S += w; D2 += q2.y * q2.y * w; }
+                    T = test_T;
+                    last = (unsigned int)(k * BATCH + j + 1);
                 }
             }
         }
@@ -141,10 +158,10 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 // ---- backward -----------------------------------------------------------------------------------
 // Back-to-front replay over the first max(n_contrib) entries of the tile list.  Each contributing
 // (pixel, Gaussian) pair produces 12 moments (bwd_pair2); per (warp, entry) the 32 lanes' moments
-// are combined with a 16-shuffle reduce-scatter and added to a per-batch shared-memory
-// accumulator; after each batch one thread per entry turns its summed moments into the final
-// gradient row (bwd_finalize) and flushes it to the per-Gaussian accumulator with three vector
-// atomics (red.global.add.v4.f32).
+// are combined with a shuffle reduce-scatter and added to a per-batch shared-memory accumulator;
+// after each batch one thread per entry turns its summed moments into the final gradient row
+// (bwd_finalize) and flushes it to the per-Gaussian accumulator with three vector atomics
+// (red.global.add.v4.f32).
 template <bool FUSED>
 __global__ void __launch_bounds__(CTA)
 k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
@@ -157,14 +174,15 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
     __shared__ __align__(16) float s_acc[BATCH * ACC_F];
     __shared__ unsigned int s_id[2][BATCH];
     __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ unsigned char s_list[CTA / 32][BATCH];
     __shared__ unsigned int s_maxlast;
     const int tile = blockIdx.x;
     const unsigned int start = tile_offset[tile];
     const int n = (int)(tile_offset[tile + 1] - start);
     if (n == 0) return;
     const bool use_tma = (flags & 1u) == 0;
-    const int lane = threadIdx.x & 31;
-    const unsigned int warp_bit = 1u << (threadIdx.x >> 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int warp_bit = 1u << warp;
     const TilePix pix = tile_pixel(cc, tile);
     const float pxf = (float)pix.px, pyf = (float)pix.py;
     const size_t HW = (size_t)cc.W * cc.H, p = (size_t)pix.py * cc.W + pix.px;
@@ -181,10 +199,8 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
     __syncthreads();
 
     const int last = pix.inside ? (int)n_contrib[p] : 0;
-    {
-        const unsigned int wmax = __reduce_max_sync(FULL, (unsigned int)last);
-        if (lane == 0 && wmax) atomicMax(&s_maxlast, wmax);
-    }
+    const int warp_last = (int)__reduce_max_sync(FULL, (unsigned int)last);   // this warp's deepest contributor
+    if (lane == 0 && warp_last) atomicMax(&s_maxlast, (unsigned int)warp_last);
     __syncthreads();
     const int maxlast = min((int)s_maxlast, n);
     if (maxlast == 0) return;
@@ -246,25 +262,28 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
         }
         const float4 *sb = s_rec[buf];
 
-        for (int j = cnt - 1; j >= 0; --j) {
-            const float4 q2 = sb[j * 3 + 2];
-            if (!(__float_as_uint(q2.z) & warp_bit)) continue;          // warp-uniform: block not reached
-            const int gidx = k * BATCH + j;
+        // entries of this batch that can matter to this warp: mask hit AND not deeper than the warp's
+        // deepest contributor
+        const int limit = min(cnt, warp_last - k * BATCH);
+        const int nrel = limit > 0 ? compact_entries(sb, limit, warp_bit, lane, s_list[warp]) : 0;
+        for (int i = nrel - 1; i >= 0; --i) {
+            const int j = s_list[warp][i];
             const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
             const float dx = q0.x - pxf, dy = q0.y - pyf;
             const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
             const float G = fast_exp2(p2);
             const float alpha = fminf(ALPHA_MAX, q1.y * G);
-            const bool valid = (gidx < last) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
+            const bool valid = (k * BATCH + j < last) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
             if (!__any_sync(FULL, valid)) continue;
-            float v[16];
+            float v[12];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = 0.f;
-            if (valid)
+            for (int q = 0; q < 12; ++q) v[q] = 0.f;
+            if (valid) {
+                const float4 q2 = sb[j * 3 + 2];
                 bwd_pair2<FUSED>(ps, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final, bgdot_rgb, bgdot_dep, v);
-            warp_reduce_scatter16(v, lane);
-            const int idx = lane >> 1;
-            if ((lane & 1) == 0 && idx < ACC_F && v[0] != 0.f) atomicAdd(&s_acc[j * ACC_F + idx], v[0]);
+            }
+            const int idx = warp_reduce_scatter12(v, lane);
+            if (idx >= 0 && v[0] != 0.f) atomicAdd(&s_acc[j * ACC_F + idx], v[0]);
         }
 
         __syncthreads();   // all warps' shared-memory adds for this batch are in

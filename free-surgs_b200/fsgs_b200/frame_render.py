@@ -66,7 +66,7 @@ class _RenderFused(torch.autograd.Function):
         _lib.check(rc)
         empty = torch.empty(0, dtype=torch.uint8, device=dev)
         ctx.save_for_backward(*t, *[arena.tensors.get(k, empty) for k in ("geom", "binning", "img")])
-        ctx.lease = arena.lease                # scratch goes back to the workspace pool when this node dies
+        ctx.lease = arena.finish()             # scratch goes back to the workspace pool when this node dies
         ctx.st, ctx.P, ctx.num_rendered, ctx.num_rect = st, P, int(nr.value), int(nrect.value)
         ctx.flags = (bool(gs_grad), bool(cam_grad))
         ctx.mark_non_differentiable(radii)
@@ -95,7 +95,7 @@ class _RenderFused(torch.autograd.Function):
                     _ptr(img), _ptr(gp), _ptr(scratch), int(gs_grad), int(cam_grad), _ptr(g["xyz"]), _ptr(g["f_dc"]),
                     _ptr(g["f_rest"]), _ptr(g["opacity"]), _ptr(g["scaling"]), _ptr(g["rotation"]), _ptr(g["pose"]),
                     _ptr(g["means2D"]), _stream(dev))
-            arena.lease.release()              # kernels are enqueued; reuse is ordered on this stream
+            arena.finish().release()           # kernels are enqueued; reuse is ordered on this stream
             _lib.check(rc)
         return (g["xyz"], g["f_dc"], g["f_rest"], g["opacity"], g["scaling"], g["rotation"],
                 g["pose"] if cam_grad else None, g["means2D"], None, None, None, None, None)

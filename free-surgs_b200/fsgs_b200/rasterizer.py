@@ -52,7 +52,7 @@ class _WorkspacePool:
 
     def __init__(self):
         import threading
-        self._lock = threading.Lock()
+        self._lock = threading.RLock()     # re-entrant: a lease may be garbage-collected inside acquire()
         self._free = {}
 
     def acquire(self, key, nbytes: int, device, headroom: float = 1.0) -> torch.Tensor:
@@ -133,6 +133,14 @@ class _Arena:
         self._cbs.append(fn)
         return fn
 
+    def finish(self) -> "_Lease":
+        """Call after the library returns: drops the ctypes callbacks (they close over ``self`` -- a
+        reference cycle that would otherwise keep the lease alive until the cyclic GC runs) and hands
+        out the lease, whose lifetime alone decides when the buffers go back to the pool."""
+        self._cbs.clear()
+        lease, self.lease = self.lease, None
+        return lease
+
 
 def _f32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
     if t is None or t.numel() == 0:
@@ -197,8 +205,9 @@ def rasterize_gaussians(bg, means3D, colors_precomp, opacities, scales, rotation
     empty = torch.empty(0, dtype=torch.uint8, device=dev)
     bufs = [arena.tensors.get(k, empty) for k in ("geom", "binning", "img")]
     rasterize_gaussians.last_num_rect = int(nrect.value)
+    lease = arena.finish()
     for b in bufs:                  # the buffers return to the workspace pool once the caller drops all three
-        b._fsgs_lease = arena.lease
+        b._fsgs_lease = lease
     return int(nr.value), color, depth, radii, bufs[0], bufs[1], bufs[2]
 
 
@@ -238,7 +247,7 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors_precomp, scales, rot
             _ptr(t["campos"]), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer), _ptr(t["gc"]), _ptr(t["gd"]),
             _ptr(scratch), _ptr(g["means2D"]), _ptr(g["colors"]), _ptr(g["opacity"]), _ptr(g["means3D"]),
             _ptr(g["cov3D"]), _ptr(g["sh"]) if n_coeffs > 0 else None, _ptr(g["scales"]), _ptr(g["rots"]), _stream(dev))
-    arena.lease.release()                 # kernels are enqueued; reuse is ordered on this stream
+    arena.finish().release()              # kernels are enqueued; reuse is ordered on this stream
     _lib.check(rc)
     return tuple(g[k] for k in ("means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rots"))
 
