@@ -226,6 +226,10 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
         }
     }
     const float kx = 0.5f * cc.W, ky = 0.5f * cc.H;
+    // which upstream planes are non-zero anywhere in this warp's block (uniform per warp):
+    // 0 = colour only (pose tracking), 1 = + depth (mapping), 2 = + silhouette / depth^2
+    int level = __any_sync(FULL, g[3] != 0.f) ? 1 : 0;
+    if (FUSED && __any_sync(FULL, g[4] != 0.f || g[5] != 0.f)) level = 2;
 
     BwdPixel ps;
     ps.T = T_final; ps.last_alpha = 0.f;
@@ -280,7 +284,12 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
             for (int q = 0; q < 12; ++q) v[q] = 0.f;
             if (valid) {
                 const float4 q2 = sb[j * 3 + 2];
-                bwd_pair2<FUSED>(ps, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final, bgdot_rgb, bgdot_dep, v);
+                if (level == 0)
+                    bwd_pair2<FUSED, 0>(ps, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final, bgdot_rgb, bgdot_dep, v);
+                else if (!FUSED || level == 1)
+                    bwd_pair2<FUSED, 1>(ps, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final, bgdot_rgb, bgdot_dep, v);
+                else
+                    bwd_pair2<FUSED, 2>(ps, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final, bgdot_rgb, bgdot_dep, v);
             }
             const int idx = warp_reduce_scatter12(v, lane);
             if (idx >= 0 && v[0] != 0.f) atomicAdd(&s_acc[j * ACC_F + idx], v[0]);

@@ -231,33 +231,42 @@ k_scatter(CamConst cc, int P, const float4 *__restrict__ records, const unsigned
 // A data-independent compare-exchange network whose comparators all point the same way, so a list
 // of arbitrary length n behaves as if padded with +inf to the next power of two.
 template <typename KeyPtr>
+__device__ __forceinline__ void tile_sort_ce(KeyPtr a, int lo, int hi, int n) {
+    if (hi < n) {
+        const unsigned long long x = a[lo], y = a[hi];
+        if (x > y) { a[lo] = y; a[hi] = x; }
+    }
+}
+// Pair p = tid + 256*i: the 32 pairs a warp handles per i cover 64 contiguous elements, so every
+// step whose comparator blocks are <= 64 elements wide only needs a warp barrier; block barriers
+// are reserved for the few wide steps (6 instead of 45 for a 512-entry list).
+__device__ __forceinline__ void tile_sort_sync(int this_block, int next_block) {
+    if (this_block > 64 || next_block > 64) __syncthreads();
+    else __syncwarp();
+}
+template <typename KeyPtr>
 __device__ __forceinline__ void tile_sort_network(KeyPtr a, int n) {
-    int N = 1;
-    while (N < n) N <<= 1;
-    const int half = N >> 1;
-    for (int k = 2; k <= N; k <<= 1) {
-        const int hk = k >> 1;
-        for (int p = threadIdx.x; p < half; p += blockDim.x) {
-            const int blk = p / hk, r = p - blk * hk;
-            const int lo = blk * k + r, hi = blk * k + (k - 1 - r);
-            if (hi < n) {
-                const unsigned long long x = a[lo], y = a[hi];
-                if (x > y) { a[lo] = y; a[hi] = x; }
-            }
+    int lgN = 0;
+    while ((1 << lgN) < n) ++lgN;
+    const int half = (1 << lgN) >> 1;
+    for (int m = 1; m <= lgN; ++m) {
+        const int k = 1 << m, hk = k >> 1;
+        for (int p = threadIdx.x; p < half; p += blockDim.x) {          // "flip": i <-> block_end - i
+            const int blk = p >> (m - 1), r = p & (hk - 1);
+            tile_sort_ce(a, (blk << m) + r, (blk << m) + (k - 1 - r), n);
         }
-        __syncthreads();
-        for (int j = k >> 2; j > 0; j >>= 1) {
+        tile_sort_sync(k, m >= 2 ? (k >> 1) : 4);
+        for (int s = m - 2; s >= 0; --s) {                                // half-cleaners, distance j = 2^s
+            const int j = 1 << s;
             for (int p = threadIdx.x; p < half; p += blockDim.x) {
-                const int blk = p / j, r = p - blk * j;
-                const int lo = blk * 2 * j + r, hi = lo + j;
-                if (hi < n) {
-                    const unsigned long long x = a[lo], y = a[hi];
-                    if (x > y) { a[lo] = y; a[hi] = x; }
-                }
+                const int blk = p >> s, r = p & (j - 1);
+                const int lo = (blk << (s + 1)) + r;
+                tile_sort_ce(a, lo, lo + j, n);
             }
-            __syncthreads();
+            tile_sort_sync(2 * j, s > 0 ? j : 2 * k);
         }
     }
+    __syncthreads();
 }
 
 constexpr int SORT_SMEM_KEYS = 8192;   // 64 KB of dynamic shared memory

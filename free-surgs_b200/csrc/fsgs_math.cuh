@@ -706,7 +706,10 @@ FSGS_HD unsigned block_mask(float px, float py, float A, float B, float C, float
 // per-Gaussian gradients each pixel adds the moments of q = G*o*dL/dalpha over d = centre - pixel;
 // bwd_finalize turns the summed moments into the accumulator row once per (tile, Gaussian).
 //   v = [Sx, Sy, Sxx, Sxy, Syy, S0 | d r, d g, d b, d z | Sx_rgb, Sy_rgb]
-template <bool FUSED>
+// LEVEL says which upstream gradients are non-zero for the whole warp (decided once per warp, so the
+// dispatch is uniform): 0 = colour planes only, 1 = + the depth plane, 2 = + silhouette / depth^2
+// (fused flavour only).  Skipped planes contribute exact zeros, so the result is unchanged.
+template <bool FUSED, int LEVEL>
 FSGS_HD void bwd_pair2(BwdPixel &s, float opacity, float cr, float cg, float cb, float z, float dx, float dy,
                        float G, float alpha, const float *g, float T_final, float bgdot_rgb, float bgdot_dep,
                        float *v) {
@@ -718,21 +721,26 @@ FSGS_HD void bwd_pair2(BwdPixel &s, float opacity, float cr, float cg, float cb,
     s.acc_g = la * s.lc_g + lb * s.acc_g; s.lc_g = cg;
     s.acc_b = la * s.lc_b + lb * s.acc_b; s.lc_b = cb;
     float da_rgb = (cr - s.acc_r) * g[0] + (cg - s.acc_g) * g[1] + (cb - s.acc_b) * g[2];
-    float dz = w * g[3];
-    if (FUSED) {
-        s.acc_s = la + lb * s.acc_s;
-        s.acc_d2 = la * (s.lc_d * s.lc_d) + lb * s.acc_d2;
-    }
-    s.acc_d = la * s.lc_d + lb * s.acc_d; s.lc_d = z;
-    float da_dep = (z - s.acc_d) * g[3];
-    if (FUSED) {
-        da_dep += (1.f - s.acc_s) * g[4] + (z * z - s.acc_d2) * g[5];
-        dz += w * 2.f * z * g[5];
+    float dz = 0.f, da_dep = 0.f;
+    if (LEVEL >= 1) {
+        dz = w * g[3];
+        if (FUSED && LEVEL >= 2) {
+            s.acc_s = la + lb * s.acc_s;
+            s.acc_d2 = la * (s.lc_d * s.lc_d) + lb * s.acc_d2;
+        }
+        s.acc_d = la * s.lc_d + lb * s.acc_d; s.lc_d = z;
+        da_dep = (z - s.acc_d) * g[3];
+        if (FUSED && LEVEL >= 2) {
+            da_dep += (1.f - s.acc_s) * g[4] + (z * z - s.acc_d2) * g[5];
+            dz += w * 2.f * z * g[5];
+        }
     }
     const float tf = -T_final * inv;
     da_rgb = da_rgb * s.T + tf * bgdot_rgb;
-    da_dep = da_dep * s.T;
-    if (FUSED) da_dep += tf * bgdot_dep;
+    if (LEVEL >= 1) {
+        da_dep = da_dep * s.T;
+        if (FUSED) da_dep += tf * bgdot_dep;
+    }
     s.last_alpha = alpha;
     const float Go = G * opacity;
     const float q = Go * (da_rgb + da_dep);

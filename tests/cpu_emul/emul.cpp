@@ -141,6 +141,22 @@ void composite_bwd(const CamConst &cc, size_t P, const std::vector<std::vector<S
     acc.assign(P * 12, 0.f);
     std::vector<double> acc64(P * 12, 0.0);   // order-independent accumulation of the finalised rows
     const float kx = 0.5f * cc.W, ky = 0.5f * cc.H;
+    // per 8x4 warp block: which upstream planes are non-zero (the kernel's warp-uniform `level`)
+    const int bw = (cc.W + 7) / 8, bh = (cc.H + 3) / 4;
+    std::vector<int> block_level((size_t)bw * bh, 0);
+    for (int py = 0; py < cc.H; ++py)
+        for (int px = 0; px < cc.W; ++px) {
+            const size_t p = (size_t)py * cc.W + px;
+            int lv = 0;
+            if (FUSED) {
+                if (dplanes[3 * HW + p] != 0.f) lv = 1;
+                if (dplanes[4 * HW + p] != 0.f || dplanes[5 * HW + p] != 0.f) lv = 2;
+            } else if (ddepth && ddepth[p] != 0.f) {
+                lv = 1;
+            }
+            int &b = block_level[(size_t)(py / 4) * bw + px / 8];
+            b = std::max(b, lv);
+        }
     for (size_t t = 0; t < SR.size(); ++t) {
         const auto &lst = SR[t];
         if (lst.empty()) continue;
@@ -171,7 +187,13 @@ void composite_bwd(const CamConst &cc, size_t P, const std::vector<std::vector<S
                     const float alpha = fminf(ALPHA_MAX, r.o * G);
                     if (!(p2 <= 0.f && alpha >= ALPHA_MIN)) continue;
                     float v[12];
-                    bwd_pair2<FUSED>(s, r.o, r.r, r.g, r.b, r.z, dx, dy, G, alpha, g, final_T[p], bgdot_rgb, bgdot_dep, v);
+                    const int level = block_level[(size_t)(py / 4) * ((cc.W + 7) / 8) + px / 8];
+                    if (level == 0)
+                        bwd_pair2<FUSED, 0>(s, r.o, r.r, r.g, r.b, r.z, dx, dy, G, alpha, g, final_T[p], bgdot_rgb, bgdot_dep, v);
+                    else if (!FUSED || level == 1)
+                        bwd_pair2<FUSED, 1>(s, r.o, r.r, r.g, r.b, r.z, dx, dy, G, alpha, g, final_T[p], bgdot_rgb, bgdot_dep, v);
+                    else
+                        bwd_pair2<FUSED, 2>(s, r.o, r.r, r.g, r.b, r.z, dx, dy, G, alpha, g, final_T[p], bgdot_rgb, bgdot_dep, v);
                     for (int k = 0; k < 12; ++k) mom[(size_t)j * 12 + k] += v[k];
                 }
             }

@@ -18,8 +18,8 @@ from oracle import raster_oracle as ro  # noqa: E402
 from oracle import render_oracle as R  # noqa: E402
 
 
-@pytest.mark.parametrize("gs_grad,cam_grad,sh_deg", [(True, True, 3), (False, True, 2), (True, False, 0)])
-def test_fused_render_emulation_matches_oracle(gs_grad, cam_grad, sh_deg):
+@pytest.mark.parametrize("gs_grad,cam_grad,sh_deg,n_grad_planes", [(True, True, 3, 6), (False, True, 2, 3), (True, False, 0, 4)])
+def test_fused_render_emulation_matches_oracle(gs_grad, cam_grad, sh_deg, n_grad_planes):
     P, W, H = 900, 168, 120
     sc = make_scene(P, W, H, size_mult=2.0, seed=4)
     dt = torch.float64
@@ -27,6 +27,7 @@ def test_fused_render_emulation_matches_oracle(gs_grad, cam_grad, sh_deg):
     r, t = sc.pose_q.to(dt).requires_grad_(True), sc.pose_t.to(dt).requires_grad_(True)
     out = R.render(params, r, t, sc.camera, sh_deg, sc.camera.campos, gs_grad, cam_grad, want_aux=True)
     G6 = torch.randn(6, H, W, generator=torch.Generator().manual_seed(1))
+    G6[n_grad_planes:] = 0            # 3 = pose tracking (colour loss only), 4 = mapping (+ depth), 6 = everything
     ref_planes = torch.cat([out["render"], out["_depth_sil"]], 0)
     out["render_w2c"].retain_grad()
     # viewspace gradient of the reference comes from the RGB pass only
