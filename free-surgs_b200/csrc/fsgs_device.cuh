@@ -124,6 +124,41 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
                  : "memory");
 }
 
+// shared -> global 1-D bulk copy (TMA store); completion tracked with bulk async-groups
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// make this thread's generic-proxy shared-memory writes visible to the async proxy (before a TMA store)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Stage the CTA's slice of a [P, row_floats] float array into shared memory: one bulk TMA copy for the
+// largest 16-byte-multiple prefix, plain loads for the (at most 3-row) remainder.  `count` rows starting at
+// row `base`.  Call from all threads; returns after the data has landed.  Requires src 16-B aligned.
+template <int ROW_FLOATS>
+__device__ __forceinline__ void stage_rows_tma(float *s_dst, const float *__restrict__ src, int base, int count,
+                                               uint64_t *bar, unsigned long long *err) {
+    const int rows_tma = count & ~3;                                 // rows*ROW_FLOATS*4 B multiple of 16
+    const float *g = src + (size_t)base * ROW_FLOATS;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        if (rows_tma > 0) {
+            const uint32_t bytes = (uint32_t)rows_tma * ROW_FLOATS * 4u;
+            mbar_arrive_expect_tx(bar, bytes);
+            tma_load_1d(s_dst, g, bytes, bar);
+        }
+    }
+    for (int q = rows_tma * ROW_FLOATS + threadIdx.x; q < count * ROW_FLOATS; q += blockDim.x) s_dst[q] = __ldg(g + q);
+    __syncthreads();                                                  // barrier initialised + remainder visible
+    if (rows_tma > 0) mbar_wait(bar, 0u, err);
+}
+
 // gauss_power (pinned operation order) lives in fsgs_math.cuh so the CPU emulation shares it.
 __device__ __forceinline__ float gauss_weight(float power) {
 #ifdef FSGS_PRECISE_EXP

@@ -73,12 +73,22 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
                        const float *__restrict__ grad_acc, int gs_grad, int cam_grad, float *__restrict__ dL_dxyz,
                        float *__restrict__ dL_dfdc, float *__restrict__ dL_dfrest, float *__restrict__ dL_dopacity_raw,
                        float *__restrict__ dL_dscaling_raw, float *__restrict__ dL_drotation_raw,
-                       float *__restrict__ dL_dpose, float *__restrict__ dL_dmeans2D) {
+                       float *__restrict__ dL_dpose, float *__restrict__ dL_dmeans2D, int use_tma,
+                       unsigned long long *__restrict__ err) {
+    // SH coefficients in, SH gradients out through ONE shared-memory buffer: bulk TMA load of the CTA's
+    // 256 x 180 B slice, each thread turns its 45 coefficients into their gradients in place, bulk TMA
+    // store to dL/dfeatures_rest (the plain path does 45 scalar loads + 45 scalar stores at a 180 B stride).
+    __shared__ __align__(128) float s_rest[CTA * 45];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ float s_pose[16];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    const int base = blockIdx.x * blockDim.x, count = min((int)blockDim.x, P - base);
+    const bool staged = dL_dfrest != nullptr && (reinterpret_cast<uintptr_t>(f_rest) & 15u) == 0 &&
+                        (reinterpret_cast<uintptr_t>(dL_dfrest) & 15u) == 0 && use_tma;
     if (threadIdx.x < 16) s_pose[threadIdx.x] = 0.f;
-    __syncthreads();
+    if (staged) stage_rows_tma<45>(s_rest, f_rest, base, count, &s_bar, err);
+    else __syncthreads();
     float pg[16];   // pose-gradient contributions of this Gaussian: g_r * [x y z 1]_c at [4r + c]
 #pragma unroll
     for (int k = 0; k < 16; ++k) pg[k] = 0.f;
@@ -87,7 +97,8 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
         const int radius = __float_as_int(records[n * 3 + 2].z);
         float dxyz[3] = {0.f, 0.f, 0.f}, ds_raw[3] = {0.f, 0.f, 0.f}, dq_raw[4] = {0.f, 0.f, 0.f, 0.f};
         float dop_raw = 0.f, dfdc[3] = {0.f, 0.f, 0.f}, m2d[2] = {0.f, 0.f};
-        float *drest = dL_dfrest ? dL_dfrest + 45 * n : nullptr;
+        float *drest = staged ? s_rest + 45 * threadIdx.x : (dL_dfrest ? dL_dfrest + 45 * n : nullptr);
+        const float *rest = staged ? s_rest + 45 * threadIdx.x : f_rest + 45 * n;
         if (radius > 0) {
             float a[ACC_F];
             load_acc(grad_acc, i, a);
@@ -101,7 +112,7 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
             const float sc[3] = {scaling_raw[3 * n], scaling_raw[3 * n + 1], scaling_raw[3 * n + 2]};
             const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
             const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-            fused_backward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, f_rest + 45 * n, opacity_raw[i], sc, q, clamped[i], a,
+            fused_backward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, rest, opacity_raw[i], sc, q, clamped[i], a,
                                gs_grad, cam_grad, dxyz, dfdc, drest, dop_raw, ds_raw, dq_raw, pg, m2d);
         } else if (drest) {
             for (int k = 0; k < 45; ++k) drest[k] = 0.f;
@@ -112,6 +123,16 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
         if (dL_dscaling_raw) { dL_dscaling_raw[3 * n] = ds_raw[0]; dL_dscaling_raw[3 * n + 1] = ds_raw[1]; dL_dscaling_raw[3 * n + 2] = ds_raw[2]; }
         if (dL_drotation_raw) *reinterpret_cast<float4 *>(dL_drotation_raw + 4 * n) = make_float4(dq_raw[0], dq_raw[1], dq_raw[2], dq_raw[3]);
         if (dL_dmeans2D) { dL_dmeans2D[3 * n] = m2d[0]; dL_dmeans2D[3 * n + 1] = m2d[1]; dL_dmeans2D[3 * n + 2] = 0.f; }
+    }
+    if (staged) {
+        // gradients -> global: bulk store for the 16-byte-multiple prefix, plain stores for <= 3 rows
+        fence_proxy_async_smem();
+        __syncthreads();
+        const int rows_tma = count & ~3;
+        float *gdst = dL_dfrest + (size_t)base * 45;
+        if (threadIdx.x == 0 && rows_tma > 0) tma_store_1d(gdst, s_rest, (uint32_t)rows_tma * 180u);
+        for (int q = rows_tma * 45 + threadIdx.x; q < count * 45; q += blockDim.x) gdst[q] = s_rest[q];
+        if (threadIdx.x == 0 && rows_tma > 0) tma_store_commit_and_wait();   // smem must outlive the read
     }
     if (cam_grad && dL_dpose) {
         warp_reduce_scatter16(pg, lane);

@@ -129,7 +129,15 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
                    float4 *__restrict__ records, uint8_t *__restrict__ clamped, int *__restrict__ radii,
                    unsigned int *__restrict__ tile_count, unsigned long long *__restrict__ counters,
                    unsigned int flags) {
+    // The 180 B/Gaussian of higher-order SH coefficients (76 % of the input bytes) are contiguous per
+    // CTA: one bulk TMA copy stages them; threads then read their own 45 floats at a conflict-free
+    // stride.  FSGS_FLAG_NO_TMA (or a mis-aligned tensor) reads them straight from global memory.
+    __shared__ __align__(128) float s_rest[CTA * 45];
+    __shared__ __align__(8) uint64_t s_bar;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int base = blockIdx.x * blockDim.x;
+    const bool staged = (flags & 1u) == 0 && (reinterpret_cast<uintptr_t>(f_rest) & 15u) == 0;
+    if (staged) stage_rows_tma<45>(s_rest, f_rest, base, min((int)blockDim.x, P - base), &s_bar, counters + CNT_ERR);
     unsigned int rect_tiles = 0;
     if (i < P) {
         float V[16], PM[16], Rt[12], cp[3];
@@ -147,8 +155,8 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
         float rgb[3], opacity = 0.f;
         uint8_t cl = 0;
         int radius = 0;
-        if (fused_forward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, f_rest + 45 * n, opacity_raw[i], sc, q, sp, opacity,
-                              rgb, cl)) {
+        const float *rest = staged ? s_rest + 45 * threadIdx.x : f_rest + 45 * n;
+        if (fused_forward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, rest, opacity_raw[i], sc, q, sp, opacity, rgb, cl)) {
             radius = sp.radius;
             rect_tiles = (unsigned int)((sp.rmaxx - sp.rminx) * (sp.rmaxy - sp.rminy));
             const int tiles = for_each_tile(cc, sp.px, sp.py, sp.conx, sp.cony, sp.conz, opacity, sp.radius,

@@ -455,8 +455,10 @@ FSGS_HD void sh_to_rgb_backward(int deg, int n_coeffs, const float *dir, float i
     float ddir[3] = {0.f, 0.f, 0.f};
     for (int k = 0; k < n_coeffs; ++k) {
         if (k < nb) {
-            dcoef(k, 0, B[k] * gc[0]); dcoef(k, 1, B[k] * gc[1]); dcoef(k, 2, B[k] * gc[2]);
+            // read the coefficients BEFORE writing their gradients: the fused backward kernel computes
+            // in place (gradient overwrites the coefficient in its shared-memory staging buffer)
             const float t = coef(k, 0) * gc[0] + coef(k, 1) * gc[1] + coef(k, 2) * gc[2];
+            dcoef(k, 0, B[k] * gc[0]); dcoef(k, 1, B[k] * gc[1]); dcoef(k, 2, B[k] * gc[2]);
             ddir[0] += dB[k][0] * t; ddir[1] += dB[k][1] * t; ddir[2] += dB[k][2] * t;
         } else {
             dcoef(k, 0, 0.f); dcoef(k, 1, 0.f); dcoef(k, 2, 0.f);

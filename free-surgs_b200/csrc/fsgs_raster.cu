@@ -463,7 +463,8 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
         cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
         projmatrix, reinterpret_cast<const float4 *>(g + gl.records), reinterpret_cast<const uint8_t *>(g + gl.clamped),
         acc, gs_grad, cam_grad, dL_dxyz, dL_dfeatures_dc, dL_dfeatures_rest, dL_dopacity_raw, dL_dscaling_raw,
-        dL_drotation_raw, dL_dpose, dL_dmeans2D);
+        dL_drotation_raw, dL_dpose, dL_dmeans2D, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1,
+        const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
     prof_end(K_PRE_FUSED_BWD, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused_bwd");
     return FSGS_OK;
