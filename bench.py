@@ -164,6 +164,7 @@ def run_reference(args):
 def run_ours(args):
     import torch.distributed as dist
     from fsgs_b200 import _lib, model
+    from fsgs_b200 import dist as fsgs_dist
     from fsgs_b200 import frame_render as render
     from fsgs_b200.synth import frame_pose_params, make_scene
 
@@ -200,9 +201,7 @@ def run_ours(args):
         loss = (out["render"] * G[:3]).sum() + (out["render_dep"] * G[3]).sum()
         loss.backward()
         if world > 1:
-            hs = [dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True) for p in grads]
-            for h in hs:
-                h.wait()
+            fsgs_dist.allreduce_gaussian_grads(pc.params)       # one NCCL all-reduce of the flat model gradient
         last["stats"] = out["num_rendered"]
         return loss
 

@@ -30,6 +30,26 @@ def _is_dist(group=None) -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
 
+def _shared_flat(tensors):
+    """If the gradient tensors tile one contiguous float32 storage exactly (as the fused backward
+    allocates them), return a flat alias of that storage, else None."""
+    try:
+        if any(t.dtype != torch.float32 or not t.is_contiguous() for t in tensors):
+            return None
+        st = tensors[0].untyped_storage()
+        if any(t.untyped_storage().data_ptr() != st.data_ptr() for t in tensors):
+            return None
+        spans = sorted((t.storage_offset(), t.storage_offset() + t.numel()) for t in tensors)
+        if spans[0][0] != 0 or any(a[1] != b[0] for a, b in zip(spans, spans[1:])):
+            return None
+        total = spans[-1][1]
+        if total * 4 != st.nbytes():
+            return None
+        return torch.empty(0, dtype=torch.float32, device=tensors[0].device).set_(st, 0, (total,))
+    except Exception:  # noqa: BLE001 -- any exotic tensor subclass: just take the generic path
+        return None
+
+
 def allreduce_gaussian_grads(params: dict, group=None, bucket: bool = True) -> int:
     """Sum the gradients of the six Gaussian parameter tensors over the ranks, in place.
     A rank that rendered no frame (or whose tensor got no gradient) contributes zeros.
@@ -43,6 +63,10 @@ def allreduce_gaussian_grads(params: dict, group=None, bucket: bool = True) -> i
         tensors.append(p.grad)
     nbytes = sum(t.numel() * t.element_size() for t in tensors)
     if not _is_dist(group):
+        return nbytes
+    flat = _shared_flat(tensors)
+    if flat is not None:          # the fused backward hands out views of one buffer: one collective, no copies
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         return nbytes
     if bucket:
         flat = torch.cat([t.reshape(-1) for t in tensors])

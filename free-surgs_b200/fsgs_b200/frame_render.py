@@ -81,8 +81,20 @@ class _RenderFused(torch.autograd.Function):
         gs_grad, cam_grad = ctx.flags
         # every output is fully overwritten by the library (zeros where a Gaussian is not visible)
         z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        g = dict(xyz=z(P, 3), f_dc=z(P, 1, 3), f_rest=z(P, 15, 3), opacity=z(P, 1), scaling=z(P, 3), rotation=z(P, 4),
-                 pose=z(4, 4), means2D=z(P, 3))
+        # The six Gaussian-parameter gradients are carved out of ONE flat buffer (59 floats/Gaussian, in the
+        # order of fsgs_b200.dist.PARAM_KEYS): autograd adopts the views as .grad, and the frame-parallel path
+        # can then sum-all-reduce the whole model gradient with a single collective and no packing copies.
+        # (rotation and f_rest first: their float4 / bulk-TMA stores need 16-byte alignment for any P)
+        flat = z(P * 59)
+        g, off = {}, 0
+        for name, shape in (("rotation", (P, 4)), ("f_rest", (P, 15, 3)), ("xyz", (P, 3)), ("f_dc", (P, 1, 3)),
+                            ("scaling", (P, 3)), ("opacity", (P, 1))):
+            n = 1
+            for s_ in shape:
+                n *= s_
+            g[name] = flat[off:off + n].view(*shape)
+            off += n
+        g["pose"], g["means2D"] = z(4, 4), z(P, 3)
         if P == 0:
             g["pose"].zero_()
         if P > 0:

@@ -41,6 +41,22 @@ def _worker(rank, world, port, bucket, q):
         for k, p in params.items():
             want = sum(_grad(r, k) for r in range(world) if not (r == 1 and k == "_opacity"))
             assert torch.allclose(p.grad, want, atol=1e-6), k
+        # gradients handed out as views of one flat buffer (what the fused backward does): detected and
+        # reduced with a single collective
+        flat = torch.zeros(7 * 59)
+        views, off = {}, 0
+        for k in ("_rotation", "_features_rest", "_xyz", "_features_dc", "_scaling", "_opacity"):
+            n = int(torch.tensor(SHAPES[k]).prod())
+            views[k] = flat[off:off + n].view(*SHAPES[k])
+            off += n
+        p2 = {k: torch.zeros(*s, requires_grad=True) for k, s in SHAPES.items()}
+        for k, p in p2.items():
+            views[k].copy_(_grad(rank, k))
+            p.grad = views[k]
+        assert fd._shared_flat([p2[k].grad for k in fd.PARAM_KEYS]) is not None
+        fd.allreduce_gaussian_grads(p2, bucket=bucket)
+        for k, p in p2.items():
+            assert torch.allclose(p.grad, sum(_grad(r, k) for r in range(world)), atol=1e-6), k
         var = {"xyz_gradient_accum": torch.full((7, 1), float(rank + 1)), "denom": torch.ones(7, 1),
                "max_radii2D": torch.arange(7.0) * (rank + 1)}
         fd.allreduce_densification_stats(var)
