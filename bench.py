@@ -271,30 +271,34 @@ def run_ours(args):
             G_in[b].copy_(G_host, non_blocking=True)
             copied[b].record(copy_stream)
 
-    for e in consumed:
-        e.record(main)
-    barrier()
-    e2e_start, e2e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_start.record(main)
-    copy_stream.wait_event(e2e_start)
-    prefetch(0)
-    for k in range(args.steps):
-        b = k & 1
-        flush.zero_()
-        main.wait_event(copied[b])
-        if k + 1 < args.steps:
-            prefetch(k + 1)
-        loss = step(G_in[b])
-        consumed[b].record(main)
-        packed = torch.cat([loss.detach().reshape(1), poses.pose_param_net.r.grad.reshape(-1),
-                            poses.pose_param_net.t.grad.reshape(-1)])
-        result_host.copy_(packed, non_blocking=True)
-        result_ready.record(main)
-        result_ready.synchronize()                        # the host now holds this step's loss and pose gradient
-        loss_host = float(result_host[0])
-    e2e_end.record(main)
-    barrier()
-    ms_e2e = e2e_start.elapsed_time(e2e_end) / args.steps
+    def run_e2e(n_steps):
+        for e in consumed:
+            e.record(main)
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(main)
+        copy_stream.wait_event(t0)
+        prefetch(0)
+        for k in range(n_steps):
+            b = k & 1
+            flush.zero_()
+            main.wait_event(copied[b])
+            if k + 1 < n_steps:
+                prefetch(k + 1)
+            loss = step(G_in[b])
+            consumed[b].record(main)
+            packed = torch.cat([loss.detach().reshape(1), poses.pose_param_net.r.grad.reshape(-1),
+                                poses.pose_param_net.t.grad.reshape(-1)])
+            result_host.copy_(packed, non_blocking=True)
+            result_ready.record(main)
+            result_ready.synchronize()                    # the host now holds this step's loss and pose gradient
+            _ = float(result_host[0])
+        t1.record(main)
+        barrier()
+        return t0.elapsed_time(t1) / n_steps
+
+    run_e2e(3)                                            # warm the side stream / pinned mailbox path
+    ms_e2e = run_e2e(args.steps)
 
     # ---- pose-gradient latency: tracking-mode step (gs_grad=False, cam_grad=True), RGB loss only ----
     def track_step():
