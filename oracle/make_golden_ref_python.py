@@ -97,7 +97,7 @@ def _cpu_redirect():
     """Make the reference's hard-coded 'cuda' land on the CPU (this container has no GPU)."""
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.nn.Module.cuda = lambda self, *a, **k: self
-    for name in ("zeros", "ones", "eye", "tensor", "zeros_like", "ones_like", "empty", "arange", "full"):
+    for name in ("zeros", "ones", "eye", "tensor", "zeros_like", "ones_like", "empty", "arange", "full", "randint"):
         orig = getattr(torch, name)
 
         def wrapped(*a, __orig=orig, **k):
@@ -192,6 +192,34 @@ def main():
                                                  torch.zeros_like(xyz), camera_center=fake.cam_center)
         out[f"rendervar_colors_deg{deg}"] = rv["colors_precomp"]
     out["cam_center_used"] = fake.cam_center
+
+    # ---- losses the mapping / tracking steps apply to the render (utils/loss_utils.py:40-127) -------------
+    from utils import loss_utils as lu                       # noqa: E402
+    gl = torch.Generator().manual_seed(77)
+    img = torch.rand(3, 256, 384, generator=gl)
+    gt = (img + 0.1 * torch.randn(3, 256, 384, generator=gl)).clamp(0, 1)
+    msk = (torch.rand(1, 256, 384, generator=gl) > 0.2)
+    dep_a = torch.rand(256, 384, generator=gl) + 0.5
+    dep_b = dep_a * 1.7 + 0.05 * torch.randn(256, 384, generator=gl)
+    out.update(loss_img=img, loss_gt=gt, loss_mask=msk, loss_dep_a=dep_a, loss_dep_b=dep_b)
+    out["loss_l1"] = lu.l1_loss(img, gt)
+    out["loss_ssim"] = lu.ssim(img, gt)
+    out["loss_rgb"] = lu.rgb_loss_func(img, gt)
+    out["loss_rgb_masked"] = lu.rgb_loss_func(img, gt, mask=msk)
+    out["loss_pearson"] = lu.pearson_depth_loss(dep_a, dep_b)
+    torch.manual_seed(1234)
+    out["loss_local_pearson"] = lu.local_pearson_loss(dep_a, dep_b, 128, 0.5)
+    out["loss_local_pearson_seed"] = torch.tensor(1234)
+    # gradient of the mapping-style combination w.r.t. the rendered image / depth
+    img_g = img.clone().requires_grad_(True)
+    dep_g = dep_b.clone().requires_grad_(True)
+    torch.manual_seed(1234)
+    total = lu.rgb_loss_func(img_g, gt) * 5.0 + lu.pearson_depth_loss(dep_a, dep_g) * 0.05 + \
+        lu.local_pearson_loss(dep_a, dep_g, 128, 0.5) * 0.15
+    total.backward()
+    out["loss_total"] = total.detach()
+    out["loss_dimg"] = img_g.grad[:, ::8, ::8].clone()
+    out["loss_ddep"] = dep_g.grad[::8, ::8].clone()
 
     arrays = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
