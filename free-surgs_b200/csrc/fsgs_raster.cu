@@ -57,14 +57,14 @@ int make_cam(const fsgs_settings *st, CamConst &cc) {
 }
 
 int check_arch() {
-    static int cached = 0;   // 0 unknown, 1 ok, -1 bad
-    if (cached == 0) {
-        int dev = 0, major = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return FSGS_E_CUDA;
-        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return FSGS_E_CUDA;
-        cached = (major == 10) ? 1 : -1;
-    }
-    return cached == 1 ? FSGS_OK : FSGS_E_ARCH;
+    static signed char cached[64] = {0};   // per device: 0 unknown, 1 ok, -1 bad
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return FSGS_E_CUDA;
+    if (dev >= 0 && dev < 64 && cached[dev] != 0) return cached[dev] == 1 ? FSGS_OK : FSGS_E_ARCH;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return FSGS_E_CUDA;
+    const signed char v = (major == 10) ? 1 : -1;
+    if (dev >= 0 && dev < 64) cached[dev] = v;
+    return v == 1 ? FSGS_OK : FSGS_E_ARCH;
 }
 
 inline int blocks(int n) { return (n + CTA - 1) / CTA; }
@@ -176,11 +176,14 @@ int alloc_fixed(int P, const CamConst &cc, fsgs_alloc_fn geom_alloc, void *geom_
 }
 
 int one_time_setup() {
-    static int done = 0;
-    if (!done) {
+    // function attributes are per device: remember which devices of this process have been set up
+    static bool done[64] = {false};
+    int dev = 0;
+    FSGS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
         FSGS_CUDA(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(SORT_SMEM_KEYS * sizeof(unsigned long long))));
-        done = 1;
+        if (dev >= 0 && dev < 64) done[dev] = true;
     }
     return FSGS_OK;
 }
