@@ -146,7 +146,7 @@ def render(viewpoint_camera, index, pc, gs_grad=True, cam_grad=True):
     """Same signature, return dict and side effects as the reference's ``render``."""
     xyz = pc.params['_xyz']
     means2D = torch.zeros_like(xyz, requires_grad=True, device=xyz.device) + 0
-    if gs_grad:
+    if gs_grad and means2D.requires_grad:        # (under torch.no_grad() there is nothing to retain)
         means2D.retain_grad()
     viewmatrix_cur = viewpoint_camera.get_pose(index)
     pose = viewmatrix_cur if cam_grad else viewmatrix_cur.detach()
