@@ -100,6 +100,18 @@ def ncu_traffic(kernel, P, m):
     return None
 
 
+def ncu_instructions(kernel, P, m):
+    """Executed warp-instructions per launch of `kernel` from the same committed capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        d = json.load(open(path))
+        if int(d["workload"]["P"]) == int(P) and float(d["workload"]["m"]) == float(m):
+            return d.get("warp_instructions_per_launch", {}).get(kernel)
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def algorithmic_bytes(P, R, HW):
     """SURVEY.md 8d, fused render(): B_min = 724 P + 48 HW, B_model = B_min + 168 R (R = tile instances
     actually composited).  Per kernel: composite_bwd reads 48 B record + 4 B id and
@@ -369,6 +381,13 @@ def run_ours(args):
                                "achieved_model_GBs": bytes_["frame_model"] / (ms_step * 1e-3) / 1e9,
                                "frac_model": bytes_["frame_model"] / (ms_step * 1e-3) / 1e9 / peak,
                                "frac_min": bytes_["frame_min"] / (ms_step * 1e-3) / 1e9 / peak},
+            # the compositors are FP32-issue bound, not HBM bound: executed warp-instructions
+            # (committed ncu capture) / live launch time against 148 SMs x 4 schedulers x the sampled SM clock
+            "roofline_issue": (lambda n: None if not n or not clocks or not clocks.get("sm_mhz") else {
+                "kernel": top, "warp_instructions_per_launch": n,
+                "achieved_ginst_per_s": n / (kern[top] * 1e-3) / 1e9,
+                "peak_ginst_per_s": 148 * 4 * clocks["sm_mhz"] * 1e6 / 1e9,
+                "frac": n / (kern[top] * 1e-3) / (148 * 4 * clocks["sm_mhz"] * 1e6)})(ncu_instructions(top, args.P, args.m)),
             "kernel_ms": {k: round(v, 4) for k, v in kern.items() if v > 0},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(G_host.numel() * 4),
