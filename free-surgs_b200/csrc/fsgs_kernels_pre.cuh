@@ -50,6 +50,55 @@ __device__ __forceinline__ int for_each_tile(const CamConst &cc, float px, float
     return n;
 }
 
+// Warp-cooperative version: the 32 lanes of a warp each own one Gaussian, but the candidate
+// (Gaussian, tile) pairs of the whole warp are enumerated together, 32 per round, so a splat
+// covering 40 tiles no longer leaves 31 lanes idle (ncu: 8-12 active lanes per instruction with the
+// per-thread loops).  Every lane of the warp must call this (active = false when it has no splat).
+// f(owner_lane, tile_index) is called, by an arbitrary lane, once for every kept tile.
+template <typename F>
+__device__ __forceinline__ void warp_for_each_tile(int gx, int gy, bool active, float px, float py, float A, float B,
+                                                   float C, float opacity, int radius, bool no_cull, int lane, F &&f) {
+    TileRange tr;
+    tr.x0 = tr.y0 = tr.x1 = tr.y1 = 0; tr.tau = -1.f;
+    if (active) tr = tile_range_ni(gx, gy, px, py, A, B, C, opacity, radius, no_cull ? 1 : 0);
+    const int w = tr.x1 - tr.x0;
+    const unsigned int c = (unsigned int)(w * (tr.y1 - tr.y0));
+    unsigned int incl = c;                                   // inclusive prefix sum of candidate counts
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int nb = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += nb;
+    }
+    const unsigned int total = __shfl_sync(FULL, incl, 31);
+    const unsigned int excl = incl - c;
+    const float inv_w = w > 0 ? 1.0f / (float)w : 0.f;
+    for (unsigned int base = 0; base < total; base += 32) {
+        const unsigned int q = base + lane;
+        // owner = first lane whose inclusive count exceeds q (5-step search over the warp's prefix sums)
+        int owner = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const unsigned int v = __shfl_sync(FULL, incl, owner + step - 1);
+            if (v <= q) owner += step;
+        }
+        owner = min(owner, 31);
+        const float opx = __shfl_sync(FULL, px, owner), opy = __shfl_sync(FULL, py, owner);
+        const float oA = __shfl_sync(FULL, A, owner), oB = __shfl_sync(FULL, B, owner), oC = __shfl_sync(FULL, C, owner);
+        const float otau = __shfl_sync(FULL, tr.tau, owner), oinv = __shfl_sync(FULL, inv_w, owner);
+        const int ox0 = __shfl_sync(FULL, tr.x0, owner), oy0 = __shfl_sync(FULL, tr.y0, owner);
+        const int ow = __shfl_sync(FULL, w, owner);
+        const unsigned int oexcl = __shfl_sync(FULL, excl, owner);
+        if (q < total) {
+            const int local = (int)(q - oexcl);
+            int row = (int)(((float)local + 0.5f) * oinv);       // local / ow for the small integers involved
+            row -= (row * ow > local) ? 1 : 0;
+            row += ((row + 1) * ow <= local) ? 1 : 0;
+            const int tx = ox0 + (local - row * ow), ty = oy0 + row;
+            if (tile_hit_ni(opx, opy, oA, oB, oC, otau, tx, ty)) f(owner, ty * gx + tx);
+        }
+    }
+}
+
 __device__ __forceinline__ void load16(const float *__restrict__ p, float *o) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) o[i] = __ldg(p + i);
@@ -87,7 +136,12 @@ k_preprocess_api(CamConst cc, int P, const float *__restrict__ means3D, const fl
                  uint8_t *__restrict__ clamped, int *__restrict__ radii, unsigned int *__restrict__ tile_count,
                  unsigned long long *__restrict__ counters, unsigned int flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     unsigned int rect_tiles = 0;
+    Splat sp;
+    sp.px = sp.py = sp.conx = sp.cony = sp.conz = 0.f; sp.radius = 0;
+    float opacity = 0.f;
+    bool vis = false;
     if (i < P) {
         float V[16], PM[16], cp[3] = {0.f, 0.f, 0.f};
         load16(viewmatrix, V);
@@ -95,26 +149,24 @@ k_preprocess_api(CamConst cc, int P, const float *__restrict__ means3D, const fl
         if (shs) { cp[0] = __ldg(campos); cp[1] = __ldg(campos + 1); cp[2] = __ldg(campos + 2); }
         const size_t n = (size_t)i;
         const float mean[3] = {means3D[3 * n], means3D[3 * n + 1], means3D[3 * n + 2]};
-        Splat sp;
         float rgb[3];
         uint8_t cl = 0;
-        int radius = 0;
-        if (api_forward_one(cc, V, PM, cp, mean, colors_precomp ? colors_precomp + 3 * n : nullptr,
-                            shs ? shs + n * cc.n_coeffs * 3 : nullptr, scales ? scales + 3 * n : nullptr,
-                            rotations ? rotations + 4 * n : nullptr, cov3D_precomp ? cov3D_precomp + 6 * n : nullptr, sp,
-                            rgb, cl)) {
-            radius = sp.radius;
-            const float opacity = opacities[i];
+        vis = api_forward_one(cc, V, PM, cp, mean, colors_precomp ? colors_precomp + 3 * n : nullptr,
+                              shs ? shs + n * cc.n_coeffs * 3 : nullptr, scales ? scales + 3 * n : nullptr,
+                              rotations ? rotations + 4 * n : nullptr, cov3D_precomp ? cov3D_precomp + 6 * n : nullptr, sp,
+                              rgb, cl);
+        if (vis) {
+            opacity = opacities[i];
             rect_tiles = (unsigned int)((sp.rmaxx - sp.rminx) * (sp.rmaxy - sp.rminy));
-            const int tiles = for_each_tile(cc, sp.px, sp.py, sp.conx, sp.cony, sp.conz, opacity, sp.radius,
-                                            (flags & 2u) != 0, [&](int t) { atomicAdd(&tile_count[t], 1u); });
-            store_record(records, i, sp, opacity, rgb[0], rgb[1], rgb[2], tiles);
+            store_record(records, i, sp, opacity, rgb[0], rgb[1], rgb[2], 1);
         } else {
             store_empty_record(records, i);
         }
         clamped[i] = cl;
-        radii[i] = radius;
+        radii[i] = vis ? sp.radius : 0;
     }
+    warp_for_each_tile(cc.gx, cc.gy, vis, sp.px, sp.py, sp.conx, sp.cony, sp.conz, opacity, sp.radius, (flags & 2u) != 0,
+                       lane, [&](int, int t) { atomicAdd(&tile_count[t], 1u); });
     block_add_u64(&counters[CNT_RECT], rect_tiles);
 }
 
@@ -138,7 +190,12 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
     const int base = blockIdx.x * blockDim.x;
     const bool staged = (flags & 1u) == 0 && (reinterpret_cast<uintptr_t>(f_rest) & 15u) == 0;
     if (staged) stage_rows_tma<45>(s_rest, f_rest, base, min((int)blockDim.x, P - base), &s_bar, counters + CNT_ERR);
+    const int lane = threadIdx.x & 31;
     unsigned int rect_tiles = 0;
+    Splat sp;
+    sp.px = sp.py = sp.conx = sp.cony = sp.conz = 0.f; sp.radius = 0;
+    float opacity = 0.f;
+    bool vis = false;
     if (i < P) {
         float V[16], PM[16], Rt[12], cp[3];
         load16(viewmatrix, V);
@@ -151,23 +208,21 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
         const float sc[3] = {scaling_raw[3 * n], scaling_raw[3 * n + 1], scaling_raw[3 * n + 2]};
         const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
         const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-        Splat sp;
-        float rgb[3], opacity = 0.f;
+        float rgb[3];
         uint8_t cl = 0;
-        int radius = 0;
         const float *rest = staged ? s_rest + 45 * threadIdx.x : f_rest + 45 * n;
-        if (fused_forward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, rest, opacity_raw[i], sc, q, sp, opacity, rgb, cl)) {
-            radius = sp.radius;
+        vis = fused_forward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, rest, opacity_raw[i], sc, q, sp, opacity, rgb, cl);
+        if (vis) {
             rect_tiles = (unsigned int)((sp.rmaxx - sp.rminx) * (sp.rmaxy - sp.rminy));
-            const int tiles = for_each_tile(cc, sp.px, sp.py, sp.conx, sp.cony, sp.conz, opacity, sp.radius,
-                                            (flags & 2u) != 0, [&](int t) { atomicAdd(&tile_count[t], 1u); });
-            store_record(records, i, sp, opacity, rgb[0], rgb[1], rgb[2], tiles);
+            store_record(records, i, sp, opacity, rgb[0], rgb[1], rgb[2], 1);
         } else {
             store_empty_record(records, i);
         }
         clamped[i] = cl;
-        radii[i] = radius;
+        radii[i] = vis ? sp.radius : 0;
     }
+    warp_for_each_tile(cc.gx, cc.gy, vis, sp.px, sp.py, sp.conx, sp.cony, sp.conz, opacity, sp.radius, (flags & 2u) != 0,
+                       lane, [&](int, int t) { atomicAdd(&tile_count[t], 1u); });
     block_add_u64(&counters[CNT_RECT], rect_tiles);
 }
 
@@ -223,16 +278,24 @@ __global__ void __launch_bounds__(CTA)
 k_scatter(CamConst cc, int P, const float4 *__restrict__ records, const unsigned int *__restrict__ tile_offset,
           unsigned int *__restrict__ cursor, unsigned long long *__restrict__ keys, unsigned int flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const float4 q2 = records[(size_t)i * 3 + 2];
-    if (__float_as_int(q2.w) <= 0) return;
-    const float4 q0 = records[(size_t)i * 3 + 0];
-    const float4 q1 = records[(size_t)i * 3 + 1];
-    const unsigned long long key_hi = ((unsigned long long)__float_as_uint(q2.y)) << 32;
-    for_each_tile(cc, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_int(q2.z), (flags & 2u) != 0, [&](int t) {
-        const unsigned int slot = atomicAdd(&cursor[t], 1u);
-        keys[(size_t)tile_offset[t] + slot] = key_hi | (unsigned int)i;
-    });
+    const int lane = threadIdx.x & 31;
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
+    if (i < P) {
+        q2 = records[(size_t)i * 3 + 2];
+        if (__float_as_int(q2.z) > 0) { q0 = records[(size_t)i * 3 + 0]; q1 = records[(size_t)i * 3 + 1]; }
+    }
+    const bool vis = __float_as_int(q2.z) > 0;
+    __shared__ unsigned int s_depth[CTA];                 // depth keys of the CTA's splats, read by other lanes
+    s_depth[threadIdx.x] = __float_as_uint(q2.y);
+    __syncwarp();
+    const unsigned int warp_first = (unsigned int)(i - lane);
+    warp_for_each_tile(cc.gx, cc.gy, vis, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, __float_as_int(q2.z), (flags & 2u) != 0, lane,
+                       [&](int owner, int t) {
+                           // called by an arbitrary lane: fetch nothing else from the owner but its depth key
+                           const unsigned int slot = atomicAdd(&cursor[t], 1u);
+                           keys[(size_t)tile_offset[t] + slot] =
+                               ((unsigned long long)s_depth[(threadIdx.x & ~31) + owner] << 32) | (warp_first + owner);
+                       });
 }
 
 // ---- K4+K5: per-tile sort by (depth bits, Gaussian id) and gather of the splat records -------------
