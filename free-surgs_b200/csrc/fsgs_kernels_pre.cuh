@@ -301,11 +301,24 @@ k_scatter(CamConst cc, int P, const float4 *__restrict__ records, const unsigned
 // ---- K4+K5: per-tile sort by (depth bits, Gaussian id) and gather of the splat records -------------
 // A data-independent compare-exchange network whose comparators all point the same way, so a list
 // of arbitrary length n behaves as if padded with +inf to the next power of two.
-template <typename KeyPtr>
-__device__ __forceinline__ void tile_sort_ce(KeyPtr a, int lo, int hi, int n) {
+// Key storage accessors: the shared-memory one names the dynamic shared array directly, so the
+// compiler emits LDS/STS (a plain pointer shared between the two instantiations would force generic
+// loads with run-time address-space resolution -- ncu showed 47 instructions per compare-exchange).
+extern __shared__ __align__(16) unsigned long long fsgs_sort_smem[];
+struct SmemKeys {
+    __device__ __forceinline__ unsigned long long ld(int i) const { return fsgs_sort_smem[i]; }
+    __device__ __forceinline__ void st(int i, unsigned long long v) const { fsgs_sort_smem[i] = v; }
+};
+struct GmemKeys {
+    unsigned long long *p;
+    __device__ __forceinline__ unsigned long long ld(int i) const { return p[i]; }
+    __device__ __forceinline__ void st(int i, unsigned long long v) const { p[i] = v; }
+};
+template <typename Keys>
+__device__ __forceinline__ void tile_sort_ce(const Keys &a, int lo, int hi, int n) {
     if (hi < n) {
-        const unsigned long long x = a[lo], y = a[hi];
-        if (x > y) { a[lo] = y; a[hi] = x; }
+        const unsigned long long x = a.ld(lo), y = a.ld(hi);
+        if (x > y) { a.st(lo, y); a.st(hi, x); }
     }
 }
 // Pair p = tid + 256*i: the 32 pairs a warp handles per i cover 64 contiguous elements, so every
@@ -315,23 +328,22 @@ __device__ __forceinline__ void tile_sort_sync(int this_block, int next_block) {
     if (this_block > 64 || next_block > 64) __syncthreads();
     else __syncwarp();
 }
-template <typename KeyPtr>
-__device__ __forceinline__ void tile_sort_network(KeyPtr a, int n) {
+template <typename Keys>
+__device__ __forceinline__ void tile_sort_network(const Keys &a, int n) {
     int lgN = 0;
     while ((1 << lgN) < n) ++lgN;
     const int half = (1 << lgN) >> 1;
     for (int m = 1; m <= lgN; ++m) {
         const int k = 1 << m, hk = k >> 1;
-        for (int p = threadIdx.x; p < half; p += blockDim.x) {          // "flip": i <-> block_end - i
+        for (int p = threadIdx.x; p < half; p += CTA) {                  // "flip": i <-> block_end - i
             const int blk = p >> (m - 1), r = p & (hk - 1);
             tile_sort_ce(a, (blk << m) + r, (blk << m) + (k - 1 - r), n);
         }
         tile_sort_sync(k, m >= 2 ? (k >> 1) : 4);
         for (int s = m - 2; s >= 0; --s) {                                // half-cleaners, distance j = 2^s
             const int j = 1 << s;
-            for (int p = threadIdx.x; p < half; p += blockDim.x) {
-                const int blk = p >> s, r = p & (j - 1);
-                const int lo = (blk << (s + 1)) + r;
+            for (int p = threadIdx.x; p < half; p += CTA) {
+                const int lo = ((p >> s) << (s + 1)) + (p & (j - 1));
                 tile_sort_ce(a, lo, lo + j, n);
             }
             tile_sort_sync(2 * j, s > 0 ? j : 2 * k);
@@ -359,7 +371,7 @@ __device__ __forceinline__ void emit_sorted_record(const float4 *__restrict__ re
 __global__ void __launch_bounds__(CTA)
 k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long long *__restrict__ keys,
             const float4 *__restrict__ records, float4 *__restrict__ sorted_rec, unsigned int flags) {
-    extern __shared__ __align__(16) unsigned long long s_keys[];
+    unsigned long long *s_keys = fsgs_sort_smem;
     const unsigned int start = tile_offset[blockIdx.x];
     const int n = (int)(tile_offset[blockIdx.x + 1] - start);
     if (n == 0) return;
@@ -369,7 +381,7 @@ k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long 
     if (n <= SORT_SMEM_KEYS) {
         for (int p = threadIdx.x; p < n; p += blockDim.x) s_keys[p] = g[p];
         __syncthreads();
-        if (n > 1) tile_sort_network(s_keys, n);
+        if (n > 1) tile_sort_network(SmemKeys{}, n);
         for (int p = threadIdx.x; p < n; p += blockDim.x) {
             const unsigned long long k = s_keys[p];
             g[p] = k;
@@ -377,7 +389,7 @@ k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long 
         }
     } else {
         // rare: list longer than the shared-memory window -> same network in global memory (L2)
-        tile_sort_network(g, n);
+        tile_sort_network(GmemKeys{g}, n);
         for (int p = threadIdx.x; p < n; p += blockDim.x)
             emit_sorted_record(records, (unsigned int)g[p], sorted_rec + ((size_t)start + p) * 3, tile_x0, tile_y0, no_cull);
     }
