@@ -118,6 +118,18 @@ def test_fused_render_small_vs_autograd_oracle(gs_grad, cam_grad, sh_deg, which)
     _compare_fused(sc, *got, *ref, gs_grad, cam_grad)
 
 
+@pytest.mark.parametrize("P", [1203, 257, 5])
+def test_fused_render_ragged_gaussian_counts(P):
+    """Gaussian counts that are not multiples of 4 / 32 / 256: the bulk-TMA staging of the SH rows takes its
+    plain-load remainder path, the flat gradient buffer carves sub-tensors at odd offsets, tail warps and a
+    tail CTA are partially filled."""
+    sc = make_scene(P, 120, 88, size_mult=2.0, seed=11)
+    G6 = torch.randn(6, sc.height, sc.width, generator=torch.Generator().manual_seed(2))
+    *ref, G6m = _oracle_fused(sc, G6, True, True, 3, "py")
+    got = _run_fused(sc, G6m, True, True, 3, "fused")
+    _compare_fused(sc, *got, *ref, True, True)
+
+
 @pytest.mark.parametrize("mode,sh_deg", [("sh", 3), ("sh", 1), ("precomp", 0), ("cov", 0)])
 def test_api_rasterizer_small_vs_autograd_oracle(mode, sh_deg):
     _, _, rasterizer, _ = _gpu_modules()

@@ -95,3 +95,59 @@ def test_mapping_step_reduces_the_render_loss():
         l0 = loss.item() if l0 is None else l0
         l1 = loss.item()
     assert l1 < 0.3 * l0, (l0, l1)
+
+
+def test_concurrent_threads_and_side_stream_give_identical_frames():
+    """The reference calls the rasteriser from the training thread AND from the viewer thread
+    (train.py:124-152); the library keeps no global mutable state besides the scratch pool (locked,
+    stream-keyed).  Two Python threads rendering concurrently, and a render on a non-default stream,
+    must reproduce the serial result bit for bit."""
+    import threading
+    render, model, sc, poses, pc = _setup(P=15000, W=256, H=192)
+    with torch.no_grad():
+        ref = render.render(poses, 0, pc, gs_grad=False, cam_grad=False)
+        ref_planes = torch.cat([ref["render"], ref["render_dep"][None]]).clone()
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            torch.cuda.set_device(0)
+            outs = []
+            for _ in range(6):
+                with torch.no_grad():
+                    o = render.render(poses, 0, pc, gs_grad=False, cam_grad=False)
+                outs.append(torch.cat([o["render"], o["render_dep"][None]]).clone())
+            results[tid] = outs
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+    for outs in results.values():
+        for o in outs:
+            assert torch.equal(o, ref_planes)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.no_grad():
+        o = render.render(poses, 0, pc, gs_grad=False, cam_grad=False)
+        side_planes = torch.cat([o["render"], o["render_dep"][None]]).clone()
+    side.synchronize()
+    assert torch.equal(side_planes, ref_planes)
+    # training step on the side stream: gradients equal the default-stream ones up to atomics order
+    G = torch.randn(3, 192, 256, generator=torch.Generator().manual_seed(9)).to(DEV)
+    grads = {}
+    for name, stream in (("default", torch.cuda.current_stream()), ("side", side)):
+        pc.zero_grad()
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            out = render.render(poses, 0, pc, gs_grad=True, cam_grad=True)
+            (out["render"] * G).sum().backward()
+        stream.synchronize()
+        grads[name] = {k: v.grad.detach().clone() for k, v in pc.params.items()}
+    for k in grads["default"]:
+        assert rel_err(grads["side"][k], grads["default"][k]) < 1e-5, k
