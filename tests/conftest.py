@@ -18,6 +18,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """Build the native pieces when a fresh checkout has not been through ``__graft_entry__.build()`` yet
+    (nvcc cross-compiles sm_100a without a GPU).  On the GPU box the prebuilt in-tree files are used."""
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, "free-surgs_b200", "fsgs_b200", "libfsgs_raster.so")
+    if not os.path.exists(lib) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "free-surgs_b200", "csrc")], check=True,
+                       stdout=subprocess.DEVNULL)
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_build", "liboracle_f64.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
