@@ -19,6 +19,16 @@
 
 #include "fsgs_device.cuh"
 
+// Launch bounds of the two compositors.  A/B-tested on B200 (round 1): forcing more resident CTAs
+// (-DFSGS_FWD_LB="CTA,6", -DFSGS_BWD_LB="CTA,5") spills and is slower; forcing fewer ("CTA,1") lets
+// ptxas use more registers and loses occupancy.  The plain bound (48 / 62-63 registers) is the best.
+#ifndef FSGS_FWD_LB
+#define FSGS_FWD_LB CTA
+#endif
+#ifndef FSGS_BWD_LB
+#define FSGS_BWD_LB CTA
+#endif
+
 namespace fsgs {
 
 struct TilePix {
@@ -62,7 +72,7 @@ __device__ __forceinline__ int compact_entries(const float4 *sb, int limit, unsi
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(CTA)
+__global__ void __launch_bounds__(FSGS_FWD_LB)
 k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const float4 *__restrict__ sorted_rec,
                 const float *__restrict__ bg, float *__restrict__ out_planes, float *__restrict__ out_depth,
                 float *__restrict__ final_T, unsigned int *__restrict__ n_contrib, unsigned int flags,
@@ -163,7 +173,7 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 // (bwd_finalize) and flushes it to the per-Gaussian accumulator with three vector atomics
 // (red.global.add.v4.f32).
 template <bool FUSED>
-__global__ void __launch_bounds__(CTA)
+__global__ void __launch_bounds__(FSGS_BWD_LB)
 k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
                 const unsigned long long *__restrict__ keys, const float4 *__restrict__ sorted_rec,
                 const float *__restrict__ bg, const float *__restrict__ final_T,

@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfsgs_raster.so")
+LIB_PATH = os.environ.get("FSGS_RASTER_LIB") or os.path.join(_HERE, "libfsgs_raster.so")   # override: A/B builds
 CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
 FLAG_NO_TMA = 1
