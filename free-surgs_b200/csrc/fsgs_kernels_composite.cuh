@@ -165,7 +165,7 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
     }
 }
 
-// ---- backward -----------------------------------------------------------------------------------
+// ---- backward, first formulation (kept for A/B: FSGS_FLAG_BWD_SHUFFLE) ---------------------------
 // Back-to-front replay over the first max(n_contrib) entries of the tile list.  Each contributing
 // (pixel, Gaussian) pair produces 12 moments (bwd_pair2); per (warp, entry) the 32 lanes' moments
 // are combined with a shuffle reduce-scatter and added to a per-batch shared-memory accumulator;
@@ -174,7 +174,7 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 // (red.global.add.v4.f32).
 template <bool FUSED>
 __global__ void __launch_bounds__(FSGS_BWD_LB)
-k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
+k_composite_bwd_shfl(CamConst cc, const unsigned int *__restrict__ tile_offset,
                 const unsigned long long *__restrict__ keys, const float4 *__restrict__ sorted_rec,
                 const float *__restrict__ bg, const float *__restrict__ final_T,
                 const unsigned int *__restrict__ n_contrib, const float *__restrict__ dL_dplanes,
@@ -317,6 +317,299 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
                 float o[12];
                 bwd_finalize(m, r0.z, r0.w, r1.x, r1.y, kx, ky, FUSED, o);
                 float4 *dst = reinterpret_cast<float4 *>(grad_acc + (size_t)s_id[buf][threadIdx.x] * ACC_F);
+                atomicAdd(dst, make_float4(o[0], o[1], o[2], o[3]));
+                atomicAdd(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
+                atomicAdd(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                row[0] = z4; row[1] = z4; row[2] = z4;
+            }
+        }
+    }
+}
+
+// ---- backward, transposed two-phase formulation (default) ---------------------------------------
+// The shuffle formulation above spends ~50 of its ~150 instructions per (warp, entry) visit on the
+// 32-lane reduce-scatter of the 12 moments.  Here the reduction is replaced by a change of thread
+// layout through shared memory:
+//
+//   phase A (lane = pixel of the warp's 8x4 block, as in the forward): for each relevant entry,
+//     evaluate alpha, advance the pixel's replay state and write the three scalars the moments are
+//     linear in -- q = G*o*dL/dalpha, w = alpha*T, q_rgb -- to s_pair[component][slot][pixel].
+//     Non-contributing lanes go through the same arithmetic with alpha = G*o = 0 (an exact no-op on
+//     the state, see bwd_pair_weights), so the phase is branch-free.
+//   phase B (every PCHUNK = 8 entries; lane = (slot, pixel row)): each lane sums ITS entry's moments
+//     over the 8 pixels of ITS row in registers -- dy is constant along the row, so only
+//     S0, Sx, Sxx (+ the RGB-only pair and the colour sums) are accumulated and Sy, Sxy, Syy follow
+//     from dy -- then a 2-step reduce-scatter over the 4 rows (9 shuffles per 8 entries instead of
+//     13 per entry) and three shared-memory adds per lane into the per-batch accumulator.
+//
+// Shared memory (dynamic, 54.3 KB -> 4 CTAs/SM): records 2 x 128 x 48 B (bulk-TMA double buffer),
+// accumulator 128 x 48 B, s_pair 8 warps x 3 x 8 x 32 floats (pixel index XOR-swizzled by the slot's
+// low bit so that both the phase-A scalar stores and the phase-B 128-bit row loads are bank-conflict
+// free), per-pixel upstream gradients 8 warps x 2 x 4 x 9 float4 (row stride 9 for the same reason).
+constexpr int BWD_BATCH = 128;
+constexpr int PCHUNK = 8;
+constexpr int PAIR_COMP = 3;
+constexpr int NWARP = CTA / 32;
+constexpr int SG_ROW = 9;   // float4 per pixel row of s_g (8 used)
+
+struct BwdSmem {
+    float4 rec[2][BWD_BATCH * REC_F4];
+    float acc[BWD_BATCH * ACC_F];
+    float pair[NWARP][PAIR_COMP][PCHUNK][32];
+    float4 g[NWARP][2][4 * SG_ROW];
+    unsigned int id[2][BWD_BATCH];
+    uint64_t full[2];
+    unsigned int maxlast;
+    unsigned char list[NWARP][BWD_BATCH];
+    unsigned char slot_j[NWARP][PCHUNK];
+};
+
+// Phase B for the first `nslots` slots of this warp's chunk.  All 32 lanes call it.
+template <bool FUSED, int LEVEL>
+__device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int warp, int lane, int nslots, float bx,
+                                            float by) {
+    const int e = lane >> 2, row = lane & 3;
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = 0.f;
+    int j = 0;
+    if (e < nslots) {
+        j = sm.slot_j[warp][e];
+        const float4 q0 = sb[j * 3];
+        const float dx0 = q0.x - bx, dy = q0.y - (by + (float)row);
+        float S0 = 0.f, Sx = 0.f, Sxx = 0.f, R0 = 0.f, Rx = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, cz = 0.f, cz2 = 0.f;
+        const int sw = (e & 1);   // swizzle of the 16-byte chunk index
+        const float4 *pq = reinterpret_cast<const float4 *>(&sm.pair[warp][0][e][0]);
+        const float4 *pw = reinterpret_cast<const float4 *>(&sm.pair[warp][1][e][0]);
+        const float4 *pr = reinterpret_cast<const float4 *>(&sm.pair[warp][2][e][0]);
+        const float4 *pg = &sm.g[warp][0][row * SG_ROW];
+        const float4 *pg2 = &sm.g[warp][1][row * SG_ROW];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = (row * 2 + h) ^ sw;
+            const float4 qv = pq[c], wv = pw[c];
+            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FUSED && LEVEL >= 1) rv = pr[c];
+            const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, wa[4] = {wv.x, wv.y, wv.z, wv.w},
+                        ra[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = h * 4 + k;
+                const float dx = dx0 - (float)i;
+                const float4 g4 = pg[i];
+                const float qx = qa[k] * dx;
+                S0 += qa[k]; Sx += qx; Sxx = fmaf(qx, dx, Sxx);
+                if (FUSED && LEVEL >= 1) { R0 += ra[k]; Rx = fmaf(ra[k], dx, Rx); }
+                cr = fmaf(wa[k], g4.x, cr); cg = fmaf(wa[k], g4.y, cg); cb = fmaf(wa[k], g4.z, cb);
+                if (LEVEL >= 1) cz = fmaf(wa[k], g4.w, cz);
+                if (FUSED && LEVEL >= 2) cz2 = fmaf(wa[k], pg2[i].y, cz2);
+            }
+        }
+        if (FUSED && LEVEL == 0) { R0 = S0; Rx = Sx; }   // no depth-side gradient: q_rgb == q
+        v[0] = Sx; v[1] = dy * S0; v[2] = Sxx; v[3] = dy * Sx; v[4] = dy * dy * S0; v[5] = S0;
+        v[6] = cr; v[7] = cg; v[8] = cb;
+        v[9] = cz;
+        if (FUSED && LEVEL >= 2) v[9] = fmaf(2.f * sb[j * 3 + 2].y, cz2, cz);
+        if (FUSED) { v[10] = Rx; v[11] = dy * R0; }
+    }
+    // reduce-scatter over the 4 pixel rows (lane bits 1, 0): 12 -> 6 -> 3 values per lane
+    {
+        const bool up = (lane & 2) != 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const float keep = up ? v[i + 6] : v[i], send = up ? v[i] : v[i + 6];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 2);
+        }
+    }
+    {
+        const bool up = (lane & 1) != 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float keep = up ? v[i + 3] : v[i], send = up ? v[i] : v[i + 3];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 1);
+        }
+    }
+    if (e < nslots) {
+        float *dst = &sm.acc[j * ACC_F + ((lane >> 1) & 1) * 6 + (lane & 1) * 3];
+        if (v[0] != 0.f) atomicAdd(dst, v[0]);
+        if (v[1] != 0.f) atomicAdd(dst + 1, v[1]);
+        if (v[2] != 0.f) atomicAdd(dst + 2, v[2]);
+    }
+}
+
+// One staged batch, back to front, for one warp (phase A + embedded phase B).
+template <bool FUSED, int LEVEL>
+__device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int warp, int lane, int nrel, int kbase,
+                                          int last, float pxf, float pyf, float bx, float by, const float *g,
+                                          float T_final, float bgdot_rgb, float bgdot_dep, BwdPixel &ps) {
+    int slot = 0;
+    for (int i = nrel - 1; i >= 0; --i) {
+        const int j = sm.list[warp][i];
+        const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
+        const float dx = q0.x - pxf, dy = q0.y - pyf;
+        const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
+        const float G = fast_exp2(p2);
+        const float alpha = fminf(ALPHA_MAX, q1.y * G);
+        const bool valid = (kbase + j < last) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
+        if (!__any_sync(FULL, valid)) continue;
+        const float4 q2 = sb[j * 3 + 2];
+        float q, w, q_rgb;
+        bwd_pair_weights<FUSED, LEVEL>(ps, valid ? G * q1.y : 0.f, valid ? alpha : 0.f, q1.z, q1.w, q2.x, q2.y, g,
+                                       T_final, bgdot_rgb, bgdot_dep, q, w, q_rgb);
+        const int px = lane ^ ((slot & 1) << 2);
+        sm.pair[warp][0][slot][px] = q;
+        sm.pair[warp][1][slot][px] = w;
+        if (FUSED && LEVEL >= 1) sm.pair[warp][2][slot][px] = q_rgb;
+        sm.slot_j[warp][slot] = (unsigned char)j;
+        if (++slot == PCHUNK) {
+            __syncwarp();
+            bwd_phase_b<FUSED, LEVEL>(sm, sb, warp, lane, PCHUNK, bx, by);
+            __syncwarp();
+            slot = 0;
+        }
+    }
+    if (slot) {
+        __syncwarp();
+        bwd_phase_b<FUSED, LEVEL>(sm, sb, warp, lane, slot, bx, by);
+        __syncwarp();
+    }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(FSGS_BWD_LB)
+k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
+                const unsigned long long *__restrict__ keys, const float4 *__restrict__ sorted_rec,
+                const float *__restrict__ bg, const float *__restrict__ final_T,
+                const unsigned int *__restrict__ n_contrib, const float *__restrict__ dL_dplanes,
+                const float *__restrict__ dL_ddepth, float *__restrict__ grad_acc, unsigned int flags,
+                unsigned long long *__restrict__ err) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BwdSmem &sm = *reinterpret_cast<BwdSmem *>(smem_raw);
+    const int tile = blockIdx.x;
+    const unsigned int start = tile_offset[tile];
+    const int n = (int)(tile_offset[tile + 1] - start);
+    if (n == 0) return;
+    const bool use_tma = (flags & 1u) == 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int warp_bit = 1u << warp;
+    const TilePix pix = tile_pixel(cc, tile);
+    const float pxf = (float)pix.px, pyf = (float)pix.py;
+    const float bx = (float)(pix.px - (lane & 7)), by = (float)(pix.py - (lane >> 3));   // block corner
+    const size_t HW = (size_t)cc.W * cc.H, p = (size_t)pix.py * cc.W + pix.px;
+
+    if (threadIdx.x == 0) {
+        sm.maxlast = 0;
+        if (use_tma) {
+            mbar_init(&sm.full[0], 1);
+            mbar_init(&sm.full[1], 1);
+            mbar_fence_init();
+        }
+    }
+    for (int q = threadIdx.x; q < BWD_BATCH * ACC_F; q += CTA) sm.acc[q] = 0.f;
+    __syncthreads();
+
+    const int last = pix.inside ? (int)n_contrib[p] : 0;
+    const int warp_last = (int)__reduce_max_sync(FULL, (unsigned int)last);   // this warp's deepest contributor
+    if (lane == 0 && warp_last) atomicMax(&sm.maxlast, (unsigned int)warp_last);
+    __syncthreads();
+    const int maxlast = min((int)sm.maxlast, n);
+    if (maxlast == 0) return;
+    const int nb = (maxlast + BWD_BATCH - 1) / BWD_BATCH;
+
+    constexpr int NG = FUSED ? 6 : 4;   // pixel gradients: planes (+ depth plane for the API flavour)
+    float g[NG];
+    const float T_final = pix.inside ? final_T[p] : 0.f;
+    float bgdot_rgb = 0.f, bgdot_dep = 0.f;
+    {
+        const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
+#pragma unroll
+        for (int ch = 0; ch < NG; ++ch) g[ch] = 0.f;
+        if (pix.inside) {
+            g[0] = dL_dplanes[p]; g[1] = dL_dplanes[HW + p]; g[2] = dL_dplanes[2 * HW + p];
+            if (FUSED) {
+                g[3] = dL_dplanes[3 * HW + p]; g[4] = dL_dplanes[4 * HW + p]; g[5] = dL_dplanes[5 * HW + p];
+                bgdot_dep = b0 * g[3] + b1 * g[4] + b2 * g[5];
+            } else {
+                g[3] = dL_ddepth ? dL_ddepth[p] : 0.f;
+            }
+            bgdot_rgb = b0 * g[0] + b1 * g[1] + b2 * g[2];
+        }
+        // phase B reads the block's upstream gradients by (row, column)
+        sm.g[warp][0][(lane >> 3) * SG_ROW + (lane & 7)] = make_float4(g[0], g[1], g[2], g[3]);
+        if (FUSED) sm.g[warp][1][(lane >> 3) * SG_ROW + (lane & 7)] = make_float4(g[4], g[5], 0.f, 0.f);
+    }
+    const float kx = 0.5f * cc.W, ky = 0.5f * cc.H;
+    // which upstream planes are non-zero anywhere in this warp's block (uniform per warp):
+    // 0 = colour only (pose tracking), 1 = + depth (mapping), 2 = + silhouette / depth^2
+    int level = __any_sync(FULL, g[3] != 0.f) ? 1 : 0;
+    if (FUSED && __any_sync(FULL, g[4] != 0.f || g[5] != 0.f)) level = 2;
+
+    BwdPixel ps;
+    ps.T = T_final; ps.last_alpha = 0.f;
+    ps.acc_r = ps.acc_g = ps.acc_b = ps.acc_d = ps.acc_s = ps.acc_d2 = 0.f;
+    ps.lc_r = ps.lc_g = ps.lc_b = ps.lc_d = 0.f;
+
+    const float4 *src = sorted_rec + (size_t)start * REC_F4;
+    const unsigned long long *kp = keys + start;
+    auto batch_cnt = [&](int k) { return min(BWD_BATCH, maxlast - k * BWD_BATCH); };
+
+    // prologue: stage the LAST batch
+    {
+        const int k = nb - 1;
+        if (use_tma && threadIdx.x == 0)
+            stage_issue_tma(sm.rec[0], src + (size_t)k * BWD_BATCH * REC_F4, batch_cnt(k), &sm.full[0]);
+        if (threadIdx.x < batch_cnt(k)) sm.id[0][threadIdx.x] = (unsigned int)kp[(size_t)k * BWD_BATCH + threadIdx.x];
+    }
+
+    for (int it = 0; it < nb; ++it) {
+        const int k = nb - 1 - it;
+        const int buf = it & 1;
+        const int cnt = batch_cnt(k);
+        __syncthreads();   // batch it-1 fully consumed and flushed; id[buf] written
+        if (it + 1 < nb) {
+            const int kn = k - 1;
+            if (use_tma && threadIdx.x == 0)
+                stage_issue_tma(sm.rec[buf ^ 1], src + (size_t)kn * BWD_BATCH * REC_F4, batch_cnt(kn), &sm.full[buf ^ 1]);
+            if (threadIdx.x < batch_cnt(kn))
+                sm.id[buf ^ 1][threadIdx.x] = (unsigned int)kp[(size_t)kn * BWD_BATCH + threadIdx.x];
+        }
+        if (use_tma) {
+            mbar_wait(&sm.full[buf], (uint32_t)(it >> 1) & 1u, err);
+        } else {
+            stage_plain(sm.rec[buf], src + (size_t)k * BWD_BATCH * REC_F4, cnt);
+            __syncthreads();
+        }
+        const float4 *sb = sm.rec[buf];
+
+        // entries of this batch that can matter to this warp: mask hit AND not deeper than the warp's
+        // deepest contributor
+        const int limit = min(cnt, warp_last - k * BWD_BATCH);
+        const int nrel = limit > 0 ? compact_entries(sb, limit, warp_bit, lane, sm.list[warp]) : 0;
+        if (nrel > 0) {
+            if (level == 0)
+                bwd_batch<FUSED, 0>(sm, sb, warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, g, T_final,
+                                    bgdot_rgb, bgdot_dep, ps);
+            else if (!FUSED || level == 1)
+                bwd_batch<FUSED, 1>(sm, sb, warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, g, T_final,
+                                    bgdot_rgb, bgdot_dep, ps);
+            else
+                bwd_batch<FUSED, 2>(sm, sb, warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, g, T_final,
+                                    bgdot_rgb, bgdot_dep, ps);
+        }
+
+        __syncthreads();   // all warps' shared-memory adds for this batch are in
+        if (threadIdx.x < cnt) {
+            float4 *row = reinterpret_cast<float4 *>(&sm.acc[threadIdx.x * ACC_F]);
+            const float4 a = row[0], b = row[1], c = row[2];
+            const bool nz = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) |
+                            (b.z != 0.f) | (b.w != 0.f) | (c.x != 0.f) | (c.y != 0.f) | (c.z != 0.f) | (c.w != 0.f);
+            if (nz) {
+                const float m[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+                const float4 r0 = sb[threadIdx.x * 3], r1 = sb[threadIdx.x * 3 + 1];
+                float o[12];
+                bwd_finalize(m, r0.z, r0.w, r1.x, r1.y, kx, ky, FUSED, o);
+                float4 *dst = reinterpret_cast<float4 *>(grad_acc + (size_t)sm.id[buf][threadIdx.x] * ACC_F);
                 atomicAdd(dst, make_float4(o[0], o[1], o[2], o[3]));
                 atomicAdd(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
                 atomicAdd(dst + 2, make_float4(o[8], o[9], o[10], o[11]));

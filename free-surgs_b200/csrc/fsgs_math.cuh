@@ -711,31 +711,37 @@ FSGS_HD unsigned block_mask(float px, float py, float A, float B, float C, float
 // LEVEL says which upstream gradients are non-zero for the whole warp (decided once per warp, so the
 // dispatch is uniform): 0 = colour planes only, 1 = + the depth plane, 2 = + silhouette / depth^2
 // (fused flavour only).  Skipped planes contribute exact zeros, so the result is unchanged.
+//
+// The pair is split in two halves so that the CUDA kernel can run them on different thread
+// layouts (fsgs_kernels_composite.cuh):
+//   bwd_pair_weights : the per-PIXEL half -- advances the pixel's replay state and returns the three
+//                      scalars everything else is linear in:  q = G*o*dL/dalpha,  w = alpha*T,
+//                      q_rgb = G*o*(dL/dalpha of the RGB planes only).
+//                      `Go` = G*opacity and `alpha` may both be passed as 0 for a pair that does not
+//                      contribute: the state then advances by an exact no-op (T*1, acc' folded with
+//                      weight 0 at the next step) and q = w = q_rgb = 0.
+//   bwd_pair_moments : the per-GAUSSIAN half -- the 12 moments of one pair from (q, w, q_rgb).
 template <bool FUSED, int LEVEL>
-FSGS_HD void bwd_pair2(BwdPixel &s, float opacity, float cr, float cg, float cb, float z, float dx, float dy,
-                       float G, float alpha, const float *g, float T_final, float bgdot_rgb, float bgdot_dep,
-                       float *v) {
+FSGS_HD void bwd_pair_weights(BwdPixel &s, float Go, float alpha, float cr, float cg, float cb, float z,
+                              const float *g, float T_final, float bgdot_rgb, float bgdot_dep, float &q, float &w,
+                              float &q_rgb) {
     const float inv = fast_rcp(1.f - alpha);
     s.T = s.T * inv;
-    const float w = alpha * s.T;
+    w = alpha * s.T;
     const float la = s.last_alpha, lb = 1.f - s.last_alpha;
     s.acc_r = la * s.lc_r + lb * s.acc_r; s.lc_r = cr;
     s.acc_g = la * s.lc_g + lb * s.acc_g; s.lc_g = cg;
     s.acc_b = la * s.lc_b + lb * s.acc_b; s.lc_b = cb;
     float da_rgb = (cr - s.acc_r) * g[0] + (cg - s.acc_g) * g[1] + (cb - s.acc_b) * g[2];
-    float dz = 0.f, da_dep = 0.f;
+    float da_dep = 0.f;
     if (LEVEL >= 1) {
-        dz = w * g[3];
         if (FUSED && LEVEL >= 2) {
             s.acc_s = la + lb * s.acc_s;
             s.acc_d2 = la * (s.lc_d * s.lc_d) + lb * s.acc_d2;
         }
         s.acc_d = la * s.lc_d + lb * s.acc_d; s.lc_d = z;
         da_dep = (z - s.acc_d) * g[3];
-        if (FUSED && LEVEL >= 2) {
-            da_dep += (1.f - s.acc_s) * g[4] + (z * z - s.acc_d2) * g[5];
-            dz += w * 2.f * z * g[5];
-        }
+        if (FUSED && LEVEL >= 2) da_dep += (1.f - s.acc_s) * g[4] + (z * z - s.acc_d2) * g[5];
     }
     const float tf = -T_final * inv;
     da_rgb = da_rgb * s.T + tf * bgdot_rgb;
@@ -744,17 +750,35 @@ FSGS_HD void bwd_pair2(BwdPixel &s, float opacity, float cr, float cg, float cb,
         if (FUSED) da_dep += tf * bgdot_dep;
     }
     s.last_alpha = alpha;
-    const float Go = G * opacity;
-    const float q = Go * (da_rgb + da_dep);
+    q = Go * (da_rgb + da_dep);
+    q_rgb = Go * da_rgb;
+}
+
+template <bool FUSED, int LEVEL>
+FSGS_HD void bwd_pair_moments(float q, float w, float q_rgb, float z, float dx, float dy, const float *g, float *v) {
     const float qx = q * dx, qy = q * dy;
     v[0] = qx; v[1] = qy; v[2] = qx * dx; v[3] = qx * dy; v[4] = qy * dy; v[5] = q;
-    v[6] = w * g[0]; v[7] = w * g[1]; v[8] = w * g[2]; v[9] = dz;
+    v[6] = w * g[0]; v[7] = w * g[1]; v[8] = w * g[2];
+    float dz = 0.f;
+    if (LEVEL >= 1) {
+        dz = w * g[3];
+        if (FUSED && LEVEL >= 2) dz += w * 2.f * z * g[5];
+    }
+    v[9] = dz;
     if (FUSED) {
-        const float q_rgb = Go * da_rgb;
         v[10] = q_rgb * dx; v[11] = q_rgb * dy;
     } else {
         v[10] = 0.f; v[11] = 0.f;
     }
+}
+
+template <bool FUSED, int LEVEL>
+FSGS_HD void bwd_pair2(BwdPixel &s, float opacity, float cr, float cg, float cb, float z, float dx, float dy,
+                       float G, float alpha, const float *g, float T_final, float bgdot_rgb, float bgdot_dep,
+                       float *v) {
+    float q, w, q_rgb;
+    bwd_pair_weights<FUSED, LEVEL>(s, G * opacity, alpha, cr, cg, cb, z, g, T_final, bgdot_rgb, bgdot_dep, q, w, q_rgb);
+    bwd_pair_moments<FUSED, LEVEL>(q, w, q_rgb, z, dx, dy, g, v);
 }
 
 // Summed moments of one (tile, Gaussian) -> accumulator row (layout in fsgs_device.cuh).

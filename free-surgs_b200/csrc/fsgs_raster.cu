@@ -183,6 +183,10 @@ int one_time_setup() {
     if (dev < 0 || dev >= 64 || !done[dev]) {
         FSGS_CUDA(cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(SORT_SMEM_KEYS * sizeof(unsigned long long))));
+        FSGS_CUDA(cudaFuncSetAttribute(k_composite_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(BwdSmem)));
+        FSGS_CUDA(cudaFuncSetAttribute(k_composite_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(BwdSmem)));
         if (dev >= 0 && dev < 64) done[dev] = true;
     }
     return FSGS_OK;
@@ -316,6 +320,7 @@ int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rend
     if (!geom || !img || !binning || !dL_dout_color || !grad_scratch || !means3D || !viewmatrix || !projmatrix || !bg)
         return FSGS_E_INVALID;
     if ((rc = check_arch())) return rc;
+    if ((rc = one_time_setup())) return rc;
     const GeomLayout gl = geom_layout(P);
     const ImgLayout il = img_layout(cc.W, cc.H);
     const BinLayout bl = bin_layout(num_rendered);
@@ -325,7 +330,15 @@ int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rend
     FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
     if (num_rendered > 0) {
         prof_begin(K_COMP_BWD, stream);
-        k_composite_bwd<false><<<il.tiles, CTA, 0, stream>>>(
+        if (st->flags & FSGS_FLAG_BWD_SHUFFLE)
+            k_composite_bwd_shfl<false><<<il.tiles, CTA, 0, stream>>>(
+            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
+            reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
+            bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
+            dL_dout_color, dL_dout_depth, acc, (unsigned)st->flags,
+            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
+        else
+            k_composite_bwd<false><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
             reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
@@ -443,6 +456,7 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
         !opacity_raw || !scaling_raw || !rotation_raw || !pose || !cam_center || !viewmatrix || !projmatrix || !bg)
         return FSGS_E_INVALID;
     if ((rc = check_arch())) return rc;
+    if ((rc = one_time_setup())) return rc;
     const GeomLayout gl = geom_layout(P);
     const ImgLayout il = img_layout(cc.W, cc.H);
     const BinLayout bl = bin_layout(num_rendered);
@@ -452,7 +466,15 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
     FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
     if (num_rendered > 0) {
         prof_begin(K_COMP_BWD, stream);
-        k_composite_bwd<true><<<il.tiles, CTA, 0, stream>>>(
+        if (st->flags & FSGS_FLAG_BWD_SHUFFLE)
+            k_composite_bwd_shfl<true><<<il.tiles, CTA, 0, stream>>>(
+            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
+            reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
+            bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
+            dL_dplanes, nullptr, acc, (unsigned)st->flags,
+            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
+        else
+            k_composite_bwd<true><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
             reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),

@@ -71,6 +71,7 @@ typedef struct fsgs_settings {
 
 #define FSGS_FLAG_NO_TMA 1u        /* stage tile batches with plain loads instead of bulk TMA     */
 #define FSGS_FLAG_NO_TILE_CULL 2u  /* keep every tile of the reference's 3-sigma rectangle        */
+#define FSGS_FLAG_BWD_SHUFFLE 4u   /* backward compositor: first (warp-shuffle reduce) formulation */
 
 /* ------------------------------------------------------------------------------------------
  * API-level rasteriser (one GaussianRasterizer call).

@@ -1,0 +1,100 @@
+// Microbenchmark: issue rate of scalar FFMA/FMUL/FADD/FSEL vs packed fma/mul/add.f32x2 on sm_100a.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o f32x2 f32x2.cu && ./f32x2
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define ITER 4096
+template <int MODE>
+__global__ void k(float *out, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    unsigned long long p0, p1, p2, p3, pa, pb;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(p0) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(p1) : "f"(x2), "f"(x3));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(p2) : "f"(x4), "f"(x5));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(p3) : "f"(x6), "f"(x7));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(pa) : "f"(a));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(pb) : "f"(b));
+#pragma unroll 1
+    for (int i = 0; i < ITER; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (MODE == 0) {   // 8 scalar FFMA (3-reg)
+                x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+                x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+            } else if (MODE == 1) {   // 4 packed FFMA2 = 8 FMAs
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p0) : "l"(pa), "l"(pb));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p1) : "l"(pa), "l"(pb));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p2) : "l"(pa), "l"(pb));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p3) : "l"(pa), "l"(pb));
+            } else if (MODE == 2) {   // 8 scalar FMUL
+                x0 = x0 * a; x1 = x1 * a; x2 = x2 * a; x3 = x3 * a; x4 = x4 * a; x5 = x5 * a; x6 = x6 * a; x7 = x7 * a;
+            } else if (MODE == 3) {   // 4 packed FMUL2
+                asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p0) : "l"(pa));
+                asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p1) : "l"(pa));
+                asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p2) : "l"(pa));
+                asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p3) : "l"(pa));
+            } else if (MODE == 4) {   // 8 scalar FADD
+                x0 = x0 + a; x1 = x1 + a; x2 = x2 + a; x3 = x3 + a; x4 = x4 + a; x5 = x5 + a; x6 = x6 + a; x7 = x7 + a;
+            } else if (MODE == 5) {   // 4 packed FADD2
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p0) : "l"(pa));
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p1) : "l"(pa));
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p2) : "l"(pa));
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p3) : "l"(pa));
+            } else if (MODE == 6) {   // 4 FFMA + 4 FSEL-ish (alu pipe: FMNMX)
+                x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+                x4 = fminf(x4, x0); x5 = fminf(x5, x1); x6 = fminf(x6, x2); x7 = fminf(x7, x3);
+            } else if (MODE == 7) {   // 2 FFMA2 + 4 FMNMX
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p0) : "l"(pa), "l"(pb));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p1) : "l"(pa), "l"(pb));
+                x4 = fminf(x4, a); x5 = fminf(x5, b); x6 = fminf(x6, a); x7 = fminf(x7, b);
+            } else if (MODE == 8) {   // 8 SHFL
+                x0 = __shfl_xor_sync(~0u, x0, 1); x1 = __shfl_xor_sync(~0u, x1, 2); x2 = __shfl_xor_sync(~0u, x2, 4);
+                x3 = __shfl_xor_sync(~0u, x3, 8); x4 = __shfl_xor_sync(~0u, x4, 16); x5 = __shfl_xor_sync(~0u, x5, 1);
+                x6 = __shfl_xor_sync(~0u, x6, 2); x7 = __shfl_xor_sync(~0u, x7, 4);
+            } else if (MODE == 9) {   // 4 SHFL + 4 FFMA
+                x0 = __shfl_xor_sync(~0u, x0, 1); x1 = __shfl_xor_sync(~0u, x1, 2); x2 = __shfl_xor_sync(~0u, x2, 4);
+                x3 = __shfl_xor_sync(~0u, x3, 8);
+                x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+            }
+        }
+    }
+    float y0, y1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(y0), "=f"(y1) : "l"(p0));
+    float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 + y0 + y1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(y0), "=f"(y1) : "l"(p1)); s += y0 + y1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(y0), "=f"(y1) : "l"(p2)); s += y0 + y1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(y0), "=f"(y1) : "l"(p3)); s += y0 + y1;
+    if (s == 12345.678f) out[0] = s;
+}
+
+template <int MODE>
+void run(const char *name, int ops_per_unroll) {
+    float *d; cudaMalloc(&d, 4);
+    int blocks = 148 * 8, threads = 256;
+    k<MODE><<<blocks, threads>>>(d, 1.0001f, 0.5f);
+    cudaDeviceSynchronize();
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    k<MODE><<<blocks, threads>>>(d, 1.0001f, 0.5f);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double warp_inst = (double)blocks * threads / 32 * ITER * 8.0 * ops_per_unroll;
+    // per SMSP per clock at 1.965 GHz
+    double rate = warp_inst / (ms * 1e-3) / (148.0 * 4) / 1.965e9;
+    printf("%-28s %8.3f ms  %6.3f warp-inst/clk/SMSP (assuming 1965 MHz)\n", name, ms, rate);
+    cudaFree(d);
+}
+
+int main() {
+    run<0>("8x FFMA", 8);
+    run<1>("4x FFMA2", 4);
+    run<2>("8x FMUL", 8);
+    run<3>("4x FMUL2", 4);
+    run<4>("8x FADD", 8);
+    run<5>("4x FADD2", 4);
+    run<6>("4 FFMA + 4 FMNMX", 8);
+    run<7>("2 FFMA2 + 4 FMNMX", 6);
+    run<8>("8x SHFL", 8);
+    run<9>("4 SHFL + 4 FFMA", 8);
+    return 0;
+}
