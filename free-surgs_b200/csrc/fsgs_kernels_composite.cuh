@@ -19,15 +19,21 @@
 
 #include "fsgs_device.cuh"
 
-// Launch bounds of the two compositors.  A/B-tested on B200 (round 1): forcing more resident CTAs
-// (-DFSGS_FWD_LB="CTA,6", -DFSGS_BWD_LB="CTA,5") spills and is slower; forcing fewer ("CTA,1") lets
-// ptxas use more registers and loses occupancy.  The plain bound (48 / 62-63 registers) is the best.
-#ifndef FSGS_FWD_LB
+// Launch bounds of the two compositors, A/B-tested on B200 (round 1).  Forward: the plain bound
+// (48 registers) is the best; 6 resident CTAs spill.  Backward (two-phase): 4 resident CTAs
+// (64 registers, no spills, 4 x 48 KB shared memory) beat the unconstrained 80-register build
+// (0.657 vs 0.679 ms at config 2).
+// (-DFSGS_FWD_MINB=n / -DFSGS_BWD_MINB=n set the min-resident-CTAs operand for A/B builds; nvcc splits
+// commas inside -D values, hence the two-macro form.)
+#ifdef FSGS_FWD_MINB
+#define FSGS_FWD_LB CTA, FSGS_FWD_MINB
+#else
 #define FSGS_FWD_LB CTA
 #endif
-#ifndef FSGS_BWD_LB
-#define FSGS_BWD_LB CTA
+#ifndef FSGS_BWD_MINB
+#define FSGS_BWD_MINB 4
 #endif
+#define FSGS_BWD_LB CTA, FSGS_BWD_MINB
 
 namespace fsgs {
 
@@ -336,17 +342,21 @@ k_composite_bwd_shfl(CamConst cc, const unsigned int *__restrict__ tile_offset,
 //     evaluate alpha, advance the pixel's replay state and write the three scalars the moments are
 //     linear in -- q = G*o*dL/dalpha, w = alpha*T, q_rgb -- to s_pair[component][slot][pixel].
 //     Non-contributing lanes go through the same arithmetic with alpha = G*o = 0 (an exact no-op on
-//     the state, see bwd_pair_weights), so the phase is branch-free.
-//   phase B (every PCHUNK = 8 entries; lane = (slot, pixel row)): each lane sums ITS entry's moments
-//     over the 8 pixels of ITS row in registers -- dy is constant along the row, so only
-//     S0, Sx, Sxx (+ the RGB-only pair and the colour sums) are accumulated and Sy, Sxy, Syy follow
-//     from dy -- then a 2-step reduce-scatter over the 4 rows (9 shuffles per 8 entries instead of
-//     13 per entry) and three shared-memory adds per lane into the per-batch accumulator.
+//     the state, see bwd_pair_weights), so the phase is branch-free.  Entries are taken in aligned
+//     chunks of PCHUNK = 8 list positions (one 64-bit load of the 8 list bytes per chunk).
+//   phase B (once per chunk; lane = (slot, pixel row)): each lane sums ITS entry's moments over the
+//     8 pixels of ITS row in registers -- dy is constant along the row, so only S0, Sx, Sxx (+ the
+//     RGB-only pair and the colour sums) are accumulated and Sy, Sxy, Syy follow from dy -- then a
+//     2-step reduce-scatter over the 4 rows (9 shuffles per 8 entries instead of 13 per entry), the
+//     moments -> gradient-row map (linear, so it can be applied to the warp's partial sums), and ONE
+//     red.global.add.v4.f32 per lane (3 lanes x 16 B = the entry's 48-byte accumulator row).
+//     There is no shared-memory accumulator: float atomics on shared memory are CAS loops
+//     (ATOMS.CAST.SPIN, ~10 wavefronts each), the L2 does them natively.
 //
-// Shared memory (dynamic, 54.3 KB -> 4 CTAs/SM): records 2 x 128 x 48 B (bulk-TMA double buffer),
-// accumulator 128 x 48 B, s_pair 8 warps x 3 x 8 x 32 floats (pixel index XOR-swizzled by the slot's
-// low bit so that both the phase-A scalar stores and the phase-B 128-bit row loads are bank-conflict
-// free), per-pixel upstream gradients 8 warps x 2 x 4 x 9 float4 (row stride 9 for the same reason).
+// Shared memory (dynamic, ~48 KB -> 4 CTAs/SM): records 2 x 128 x 48 B (bulk-TMA double buffer),
+// s_pair 8 warps x 3 x 8 x 32 floats (pixel index XOR-swizzled by the slot's low bit so that both
+// the phase-A scalar stores and the phase-B 128-bit row loads are bank-conflict free), per-pixel
+// upstream gradients 8 warps x 2 x 4 x 9 float4 (row stride 9 for the same reason).
 constexpr int BWD_BATCH = 128;
 constexpr int PCHUNK = 8;
 constexpr int PAIR_COMP = 3;
@@ -355,28 +365,33 @@ constexpr int SG_ROW = 9;   // float4 per pixel row of s_g (8 used)
 
 struct BwdSmem {
     float4 rec[2][BWD_BATCH * REC_F4];
-    float acc[BWD_BATCH * ACC_F];
     float pair[NWARP][PAIR_COMP][PCHUNK][32];
     float4 g[NWARP][2][4 * SG_ROW];
     unsigned int id[2][BWD_BATCH];
     uint64_t full[2];
+    unsigned char list[NWARP][BWD_BATCH];   // 8-byte aligned rows (read 8 entries at a time)
     unsigned int maxlast;
-    unsigned char list[NWARP][BWD_BATCH];
-    unsigned char slot_j[NWARP][PCHUNK];
 };
 
-// Phase B for the first `nslots` slots of this warp's chunk.  All 32 lanes call it.
+__device__ __forceinline__ int list_byte(uint2 packed, int s) {
+    return (int)(((s < 4 ? packed.x : packed.y) >> (8 * (s & 3))) & 0xffu);
+}
+
+// Phase B for the first `cn` slots of this warp's chunk.  All 32 lanes call it.
 template <bool FUSED, int LEVEL>
-__device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int warp, int lane, int nslots, float bx,
-                                            float by) {
+__device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, const unsigned int *ids, int warp, int lane,
+                                            int cn, uint2 packed, float bx, float by, float kx, float ky,
+                                            float *__restrict__ grad_acc) {
     const int e = lane >> 2, row = lane & 3;
+    const bool act = e < cn;
+    const int j = list_byte(packed, e);
     float v[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) v[k] = 0.f;
-    int j = 0;
-    if (e < nslots) {
-        j = sm.slot_j[warp][e];
+    float a2 = 0.f, b2 = 0.f;
+    if (act) {
         const float4 q0 = sb[j * 3];
+        a2 = q0.z; b2 = q0.w;
         const float dx0 = q0.x - bx, dy = q0.y - (by + (float)row);
         float S0 = 0.f, Sx = 0.f, Sxx = 0.f, R0 = 0.f, Rx = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, cz = 0.f, cz2 = 0.f;
         const int sw = (e & 1);   // swizzle of the 16-byte chunk index
@@ -406,14 +421,15 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int w
                 if (FUSED && LEVEL >= 2) cz2 = fmaf(wa[k], pg2[i].y, cz2);
             }
         }
-        if (FUSED && LEVEL == 0) { R0 = S0; Rx = Sx; }   // no depth-side gradient: q_rgb == q
+        if (!FUSED || LEVEL == 0) { R0 = S0; Rx = Sx; }   // no depth-side gradient (or API flavour): q_rgb == q
         v[0] = Sx; v[1] = dy * S0; v[2] = Sxx; v[3] = dy * Sx; v[4] = dy * dy * S0; v[5] = S0;
         v[6] = cr; v[7] = cg; v[8] = cb;
         v[9] = cz;
         if (FUSED && LEVEL >= 2) v[9] = fmaf(2.f * sb[j * 3 + 2].y, cz2, cz);
-        if (FUSED) { v[10] = Rx; v[11] = dy * R0; }
+        v[10] = Rx; v[11] = dy * R0;
     }
-    // reduce-scatter over the 4 pixel rows (lane bits 1, 0): 12 -> 6 -> 3 values per lane
+    // reduce-scatter over the 4 pixel rows (lane bits 1, 0): 12 -> 6 -> 3 values per lane;
+    // afterwards the lane of row r holds the warp-block sums of moments 3r .. 3r+2 in v[0..2]
     {
         const bool up = (lane & 2) != 0;
 #pragma unroll
@@ -430,48 +446,66 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int w
             v[i] = keep + __shfl_xor_sync(FULL, send, 1);
         }
     }
-    if (e < nslots) {
-        float *dst = &sm.acc[j * ACC_F + ((lane >> 1) & 1) * 6 + (lane & 1) * 3];
-        if (v[0] != 0.f) atomicAdd(dst, v[0]);
-        if (v[1] != 0.f) atomicAdd(dst + 1, v[1]);
-        if (v[2] != 0.f) atomicAdd(dst + 2, v[2]);
+    // moments -> accumulator row (bwd_finalize in fsgs_math.cuh, applied to this lane's three moments)
+    float t0 = v[0], t1 = v[1], t2 = v[2];
+    unsigned int gid = 0;
+    if (act) {
+        gid = ids[j];
+        const float2 q1 = *reinterpret_cast<const float2 *>(&sb[j * 3 + 1]);   // (c2, opacity)
+        float A, B, C;
+        unscale_conic(a2, b2, q1.x, A, B, C);
+        if (row == 0) {
+            t0 = -kx * (A * v[0] + B * v[1]); t1 = -ky * (C * v[1] + B * v[0]); t2 = -0.5f * v[2];
+        } else if (row == 1) {
+            t0 = -0.5f * v[0]; t1 = -0.5f * v[1]; t2 = v[2] / q1.y;
+        } else if (row == 3) {
+            t1 = -kx * (A * v[1] + B * v[2]); t2 = -ky * (C * v[2] + B * v[1]);
+        }
+    }
+    // regroup 4 lanes x 3 floats -> 3 lanes x float4
+    const float n0 = __shfl_down_sync(FULL, t0, 1), n1 = __shfl_down_sync(FULL, t1, 1), n2 = __shfl_down_sync(FULL, t2, 1);
+    if (act && row < 3) {
+        float4 o;
+        o.x = row == 0 ? t0 : (row == 1 ? t1 : t2);
+        o.y = row == 0 ? t1 : (row == 1 ? t2 : n0);
+        o.z = row == 0 ? t2 : (row == 1 ? n0 : n1);
+        o.w = row == 0 ? n0 : (row == 1 ? n1 : n2);
+        if ((o.x != 0.f) | (o.y != 0.f) | (o.z != 0.f) | (o.w != 0.f))
+            atomicAdd(reinterpret_cast<float4 *>(grad_acc + (size_t)gid * ACC_F) + row, o);
     }
 }
 
 // One staged batch, back to front, for one warp (phase A + embedded phase B).
 template <bool FUSED, int LEVEL>
-__device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int warp, int lane, int nrel, int kbase,
-                                          int last, float pxf, float pyf, float bx, float by, const float *g,
-                                          float T_final, float bgdot_rgb, float bgdot_dep, BwdPixel &ps) {
-    int slot = 0;
-    for (int i = nrel - 1; i >= 0; --i) {
-        const int j = sm.list[warp][i];
-        const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
-        const float dx = q0.x - pxf, dy = q0.y - pyf;
-        const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
-        const float G = fast_exp2(p2);
-        const float alpha = fminf(ALPHA_MAX, q1.y * G);
-        const bool valid = (kbase + j < last) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
-        if (!__any_sync(FULL, valid)) continue;
-        const float4 q2 = sb[j * 3 + 2];
-        float q, w, q_rgb;
-        bwd_pair_weights<FUSED, LEVEL>(ps, valid ? G * q1.y : 0.f, valid ? alpha : 0.f, q1.z, q1.w, q2.x, q2.y, g,
-                                       T_final, bgdot_rgb, bgdot_dep, q, w, q_rgb);
-        const int px = lane ^ ((slot & 1) << 2);
-        sm.pair[warp][0][slot][px] = q;
-        sm.pair[warp][1][slot][px] = w;
-        if (FUSED && LEVEL >= 1) sm.pair[warp][2][slot][px] = q_rgb;
-        sm.slot_j[warp][slot] = (unsigned char)j;
-        if (++slot == PCHUNK) {
-            __syncwarp();
-            bwd_phase_b<FUSED, LEVEL>(sm, sb, warp, lane, PCHUNK, bx, by);
-            __syncwarp();
-            slot = 0;
+__device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, const unsigned int *ids, int warp, int lane,
+                                          int nrel, int kbase, int last, float pxf, float pyf, float bx, float by,
+                                          float kx, float ky, const float *g, float T_final, float bgdot_rgb,
+                                          float bgdot_dep, BwdPixel &ps, float *__restrict__ grad_acc) {
+    for (int c0 = ((nrel - 1) / PCHUNK) * PCHUNK; c0 >= 0; c0 -= PCHUNK) {
+        const int cn = min(PCHUNK, nrel - c0);                 // this chunk: list positions c0 .. c0+cn-1
+        const uint2 packed = *reinterpret_cast<const uint2 *>(&sm.list[warp][c0]);
+#pragma unroll
+        for (int s = PCHUNK - 1; s >= 0; --s) {               // back to front
+            if (s < cn) {
+                const int j = list_byte(packed, s);
+                const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
+                const float2 q2 = *reinterpret_cast<const float2 *>(&sb[j * 3 + 2]);   // (b, depth)
+                const float dx = q0.x - pxf, dy = q0.y - pyf;
+                const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
+                const float G = fast_exp2(p2);
+                const float alpha = fminf(ALPHA_MAX, q1.y * G);
+                const bool valid = (kbase + j < last) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
+                float q, w, q_rgb;
+                bwd_pair_weights<FUSED, LEVEL>(ps, valid ? G * q1.y : 0.f, valid ? alpha : 0.f, q1.z, q1.w, q2.x, q2.y,
+                                               g, T_final, bgdot_rgb, bgdot_dep, q, w, q_rgb);
+                const int px = lane ^ ((s & 1) << 2);
+                sm.pair[warp][0][s][px] = q;
+                sm.pair[warp][1][s][px] = w;
+                if (FUSED && LEVEL >= 1) sm.pair[warp][2][s][px] = q_rgb;
+            }
         }
-    }
-    if (slot) {
         __syncwarp();
-        bwd_phase_b<FUSED, LEVEL>(sm, sb, warp, lane, slot, bx, by);
+        bwd_phase_b<FUSED, LEVEL>(sm, sb, ids, warp, lane, cn, packed, bx, by, kx, ky, grad_acc);
         __syncwarp();
     }
 }
@@ -506,7 +540,6 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
             mbar_fence_init();
         }
     }
-    for (int q = threadIdx.x; q < BWD_BATCH * ACC_F; q += CTA) sm.acc[q] = 0.f;
     __syncthreads();
 
     const int last = pix.inside ? (int)n_contrib[p] : 0;
@@ -566,7 +599,7 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
         const int k = nb - 1 - it;
         const int buf = it & 1;
         const int cnt = batch_cnt(k);
-        __syncthreads();   // batch it-1 fully consumed and flushed; id[buf] written
+        __syncthreads();   // every warp is done with batch it-1 (buffer buf^1); id[buf] and s_g written
         if (it + 1 < nb) {
             const int kn = k - 1;
             if (use_tma && threadIdx.x == 0)
@@ -588,34 +621,14 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
         const int nrel = limit > 0 ? compact_entries(sb, limit, warp_bit, lane, sm.list[warp]) : 0;
         if (nrel > 0) {
             if (level == 0)
-                bwd_batch<FUSED, 0>(sm, sb, warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, g, T_final,
-                                    bgdot_rgb, bgdot_dep, ps);
+                bwd_batch<FUSED, 0>(sm, sb, sm.id[buf], warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, kx, ky, g,
+                                    T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
             else if (!FUSED || level == 1)
-                bwd_batch<FUSED, 1>(sm, sb, warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, g, T_final,
-                                    bgdot_rgb, bgdot_dep, ps);
+                bwd_batch<FUSED, 1>(sm, sb, sm.id[buf], warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, kx, ky, g,
+                                    T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
             else
-                bwd_batch<FUSED, 2>(sm, sb, warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, g, T_final,
-                                    bgdot_rgb, bgdot_dep, ps);
-        }
-
-        __syncthreads();   // all warps' shared-memory adds for this batch are in
-        if (threadIdx.x < cnt) {
-            float4 *row = reinterpret_cast<float4 *>(&sm.acc[threadIdx.x * ACC_F]);
-            const float4 a = row[0], b = row[1], c = row[2];
-            const bool nz = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) |
-                            (b.z != 0.f) | (b.w != 0.f) | (c.x != 0.f) | (c.y != 0.f) | (c.z != 0.f) | (c.w != 0.f);
-            if (nz) {
-                const float m[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-                const float4 r0 = sb[threadIdx.x * 3], r1 = sb[threadIdx.x * 3 + 1];
-                float o[12];
-                bwd_finalize(m, r0.z, r0.w, r1.x, r1.y, kx, ky, FUSED, o);
-                float4 *dst = reinterpret_cast<float4 *>(grad_acc + (size_t)sm.id[buf][threadIdx.x] * ACC_F);
-                atomicAdd(dst, make_float4(o[0], o[1], o[2], o[3]));
-                atomicAdd(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
-                atomicAdd(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                row[0] = z4; row[1] = z4; row[2] = z4;
-            }
+                bwd_batch<FUSED, 2>(sm, sb, sm.id[buf], warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, kx, ky, g,
+                                    T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
         }
     }
 }

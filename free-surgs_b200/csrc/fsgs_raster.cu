@@ -187,6 +187,11 @@ int one_time_setup() {
                                        (int)sizeof(BwdSmem)));
         FSGS_CUDA(cudaFuncSetAttribute(k_composite_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(BwdSmem)));
+        // 4 resident CTAs x ~48 KB: ask for the large shared-memory carve-out
+        FSGS_CUDA(cudaFuncSetAttribute(k_composite_bwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
+        FSGS_CUDA(cudaFuncSetAttribute(k_composite_bwd<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
         if (dev >= 0 && dev < 64) done[dev] = true;
     }
     return FSGS_OK;
