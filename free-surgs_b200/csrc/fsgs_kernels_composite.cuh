@@ -179,7 +179,7 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 // (bwd_finalize) and flushes it to the per-Gaussian accumulator with three vector atomics
 // (red.global.add.v4.f32).
 template <bool FUSED>
-__global__ void __launch_bounds__(FSGS_BWD_LB)
+__global__ void __launch_bounds__(CTA)
 k_composite_bwd_shfl(CamConst cc, const unsigned int *__restrict__ tile_offset,
                 const unsigned long long *__restrict__ keys, const float4 *__restrict__ sorted_rec,
                 const float *__restrict__ bg, const float *__restrict__ final_T,
@@ -248,9 +248,8 @@ k_composite_bwd_shfl(CamConst cc, const unsigned int *__restrict__ tile_offset,
     if (FUSED && __any_sync(FULL, g[4] != 0.f || g[5] != 0.f)) level = 2;
 
     BwdPixel ps;
-    ps.T = T_final; ps.last_alpha = 0.f;
+    ps.T = T_final;
     ps.acc_r = ps.acc_g = ps.acc_b = ps.acc_d = ps.acc_s = ps.acc_d2 = 0.f;
-    ps.lc_r = ps.lc_g = ps.lc_b = ps.lc_d = 0.f;
 
     const float4 *src = sorted_rec + (size_t)start * REC_F4;
     const unsigned long long *kp = keys + start;
@@ -478,7 +477,7 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, const
 // One staged batch, back to front, for one warp (phase A + embedded phase B).
 template <bool FUSED, int LEVEL>
 __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, const unsigned int *ids, int warp, int lane,
-                                          int nrel, int kbase, int last, float pxf, float pyf, float bx, float by,
+                                          int nrel, int last_rel, float pxf, float pyf, float bx, float by,
                                           float kx, float ky, const float *g, float T_final, float bgdot_rgb,
                                           float bgdot_dep, BwdPixel &ps, float *__restrict__ grad_acc) {
     for (int c0 = ((nrel - 1) / PCHUNK) * PCHUNK; c0 >= 0; c0 -= PCHUNK) {
@@ -494,7 +493,7 @@ __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, const u
                 const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
                 const float G = fast_exp2(p2);
                 const float alpha = fminf(ALPHA_MAX, q1.y * G);
-                const bool valid = (kbase + j < last) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
+                const bool valid = (j < last_rel) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
                 float q, w, q_rgb;
                 bwd_pair_weights<FUSED, LEVEL>(ps, valid ? G * q1.y : 0.f, valid ? alpha : 0.f, q1.z, q1.w, q2.x, q2.y,
                                                g, T_final, bgdot_rgb, bgdot_dep, q, w, q_rgb);
@@ -579,9 +578,8 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
     if (FUSED && __any_sync(FULL, g[4] != 0.f || g[5] != 0.f)) level = 2;
 
     BwdPixel ps;
-    ps.T = T_final; ps.last_alpha = 0.f;
+    ps.T = T_final;
     ps.acc_r = ps.acc_g = ps.acc_b = ps.acc_d = ps.acc_s = ps.acc_d2 = 0.f;
-    ps.lc_r = ps.lc_g = ps.lc_b = ps.lc_d = 0.f;
 
     const float4 *src = sorted_rec + (size_t)start * REC_F4;
     const unsigned long long *kp = keys + start;
@@ -621,13 +619,13 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
         const int nrel = limit > 0 ? compact_entries(sb, limit, warp_bit, lane, sm.list[warp]) : 0;
         if (nrel > 0) {
             if (level == 0)
-                bwd_batch<FUSED, 0>(sm, sb, sm.id[buf], warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 0>(sm, sb, sm.id[buf], warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
             else if (!FUSED || level == 1)
-                bwd_batch<FUSED, 1>(sm, sb, sm.id[buf], warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 1>(sm, sb, sm.id[buf], warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
             else
-                bwd_batch<FUSED, 2>(sm, sb, sm.id[buf], warp, lane, nrel, k * BWD_BATCH, last, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 2>(sm, sb, sm.id[buf], warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
         }
     }

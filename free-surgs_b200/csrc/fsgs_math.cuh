@@ -361,67 +361,9 @@ FSGS_HD float gauss_power(float A, float B, float C, float dx, float dy) {
 
 // Per-pixel state of the back-to-front replay (K7).
 struct BwdPixel {
-    float T, last_alpha;
-    float acc_r, acc_g, acc_b, acc_d, acc_s, acc_d2;   // "accum_rec" per plane
-    float lc_r, lc_g, lc_b, lc_d;                      // colour / depth of the previously replayed entry
+    float T;
+    float acc_r, acc_g, acc_b, acc_d, acc_s, acc_d2;   // per plane: the colour seen behind the current entry
 };
-
-// One contributing (pixel, Gaussian) pair of the backward compositor.
-//   record: (x, y | conA, conB, conC | opacity | r, g, b | z);  dx,dy = centre - pixel; G = exp(power)
-//   g[]   : dL/d(plane) at this pixel -- FUSED: 6 planes (RGB | depth, silhouette, depth^2);
-//           otherwise 3 colour planes + the package's depth plane in g[3]
-//   v[12] : this pair's contribution to the Gaussian's accumulator row (layout in fsgs_device.cuh)
-template <bool FUSED>
-FSGS_HD void bwd_pair(BwdPixel &s, float conA, float conB, float conC, float opacity, float cr, float cg, float cb,
-                      float z, float dx, float dy, float G, float alpha, const float *g, float T_final,
-                      float bgdot_rgb, float bgdot_dep, float ddelx_dx, float ddely_dy, float *v) {
-    const float one_m = 1.f - alpha;
-    s.T = s.T / one_m;
-    const float w = alpha * s.T;
-    const float la = s.last_alpha, lb = 1.f - s.last_alpha;
-    s.acc_r = la * s.lc_r + lb * s.acc_r; s.lc_r = cr;
-    s.acc_g = la * s.lc_g + lb * s.acc_g; s.lc_g = cg;
-    s.acc_b = la * s.lc_b + lb * s.acc_b; s.lc_b = cb;
-    float da_rgb = (cr - s.acc_r) * g[0] + (cg - s.acc_g) * g[1] + (cb - s.acc_b) * g[2];
-    // The fused flavour's extra planes carry the colours (z, 1, z^2); their recurrences read the
-    // previously replayed entry's colour, so they are advanced before lc_d is overwritten.
-    float dz = w * g[3];
-    if (FUSED) {
-        s.acc_s = la + lb * s.acc_s;
-        s.acc_d2 = la * (s.lc_d * s.lc_d) + lb * s.acc_d2;
-    }
-    s.acc_d = la * s.lc_d + lb * s.acc_d; s.lc_d = z;
-    float da_dep = (z - s.acc_d) * g[3];
-    if (FUSED) {
-        da_dep += (1.f - s.acc_s) * g[4] + (z * z - s.acc_d2) * g[5];
-        dz += w * 2.f * z * g[5];
-    }
-    da_rgb *= s.T; da_dep *= s.T;
-    const float tf = -T_final / one_m;
-    da_rgb += tf * bgdot_rgb;
-    if (FUSED) da_dep += tf * bgdot_dep;
-    s.last_alpha = alpha;
-    const float dL_dalpha = da_rgb + da_dep;
-    const float dL_dG = opacity * dL_dalpha;
-    const float gdx = G * dx, gdy = G * dy;
-    const float dG_ddelx = -gdx * conA - gdy * conB;
-    const float dG_ddely = -gdy * conC - gdx * conB;
-    v[0] = dL_dG * dG_ddelx * ddelx_dx;
-    v[1] = dL_dG * dG_ddely * ddely_dy;
-    v[2] = -0.5f * gdx * dx * dL_dG;
-    v[3] = -0.5f * gdx * dy * dL_dG;
-    v[4] = -0.5f * gdy * dy * dL_dG;
-    v[5] = G * dL_dalpha;
-    v[6] = w * g[0]; v[7] = w * g[1]; v[8] = w * g[2];
-    v[9] = dz;
-    if (FUSED) {
-        const float dG_rgb = opacity * da_rgb;
-        v[10] = dG_rgb * dG_ddelx * ddelx_dx;
-        v[11] = dG_rgb * dG_ddely * ddely_dy;
-    } else {
-        v[10] = v[0]; v[11] = v[1];
-    }
-}
 
 // ---- whole-Gaussian forward / backward bodies (shared by the CUDA kernels and the CPU emulation) --
 // SH -> RGB (+0.5, clamp at 0, remember which channels were clamped).  coef(k, ch) returns the
@@ -725,23 +667,26 @@ template <bool FUSED, int LEVEL>
 FSGS_HD void bwd_pair_weights(BwdPixel &s, float Go, float alpha, float cr, float cg, float cb, float z,
                               const float *g, float T_final, float bgdot_rgb, float bgdot_dep, float &q, float &w,
                               float &q_rgb) {
+    // s.acc_* hold, for the entry being replayed, the colour seen BEHIND it (upstream's accum_rec after
+    // its "last_alpha * last_color + (1 - last_alpha) * accum_rec" update).  The update for the next
+    // (nearer) entry is applied here, right after use, in the algebraically identical form
+    // acc + alpha * (c - acc): one FMA per plane, and no last_alpha / last_colour state to carry.
     const float inv = fast_rcp(1.f - alpha);
     s.T = s.T * inv;
     w = alpha * s.T;
-    const float la = s.last_alpha, lb = 1.f - s.last_alpha;
-    s.acc_r = la * s.lc_r + lb * s.acc_r; s.lc_r = cr;
-    s.acc_g = la * s.lc_g + lb * s.acc_g; s.lc_g = cg;
-    s.acc_b = la * s.lc_b + lb * s.acc_b; s.lc_b = cb;
-    float da_rgb = (cr - s.acc_r) * g[0] + (cg - s.acc_g) * g[1] + (cb - s.acc_b) * g[2];
+    const float er = cr - s.acc_r, eg = cg - s.acc_g, eb = cb - s.acc_b;
+    float da_rgb = er * g[0] + eg * g[1] + eb * g[2];
+    s.acc_r = fmaf(alpha, er, s.acc_r); s.acc_g = fmaf(alpha, eg, s.acc_g); s.acc_b = fmaf(alpha, eb, s.acc_b);
     float da_dep = 0.f;
     if (LEVEL >= 1) {
+        const float ed = z - s.acc_d;
+        da_dep = ed * g[3];
+        s.acc_d = fmaf(alpha, ed, s.acc_d);
         if (FUSED && LEVEL >= 2) {
-            s.acc_s = la + lb * s.acc_s;
-            s.acc_d2 = la * (s.lc_d * s.lc_d) + lb * s.acc_d2;
+            const float es = 1.f - s.acc_s, e2 = z * z - s.acc_d2;
+            da_dep += es * g[4] + e2 * g[5];
+            s.acc_s = fmaf(alpha, es, s.acc_s); s.acc_d2 = fmaf(alpha, e2, s.acc_d2);
         }
-        s.acc_d = la * s.lc_d + lb * s.acc_d; s.lc_d = z;
-        da_dep = (z - s.acc_d) * g[3];
-        if (FUSED && LEVEL >= 2) da_dep += (1.f - s.acc_s) * g[4] + (z * z - s.acc_d2) * g[5];
     }
     const float tf = -T_final * inv;
     da_rgb = da_rgb * s.T + tf * bgdot_rgb;
@@ -749,7 +694,6 @@ FSGS_HD void bwd_pair_weights(BwdPixel &s, float Go, float alpha, float cr, floa
         da_dep = da_dep * s.T;
         if (FUSED) da_dep += tf * bgdot_dep;
     }
-    s.last_alpha = alpha;
     q = Go * (da_rgb + da_dep);
     q_rgb = Go * da_rgb;
 }
