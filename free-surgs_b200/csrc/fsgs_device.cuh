@@ -18,7 +18,8 @@ constexpr uint32_t FULL = 0xffffffffu;
 
 // ---- splat record (48 B, 16-B aligned; one per Gaussian, and one per sorted tile instance) ----
 //   q0 = (x, y, conic.x, conic.y)   q1 = (conic.z, opacity, r, g)   q2 = (b, depth, radius, tiles)
-// radius / tiles are int bit patterns.
+// radius / tiles are int bit patterns.  The sorted per-instance copy carries the conic pre-scaled for a
+// base-2 exponent, the 8x4-block reach mask in q2.z and the Gaussian id in q2.w.
 //
 // ---- gradient accumulator row (48 B) written by the backward compositor ----
 //   [0..3]  = d(mean2D.x), d(mean2D.y), d(conic.x), d(conic.y)
@@ -71,8 +72,10 @@ __host__ inline BinLayout bin_layout(int64_t R) {
     BinLayout L;
     const size_t n = R > 0 ? (size_t)R : 1;
     size_t o = 0;
-    L.keys = o; o = align_up(o + n * 8, 256);
+    // records first: the backward only needs them, so their offset must not depend on the capacity the
+    // forward allocated (which may exceed the instance count, see forward_tail)
     L.records = o; o = align_up(o + n * 48, 256);
+    L.keys = o; o = align_up(o + n * 8, 256);
     L.total = o;
     return L;
 }

@@ -82,10 +82,12 @@ __global__ void __launch_bounds__(FSGS_FWD_LB)
 k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const float4 *__restrict__ sorted_rec,
                 const float *__restrict__ bg, float *__restrict__ out_planes, float *__restrict__ out_depth,
                 float *__restrict__ final_T, unsigned int *__restrict__ n_contrib, unsigned int flags,
-                unsigned long long *__restrict__ err) {
+                unsigned long long *__restrict__ err, const unsigned long long *__restrict__ counters,
+                unsigned long long capacity) {
     __shared__ __align__(128) float4 s_rec[2][BATCH * REC_F4];
     __shared__ __align__(8) uint64_t s_full[2];
     __shared__ unsigned char s_list[CTA / 32][BATCH];
+    if (counters[CNT_R] > capacity) return;   // optimistic launch into a too-small buffer: the host relaunches
     const int tile = blockIdx.x;
     const unsigned int start = tile_offset[tile];
     const int n = (int)(tile_offset[tile + 1] - start);
@@ -180,15 +182,13 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 // (red.global.add.v4.f32).
 template <bool FUSED>
 __global__ void __launch_bounds__(CTA)
-k_composite_bwd_shfl(CamConst cc, const unsigned int *__restrict__ tile_offset,
-                const unsigned long long *__restrict__ keys, const float4 *__restrict__ sorted_rec,
+k_composite_bwd_shfl(CamConst cc, const unsigned int *__restrict__ tile_offset, const float4 *__restrict__ sorted_rec,
                 const float *__restrict__ bg, const float *__restrict__ final_T,
                 const unsigned int *__restrict__ n_contrib, const float *__restrict__ dL_dplanes,
                 const float *__restrict__ dL_ddepth, float *__restrict__ grad_acc, unsigned int flags,
                 unsigned long long *__restrict__ err) {
     __shared__ __align__(128) float4 s_rec[2][BATCH * REC_F4];
     __shared__ __align__(16) float s_acc[BATCH * ACC_F];
-    __shared__ unsigned int s_id[2][BATCH];
     __shared__ __align__(8) uint64_t s_full[2];
     __shared__ unsigned char s_list[CTA / 32][BATCH];
     __shared__ unsigned int s_maxlast;
@@ -252,26 +252,23 @@ k_composite_bwd_shfl(CamConst cc, const unsigned int *__restrict__ tile_offset,
     ps.acc_r = ps.acc_g = ps.acc_b = ps.acc_d = ps.acc_s = ps.acc_d2 = 0.f;
 
     const float4 *src = sorted_rec + (size_t)start * REC_F4;
-    const unsigned long long *kp = keys + start;
     auto batch_cnt = [&](int k) { return min(BATCH, maxlast - k * BATCH); };
 
     // prologue: stage the LAST batch
     {
         const int k = nb - 1;
         if (use_tma && threadIdx.x == 0) stage_issue_tma(s_rec[0], src + (size_t)k * BATCH * REC_F4, batch_cnt(k), &s_full[0]);
-        if (threadIdx.x < batch_cnt(k)) s_id[0][threadIdx.x] = (unsigned int)kp[(size_t)k * BATCH + threadIdx.x];
     }
 
     for (int it = 0; it < nb; ++it) {
         const int k = nb - 1 - it;
         const int buf = it & 1;
         const int cnt = batch_cnt(k);
-        __syncthreads();   // batch it-1 fully consumed and flushed; s_id[buf] written
+        __syncthreads();   // batch it-1 fully consumed and flushed
         if (it + 1 < nb) {
             const int kn = k - 1;
             if (use_tma && threadIdx.x == 0)
                 stage_issue_tma(s_rec[buf ^ 1], src + (size_t)kn * BATCH * REC_F4, batch_cnt(kn), &s_full[buf ^ 1]);
-            if (threadIdx.x < batch_cnt(kn)) s_id[buf ^ 1][threadIdx.x] = (unsigned int)kp[(size_t)kn * BATCH + threadIdx.x];
         }
         if (use_tma) {
             mbar_wait(&s_full[buf], (uint32_t)(it >> 1) & 1u, err);
@@ -321,7 +318,8 @@ k_composite_bwd_shfl(CamConst cc, const unsigned int *__restrict__ tile_offset,
                 const float4 r0 = sb[threadIdx.x * 3], r1 = sb[threadIdx.x * 3 + 1];
                 float o[12];
                 bwd_finalize(m, r0.z, r0.w, r1.x, r1.y, kx, ky, FUSED, o);
-                float4 *dst = reinterpret_cast<float4 *>(grad_acc + (size_t)s_id[buf][threadIdx.x] * ACC_F);
+                const unsigned int gid = __float_as_uint(sb[threadIdx.x * 3 + 2].w);
+                float4 *dst = reinterpret_cast<float4 *>(grad_acc + (size_t)gid * ACC_F);
                 atomicAdd(dst, make_float4(o[0], o[1], o[2], o[3]));
                 atomicAdd(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
                 atomicAdd(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
@@ -366,7 +364,6 @@ struct BwdSmem {
     float4 rec[2][BWD_BATCH * REC_F4];
     float pair[NWARP][PAIR_COMP][PCHUNK][32];
     float4 g[NWARP][2][4 * SG_ROW];
-    unsigned int id[2][BWD_BATCH];
     uint64_t full[2];
     unsigned char list[NWARP][BWD_BATCH];   // 8-byte aligned rows (read 8 entries at a time)
     unsigned int maxlast;
@@ -378,7 +375,7 @@ __device__ __forceinline__ int list_byte(uint2 packed, int s) {
 
 // Phase B for the first `cn` slots of this warp's chunk.  All 32 lanes call it.
 template <bool FUSED, int LEVEL>
-__device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, const unsigned int *ids, int warp, int lane,
+__device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int warp, int lane,
                                             int cn, uint2 packed, float bx, float by, float kx, float ky,
                                             float *__restrict__ grad_acc) {
     const int e = lane >> 2, row = lane & 3;
@@ -449,7 +446,7 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, const
     float t0 = v[0], t1 = v[1], t2 = v[2];
     unsigned int gid = 0;
     if (act) {
-        gid = ids[j];
+        gid = __float_as_uint(sb[j * 3 + 2].w);
         const float2 q1 = *reinterpret_cast<const float2 *>(&sb[j * 3 + 1]);   // (c2, opacity)
         float A, B, C;
         unscale_conic(a2, b2, q1.x, A, B, C);
@@ -476,7 +473,7 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, const
 
 // One staged batch, back to front, for one warp (phase A + embedded phase B).
 template <bool FUSED, int LEVEL>
-__device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, const unsigned int *ids, int warp, int lane,
+__device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int warp, int lane,
                                           int nrel, int last_rel, float pxf, float pyf, float bx, float by,
                                           float kx, float ky, const float *g, float T_final, float bgdot_rgb,
                                           float bgdot_dep, BwdPixel &ps, float *__restrict__ grad_acc) {
@@ -504,15 +501,14 @@ __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, const u
             }
         }
         __syncwarp();
-        bwd_phase_b<FUSED, LEVEL>(sm, sb, ids, warp, lane, cn, packed, bx, by, kx, ky, grad_acc);
+        bwd_phase_b<FUSED, LEVEL>(sm, sb, warp, lane, cn, packed, bx, by, kx, ky, grad_acc);
         __syncwarp();
     }
 }
 
 template <bool FUSED>
 __global__ void __launch_bounds__(FSGS_BWD_LB)
-k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
-                const unsigned long long *__restrict__ keys, const float4 *__restrict__ sorted_rec,
+k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const float4 *__restrict__ sorted_rec,
                 const float *__restrict__ bg, const float *__restrict__ final_T,
                 const unsigned int *__restrict__ n_contrib, const float *__restrict__ dL_dplanes,
                 const float *__restrict__ dL_ddepth, float *__restrict__ grad_acc, unsigned int flags,
@@ -582,7 +578,6 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
     ps.acc_r = ps.acc_g = ps.acc_b = ps.acc_d = ps.acc_s = ps.acc_d2 = 0.f;
 
     const float4 *src = sorted_rec + (size_t)start * REC_F4;
-    const unsigned long long *kp = keys + start;
     auto batch_cnt = [&](int k) { return min(BWD_BATCH, maxlast - k * BWD_BATCH); };
 
     // prologue: stage the LAST batch
@@ -590,20 +585,17 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
         const int k = nb - 1;
         if (use_tma && threadIdx.x == 0)
             stage_issue_tma(sm.rec[0], src + (size_t)k * BWD_BATCH * REC_F4, batch_cnt(k), &sm.full[0]);
-        if (threadIdx.x < batch_cnt(k)) sm.id[0][threadIdx.x] = (unsigned int)kp[(size_t)k * BWD_BATCH + threadIdx.x];
     }
 
     for (int it = 0; it < nb; ++it) {
         const int k = nb - 1 - it;
         const int buf = it & 1;
         const int cnt = batch_cnt(k);
-        __syncthreads();   // every warp is done with batch it-1 (buffer buf^1); id[buf] and s_g written
+        __syncthreads();   // every warp is done with batch it-1 (buffer buf^1); s_g written
         if (it + 1 < nb) {
             const int kn = k - 1;
             if (use_tma && threadIdx.x == 0)
                 stage_issue_tma(sm.rec[buf ^ 1], src + (size_t)kn * BWD_BATCH * REC_F4, batch_cnt(kn), &sm.full[buf ^ 1]);
-            if (threadIdx.x < batch_cnt(kn))
-                sm.id[buf ^ 1][threadIdx.x] = (unsigned int)kp[(size_t)kn * BWD_BATCH + threadIdx.x];
         }
         if (use_tma) {
             mbar_wait(&sm.full[buf], (uint32_t)(it >> 1) & 1u, err);
@@ -619,13 +611,13 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset,
         const int nrel = limit > 0 ? compact_entries(sb, limit, warp_bit, lane, sm.list[warp]) : 0;
         if (nrel > 0) {
             if (level == 0)
-                bwd_batch<FUSED, 0>(sm, sb, sm.id[buf], warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 0>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
             else if (!FUSED || level == 1)
-                bwd_batch<FUSED, 1>(sm, sb, sm.id[buf], warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 1>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
             else
-                bwd_batch<FUSED, 2>(sm, sb, sm.id[buf], warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 2>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
         }
     }

@@ -276,7 +276,9 @@ k_tile_scan(int tiles, const unsigned int *__restrict__ tile_count, unsigned int
 // ---- K3: scatter (depth, id) keys into the per-tile segments ----------------------------------------
 __global__ void __launch_bounds__(CTA)
 k_scatter(CamConst cc, int P, const float4 *__restrict__ records, const unsigned int *__restrict__ tile_offset,
-          unsigned int *__restrict__ cursor, unsigned long long *__restrict__ keys, unsigned int flags) {
+          unsigned int *__restrict__ cursor, unsigned long long *__restrict__ keys, unsigned int flags,
+          const unsigned long long *__restrict__ counters, unsigned long long capacity) {
+    if (counters[CNT_R] > capacity) return;   // optimistic launch into a too-small buffer: the host relaunches
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
@@ -365,12 +367,14 @@ __device__ __forceinline__ void emit_sorted_record(const float4 *__restrict__ re
     const unsigned mask = no_cull ? 0xffu : block_mask(a.x, a.y, a.z, a.w, b.x, b.y, tile_x0, tile_y0);
     dst[0] = make_float4(a.x, a.y, a2, b2);
     dst[1] = make_float4(c2, b.y, b.z, b.w);
-    dst[2] = make_float4(c.x, c.y, __uint_as_float(mask), 0.f);
+    dst[2] = make_float4(c.x, c.y, __uint_as_float(mask), __uint_as_float(id));
 }
 
 __global__ void __launch_bounds__(CTA)
 k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long long *__restrict__ keys,
-            const float4 *__restrict__ records, float4 *__restrict__ sorted_rec, unsigned int flags) {
+            const float4 *__restrict__ records, float4 *__restrict__ sorted_rec, unsigned int flags,
+            const unsigned long long *__restrict__ counters, unsigned long long capacity) {
+    if (counters[CNT_R] > capacity) return;
     unsigned long long *s_keys = fsgs_sort_smem;
     const unsigned int start = tile_offset[blockIdx.x];
     const int n = (int)(tile_offset[blockIdx.x + 1] - start);
@@ -383,8 +387,7 @@ k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long 
         __syncthreads();
         if (n > 1) tile_sort_network(SmemKeys{}, n);
         for (int p = threadIdx.x; p < n; p += blockDim.x) {
-            const unsigned long long k = s_keys[p];
-            g[p] = k;
+            const unsigned long long k = s_keys[p];   // (the sorted keys themselves are not needed again)
             emit_sorted_record(records, (unsigned int)k, sorted_rec + ((size_t)start + p) * 3, tile_x0, tile_y0, no_cull);
         }
     } else {

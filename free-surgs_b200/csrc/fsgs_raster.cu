@@ -107,7 +107,34 @@ struct Buffers {
     BinLayout bl;
 };
 
-// Shared tail of both forward flavours: scan -> R read-back -> scatter -> sort -> composite.
+// ---- instance-count read-back without idling the GPU ----------------------------------------------
+// The binning buffer is sized by R (tile instances), which only the device knows after k_tile_scan.
+// Blocking on that number leaves the GPU idle while the host wakes up, runs the allocation callback and
+// launches the rest of the forward.  Instead, when a previous forward on this device left a hint,
+// the tail (scatter -> sort -> composite) is launched OPTIMISTICALLY into a buffer sized from the hint
+// before the host waits for R; every tail kernel compares the device-side R with that capacity and
+// returns at once if it does not fit, in which case the host allocates the exact size and launches
+// the tail again.  Results never depend on the hint -- it only decides whether the GPU waits.
+struct HostMailbox {
+    unsigned long long *pinned = nullptr;   // 4 counters, page-locked so the D2H copy is truly asynchronous
+    cudaEvent_t ev[64] = {};                // per device: "counters have landed"
+    bool have_ev[64] = {};
+};
+thread_local HostMailbox g_mail;
+unsigned long long g_hint[64] = {};         // last R per device (benign race: performance hint only)
+
+int mailbox(int dev, unsigned long long **pinned, cudaEvent_t *ev) {
+    if (!g_mail.pinned) FSGS_CUDA(cudaHostAlloc((void **)&g_mail.pinned, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    if (!g_mail.have_ev[dev]) {
+        FSGS_CUDA(cudaEventCreateWithFlags(&g_mail.ev[dev], cudaEventDisableTiming));
+        g_mail.have_ev[dev] = true;
+    }
+    *pinned = g_mail.pinned;
+    *ev = g_mail.ev[dev];
+    return FSGS_OK;
+}
+
+// Shared tail of both forward flavours: scan -> (R read-back) -> scatter -> sort -> composite.
 template <bool FUSED>
 int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float *bg, Buffers &B,
                  fsgs_alloc_fn binning_alloc, void *binning_user, float *out_planes, float *out_depth,
@@ -118,44 +145,73 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
     unsigned int *cursor = reinterpret_cast<unsigned int *>(B.img + B.il.cursor);
     unsigned long long *counters = reinterpret_cast<unsigned long long *>(B.img + B.il.counters);
     float4 *records = reinterpret_cast<float4 *>(B.geom + B.gl.records);
+    int dev = 0;
+    FSGS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return FSGS_E_INVALID;
+    unsigned long long *h_cnt = nullptr;
+    cudaEvent_t landed;
+    int rc = mailbox(dev, &h_cnt, &landed);
+    if (rc != FSGS_OK) return rc;
 
     prof_begin(K_SCAN, stream);
     k_tile_scan<<<1, 1024, 0, stream>>>(tiles, tile_count, tile_offset, cursor, counters);
     prof_end(K_SCAN, stream);
     FSGS_LAUNCH_OK("k_tile_scan");
-    unsigned long long h_cnt[4] = {0, 0, 0, 0};
-    FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
-    FSGS_CUDA(cudaStreamSynchronize(stream));
+    FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    FSGS_CUDA(cudaEventRecord(landed, stream));
+
+    // launches scatter -> sort -> composite into a buffer of `capacity` instances
+    auto launch_tail = [&](unsigned long long capacity, bool have_instances) -> int {
+        unsigned long long *keys = reinterpret_cast<unsigned long long *>(B.bin + B.bl.keys);
+        float4 *sorted_rec = reinterpret_cast<float4 *>(B.bin + B.bl.records);
+        if (have_instances) {
+            prof_begin(K_SCATTER, stream);
+            k_scatter<<<blocks(P), CTA, 0, stream>>>(cc, P, records, tile_offset, cursor, keys, (unsigned)st->flags,
+                                                     counters, capacity);
+            prof_end(K_SCATTER, stream);
+            FSGS_LAUNCH_OK("k_scatter");
+            prof_begin(K_SORT, stream);
+            k_tile_sort<<<tiles, CTA, SORT_SMEM_KEYS * sizeof(unsigned long long), stream>>>(
+                cc.gx, tile_offset, keys, records, sorted_rec, (unsigned)st->flags, counters, capacity);
+            prof_end(K_SORT, stream);
+            FSGS_LAUNCH_OK("k_tile_sort");
+        }
+        prof_begin(K_COMP_FWD, stream);
+        k_composite_fwd<FUSED><<<tiles, CTA, 0, stream>>>(
+            cc, tile_offset, sorted_rec, bg, out_planes, out_depth, reinterpret_cast<float *>(B.img + B.il.final_T),
+            reinterpret_cast<unsigned int *>(B.img + B.il.n_contrib), (unsigned)st->flags, counters + CNT_ERR, counters,
+            capacity);
+        prof_end(K_COMP_FWD, stream);
+        FSGS_LAUNCH_OK("k_composite_fwd");
+        return FSGS_OK;
+    };
+
+    const unsigned long long hint = g_hint[dev];
+    unsigned long long capacity = 0;
+    bool launched = false;
+    if (hint > 0 && !(st->flags & FSGS_FLAG_NO_OPTIMISTIC)) {
+        capacity = hint + hint / 8 + 4096;
+        B.bl = bin_layout((int64_t)capacity);
+        B.bin = static_cast<char *>(binning_alloc(binning_user, B.bl.total));
+        if (!B.bin) return FSGS_E_ALLOC;
+        if ((rc = launch_tail(capacity, true)) != FSGS_OK) return rc;
+        launched = true;
+    }
+    FSGS_CUDA(cudaEventSynchronize(landed));
     const int64_t R = (int64_t)h_cnt[CNT_R];
     if (num_rendered_host) *num_rendered_host = R;
     if (num_rect_host) *num_rect_host = (int64_t)h_cnt[CNT_RECT];
     if (R >= (int64_t)1 << 32) return FSGS_E_INVALID;
+    g_hint[dev] = (unsigned long long)R;
 
-    B.bl = bin_layout(R);
-    B.bin = static_cast<char *>(binning_alloc(binning_user, B.bl.total));
-    if (!B.bin) return FSGS_E_ALLOC;
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(B.bin + B.bl.keys);
-    float4 *sorted_rec = reinterpret_cast<float4 *>(B.bin + B.bl.records);
-
-    if (R > 0) {
-        prof_begin(K_SCATTER, stream);
-        k_scatter<<<blocks(P), CTA, 0, stream>>>(cc, P, records, tile_offset, cursor, keys, (unsigned)st->flags);
-        prof_end(K_SCATTER, stream);
-        FSGS_LAUNCH_OK("k_scatter");
-        prof_begin(K_SORT, stream);
-        k_tile_sort<<<tiles, CTA, SORT_SMEM_KEYS * sizeof(unsigned long long), stream>>>(
-            cc.gx, tile_offset, keys, records, sorted_rec, (unsigned)st->flags);
-        prof_end(K_SORT, stream);
-        FSGS_LAUNCH_OK("k_tile_sort");
+    if (!launched || (unsigned long long)R > capacity) {
+        B.bl = bin_layout(R);
+        B.bin = static_cast<char *>(binning_alloc(binning_user, B.bl.total));
+        if (!B.bin) return FSGS_E_ALLOC;
+        if ((rc = launch_tail((unsigned long long)(R > 0 ? R : 1), R > 0)) != FSGS_OK) return rc;
     }
-    prof_begin(K_COMP_FWD, stream);
-    k_composite_fwd<FUSED><<<tiles, CTA, 0, stream>>>(
-        cc, tile_offset, sorted_rec, bg, out_planes, out_depth, reinterpret_cast<float *>(B.img + B.il.final_T),
-        reinterpret_cast<unsigned int *>(B.img + B.il.n_contrib), (unsigned)st->flags, counters + CNT_ERR);
-    prof_end(K_COMP_FWD, stream);
-    FSGS_LAUNCH_OK("k_composite_fwd");
     if (st->debug) {
-        FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, stream));
+        FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         FSGS_CUDA(cudaStreamSynchronize(stream));
         if (h_cnt[CNT_ERR]) return FSGS_E_WATCHDOG;
     }
@@ -337,15 +393,13 @@ int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rend
         prof_begin(K_COMP_BWD, stream);
         if (st->flags & FSGS_FLAG_BWD_SHUFFLE)
             k_composite_bwd_shfl<false><<<il.tiles, CTA, 0, stream>>>(
-            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
-            reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
+            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_dout_color, dL_dout_depth, acc, (unsigned)st->flags,
             const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
         else
             k_composite_bwd<false><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
-            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
-            reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
+            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_dout_color, dL_dout_depth, acc, (unsigned)st->flags,
             const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
@@ -473,15 +527,13 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
         prof_begin(K_COMP_BWD, stream);
         if (st->flags & FSGS_FLAG_BWD_SHUFFLE)
             k_composite_bwd_shfl<true><<<il.tiles, CTA, 0, stream>>>(
-            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
-            reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
+            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_dplanes, nullptr, acc, (unsigned)st->flags,
             const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
         else
             k_composite_bwd<true><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
-            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
-            reinterpret_cast<const unsigned long long *>(bn + bl.keys), reinterpret_cast<const float4 *>(bn + bl.records),
+            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_dplanes, nullptr, acc, (unsigned)st->flags,
             const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);

@@ -18,6 +18,7 @@ CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 FLAG_NO_TMA = 1
 FLAG_NO_TILE_CULL = 2
 FLAG_BWD_SHUFFLE = 4
+FLAG_NO_OPTIMISTIC = 8
 
 
 class FsgsError(RuntimeError):

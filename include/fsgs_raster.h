@@ -72,6 +72,7 @@ typedef struct fsgs_settings {
 #define FSGS_FLAG_NO_TMA 1u        /* stage tile batches with plain loads instead of bulk TMA     */
 #define FSGS_FLAG_NO_TILE_CULL 2u  /* keep every tile of the reference's 3-sigma rectangle        */
 #define FSGS_FLAG_BWD_SHUFFLE 4u   /* backward compositor: first (warp-shuffle reduce) formulation */
+#define FSGS_FLAG_NO_OPTIMISTIC 8u /* forward: always wait for the instance count before binning   */
 
 /* ------------------------------------------------------------------------------------------
  * API-level rasteriser (one GaussianRasterizer call).
@@ -165,8 +166,14 @@ size_t fsgs_geom_record_offset(int32_t P);
  *   img     : out[0] final_T f32[HW], out[1] n_contrib u32[HW], out[2] tile_count u32[T],
  *             out[3] tile_offset u32[T+1] (exclusive scan; [T] = instance count), out[4] cursor u32[T],
  *             out[5] counters u64[4] (instances, rect instances, longest list, error flag)
- *   binning : out[0] keys u64[R] ((depth float bits << 32) | Gaussian id, sorted inside each tile's
- *             [tile_offset[t], tile_offset[t+1]) segment), out[1] sorted splat records 48 B x R */
+ *   binning : out[1] = 0: depth-sorted per-instance splat records, 48 B x R, instance i of tile t at
+ *             tile_offset[t] + i: (x, y, a2, b2 | c2, opacity, r, g | b, depth, 8x4-block mask, Gaussian id)
+ *             with the conic pre-scaled for a base-2 exponent; inside each tile's segment the records
+ *             ascend by (depth float bits, Gaussian id).  out[0]: sort-key scratch ((depth bits << 32) | id),
+ *             contents unspecified after the forward.  The forward may request MORE than
+ *             fsgs_binning_bytes(R) from the allocation callback (it sizes the buffer before R is
+ *             known on the host, see FSGS_FLAG_NO_OPTIMISTIC) and may call the callback twice; the
+ *             buffer returned LAST is the one to keep for the backward. */
 void fsgs_img_offsets(int32_t image_width, int32_t image_height, size_t *out6);
 void fsgs_binning_offsets(int64_t num_rendered, size_t *out2);
 

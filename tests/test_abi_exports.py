@@ -36,7 +36,7 @@ def test_host_only_helpers():
     io = _lib.img_offsets(1280, 1024)
     assert io["n_contrib"] >= 1280 * 1024 * 4 and io["tile_offset"] > io["tile_count"]
     assert L.fsgs_img_bytes(1280, 1024) > io["counters"]
-    assert _lib.binning_offsets(100)["records"] >= 800
+    assert _lib.binning_offsets(100)["records"] == 0 and _lib.binning_offsets(100)["keys"] >= 4800
     assert L.fsgs_error_string(-4).decode().startswith("device is not compute capability 10")
     assert "k_composite_bwd" in _lib.kernel_names() and len(_lib.kernel_names()) == 12
 

@@ -205,7 +205,7 @@ def test_tma_and_culling_do_not_change_results():
     res = {}
     try:
         for name, kw in (("default", {}), ("no_tma", dict(no_tma=True)), ("no_cull", dict(no_tile_cull=True)),
-                         ("bwd_shuffle", dict(bwd_shuffle=True))):
+                         ("bwd_shuffle", dict(bwd_shuffle=True)), ("no_optimistic", dict(no_optimistic=True))):
             rasterizer.set_debug_flags(**kw)
             out, planes, g = _run_fused(sc, G6)
             res[name] = (planes, g, tuple(out["num_rendered"]))
@@ -215,8 +215,8 @@ def test_tma_and_culling_do_not_change_results():
     assert torch.equal(p0, res["no_tma"][0]), "bulk-TMA staging must be a pure data-movement change"
     assert torch.equal(p0, res["no_cull"][0]), "exact tile culling must not change any pixel"
     assert int(res["no_cull"][2][0]) == int(n0[1]) and int(n0[0]) < int(n0[1])
-    assert torch.equal(p0, res["bwd_shuffle"][0])
-    for name in ("no_tma", "no_cull", "bwd_shuffle"):
+    assert torch.equal(p0, res["bwd_shuffle"][0]) and torch.equal(p0, res["no_optimistic"][0])
+    for name in ("no_tma", "no_cull", "bwd_shuffle", "no_optimistic"):
         # float summation order only (bwd_shuffle: the two backward compositors group the per-pair sums differently)
         tol = 2e-6 if name != "bwd_shuffle" else 2e-5
         for k, v in g0.items():
@@ -317,13 +317,15 @@ def test_full_size_properties():
     T = (1280 // 16) * (1024 // 16)
     io, bo = _lib.img_offsets(1280, 1024), _lib.binning_offsets(nr)
     tile_offset = img[io["tile_offset"]:io["tile_offset"] + 4 * (T + 1)].view(torch.int32).long()
-    keys = binning[bo["keys"]:bo["keys"] + 8 * nr].view(torch.int64)
+    assert bo["records"] == 0
+    rec = binning[:48 * nr].view(torch.int32).view(nr, 12).long()
+    keys = (rec[:, 9] << 32) | rec[:, 11]              # (depth float bits, Gaussian id) of every sorted instance
     assert int(tile_offset[-1]) == nr and (tile_offset[1:] >= tile_offset[:-1]).all()
     asc = keys[1:] >= keys[:-1]                       # depth bits are positive floats -> signed compare is fine
     boundary = torch.zeros(nr - 1, dtype=torch.bool, device=DEV)
     inner = tile_offset[1:-1]
     boundary[(inner[(inner > 0) & (inner < nr)] - 1)] = True
     assert bool((asc | boundary).all()), "every tile list must be sorted by (depth bits, Gaussian id)"
-    ids = keys & 0xFFFFFFFF
+    ids = rec[:, 11]
     assert int(ids.max()) < sc.P and int((radii[ids] > 0).all())
     assert int((radii > 0).sum()) > 400_000
