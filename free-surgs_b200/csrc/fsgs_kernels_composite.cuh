@@ -77,6 +77,10 @@ __device__ __forceinline__ int compact_entries(const float4 *sb, int limit, unsi
     return n;
 }
 
+__device__ __forceinline__ int list_byte(uint2 packed, int s) {
+    return (int)(((s < 4 ? packed.x : packed.y) >> (8 * (s & 3))) & 0xffu);
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(FSGS_FWD_LB)
 k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const float4 *__restrict__ sorted_rec,
@@ -86,7 +90,7 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
                 unsigned long long capacity) {
     __shared__ __align__(128) float4 s_rec[2][BATCH * REC_F4];
     __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ unsigned char s_list[CTA / 32][BATCH];
+    __shared__ __align__(8) unsigned char s_list[CTA / 32][BATCH];   // rows read 8 entries at a time
     if (counters[CNT_R] > capacity) return;   // optimistic launch into a too-small buffer: the host relaunches
     const int tile = blockIdx.x;
     const unsigned int start = tile_offset[tile];
@@ -109,6 +113,7 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
         if (threadIdx.x == 0 && nb > 0) stage_issue_tma(s_rec[0], src, min(BATCH, n), &s_full[0]);
     }
 
+#ifdef FSGS_FWD_LEGACY
     bool done = !pix.inside;
     float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, S = 0.f, D2 = 0.f;
     unsigned int last = 0;
@@ -154,6 +159,64 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
             }
         }
     }
+
+#else
+    // A finished pixel (T would drop below 1e-4, or outside the image) is marked by the SIGN of T: the next
+    // entry's test_T = T * (1 - alpha) is then negative, fails `test_T >= T_MIN` and re-marks the pixel --
+    // no separate flag, no per-entry "done" branch.  The body is branch-free (selects), entries are taken in
+    // aligned chunks of 8 list positions (one 64-bit load of the list bytes per chunk).
+    float T = pix.inside ? 1.f : -1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, S = 0.f, D2 = 0.f;
+    unsigned int last = 0;
+
+    for (int k = 0; k < nb; ++k) {
+        const int all_done = __syncthreads_and(T < 0.f ? 1 : 0);   // everyone is also past batch k-1
+        const int buf = k & 1;
+        const int cnt = min(BATCH, n - k * BATCH);
+        if (use_tma) {
+            if (threadIdx.x == 0 && !all_done && k + 1 < nb)
+                stage_issue_tma(s_rec[buf ^ 1], src + (size_t)(k + 1) * BATCH * REC_F4, min(BATCH, n - (k + 1) * BATCH),
+                                &s_full[buf ^ 1]);
+            mbar_wait(&s_full[buf], (uint32_t)(k >> 1) & 1u, err);   // drain even when leaving
+            if (all_done) break;
+        } else {
+            if (all_done) break;
+            stage_plain(s_rec[buf], src + (size_t)k * BATCH * REC_F4, cnt);
+            __syncthreads();
+        }
+        if (__all_sync(FULL, T < 0.f)) continue;                    // this warp's pixels are finished
+        const float4 *sb = s_rec[buf];
+        const int nrel = compact_entries(sb, cnt, warp_bit, lane, s_list[warp]);
+        int lj = -1;                                                // last contributing entry of this batch
+        auto entry = [&](int j) __attribute__((always_inline)) {
+            const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
+            const float2 q2 = *reinterpret_cast<const float2 *>(&sb[j * 3 + 2]);   // (b, depth)
+            const float dx = q0.x - pxf, dy = q0.y - pyf;
+            const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
+            const float alpha = fminf(ALPHA_MAX, q1.y * fast_exp2(p2));
+            const float test_T = T * (1.f - alpha);
+            const bool pa = (p2 <= 0.f) & (alpha >= ALPHA_MIN);
+            const bool ok = pa & (test_T >= T_MIN);
+            const float w = ok ? alpha * T : 0.f;
+            C0 = fmaf(q1.z, w, C0); C1 = fmaf(q1.w, w, C1); C2 = fmaf(q2.x, w, C2); D = fmaf(q2.y, w, D);
+            if (FUSED) { S += w; D2 = fmaf(q2.y * q2.y, w, D2); }
+            if (pa & !ok) T = -fabsf(T);
+            T = ok ? test_T : T;
+            lj = ok ? j : lj;
+        };
+        for (int c0 = 0; c0 < nrel; c0 += 8) {
+            if (__all_sync(FULL, T < 0.f)) break;
+            const uint2 packed = *reinterpret_cast<const uint2 *>(&s_list[warp][c0]);
+            if (c0 + 8 <= nrel) {
+#pragma unroll
+                for (int s = 0; s < 8; ++s) entry(list_byte(packed, s));
+            } else {
+                for (int s = 0; s < nrel - c0; ++s) entry((int)s_list[warp][c0 + s]);
+            }
+        }
+        if (lj >= 0) last = (unsigned int)(k * BATCH + lj + 1);
+    }
+    T = fabsf(T);
+#endif
 
     if (pix.inside) {
         const size_t HW = (size_t)cc.W * cc.H, p = (size_t)pix.py * cc.W + pix.px;
@@ -368,10 +431,6 @@ struct BwdSmem {
     unsigned char list[NWARP][BWD_BATCH];   // 8-byte aligned rows (read 8 entries at a time)
     unsigned int maxlast;
 };
-
-__device__ __forceinline__ int list_byte(uint2 packed, int s) {
-    return (int)(((s < 4 ? packed.x : packed.y) >> (8 * (s & 3))) & 0xffu);
-}
 
 // Phase B for the first `cn` slots of this warp's chunk.  All 32 lanes call it.
 template <bool FUSED, int LEVEL>

@@ -355,6 +355,8 @@ __device__ __forceinline__ void tile_sort_network(const Keys &a, int n) {
 }
 
 constexpr int SORT_SMEM_KEYS = 8192;   // 64 KB of dynamic shared memory
+constexpr int BUCKET_MAX_KEYS = 2048;  // lists up to this length take the bucket path
+constexpr int BUCKET_MAX_FILL = 24;    // fullest bucket the rank pass accepts before falling back to the network
 
 // Gather one sorted instance: per-Gaussian record -> compositor record (conic pre-scaled for the
 // base-2 exponent, 8x4-block reach mask of this tile in q2.z).
@@ -370,6 +372,104 @@ __device__ __forceinline__ void emit_sorted_record(const float4 *__restrict__ re
     dst[2] = make_float4(c.x, c.y, __uint_as_float(mask), __uint_as_float(id));
 }
 
+// Bucket of a depth: monotone non-decreasing in z (float subtraction, multiplication by a positive
+// constant and truncation all are), so buckets are ordered like the keys.
+__device__ __forceinline__ int depth_bucket(unsigned long long key, float zmin, float inv, int nb) {
+    const float z = __uint_as_float((unsigned int)(key >> 32));
+    return min(nb - 1, (int)((z - zmin) * inv));
+}
+
+// Per-tile sort, bucket path (lists of up to BUCKET_MAX_KEYS entries; the usual case).  The depths of
+// one tile's splats are spread roughly evenly between the tile's nearest and farthest, so a linear map
+// of depth onto ~n buckets leaves about one key per bucket:
+//   1. load the keys, block-reduce min / max depth;
+//   2. histogram (shared-memory integer atomics), block exclusive scan of the bucket counts;
+//   3. scatter the keys to their bucket's segment (order inside a bucket arbitrary);
+//   4. every key ranks itself inside its bucket by comparing full 64-bit (depth, id) keys -- O(fill) with
+//      fill ~ 1 -- which gives its final position in the tile list; the compositor record is emitted
+//      straight to that position (the sorted keys themselves are never materialised).
+// ~45 instructions per key instead of the ~500 of the 45..55-step compare-exchange network.  The result is
+// the same total order on unique keys, hence bit-identical.  A tile whose fullest bucket exceeds
+// BUCKET_MAX_FILL (many equal depths, strongly clustered depths) returns false with the keys still
+// in s_in, and the caller runs the network instead.
+__device__ __forceinline__ bool tile_sort_bucket(int n, const unsigned long long *__restrict__ g,
+                                                 const float4 *__restrict__ records, float4 *__restrict__ dst,
+                                                 int tile_x0, int tile_y0, bool no_cull) {
+    unsigned long long *s_in = fsgs_sort_smem;                                   // [BUCKET_MAX_KEYS]
+    unsigned long long *s_out = fsgs_sort_smem + BUCKET_MAX_KEYS;                // [BUCKET_MAX_KEYS]
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(fsgs_sort_smem + 2 * BUCKET_MAX_KEYS);   // [nb]
+    __shared__ unsigned int s_red[3][CTA / 32];
+    __shared__ unsigned int s_warp_sum[CTA / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + CTA - 1) / CTA;          // buckets per thread in the scan (<= 8)
+    const int nb = per * CTA;                     // number of buckets: n rounded up to a multiple of the CTA
+
+    unsigned int dmin = 0xffffffffu, dmax = 0u;
+    for (int p = tid; p < n; p += CTA) {
+        const unsigned long long k = g[p];
+        s_in[p] = k;
+        const unsigned int d = (unsigned int)(k >> 32);   // depth > 0.2: bit order == numeric order
+        dmin = min(dmin, d); dmax = max(dmax, d);
+    }
+    for (int b = tid; b < nb; b += CTA) s_hist[b] = 0u;
+    dmin = __reduce_min_sync(FULL, dmin); dmax = __reduce_max_sync(FULL, dmax);
+    if (lane == 0) { s_red[0][warp] = dmin; s_red[1][warp] = dmax; }
+    __syncthreads();
+    dmin = s_red[0][lane & 7]; dmax = s_red[1][lane & 7];
+    dmin = __reduce_min_sync(FULL, dmin); dmax = __reduce_max_sync(FULL, dmax);
+    const float zmin = __uint_as_float(dmin), range = __uint_as_float(dmax) - zmin;
+    const float inv = range > 0.f ? fminf((float)nb / range, 3.0e38f) : 0.f;
+
+    for (int p = tid; p < n; p += CTA) atomicAdd(&s_hist[depth_bucket(s_in[p], zmin, inv, nb)], 1u);
+    __syncthreads();
+
+    // exclusive scan of s_hist (thread t owns buckets [t*per, (t+1)*per)) + the fullest bucket
+    unsigned int cnt[8], sum = 0, fill = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        cnt[i] = i < per ? s_hist[tid * per + i] : 0u;
+        sum += cnt[i]; fill = max(fill, cnt[i]);
+    }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    fill = __reduce_max_sync(FULL, fill);
+    if (lane == 31) s_warp_sum[warp] = incl;
+    if (lane == 0) s_red[2][warp] = fill;
+    __syncthreads();
+    unsigned int run = incl - sum;
+#pragma unroll
+    for (int w = 0; w < CTA / 32; ++w) {
+        if (w < warp) run += s_warp_sum[w];
+        fill = max(fill, s_red[2][w]);
+    }
+    if (fill > (unsigned int)BUCKET_MAX_FILL) return false;   // uniform: every thread sees the same maximum
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < per) { s_hist[tid * per + i] = run; run += cnt[i]; }
+    __syncthreads();
+
+    // scatter: afterwards s_hist[b] = END of bucket b (= start of bucket b + 1)
+    for (int p = tid; p < n; p += CTA) {
+        const unsigned long long k = s_in[p];
+        s_out[atomicAdd(&s_hist[depth_bucket(k, zmin, inv, nb)], 1u)] = k;
+    }
+    __syncthreads();
+
+    for (int p = tid; p < n; p += CTA) {
+        const unsigned long long k = s_out[p];
+        const int b = depth_bucket(k, zmin, inv, nb);
+        const int lo = b > 0 ? (int)s_hist[b - 1] : 0, hi = (int)s_hist[b];
+        int rank = lo;
+        for (int q = lo; q < hi; ++q) rank += s_out[q] < k ? 1 : 0;
+        emit_sorted_record(records, (unsigned int)k, dst + (size_t)rank * 3, tile_x0, tile_y0, no_cull);
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(CTA)
 k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long long *__restrict__ keys,
             const float4 *__restrict__ records, float4 *__restrict__ sorted_rec, unsigned int flags,
@@ -382,19 +482,26 @@ k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long 
     const int tile_x0 = (int)(blockIdx.x % gx) * TILE, tile_y0 = (int)(blockIdx.x / gx) * TILE;
     const bool no_cull = (flags & 2u) != 0;
     unsigned long long *g = keys + start;
-    if (n <= SORT_SMEM_KEYS) {
+    float4 *dst = sorted_rec + (size_t)start * 3;
+    if (n <= BUCKET_MAX_KEYS && !(flags & 16u)) {           // FSGS_FLAG_SORT_NETWORK forces the network (A/B, tests)
+        if (tile_sort_bucket(n, g, records, dst, tile_x0, tile_y0, no_cull)) return;
+        __syncthreads();                                    // keys are in s_keys[0..n): fall through to the network
+        if (n > 1) tile_sort_network(SmemKeys{}, n);
+        for (int p = threadIdx.x; p < n; p += blockDim.x)
+            emit_sorted_record(records, (unsigned int)s_keys[p], dst + (size_t)p * 3, tile_x0, tile_y0, no_cull);
+    } else if (n <= SORT_SMEM_KEYS) {
         for (int p = threadIdx.x; p < n; p += blockDim.x) s_keys[p] = g[p];
         __syncthreads();
         if (n > 1) tile_sort_network(SmemKeys{}, n);
         for (int p = threadIdx.x; p < n; p += blockDim.x) {
             const unsigned long long k = s_keys[p];   // (the sorted keys themselves are not needed again)
-            emit_sorted_record(records, (unsigned int)k, sorted_rec + ((size_t)start + p) * 3, tile_x0, tile_y0, no_cull);
+            emit_sorted_record(records, (unsigned int)k, dst + (size_t)p * 3, tile_x0, tile_y0, no_cull);
         }
     } else {
         // rare: list longer than the shared-memory window -> same network in global memory (L2)
         tile_sort_network(GmemKeys{g}, n);
         for (int p = threadIdx.x; p < n; p += blockDim.x)
-            emit_sorted_record(records, (unsigned int)g[p], sorted_rec + ((size_t)start + p) * 3, tile_x0, tile_y0, no_cull);
+            emit_sorted_record(records, (unsigned int)g[p], dst + (size_t)p * 3, tile_x0, tile_y0, no_cull);
     }
 }
 

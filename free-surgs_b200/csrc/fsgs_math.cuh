@@ -636,12 +636,37 @@ FSGS_HD bool rect_hit(float px, float py, float A, float B, float C, float tau, 
 }
 // Bit w of the mask = the 8x4 pixel block of warp w ((w&1)*8, (w>>1)*4 inside the 16x16 tile) may
 // hold a pixel this splat changes.  tile_x0/tile_y0 = pixel coordinates of the tile's corner.
+// Same test as rect_hit for each of the eight blocks (minimum of the quadratic over the block's four
+// edges, or the centre inside the block), with the per-line terms shared: the blocks have only 4 distinct
+// vertical and 8 distinct horizontal edge lines, and along a line x = const the quadratic is
+//   q(dy) = 0.5 A dx^2 + dy (0.5 C dy + B dx),   minimised at dy = -B dx / C  (clamped to the edge),
+// so each edge costs one clamp and two FMAs once -B/C, -B/A and the line terms are known.
 FSGS_HD unsigned block_mask(float px, float py, float A, float B, float C, float opacity, int tile_x0, int tile_y0) {
-    const CullEllipse e = make_cull_ellipse(px, py, A, B, C, opacity);
+    const float t = logf(255.0f * opacity);
+    const float tau = (opacity * 255.0f >= 0.999f) ? (t * 1.0005f + 0.01f) : -1.0f;   // as make_cull_ellipse
+    const float hA = 0.5f * A, hC = 0.5f * C;
+    const float nBC = -B * fast_rcp(C), nBA = -B * fast_rcp(A);
+    float dxv[4], tx[4], bx[4], sx[4];               // vertical lines x = tile_x0 + {0, 7, 8, 15}
+    for (int k = 0; k < 4; ++k) {
+        const float dx = px - (float)(tile_x0 + (k >> 1) * 8 + (k & 1) * 7);
+        dxv[k] = dx; tx[k] = nBC * dx; bx[k] = hA * dx * dx; sx[k] = B * dx;
+    }
     unsigned m = 0;
-    for (int w = 0; w < 8; ++w) {
-        const float x0 = (float)(tile_x0 + (w & 1) * 8), y0 = (float)(tile_y0 + (w >> 1) * 4);
-        if (rect_hit(px, py, A, B, C, e.tau, x0, x0 + 7.f, y0, y0 + 3.f)) m |= 1u << w;
+    for (int r = 0; r < 4; ++r) {
+        // horizontal lines y = tile_y0 + 4 r + {0, 3};  d = centre - pixel, so dy runs over [dyl, dyh]
+        const float dyh = py - (float)(tile_y0 + 4 * r), dyl = dyh - 3.0f;
+        const float tyh = nBA * dyh, tyl = nBA * dyl, byh = hC * dyh * dyh, byl = hC * dyl * dyl;
+        const float syh = B * dyh, syl = B * dyl;
+        for (int c = 0; c < 2; ++c) {
+            const float dxh = dxv[2 * c], dxl = dxv[2 * c + 1];
+            bool hit = dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f;        // centre inside the block
+            float d, q;
+            d = fminf(dyh, fmaxf(dyl, tx[2 * c]));     q = bx[2 * c] + d * (hC * d + sx[2 * c]);
+            d = fminf(dyh, fmaxf(dyl, tx[2 * c + 1])); q = fminf(q, bx[2 * c + 1] + d * (hC * d + sx[2 * c + 1]));
+            d = fminf(dxh, fmaxf(dxl, tyh));           q = fminf(q, byh + d * (hA * d + syh));
+            d = fminf(dxh, fmaxf(dxl, tyl));           q = fminf(q, byl + d * (hA * d + syl));
+            if (hit || q <= tau) m |= 1u << (2 * r + c);
+        }
     }
     return m;
 }

@@ -19,6 +19,7 @@ FLAG_NO_TMA = 1
 FLAG_NO_TILE_CULL = 2
 FLAG_BWD_SHUFFLE = 4
 FLAG_NO_OPTIMISTIC = 8
+FLAG_SORT_NETWORK = 16
 
 
 class FsgsError(RuntimeError):

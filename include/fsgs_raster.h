@@ -73,6 +73,7 @@ typedef struct fsgs_settings {
 #define FSGS_FLAG_NO_TILE_CULL 2u  /* keep every tile of the reference's 3-sigma rectangle        */
 #define FSGS_FLAG_BWD_SHUFFLE 4u   /* backward compositor: first (warp-shuffle reduce) formulation */
 #define FSGS_FLAG_NO_OPTIMISTIC 8u /* forward: always wait for the instance count before binning   */
+#define FSGS_FLAG_SORT_NETWORK 16u /* per-tile sort: always the compare-exchange network (A/B, tests) */
 
 /* ------------------------------------------------------------------------------------------
  * API-level rasteriser (one GaussianRasterizer call).

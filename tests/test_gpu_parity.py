@@ -205,7 +205,8 @@ def test_tma_and_culling_do_not_change_results():
     res = {}
     try:
         for name, kw in (("default", {}), ("no_tma", dict(no_tma=True)), ("no_cull", dict(no_tile_cull=True)),
-                         ("bwd_shuffle", dict(bwd_shuffle=True)), ("no_optimistic", dict(no_optimistic=True))):
+                         ("bwd_shuffle", dict(bwd_shuffle=True)), ("no_optimistic", dict(no_optimistic=True)),
+                         ("sort_network", dict(sort_network=True))):
             rasterizer.set_debug_flags(**kw)
             out, planes, g = _run_fused(sc, G6)
             res[name] = (planes, g, tuple(out["num_rendered"]))
@@ -216,7 +217,8 @@ def test_tma_and_culling_do_not_change_results():
     assert torch.equal(p0, res["no_cull"][0]), "exact tile culling must not change any pixel"
     assert int(res["no_cull"][2][0]) == int(n0[1]) and int(n0[0]) < int(n0[1])
     assert torch.equal(p0, res["bwd_shuffle"][0]) and torch.equal(p0, res["no_optimistic"][0])
-    for name in ("no_tma", "no_cull", "bwd_shuffle", "no_optimistic"):
+    assert torch.equal(p0, res["sort_network"][0]), "bucket sort and compare-exchange network give the same order"
+    for name in ("no_tma", "no_cull", "bwd_shuffle", "no_optimistic", "sort_network"):
         # float summation order only (bwd_shuffle: the two backward compositors group the per-pair sums differently)
         tol = 2e-6 if name != "bwd_shuffle" else 2e-5
         for k, v in g0.items():
