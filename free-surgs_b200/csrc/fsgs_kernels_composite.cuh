@@ -37,6 +37,13 @@
 
 namespace fsgs {
 
+// Derived per-pixel / per-Gaussian outputs of the reference's render() (fused flavour only; NULL = skip).
+struct RenderExtras {
+    float *uncertainty;
+    unsigned char *presence_mask, *nan_mask, *visibility;
+    float *max_radii2D;
+};
+
 struct TilePix {
     int px, py;
     bool inside;
@@ -87,7 +94,7 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
                 const float *__restrict__ bg, float *__restrict__ out_planes, float *__restrict__ out_depth,
                 float *__restrict__ final_T, unsigned int *__restrict__ n_contrib, unsigned int flags,
                 unsigned long long *__restrict__ err, const unsigned long long *__restrict__ counters,
-                unsigned long long capacity) {
+                unsigned long long capacity, RenderExtras ex) {
     __shared__ __align__(128) float4 s_rec[2][BATCH * REC_F4];
     __shared__ __align__(8) uint64_t s_full[2];
     __shared__ __align__(8) unsigned char s_list[CTA / 32][BATCH];   // rows read 8 entries at a time
@@ -230,173 +237,24 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
             out_planes[3 * HW + p] = D + T * b0;
             out_planes[4 * HW + p] = S + T * b1;
             out_planes[5 * HW + p] = D2 + T * b2;
+            // render()'s derived maps, bit-identical to the element-wise torch formulation
+            const float dep = D + T * b0, sil = S + T * b1, dsq = D2 + T * b2;
+            const float unc = __fsub_rn(dsq, __fmul_rn(dep, dep));
+            if (ex.uncertainty) ex.uncertainty[p] = unc;
+            if (ex.presence_mask) ex.presence_mask[p] = sil > 0.3f ? 1 : 0;
+            if (ex.nan_mask) ex.nan_mask[p] = (dep == dep && unc == unc) ? 1 : 0;
         } else {
             out_depth[p] = D;
         }
     }
 }
 
-// ---- backward, first formulation (kept for A/B: FSGS_FLAG_BWD_SHUFFLE) ---------------------------
+// ---- backward: transposed two-phase formulation ----------------------------------------------------
 // Back-to-front replay over the first max(n_contrib) entries of the tile list.  Each contributing
-// (pixel, Gaussian) pair produces 12 moments (bwd_pair2); per (warp, entry) the 32 lanes' moments
-// are combined with a shuffle reduce-scatter and added to a per-batch shared-memory accumulator;
-// after each batch one thread per entry turns its summed moments into the final gradient row
-// (bwd_finalize) and flushes it to the per-Gaussian accumulator with three vector atomics
-// (red.global.add.v4.f32).
-template <bool FUSED>
-__global__ void __launch_bounds__(CTA)
-k_composite_bwd_shfl(CamConst cc, const unsigned int *__restrict__ tile_offset, const float4 *__restrict__ sorted_rec,
-                const float *__restrict__ bg, const float *__restrict__ final_T,
-                const unsigned int *__restrict__ n_contrib, const float *__restrict__ dL_dplanes,
-                const float *__restrict__ dL_ddepth, float *__restrict__ grad_acc, unsigned int flags,
-                unsigned long long *__restrict__ err) {
-    __shared__ __align__(128) float4 s_rec[2][BATCH * REC_F4];
-    __shared__ __align__(16) float s_acc[BATCH * ACC_F];
-    __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ unsigned char s_list[CTA / 32][BATCH];
-    __shared__ unsigned int s_maxlast;
-    const int tile = blockIdx.x;
-    const unsigned int start = tile_offset[tile];
-    const int n = (int)(tile_offset[tile + 1] - start);
-    if (n == 0) return;
-    const bool use_tma = (flags & 1u) == 0;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned int warp_bit = 1u << warp;
-    const TilePix pix = tile_pixel(cc, tile);
-    const float pxf = (float)pix.px, pyf = (float)pix.py;
-    const size_t HW = (size_t)cc.W * cc.H, p = (size_t)pix.py * cc.W + pix.px;
-
-    if (threadIdx.x == 0) {
-        s_maxlast = 0;
-        if (use_tma) {
-            mbar_init(&s_full[0], 1);
-            mbar_init(&s_full[1], 1);
-            mbar_fence_init();
-        }
-    }
-    for (int q = threadIdx.x; q < BATCH * ACC_F; q += CTA) s_acc[q] = 0.f;
-    __syncthreads();
-
-    const int last = pix.inside ? (int)n_contrib[p] : 0;
-    const int warp_last = (int)__reduce_max_sync(FULL, (unsigned int)last);   // this warp's deepest contributor
-    if (lane == 0 && warp_last) atomicMax(&s_maxlast, (unsigned int)warp_last);
-    __syncthreads();
-    const int maxlast = min((int)s_maxlast, n);
-    if (maxlast == 0) return;
-    const int nb = (maxlast + BATCH - 1) / BATCH;
-
-    constexpr int NG = FUSED ? 6 : 4;   // pixel gradients: planes (+ depth plane for the API flavour)
-    float g[NG];
-    const float T_final = pix.inside ? final_T[p] : 0.f;
-    float bgdot_rgb = 0.f, bgdot_dep = 0.f;
-    {
-        const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
-#pragma unroll
-        for (int ch = 0; ch < NG; ++ch) g[ch] = 0.f;
-        if (pix.inside) {
-            g[0] = dL_dplanes[p]; g[1] = dL_dplanes[HW + p]; g[2] = dL_dplanes[2 * HW + p];
-            if (FUSED) {
-                g[3] = dL_dplanes[3 * HW + p]; g[4] = dL_dplanes[4 * HW + p]; g[5] = dL_dplanes[5 * HW + p];
-                bgdot_dep = b0 * g[3] + b1 * g[4] + b2 * g[5];
-            } else {
-                g[3] = dL_ddepth ? dL_ddepth[p] : 0.f;
-            }
-            bgdot_rgb = b0 * g[0] + b1 * g[1] + b2 * g[2];
-        }
-    }
-    const float kx = 0.5f * cc.W, ky = 0.5f * cc.H;
-    // which upstream planes are non-zero anywhere in this warp's block (uniform per warp):
-    // 0 = colour only (pose tracking), 1 = + depth (mapping), 2 = + silhouette / depth^2
-    int level = __any_sync(FULL, g[3] != 0.f) ? 1 : 0;
-    if (FUSED && __any_sync(FULL, g[4] != 0.f || g[5] != 0.f)) level = 2;
-
-    BwdPixel ps;
-    ps.T = T_final;
-    ps.acc_r = ps.acc_g = ps.acc_b = ps.acc_d = ps.acc_s = ps.acc_d2 = 0.f;
-
-    const float4 *src = sorted_rec + (size_t)start * REC_F4;
-    auto batch_cnt = [&](int k) { return min(BATCH, maxlast - k * BATCH); };
-
-    // prologue: stage the LAST batch
-    {
-        const int k = nb - 1;
-        if (use_tma && threadIdx.x == 0) stage_issue_tma(s_rec[0], src + (size_t)k * BATCH * REC_F4, batch_cnt(k), &s_full[0]);
-    }
-
-    for (int it = 0; it < nb; ++it) {
-        const int k = nb - 1 - it;
-        const int buf = it & 1;
-        const int cnt = batch_cnt(k);
-        __syncthreads();   // batch it-1 fully consumed and flushed
-        if (it + 1 < nb) {
-            const int kn = k - 1;
-            if (use_tma && threadIdx.x == 0)
-                stage_issue_tma(s_rec[buf ^ 1], src + (size_t)kn * BATCH * REC_F4, batch_cnt(kn), &s_full[buf ^ 1]);
-        }
-        if (use_tma) {
-            mbar_wait(&s_full[buf], (uint32_t)(it >> 1) & 1u, err);
-        } else {
-            stage_plain(s_rec[buf], src + (size_t)k * BATCH * REC_F4, cnt);
-            __syncthreads();
-        }
-        const float4 *sb = s_rec[buf];
-
-        // entries of this batch that can matter to this warp: mask hit AND not deeper than the warp's
-        // deepest contributor
-        const int limit = min(cnt, warp_last - k * BATCH);
-        const int nrel = limit > 0 ? compact_entries(sb, limit, warp_bit, lane, s_list[warp]) : 0;
-        for (int i = nrel - 1; i >= 0; --i) {
-            const int j = s_list[warp][i];
-            const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
-            const float dx = q0.x - pxf, dy = q0.y - pyf;
-            const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
-            const float G = fast_exp2(p2);
-            const float alpha = fminf(ALPHA_MAX, q1.y * G);
-            const bool valid = (k * BATCH + j < last) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
-            if (!__any_sync(FULL, valid)) continue;
-            float v[12];
-#pragma unroll
-            for (int q = 0; q < 12; ++q) v[q] = 0.f;
-            if (valid) {
-                const float4 q2 = sb[j * 3 + 2];
-                if (level == 0)
-                    bwd_pair2<FUSED, 0>(ps, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final, bgdot_rgb, bgdot_dep, v);
-                else if (!FUSED || level == 1)
-                    bwd_pair2<FUSED, 1>(ps, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final, bgdot_rgb, bgdot_dep, v);
-                else
-                    bwd_pair2<FUSED, 2>(ps, q1.y, q1.z, q1.w, q2.x, q2.y, dx, dy, G, alpha, g, T_final, bgdot_rgb, bgdot_dep, v);
-            }
-            const int idx = warp_reduce_scatter12(v, lane);
-            if (idx >= 0 && v[0] != 0.f) atomicAdd(&s_acc[j * ACC_F + idx], v[0]);
-        }
-
-        __syncthreads();   // all warps' shared-memory adds for this batch are in
-        if (threadIdx.x < cnt) {
-            float4 *row = reinterpret_cast<float4 *>(&s_acc[threadIdx.x * ACC_F]);
-            const float4 a = row[0], b = row[1], c = row[2];
-            const bool nz = (a.x != 0.f) | (a.y != 0.f) | (a.z != 0.f) | (a.w != 0.f) | (b.x != 0.f) | (b.y != 0.f) |
-                            (b.z != 0.f) | (b.w != 0.f) | (c.x != 0.f) | (c.y != 0.f) | (c.z != 0.f) | (c.w != 0.f);
-            if (nz) {
-                const float m[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-                const float4 r0 = sb[threadIdx.x * 3], r1 = sb[threadIdx.x * 3 + 1];
-                float o[12];
-                bwd_finalize(m, r0.z, r0.w, r1.x, r1.y, kx, ky, FUSED, o);
-                const unsigned int gid = __float_as_uint(sb[threadIdx.x * 3 + 2].w);
-                float4 *dst = reinterpret_cast<float4 *>(grad_acc + (size_t)gid * ACC_F);
-                atomicAdd(dst, make_float4(o[0], o[1], o[2], o[3]));
-                atomicAdd(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
-                atomicAdd(dst + 2, make_float4(o[8], o[9], o[10], o[11]));
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                row[0] = z4; row[1] = z4; row[2] = z4;
-            }
-        }
-    }
-}
-
-// ---- backward, transposed two-phase formulation (default) ---------------------------------------
-// The shuffle formulation above spends ~50 of its ~150 instructions per (warp, entry) visit on the
-// 32-lane reduce-scatter of the 12 moments.  Here the reduction is replaced by a change of thread
-// layout through shared memory:
+// (pixel, Gaussian) pair produces 12 moments; a first formulation (round-1 history, removed) combined the
+// 32 lanes' moments with a 13-shuffle reduce-scatter per (warp, entry) and spent ~50 of its ~150
+// instructions per visit there.  Here the reduction is replaced by a change of thread layout through
+// shared memory:
 //
 //   phase A (lane = pixel of the warp's 8x4 block, as in the forward): for each relevant entry,
 //     evaluate alpha, advance the pixel's replay state and write the three scalars the moments are
@@ -569,9 +427,11 @@ template <bool FUSED>
 __global__ void __launch_bounds__(FSGS_BWD_LB)
 k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const float4 *__restrict__ sorted_rec,
                 const float *__restrict__ bg, const float *__restrict__ final_T,
-                const unsigned int *__restrict__ n_contrib, const float *__restrict__ dL_dplanes,
-                const float *__restrict__ dL_ddepth, float *__restrict__ grad_acc, unsigned int flags,
-                unsigned long long *__restrict__ err) {
+                const unsigned int *__restrict__ n_contrib, const float *__restrict__ g_rgb,
+                const float *__restrict__ g_depth, const float *__restrict__ g_sil, const float *__restrict__ g_dsq,
+                float *__restrict__ grad_acc, unsigned int flags, unsigned long long *__restrict__ err) {
+    // upstream gradients: g_rgb[3,H,W] and one [H,W] plane each for depth | silhouette | depth^2 (fused
+    // flavour; the API flavour has the package's depth output in g_depth).  A NULL plane is all zeros.
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BwdSmem &sm = *reinterpret_cast<BwdSmem *>(smem_raw);
     const int tile = blockIdx.x;
@@ -613,12 +473,12 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 #pragma unroll
         for (int ch = 0; ch < NG; ++ch) g[ch] = 0.f;
         if (pix.inside) {
-            g[0] = dL_dplanes[p]; g[1] = dL_dplanes[HW + p]; g[2] = dL_dplanes[2 * HW + p];
+            if (g_rgb) { g[0] = g_rgb[p]; g[1] = g_rgb[HW + p]; g[2] = g_rgb[2 * HW + p]; }
+            if (g_depth) g[3] = g_depth[p];
             if (FUSED) {
-                g[3] = dL_dplanes[3 * HW + p]; g[4] = dL_dplanes[4 * HW + p]; g[5] = dL_dplanes[5 * HW + p];
+                if (g_sil) g[4] = g_sil[p];
+                if (g_dsq) g[5] = g_dsq[p];
                 bgdot_dep = b0 * g[3] + b1 * g[4] + b2 * g[5];
-            } else {
-                g[3] = dL_ddepth ? dL_ddepth[p] : 0.f;
             }
             bgdot_rgb = b0 * g[0] + b1 * g[1] + b2 * g[2];
         }

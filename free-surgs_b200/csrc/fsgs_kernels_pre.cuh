@@ -180,7 +180,7 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
                    const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                    float4 *__restrict__ records, uint8_t *__restrict__ clamped, int *__restrict__ radii,
                    unsigned int *__restrict__ tile_count, unsigned long long *__restrict__ counters,
-                   unsigned int flags) {
+                   unsigned int flags, unsigned char *__restrict__ visibility, float *__restrict__ max_radii2D) {
     // The 180 B/Gaussian of higher-order SH coefficients (76 % of the input bytes) are contiguous per
     // CTA: one bulk TMA copy stages them; threads then read their own 45 floats at a conflict-free
     // stride.  FSGS_FLAG_NO_TMA (or a mis-aligned tensor) reads them straight from global memory.
@@ -220,6 +220,10 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
         }
         clamped[i] = cl;
         radii[i] = vis ? sp.radius : 0;
+        // render()'s bookkeeping (gaussian_renderer/__init__.py:77-80,88): seen / visibility_filter and
+        // max_radii2D[seen] = max(radius[seen], max_radii2D[seen])
+        if (visibility) visibility[i] = vis ? 1 : 0;
+        if (max_radii2D && vis) max_radii2D[i] = fmaxf(max_radii2D[i], (float)sp.radius);
     }
     warp_for_each_tile(cc.gx, cc.gy, vis, sp.px, sp.py, sp.conx, sp.cony, sp.conz, opacity, sp.radius, (flags & 2u) != 0,
                        lane, [&](int, int t) { atomicAdd(&tile_count[t], 1u); });

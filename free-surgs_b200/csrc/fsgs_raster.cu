@@ -138,7 +138,7 @@ int mailbox(int dev, unsigned long long **pinned, cudaEvent_t *ev) {
 template <bool FUSED>
 int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float *bg, Buffers &B,
                  fsgs_alloc_fn binning_alloc, void *binning_user, float *out_planes, float *out_depth,
-                 int64_t *num_rendered_host, int64_t *num_rect_host, cudaStream_t stream) {
+                 int64_t *num_rendered_host, int64_t *num_rect_host, const RenderExtras &ex, cudaStream_t stream) {
     const int tiles = B.il.tiles;
     unsigned int *tile_count = reinterpret_cast<unsigned int *>(B.img + B.il.tile_count);
     unsigned int *tile_offset = reinterpret_cast<unsigned int *>(B.img + B.il.tile_offset);
@@ -180,7 +180,7 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
         k_composite_fwd<FUSED><<<tiles, CTA, 0, stream>>>(
             cc, tile_offset, sorted_rec, bg, out_planes, out_depth, reinterpret_cast<float *>(B.img + B.il.final_T),
             reinterpret_cast<unsigned int *>(B.img + B.il.n_contrib), (unsigned)st->flags, counters + CNT_ERR, counters,
-            capacity);
+            capacity, ex);
         prof_end(K_COMP_FWD, stream);
         FSGS_LAUNCH_OK("k_composite_fwd");
         return FSGS_OK;
@@ -261,6 +261,17 @@ __global__ void k_fill_bg(int HW, int planes, const float *__restrict__ bg, floa
     if (i >= HW) return;
     for (int c = 0; c < planes; ++c) out[(size_t)c * HW + i] = __ldg(bg + (c % 3));
     if (depth) depth[i] = 0.f;
+}
+
+// the derived maps of an empty scene: every plane equals the background
+__global__ void k_fill_extras(int HW, const float *__restrict__ bg, RenderExtras ex) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    const float dep = __ldg(bg), sil = __ldg(bg + 1), dsq = __ldg(bg + 2);
+    const float unc = __fsub_rn(dsq, __fmul_rn(dep, dep));
+    if (ex.uncertainty) ex.uncertainty[i] = unc;
+    if (ex.presence_mask) ex.presence_mask[i] = sil > 0.3f ? 1 : 0;
+    if (ex.nan_mask) ex.nan_mask[i] = (dep == dep && unc == unc) ? 1 : 0;
 }
 
 }  // namespace
@@ -362,7 +373,7 @@ int fsgs_rasterize_forward(const fsgs_settings *st, int32_t P, const float *bg, 
     prof_end(K_PRE_API, stream);
     FSGS_LAUNCH_OK("k_preprocess_api");
     return forward_tail<false>(st, cc, P, bg, B, binning_alloc, binning_user, out_color, out_depth, num_rendered_host,
-                               num_rect_host, stream);
+                               num_rect_host, RenderExtras{}, stream);
 }
 
 int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg,
@@ -391,17 +402,10 @@ int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rend
     FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
     if (num_rendered > 0) {
         prof_begin(K_COMP_BWD, stream);
-        if (st->flags & FSGS_FLAG_BWD_SHUFFLE)
-            k_composite_bwd_shfl<false><<<il.tiles, CTA, 0, stream>>>(
+        k_composite_bwd<false><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
-            dL_dout_color, dL_dout_depth, acc, (unsigned)st->flags,
-            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
-        else
-            k_composite_bwd<false><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
-            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
-            bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
-            dL_dout_color, dL_dout_depth, acc, (unsigned)st->flags,
+            dL_dout_color, dL_dout_depth, nullptr, nullptr, acc, (unsigned)st->flags,
             const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
         prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");
@@ -462,7 +466,26 @@ int fsgs_render_forward(const fsgs_settings *st, int32_t P, const float *bg, con
                         fsgs_alloc_fn geom_alloc, void *geom_user, fsgs_alloc_fn binning_alloc, void *binning_user,
                         fsgs_alloc_fn img_alloc, void *img_user, float *out_planes, int32_t *radii,
                         int64_t *num_rendered_host, int64_t *num_rect_host, void *stream_) {
+    return fsgs_render_forward_ex(st, P, bg, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose,
+                                  cam_center, viewmatrix, projmatrix, geom_alloc, geom_user, binning_alloc, binning_user,
+                                  img_alloc, img_user, out_planes, radii, num_rendered_host, num_rect_host, nullptr,
+                                  stream_);
+}
+
+int fsgs_render_forward_ex(const fsgs_settings *st, int32_t P, const float *bg, const float *xyz,
+                           const float *features_dc, const float *features_rest, const float *opacity_raw,
+                           const float *scaling_raw, const float *rotation_raw, const float *pose,
+                           const float *cam_center, const float *viewmatrix, const float *projmatrix,
+                           fsgs_alloc_fn geom_alloc, void *geom_user, fsgs_alloc_fn binning_alloc, void *binning_user,
+                           fsgs_alloc_fn img_alloc, void *img_user, float *out_planes, int32_t *radii,
+                           int64_t *num_rendered_host, int64_t *num_rect_host, const fsgs_render_extras *extras,
+                           void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    RenderExtras ex{};
+    if (extras) {
+        ex.uncertainty = extras->uncertainty; ex.presence_mask = extras->presence_mask; ex.nan_mask = extras->nan_mask;
+        ex.visibility = extras->visibility; ex.max_radii2D = extras->max_radii2D;
+    }
     CamConst cc;
     int rc = make_cam(st, cc);
     if (rc) return rc;
@@ -480,6 +503,8 @@ int fsgs_render_forward(const fsgs_settings *st, int32_t P, const float *bg, con
     if (P == 0) {
         k_fill_bg<<<blocks(HW), CTA, 0, stream>>>(HW, 6, bg, out_planes, nullptr);
         FSGS_LAUNCH_OK("k_fill_bg");
+        k_fill_extras<<<blocks(HW), CTA, 0, stream>>>(HW, bg, ex);
+        FSGS_LAUNCH_OK("k_fill_extras");
         return FSGS_OK;
     }
     Buffers B;
@@ -489,11 +514,11 @@ int fsgs_render_forward(const fsgs_settings *st, int32_t P, const float *bg, con
         cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
         projmatrix, reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped),
         radii, reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
-        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags);
+        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags, ex.visibility, ex.max_radii2D);
     prof_end(K_PRE_FUSED, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused");
     return forward_tail<true>(st, cc, P, bg, B, binning_alloc, binning_user, out_planes, nullptr, num_rendered_host,
-                              num_rect_host, stream);
+                              num_rect_host, ex, stream);
 }
 
 int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg, const float *xyz,
@@ -504,6 +529,24 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
                          int32_t gs_grad, int32_t cam_grad, float *dL_dxyz, float *dL_dfeatures_dc,
                          float *dL_dfeatures_rest, float *dL_dopacity_raw, float *dL_dscaling_raw,
                          float *dL_drotation_raw, float *dL_dpose, float *dL_dmeans2D, void *stream_) {
+    if (!dL_dplanes || !st) return FSGS_E_INVALID;
+    const size_t HW = (size_t)st->image_width * (size_t)st->image_height;
+    return fsgs_render_backward_ex(st, P, num_rendered, bg, xyz, features_dc, features_rest, opacity_raw, scaling_raw,
+                                   rotation_raw, pose, cam_center, viewmatrix, projmatrix, geom, binning, img, dL_dplanes,
+                                   dL_dplanes + 3 * HW, dL_dplanes + 4 * HW, dL_dplanes + 5 * HW, grad_scratch, gs_grad,
+                                   cam_grad, dL_dxyz, dL_dfeatures_dc, dL_dfeatures_rest, dL_dopacity_raw, dL_dscaling_raw,
+                                   dL_drotation_raw, dL_dpose, dL_dmeans2D, stream_);
+}
+
+int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg, const float *xyz,
+                            const float *features_dc, const float *features_rest, const float *opacity_raw,
+                            const float *scaling_raw, const float *rotation_raw, const float *pose,
+                            const float *cam_center, const float *viewmatrix, const float *projmatrix, const void *geom,
+                            const void *binning, const void *img, const float *dL_drgb, const float *dL_ddepth,
+                            const float *dL_dsil, const float *dL_ddepth_sq, void *grad_scratch, int32_t gs_grad,
+                            int32_t cam_grad, float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
+                            float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw, float *dL_dpose,
+                            float *dL_dmeans2D, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CamConst cc;
     int rc = make_cam(st, cc);
@@ -511,7 +554,7 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
     cc.n_coeffs = 16;
     if (dL_dpose) FSGS_CUDA(cudaMemsetAsync(dL_dpose, 0, 16 * sizeof(float), stream));
     if (P <= 0) return P == 0 ? FSGS_OK : FSGS_E_INVALID;
-    if (!geom || !img || !binning || !dL_dplanes || !grad_scratch || !xyz || !features_dc || !features_rest ||
+    if (!geom || !img || !binning || !grad_scratch || !xyz || !features_dc || !features_rest ||
         !opacity_raw || !scaling_raw || !rotation_raw || !pose || !cam_center || !viewmatrix || !projmatrix || !bg)
         return FSGS_E_INVALID;
     if ((rc = check_arch())) return rc;
@@ -525,17 +568,10 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
     FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
     if (num_rendered > 0) {
         prof_begin(K_COMP_BWD, stream);
-        if (st->flags & FSGS_FLAG_BWD_SHUFFLE)
-            k_composite_bwd_shfl<true><<<il.tiles, CTA, 0, stream>>>(
+        k_composite_bwd<true><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
-            dL_dplanes, nullptr, acc, (unsigned)st->flags,
-            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
-        else
-            k_composite_bwd<true><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
-            cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
-            bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
-            dL_dplanes, nullptr, acc, (unsigned)st->flags,
+            dL_drgb, dL_ddepth, dL_dsil, dL_ddepth_sq, acc, (unsigned)st->flags,
             const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
         prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");

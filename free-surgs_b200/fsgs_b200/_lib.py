@@ -17,7 +17,6 @@ CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
 FLAG_NO_TMA = 1
 FLAG_NO_TILE_CULL = 2
-FLAG_BWD_SHUFFLE = 4
 FLAG_NO_OPTIMISTIC = 8
 FLAG_SORT_NETWORK = 16
 
@@ -31,6 +30,12 @@ class Settings(ctypes.Structure):
                 ("tanfovx", ctypes.c_float), ("tanfovy", ctypes.c_float),
                 ("scale_modifier", ctypes.c_float), ("sh_degree", ctypes.c_int32),
                 ("n_coeffs", ctypes.c_int32), ("debug", ctypes.c_int32), ("flags", ctypes.c_int32)]
+
+
+class RenderExtras(ctypes.Structure):
+    """fsgs_render_extras: optional derived outputs of render() (device pointers, NULL = skip)."""
+    _fields_ = [("uncertainty", ctypes.c_void_p), ("presence_mask", ctypes.c_void_p), ("nan_mask", ctypes.c_void_p),
+                ("visibility", ctypes.c_void_p), ("max_radii2D", ctypes.c_void_p)]
 
 
 ALLOC_FN = ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
@@ -60,8 +65,13 @@ _SIGNATURES = {
     "fsgs_render_forward": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 11 +
                             [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp] + [_vp] * 2 +
                             [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]),
+    "fsgs_render_forward_ex": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 11 +
+                               [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp] + [_vp] * 2 +
+                               [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp, _vp]),
     "fsgs_render_backward": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 16 +
                              [_i32, _i32] + [_vp] * 9),
+    "fsgs_render_backward_ex": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 19 +
+                                [_i32, _i32] + [_vp] * 9),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -46,7 +46,7 @@ class _RenderFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, rs, cam_center,
-                active_sh_degree, gs_grad, cam_grad):
+                active_sh_degree, gs_grad, cam_grad, max_radii2D=None, want_extras=False):
         _require_cuda(xyz)
         dev = xyz.device
         P = xyz.shape[0]
@@ -58,23 +58,39 @@ class _RenderFused(torch.autograd.Function):
         radii = torch.empty(P, dtype=torch.int32, device=dev)     # the projection kernel writes every entry
         arena = _Arena(dev)
         nr, nrect = ctypes.c_int64(0), ctypes.c_int64(0)
+        # render()'s derived maps come out of the same kernels (fsgs_render_extras): one byte buffer for the
+        # three masks, the uncertainty map, and max_radii2D updated in place when it is a float32 tensor
+        extras, ex_ptr = (), None
+        if want_extras:
+            unc = torch.empty(1, H, W, dtype=torch.float32, device=dev)
+            masks = torch.empty(2 * H * W + P, dtype=torch.uint8, device=dev)
+            ex = _lib.RenderExtras(unc.data_ptr(), masks.data_ptr(), masks.data_ptr() + H * W,
+                                   masks.data_ptr() + 2 * H * W if P else None,
+                                   max_radii2D.data_ptr() if (max_radii2D is not None and P) else None)
+            ex_ptr = ctypes.cast(ctypes.pointer(ex), ctypes.c_void_p)
+            mb = masks.view(torch.bool)
+            extras = (unc, mb[:H * W].view(H, W), mb[H * W:2 * H * W].view(1, H, W), mb[2 * H * W:])
         with torch.cuda.device(dev):
-            rc = _lib.lib().fsgs_render_forward(
+            rc = _lib.lib().fsgs_render_forward_ex(
                 ctypes.byref(st), P, *[_ptr(x) for x in t], arena.callback("geom"), None, arena.callback("binning"),
                 None, arena.callback("img"), None, _ptr(planes), _ptr(radii), ctypes.byref(nr), ctypes.byref(nrect),
-                _stream(dev))
+                ex_ptr, _stream(dev))
         _lib.check(rc)
         empty = torch.empty(0, dtype=torch.uint8, device=dev)
         ctx.save_for_backward(*t, *[arena.tensors.get(k, empty) for k in ("geom", "binning", "img")])
         ctx.lease = arena.finish()             # scratch goes back to the workspace pool when this node dies
         ctx.st, ctx.P, ctx.num_rendered, ctx.num_rect = st, P, int(nr.value), int(nrect.value)
         ctx.flags = (bool(gs_grad), bool(cam_grad))
-        ctx.mark_non_differentiable(radii)
+        ctx.mark_non_differentiable(radii, *extras)
+        ctx.set_materialize_grads(False)        # an output the loss does not use arrives as None, not as zeros
         _RenderFused.last_stats = (int(nr.value), int(nrect.value))
-        return planes, radii
+        # one output per render() product, all views of the one [6,H,W] buffer the compositor writes: the upstream
+        # gradients then arrive per product and go to the library as separate planes (fsgs_render_backward_ex) --
+        # no zero-filled [6,H,W] gradient is assembled from slices by autograd
+        return (planes[0:3], planes[3], planes[4], planes[5], radii, *extras)
 
     @staticmethod
-    def backward(ctx, g_planes, _g_radii):
+    def backward(ctx, g_rgb, g_depth, g_sil, g_dsq, _g_radii=None, *_g_extras):
         *t, geom, binning, img = ctx.saved_tensors
         dev = t[1].device
         P = ctx.P
@@ -98,28 +114,51 @@ class _RenderFused(torch.autograd.Function):
         if P == 0:
             g["pose"].zero_()
         if P > 0:
-            gp = _f32(g_planes, dev)
+            gp = [None if x is None else _f32(x, dev) for x in (g_rgb, g_depth, g_sil, g_dsq)]
             arena = _Arena(dev)
             scratch = arena.take("grad_scratch", _lib.lib().fsgs_grad_scratch_bytes(P))
             with torch.cuda.device(dev):
-                rc = _lib.lib().fsgs_render_backward(
+                rc = _lib.lib().fsgs_render_backward_ex(
                     ctypes.byref(ctx.st), P, ctx.num_rendered, *[_ptr(x) for x in t], _ptr(geom), _ptr(binning),
-                    _ptr(img), _ptr(gp), _ptr(scratch), int(gs_grad), int(cam_grad), _ptr(g["xyz"]), _ptr(g["f_dc"]),
+                    _ptr(img), *[None if x is None else _ptr(x) for x in gp], _ptr(scratch), int(gs_grad), int(cam_grad),
+                    _ptr(g["xyz"]), _ptr(g["f_dc"]),
                     _ptr(g["f_rest"]), _ptr(g["opacity"]), _ptr(g["scaling"]), _ptr(g["rotation"]), _ptr(g["pose"]),
                     _ptr(g["means2D"]), _stream(dev))
             arena.finish().release()           # kernels are enqueued; reuse is ordered on this stream
             _lib.check(rc)
         return (g["xyz"], g["f_dc"], g["f_rest"], g["opacity"], g["scaling"], g["rotation"],
-                g["pose"] if cam_grad else None, g["means2D"], None, None, None, None, None)
+                g["pose"] if cam_grad else None, g["means2D"], None, None, None, None, None, None, None)
 
 
 def render_planes(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, raster_settings,
-                  cam_center, active_sh_degree, gs_grad=True, cam_grad=True):
-    """Tensor-level entry: -> (planes[6,H,W], radii[P] int32, (instances, reference-rectangle instances))."""
+                  cam_center, active_sh_degree, gs_grad=True, cam_grad=True, max_radii2D=None, want_extras=False):
+    """Tensor-level entry: -> ((rgb[3,H,W], depth[H,W], silhouette[H,W], depth_sq[H,W]), radii[P] int32,
+    (instances, reference-rectangle instances)); the four images are views of one [6,H,W] buffer.
+    With ``want_extras`` a 4th element: (uncertainty[1,H,W], presence_mask[H,W], nan_mask[1,H,W],
+    visibility[P], max_radii2D_updated_in_place: bool), produced by the forward kernels."""
     _check_identity_view(raster_settings)
-    planes, radii = _RenderFused.apply(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D,
-                                       raster_settings, cam_center, active_sh_degree, gs_grad, cam_grad)
-    return planes, radii, _RenderFused.last_stats
+    mr = max_radii2D
+    fuse_mr = (want_extras and mr is not None and mr.dtype == torch.float32 and mr.is_contiguous()
+               and mr.device == xyz.device and mr.numel() == xyz.shape[0])
+    rgb, depth, sil, dsq, radii, *extras = _RenderFused.apply(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D,
+                                                raster_settings, cam_center, active_sh_degree, gs_grad, cam_grad,
+                                                mr if fuse_mr else None, want_extras)
+    if want_extras:
+        return (rgb, depth, sil, dsq), radii, _RenderFused.last_stats, (*extras, fuse_mr)
+    return (rgb, depth, sil, dsq), radii, _RenderFused.last_stats
+
+
+def _pack_fused(pc, viewmatrix_cur, planes, radius, means2D, extras):
+    """render()'s return dict and side effects when the derived maps came out of the kernels."""
+    uncertainty, presence, nan_mask, visible, mr_done = extras
+    pc.variables['means2D'] = means2D
+    if not mr_done:
+        mr = pc.variables['max_radii2D']
+        torch.maximum(mr, radius.to(mr.dtype), out=mr)
+    pc.variables['seen'] = visible
+    return {"render": planes[0], "render_dep": planes[1], "render_w2c": viewmatrix_cur, "render_opacity": planes[2],
+            "nan_mask": nan_mask, "presence_mask": presence, "uncertainty": uncertainty,
+            "viewspace_points": means2D, "visibility_filter": visible, "radii": radius}
 
 
 def _pack(pc, viewmatrix_cur, im, depth_sil, radius, means2D):
@@ -150,11 +189,11 @@ def render(viewpoint_camera, index, pc, gs_grad=True, cam_grad=True):
         means2D.retain_grad()
     viewmatrix_cur = viewpoint_camera.get_pose(index)
     pose = viewmatrix_cur if cam_grad else viewmatrix_cur.detach()
-    planes, radius, stats = render_planes(
+    planes, radius, stats, extras = render_planes(
         xyz, pc.params['_features_dc'], pc.params['_features_rest'], pc.params['_opacity'], pc.params['_scaling'],
         pc.params['_rotation'], pose, means2D, pc.cam, viewpoint_camera.cam_center, pc.active_sh_degree,
-        gs_grad=gs_grad, cam_grad=cam_grad)
-    out = _pack(pc, viewmatrix_cur, planes[0:3], planes[3:6], radius, means2D)
+        gs_grad=gs_grad, cam_grad=cam_grad, max_radii2D=pc.variables.get('max_radii2D'), want_extras=True)
+    out = _pack_fused(pc, viewmatrix_cur, planes, radius, means2D, extras)
     out["num_rendered"] = stats
     return out
 

@@ -71,7 +71,7 @@ typedef struct fsgs_settings {
 
 #define FSGS_FLAG_NO_TMA 1u        /* stage tile batches with plain loads instead of bulk TMA     */
 #define FSGS_FLAG_NO_TILE_CULL 2u  /* keep every tile of the reference's 3-sigma rectangle        */
-#define FSGS_FLAG_BWD_SHUFFLE 4u   /* backward compositor: first (warp-shuffle reduce) formulation */
+#define FSGS_FLAG_RESERVED_4 4u    /* (was: first backward formulation, removed; ignored)          */
 #define FSGS_FLAG_NO_OPTIMISTIC 8u /* forward: always wait for the instance count before binning   */
 #define FSGS_FLAG_SORT_NETWORK 16u /* per-tile sort: always the compare-exchange network (A/B, tests) */
 
@@ -130,6 +130,30 @@ int fsgs_render_forward(const fsgs_settings *st, int32_t P, const float *bg, con
                         void *binning_user, fsgs_alloc_fn img_alloc, void *img_user, float *out_planes,
                         int32_t *radii, int64_t *num_rendered_host, int64_t *num_rect_host, void *stream);
 
+/* The same forward, additionally producing the derived outputs of the reference's render()
+ * (gaussian_renderer/__init__.py:70-88) from inside the kernels instead of a dozen element-wise passes:
+ *   uncertainty[1,H,W]   = depth^2 plane - (depth plane)^2                       (:73-75, detached)
+ *   presence_mask[H,W]   = silhouette plane > 0.3                                (:72)      uint8 0/1
+ *   nan_mask[1,H,W]      = !isnan(depth plane) & !isnan(uncertainty)             (:81)      uint8 0/1
+ *   visibility[P]        = radii > 0                                             (:77,:88)  uint8 0/1
+ *   max_radii2D[P]       = max(max_radii2D, radii), updated IN PLACE             (:78)      float32
+ * Any pointer may be NULL (that output is skipped); extras == NULL is fsgs_render_forward. */
+typedef struct fsgs_render_extras {
+    float *uncertainty;
+    uint8_t *presence_mask;
+    uint8_t *nan_mask;
+    uint8_t *visibility;
+    float *max_radii2D;
+} fsgs_render_extras;
+int fsgs_render_forward_ex(const fsgs_settings *st, int32_t P, const float *bg, const float *xyz,
+                           const float *features_dc, const float *features_rest, const float *opacity_raw,
+                           const float *scaling_raw, const float *rotation_raw, const float *pose,
+                           const float *cam_center, const float *viewmatrix, const float *projmatrix,
+                           fsgs_alloc_fn geom_alloc, void *geom_user, fsgs_alloc_fn binning_alloc,
+                           void *binning_user, fsgs_alloc_fn img_alloc, void *img_user, float *out_planes,
+                           int32_t *radii, int64_t *num_rendered_host, int64_t *num_rect_host,
+                           const fsgs_render_extras *extras, void *stream);
+
 /* Backward of the fused render.  dL_dplanes[6,H,W].  Outputs (overwritten; NULL = skip):
  * dL_dxyz[P,3], dL_dfeatures_dc[P,1,3], dL_dfeatures_rest[P,15,3], dL_dopacity_raw[P,1],
  * dL_dscaling_raw[P,3], dL_drotation_raw[P,4], dL_dpose[4,4] (row 3 = 0),
@@ -146,6 +170,21 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
                          float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
                          float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw,
                          float *dL_dpose, float *dL_dmeans2D, void *stream);
+
+/* The same backward with the upstream gradient given per output of render() instead of as one packed
+ * [6,H,W] array: dL_drgb[3,H,W] ("render"), dL_ddepth[H,W] ("render_dep"), dL_dsil[H,W]
+ * ("render_opacity"), dL_ddepth_sq[H,W] (the depth^2 plane; detached in the reference, normally NULL).
+ * A NULL plane is all zeros and is neither read nor materialised. */
+int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg,
+                            const float *xyz, const float *features_dc, const float *features_rest,
+                            const float *opacity_raw, const float *scaling_raw, const float *rotation_raw,
+                            const float *pose, const float *cam_center, const float *viewmatrix,
+                            const float *projmatrix, const void *geom, const void *binning, const void *img,
+                            const float *dL_drgb, const float *dL_ddepth, const float *dL_dsil,
+                            const float *dL_ddepth_sq, void *grad_scratch, int32_t gs_grad, int32_t cam_grad,
+                            float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
+                            float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw,
+                            float *dL_dpose, float *dL_dmeans2D, void *stream);
 
 /* Per-frame pose, LearnPose.forward (scene/pose_optimizer.py:822-877): r[1,4,N] raw quaternion
  * (w,x,y,z) and t[3,N] as the reference stores them; column `cam` -> Rt[4,4] row-major

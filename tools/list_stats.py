@@ -23,7 +23,7 @@ means2D = torch.zeros_like(xyz, requires_grad=True) + 0
 planes, radii, stats = render.render_planes(
     xyz, pc.params['_features_dc'], pc.params['_features_rest'], pc.params['_opacity'], pc.params['_scaling'],
     pc.params['_rotation'], poses.get_pose(0), means2D, pc.cam, poses.cam_center, pc.active_sh_degree)
-img = planes.grad_fn.saved_tensors[-1]
+img = planes[0].grad_fn.saved_tensors[-1]
 import ctypes  # noqa: E402
 off = (ctypes.c_size_t * 6)()
 _lib.lib().fsgs_img_offsets(W, H, off)
