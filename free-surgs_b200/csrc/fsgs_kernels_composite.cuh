@@ -291,6 +291,16 @@ struct BwdSmem {
 };
 
 // Phase B for the first `cn` slots of this warp's chunk.  All 32 lanes call it.
+//   1. lane (entry e, pixel row r) accumulates its row's sums in registers, with the pixel column i = 0..7
+//      as a compile-time constant:  S0 = sum q, S1 = sum q i, S2 = sum q i^2, R0, R1 (RGB-only q), colour sums;
+//      the moments about the entry's centre follow from dx = dx0 - i:  Sx = dx0 S0 - S1,
+//      Sxx = dx0^2 S0 - 2 dx0 S1 + S2, and Sy, Sxy, Syy from the row's constant dy.
+//   2. the moments -> accumulator-row map (bwd_finalize; linear, so it may be applied to a row's partial
+//      sums) is applied by EVERY lane to its own 12 values -- uniform code, no per-row branches;
+//   3. the four rows of an entry are combined through shared memory: each lane stores its 12 values as
+//      3 x float4 into the (now consumed) pair buffer of its warp, then lane (e, k < 3) adds the four rows
+//      of float4 k and issues ONE red.global.add.v4.f32 -- 48 B per entry in 3 lanes.
+//      (A shuffle reduce-scatter + regroup of 12 values over 4 lanes cost ~60 instructions here; this is ~25.)
 template <bool FUSED, int LEVEL>
 __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int warp, int lane,
                                             int cn, uint2 packed, float bx, float by, float kx, float ky,
@@ -298,15 +308,11 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int w
     const int e = lane >> 2, row = lane & 3;
     const bool act = e < cn;
     const int j = list_byte(packed, e);
-    float v[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) v[k] = 0.f;
-    float a2 = 0.f, b2 = 0.f;
+    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0;
     if (act) {
         const float4 q0 = sb[j * 3];
-        a2 = q0.z; b2 = q0.w;
         const float dx0 = q0.x - bx, dy = q0.y - (by + (float)row);
-        float S0 = 0.f, Sx = 0.f, Sxx = 0.f, R0 = 0.f, Rx = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, cz = 0.f, cz2 = 0.f;
+        float S0 = 0.f, S1 = 0.f, S2 = 0.f, R0 = 0.f, R1 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, cz = 0.f, cz2 = 0.f;
         const int sw = (e & 1);   // swizzle of the 16-byte chunk index
         const float4 *pq = reinterpret_cast<const float4 *>(&sm.pair[warp][0][e][0]);
         const float4 *pw = reinterpret_cast<const float4 *>(&sm.pair[warp][1][e][0]);
@@ -324,67 +330,43 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int w
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int i = h * 4 + k;
-                const float dx = dx0 - (float)i;
+                const float fi = (float)i, fi2 = (float)(i * i);
                 const float4 g4 = pg[i];
-                const float qx = qa[k] * dx;
-                S0 += qa[k]; Sx += qx; Sxx = fmaf(qx, dx, Sxx);
-                if (FUSED && LEVEL >= 1) { R0 += ra[k]; Rx = fmaf(ra[k], dx, Rx); }
+                S0 += qa[k];
+                if (i > 0) { S1 = fmaf(qa[k], fi, S1); S2 = fmaf(qa[k], fi2, S2); }
+                if (FUSED && LEVEL >= 1) { R0 += ra[k]; if (i > 0) R1 = fmaf(ra[k], fi, R1); }
                 cr = fmaf(wa[k], g4.x, cr); cg = fmaf(wa[k], g4.y, cg); cb = fmaf(wa[k], g4.z, cb);
                 if (LEVEL >= 1) cz = fmaf(wa[k], g4.w, cz);
                 if (FUSED && LEVEL >= 2) cz2 = fmaf(wa[k], pg2[i].y, cz2);
             }
         }
-        if (!FUSED || LEVEL == 0) { R0 = S0; Rx = Sx; }   // no depth-side gradient (or API flavour): q_rgb == q
-        v[0] = Sx; v[1] = dy * S0; v[2] = Sxx; v[3] = dy * Sx; v[4] = dy * dy * S0; v[5] = S0;
-        v[6] = cr; v[7] = cg; v[8] = cb;
-        v[9] = cz;
-        if (FUSED && LEVEL >= 2) v[9] = fmaf(2.f * sb[j * 3 + 2].y, cz2, cz);
-        v[10] = Rx; v[11] = dy * R0;
-    }
-    // reduce-scatter over the 4 pixel rows (lane bits 1, 0): 12 -> 6 -> 3 values per lane;
-    // afterwards the lane of row r holds the warp-block sums of moments 3r .. 3r+2 in v[0..2]
-    {
-        const bool up = (lane & 2) != 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const float keep = up ? v[i + 6] : v[i], send = up ? v[i] : v[i + 6];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 2);
-        }
-    }
-    {
-        const bool up = (lane & 1) != 0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float keep = up ? v[i + 3] : v[i], send = up ? v[i] : v[i + 3];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 1);
-        }
-    }
-    // moments -> accumulator row (bwd_finalize in fsgs_math.cuh, applied to this lane's three moments)
-    float t0 = v[0], t1 = v[1], t2 = v[2];
-    unsigned int gid = 0;
-    if (act) {
-        gid = __float_as_uint(sb[j * 3 + 2].w);
+        if (!FUSED || LEVEL == 0) { R0 = S0; R1 = S1; }   // no depth-side gradient (or API flavour): q_rgb == q
+        const float Sx = fmaf(dx0, S0, -S1), Rx = fmaf(dx0, R0, -R1);
+        const float Sxx = fmaf(dx0, fmaf(dx0, S0, -2.f * S1), S2);
+        const float Sy = dy * S0, Sxy = dy * Sx, Syy = dy * Sy, Ry = dy * R0;
+        if (FUSED && LEVEL >= 2) cz = fmaf(2.f * sb[j * 3 + 2].y, cz2, cz);
+        // moments -> accumulator row (bwd_finalize in fsgs_math.cuh) on this row's partial sums
         const float2 q1 = *reinterpret_cast<const float2 *>(&sb[j * 3 + 1]);   // (c2, opacity)
         float A, B, C;
-        unscale_conic(a2, b2, q1.x, A, B, C);
-        if (row == 0) {
-            t0 = -kx * (A * v[0] + B * v[1]); t1 = -ky * (C * v[1] + B * v[0]); t2 = -0.5f * v[2];
-        } else if (row == 1) {
-            t0 = -0.5f * v[0]; t1 = -0.5f * v[1]; t2 = v[2] / q1.y;
-        } else if (row == 3) {
-            t1 = -kx * (A * v[1] + B * v[2]); t2 = -ky * (C * v[2] + B * v[1]);
-        }
+        unscale_conic(q0.z, q0.w, q1.x, A, B, C);
+        o0 = make_float4(-kx * (A * Sx + B * Sy), -ky * (C * Sy + B * Sx), -0.5f * Sxx, -0.5f * Sxy);
+        o1 = make_float4(-0.5f * Syy, S0 * fast_rcp(q1.y), cr, cg);
+        o2 = make_float4(cb, cz, -kx * (A * Rx + B * Ry), -ky * (C * Ry + B * Rx));
     }
-    // regroup 4 lanes x 3 floats -> 3 lanes x float4
-    const float n0 = __shfl_down_sync(FULL, t0, 1), n1 = __shfl_down_sync(FULL, t1, 1), n2 = __shfl_down_sync(FULL, t2, 1);
+    __syncwarp();                                   // every lane is done reading the pair buffer
+    float4 *tp = reinterpret_cast<float4 *>(&sm.pair[warp][0][0][0]);   // [entry][row][3] float4 = 1536 B of 3072
+    if (act) { tp[lane * 3] = o0; tp[lane * 3 + 1] = o1; tp[lane * 3 + 2] = o2; }
+    __syncwarp();
     if (act && row < 3) {
+        const float4 r0 = tp[(e * 4) * 3 + row], r1 = tp[(e * 4 + 1) * 3 + row], r2 = tp[(e * 4 + 2) * 3 + row],
+                     r3 = tp[(e * 4 + 3) * 3 + row];
         float4 o;
-        o.x = row == 0 ? t0 : (row == 1 ? t1 : t2);
-        o.y = row == 0 ? t1 : (row == 1 ? t2 : n0);
-        o.z = row == 0 ? t2 : (row == 1 ? n0 : n1);
-        o.w = row == 0 ? n0 : (row == 1 ? n1 : n2);
-        if ((o.x != 0.f) | (o.y != 0.f) | (o.z != 0.f) | (o.w != 0.f))
+        o.x = (r0.x + r1.x) + (r2.x + r3.x); o.y = (r0.y + r1.y) + (r2.y + r3.y);
+        o.z = (r0.z + r1.z) + (r2.z + r3.z); o.w = (r0.w + r1.w) + (r2.w + r3.w);
+        if ((o.x != 0.f) | (o.y != 0.f) | (o.z != 0.f) | (o.w != 0.f)) {
+            const unsigned int gid = __float_as_uint(sb[j * 3 + 2].w);
             atomicAdd(reinterpret_cast<float4 *>(grad_acc + (size_t)gid * ACC_F) + row, o);
+        }
     }
 }
 
