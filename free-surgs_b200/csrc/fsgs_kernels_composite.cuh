@@ -281,12 +281,14 @@ constexpr int PAIR_COMP = 3;
 constexpr int NWARP = CTA / 32;
 constexpr int SG_ROW = 9;   // float4 per pixel row of s_g (8 used)
 
+constexpr int BWD_STAGES = 3;   // record staging ring (3 x 6 KB): warps may drift up to two batches apart
 struct BwdSmem {
-    float4 rec[2][BWD_BATCH * REC_F4];
+    float4 rec[BWD_STAGES][BWD_BATCH * REC_F4];
     float pair[NWARP][PAIR_COMP][PCHUNK][32];
     float4 g[NWARP][2][4 * SG_ROW];
-    uint64_t full[2];
+    uint64_t full[BWD_STAGES];
     unsigned char list[NWARP][BWD_BATCH];   // 8-byte aligned rows (read 8 entries at a time)
+    unsigned int done_cnt[BWD_STAGES];      // warps finished with the batch currently in each stage
     unsigned int maxlast;
 };
 
@@ -430,11 +432,11 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 
     if (threadIdx.x == 0) {
         sm.maxlast = 0;
-        if (use_tma) {
-            mbar_init(&sm.full[0], 1);
-            mbar_init(&sm.full[1], 1);
-            mbar_fence_init();
+        for (int st = 0; st < BWD_STAGES; ++st) {
+            sm.done_cnt[st] = 0u;
+            if (use_tma) mbar_init(&sm.full[st], 1);
         }
+        if (use_tma) mbar_fence_init();
     }
     __syncthreads();
 
@@ -481,34 +483,10 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
     const float4 *src = sorted_rec + (size_t)start * REC_F4;
     auto batch_cnt = [&](int k) { return min(BWD_BATCH, maxlast - k * BWD_BATCH); };
 
-    // prologue: stage the LAST batch
-    {
-        const int k = nb - 1;
-        if (use_tma && threadIdx.x == 0)
-            stage_issue_tma(sm.rec[0], src + (size_t)k * BWD_BATCH * REC_F4, batch_cnt(k), &sm.full[0]);
-    }
-
-    for (int it = 0; it < nb; ++it) {
-        const int k = nb - 1 - it;
-        const int buf = it & 1;
-        const int cnt = batch_cnt(k);
-        __syncthreads();   // every warp is done with batch it-1 (buffer buf^1); s_g written
-        if (it + 1 < nb) {
-            const int kn = k - 1;
-            if (use_tma && threadIdx.x == 0)
-                stage_issue_tma(sm.rec[buf ^ 1], src + (size_t)kn * BWD_BATCH * REC_F4, batch_cnt(kn), &sm.full[buf ^ 1]);
-        }
-        if (use_tma) {
-            mbar_wait(&sm.full[buf], (uint32_t)(it >> 1) & 1u, err);
-        } else {
-            stage_plain(sm.rec[buf], src + (size_t)k * BWD_BATCH * REC_F4, cnt);
-            __syncthreads();
-        }
-        const float4 *sb = sm.rec[buf];
-
-        // entries of this batch that can matter to this warp: mask hit AND not deeper than the warp's
-        // deepest contributor
-        const int limit = min(cnt, warp_last - k * BWD_BATCH);
+    // one staged batch for this warp: entries that can matter = mask hit AND not deeper than the warp's
+    // deepest contributor
+    auto process = [&](int k, const float4 *sb) __attribute__((always_inline)) {
+        const int limit = min(batch_cnt(k), warp_last - k * BWD_BATCH);
         const int nrel = limit > 0 ? compact_entries(sb, limit, warp_bit, lane, sm.list[warp]) : 0;
         if (nrel > 0) {
             if (level == 0)
@@ -521,6 +499,51 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
                 bwd_batch<FUSED, 2>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
         }
+    };
+
+    if (!use_tma) {
+        // FSGS_FLAG_NO_TMA: cooperative loads, two block barriers per batch
+        for (int it = 0; it < nb; ++it) {
+            const int k = nb - 1 - it;
+            __syncthreads();
+            stage_plain(sm.rec[0], src + (size_t)k * BWD_BATCH * REC_F4, batch_cnt(k));
+            __syncthreads();
+            process(k, sm.rec[0]);
+        }
+        return;
+    }
+
+    // Bulk-TMA ring without block barriers.  The warps of a tile have very different amounts of work per batch
+    // (their blocks see different splats, and a block whose pixels saturate early skips the deep batches), so a
+    // __syncthreads per batch left warps parked at the barrier (ncu: top stall reason).  Instead every warp
+    // counts itself out of a stage when it is done with the batch in it; the LAST warp out re-arms that stage's
+    // mbarrier and issues the bulk copy of the batch BWD_STAGES further on.  A warp only ever waits for data.
+    if (threadIdx.x == 0)
+        for (int it = 0; it < min(BWD_STAGES, nb); ++it) {
+            const int k = nb - 1 - it;
+            stage_issue_tma(sm.rec[it], src + (size_t)k * BWD_BATCH * REC_F4, batch_cnt(k), &sm.full[it]);
+        }
+    __syncwarp();          // this warp's rows of sm.g are written
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < nb; ++it) {
+        const int k = nb - 1 - it;
+        mbar_wait(&sm.full[stage], phase, err);
+        process(k, sm.rec[stage]);
+        __syncwarp();      // all lanes are done reading the stage
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&sm.done_cnt[stage], 1u) == (unsigned int)(NWARP - 1)) {
+                sm.done_cnt[stage] = 0u;          // next arrivals come only after the copy below has landed
+                __threadfence_block();
+                const int itn = it + BWD_STAGES;
+                if (itn < nb) {
+                    const int kn = nb - 1 - itn;
+                    stage_issue_tma(sm.rec[stage], src + (size_t)kn * BWD_BATCH * REC_F4, batch_cnt(kn), &sm.full[stage]);
+                }
+            }
+        }
+        if (++stage == BWD_STAGES) { stage = 0; phase ^= 1u; }
     }
 }
 
