@@ -328,6 +328,26 @@ def run_ours(args):
     barrier()
     ms_track = sum(a.elapsed_time(b) for a, b in tr) / args.steps
 
+    # ---- the un-fused drop-in path: what an unmodified gaussian_renderer.render executes on top of our
+    # diff_gaussian_rasterization (PyTorch pre-processing + two GaussianRasterizer calls), same loss ----
+    def two_pass_step():
+        pc.zero_grad()
+        poses.pose_param_net.zero_grad(set_to_none=True)
+        out = render.render_two_pass(poses, 0, pc, gs_grad=True, cam_grad=True)
+        ((out["render"] * G_dev[:3]).sum() + (out["render_dep"] * G_dev[3]).sum()).backward()
+    for _ in range(3):
+        two_pass_step()
+    barrier()
+    n2 = max(3, args.steps // 2)
+    tp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n2)]
+    for k in range(n2):
+        flush.zero_()
+        tp[k][0].record(); two_pass_step(); tp[k][1].record()
+    barrier()
+    ms_two_pass = sum(a.elapsed_time(b) for a, b in tp) / n2
+    if os.environ.get("BENCH_DEBUG"):
+        print("two-pass steps ms", [round(a.elapsed_time(b), 2) for a, b in tp], file=sys.stderr)
+
     # ---- per-kernel durations (separate pass; events inside the library on the launching stream) ----
     _lib.profile_enable(True)
     nprof = min(args.steps, 10)
@@ -371,6 +391,7 @@ def run_ours(args):
                        "tile_instances": R_inst, "tile_instances_reference_rect": R_rect,
                        "parallelism": f"frame-dp{world}" + ("+nccl allreduce(grads)" if world > 1 else "")},
             "pose_grad_ms_per_frame": ms_track,
+            "api_two_pass_ms_per_step": ms_two_pass,      # rank 0's; un-fused GaussianRasterizer drop-in path
             "ms_per_step_median": sorted(ms)[len(ms) // 2],
             "ms_steps": [round(x, 3) for x in ms],
             "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,

@@ -275,13 +275,19 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 // s_pair 8 warps x 3 x 8 x 32 floats (pixel index XOR-swizzled by the slot's low bit so that both
 // the phase-A scalar stores and the phase-B 128-bit row loads are bank-conflict free), per-pixel
 // upstream gradients 8 warps x 2 x 4 x 9 float4 (row stride 9 for the same reason).
-constexpr int BWD_BATCH = 128;
+#ifndef FSGS_BWD_BATCH
+#define FSGS_BWD_BATCH 128
+#endif
+#ifndef FSGS_BWD_STAGES
+#define FSGS_BWD_STAGES 3
+#endif
+constexpr int BWD_BATCH = FSGS_BWD_BATCH;
 constexpr int PCHUNK = 8;
 constexpr int PAIR_COMP = 3;
 constexpr int NWARP = CTA / 32;
 constexpr int SG_ROW = 9;   // float4 per pixel row of s_g (8 used)
 
-constexpr int BWD_STAGES = 3;   // record staging ring (3 x 6 KB): warps may drift up to two batches apart
+constexpr int BWD_STAGES = FSGS_BWD_STAGES;   // record staging ring (3 x 6 KB): warps may drift up to two batches apart
 struct BwdSmem {
     float4 rec[BWD_STAGES][BWD_BATCH * REC_F4];
     float pair[NWARP][PAIR_COMP][PCHUNK][32];
