@@ -359,7 +359,8 @@ __device__ __forceinline__ void tile_sort_network(const Keys &a, int n) {
 }
 
 constexpr int SORT_SMEM_KEYS = 8192;   // 64 KB of dynamic shared memory
-constexpr int BUCKET_MAX_KEYS = 2048;  // lists up to this length take the bucket path
+constexpr int BUCKET_MAX_KEYS = 4096;  // lists up to this length take the bucket path (48 KB of the 64 KB window)
+constexpr int BUCKET_SMEM_IN = 2048;   // ... of which lists up to this length also keep their unsorted keys in shared memory
 constexpr int BUCKET_MAX_FILL = 24;    // fullest bucket the rank pass accepts before falling back to the network
 
 // Gather one sorted instance: per-Gaussian record -> compositor record (conic pre-scaled for the
@@ -386,7 +387,8 @@ __device__ __forceinline__ int depth_bucket(unsigned long long key, float zmin, 
 // Per-tile sort, bucket path (lists of up to BUCKET_MAX_KEYS entries; the usual case).  The depths of
 // one tile's splats are spread roughly evenly between the tile's nearest and farthest, so a linear map
 // of depth onto ~n buckets leaves about one key per bucket:
-//   1. load the keys, block-reduce min / max depth;
+//   1. read the keys (staged in shared memory up to BUCKET_SMEM_IN entries, else re-read from global memory --
+//      the three passes over them hit L1/L2), block-reduce min / max depth;
 //   2. histogram (shared-memory integer atomics), block exclusive scan of the bucket counts;
 //   3. scatter the keys to their bucket's segment (order inside a bucket arbitrary);
 //   4. every key ranks itself inside its bucket by comparing full 64-bit (depth, id) keys -- O(fill) with
@@ -394,24 +396,26 @@ __device__ __forceinline__ int depth_bucket(unsigned long long key, float zmin, 
 //      straight to that position (the sorted keys themselves are never materialised).
 // ~45 instructions per key instead of the ~500 of the 45..55-step compare-exchange network.  The result is
 // the same total order on unique keys, hence bit-identical.  A tile whose fullest bucket exceeds
-// BUCKET_MAX_FILL (many equal depths, strongly clustered depths) returns false with the keys still
-// in s_in, and the caller runs the network instead.
+// BUCKET_MAX_FILL (many equal depths, strongly clustered depths) returns false and the caller runs the
+// network instead.
 __device__ __forceinline__ bool tile_sort_bucket(int n, const unsigned long long *__restrict__ g,
                                                  const float4 *__restrict__ records, float4 *__restrict__ dst,
                                                  int tile_x0, int tile_y0, bool no_cull) {
-    unsigned long long *s_in = fsgs_sort_smem;                                   // [BUCKET_MAX_KEYS]
-    unsigned long long *s_out = fsgs_sort_smem + BUCKET_MAX_KEYS;                // [BUCKET_MAX_KEYS]
-    unsigned int *s_hist = reinterpret_cast<unsigned int *>(fsgs_sort_smem + 2 * BUCKET_MAX_KEYS);   // [nb]
+    unsigned long long *s_out = fsgs_sort_smem;                                                  // [BUCKET_MAX_KEYS]
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(fsgs_sort_smem + BUCKET_MAX_KEYS);   // [nb <= BUCKET_MAX_KEYS]
+    unsigned long long *s_in = fsgs_sort_smem + BUCKET_MAX_KEYS + BUCKET_MAX_KEYS / 2;           // [BUCKET_SMEM_IN]
+    const bool in_smem = n <= BUCKET_SMEM_IN;
+    auto key_at = [&](int p) { return in_smem ? s_in[p] : __ldg(g + p); };
     __shared__ unsigned int s_red[3][CTA / 32];
     __shared__ unsigned int s_warp_sum[CTA / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + CTA - 1) / CTA;          // buckets per thread in the scan (<= 8)
+    const int per = (n + CTA - 1) / CTA;          // buckets per thread in the scan (<= 16)
     const int nb = per * CTA;                     // number of buckets: n rounded up to a multiple of the CTA
 
     unsigned int dmin = 0xffffffffu, dmax = 0u;
     for (int p = tid; p < n; p += CTA) {
-        const unsigned long long k = g[p];
-        s_in[p] = k;
+        const unsigned long long k = __ldg(g + p);
+        if (in_smem) s_in[p] = k;
         const unsigned int d = (unsigned int)(k >> 32);   // depth > 0.2: bit order == numeric order
         dmin = min(dmin, d); dmax = max(dmax, d);
     }
@@ -424,13 +428,14 @@ __device__ __forceinline__ bool tile_sort_bucket(int n, const unsigned long long
     const float zmin = __uint_as_float(dmin), range = __uint_as_float(dmax) - zmin;
     const float inv = range > 0.f ? fminf((float)nb / range, 3.0e38f) : 0.f;
 
-    for (int p = tid; p < n; p += CTA) atomicAdd(&s_hist[depth_bucket(s_in[p], zmin, inv, nb)], 1u);
+    for (int p = tid; p < n; p += CTA) atomicAdd(&s_hist[depth_bucket(key_at(p), zmin, inv, nb)], 1u);
     __syncthreads();
 
     // exclusive scan of s_hist (thread t owns buckets [t*per, (t+1)*per)) + the fullest bucket
-    unsigned int cnt[8], sum = 0, fill = 0;
+    constexpr int PER_MAX = BUCKET_MAX_KEYS / CTA;
+    unsigned int cnt[PER_MAX], sum = 0, fill = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < PER_MAX; ++i) {
         cnt[i] = i < per ? s_hist[tid * per + i] : 0u;
         sum += cnt[i]; fill = max(fill, cnt[i]);
     }
@@ -452,13 +457,13 @@ __device__ __forceinline__ bool tile_sort_bucket(int n, const unsigned long long
     }
     if (fill > (unsigned int)BUCKET_MAX_FILL) return false;   // uniform: every thread sees the same maximum
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < PER_MAX; ++i)
         if (i < per) { s_hist[tid * per + i] = run; run += cnt[i]; }
     __syncthreads();
 
     // scatter: afterwards s_hist[b] = END of bucket b (= start of bucket b + 1)
     for (int p = tid; p < n; p += CTA) {
-        const unsigned long long k = s_in[p];
+        const unsigned long long k = key_at(p);
         s_out[atomicAdd(&s_hist[depth_bucket(k, zmin, inv, nb)], 1u)] = k;
     }
     __syncthreads();
@@ -489,7 +494,9 @@ k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long 
     float4 *dst = sorted_rec + (size_t)start * 3;
     if (n <= BUCKET_MAX_KEYS && !(flags & 16u)) {           // FSGS_FLAG_SORT_NETWORK forces the network (A/B, tests)
         if (tile_sort_bucket(n, g, records, dst, tile_x0, tile_y0, no_cull)) return;
-        __syncthreads();                                    // keys are in s_keys[0..n): fall through to the network
+        __syncthreads();                                    // bucket path declined: the network, in shared memory
+        for (int p = threadIdx.x; p < n; p += blockDim.x) s_keys[p] = g[p];
+        __syncthreads();
         if (n > 1) tile_sort_network(SmemKeys{}, n);
         for (int p = threadIdx.x; p < n; p += blockDim.x)
             emit_sorted_record(records, (unsigned int)s_keys[p], dst + (size_t)p * 3, tile_x0, tile_y0, no_cull);

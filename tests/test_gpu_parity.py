@@ -282,10 +282,12 @@ def test_edge_cases():
     assert rasterizer.GaussianRasterizer(rs).markVisible(m.detach()).tolist() == [False, False]
 
 
-@pytest.mark.parametrize("n_stack", [300, 9000])
-def test_long_tile_lists_and_depth_ties(n_stack):
+@pytest.mark.parametrize("n_stack,ties", [(300, True), (9000, True), (3000, True), (3000, False)])
+def test_long_tile_lists_and_depth_ties(n_stack, ties):
     """One tile with a very long list (multi-batch staging; > 8192 entries takes the global-memory
-    sort path) and many exactly equal depths (order must fall back to the Gaussian id)."""
+    sort path) and many exactly equal depths (order must fall back to the Gaussian id; the bucket sort
+    declines such a list and the compare-exchange network takes over).  ties=False: 3000 distinct depths,
+    the bucket path with 12 buckets per thread."""
     _, _, rasterizer, _ = _gpu_modules()
     from oracle import c_oracle as co
     W = H = 32
@@ -295,7 +297,10 @@ def test_long_tile_lists_and_depth_ties(n_stack):
     means = torch.zeros(P, 3)
     means[:, 0] = (torch.rand(P, generator=g) - 0.5) * 0.01
     means[:, 1] = (torch.rand(P, generator=g) - 0.5) * 0.01
-    means[:, 2] = 1.0 + 0.25 * torch.randint(0, 4, (P,), generator=g).float()     # only 4 distinct depths
+    if ties:
+        means[:, 2] = 1.0 + 0.25 * torch.randint(0, 4, (P,), generator=g).float()     # only 4 distinct depths
+    else:
+        means[:, 2] = 1.0 + torch.rand(P, generator=g)
     d = dict(means3D=means, opacities=torch.full((P, 1), 0.005) + 0.007 * torch.rand(P, 1, generator=g),
              colors_precomp=torch.rand(P, 3, generator=g), scales=torch.full((P, 3), 0.05),
              rotations=torch.tensor([[1.0, 0, 0, 0]]).repeat(P, 1))
