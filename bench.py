@@ -209,6 +209,10 @@ def run_ours(args):
     poses, pc = model.scene_to_device(sc, dev)
     q, t = frame_pose_params(rank)            # rank g renders frame g of the sequence
     poses.set_pose(0, q, t)
+    if world > 1 and args.exchange == "compact":
+        # gradient exchange folded into the backward: 56 B/Gaussian (xyz, opacity, scaling, rotation + the masked
+        # colour gradient) all-reduced, SH gradients expanded locally afterwards (fsgs_b200/dist.py)
+        fsgs_dist.enable_frame_parallel(check_cam_center=poses.cam_center)
     HW = W * H
     # per-step host inputs (the reference copies the GT image to the GPU every iteration, train.py:174)
     G_host = torch.empty(4, H, W).pin_memory()
@@ -225,7 +229,7 @@ def run_ours(args):
         out = render.render(poses, 0, pc, gs_grad=True, cam_grad=True)
         loss = (out["render"] * G[:3]).sum() + (out["render_dep"] * G[3]).sum()
         loss.backward()
-        if world > 1:
+        if world > 1 and args.exchange == "full":
             fsgs_dist.allreduce_gaussian_grads(pc.params)       # one NCCL all-reduce of the flat model gradient
         last["stats"] = out["num_rendered"]
         return loss
@@ -389,7 +393,9 @@ def run_ours(args):
             "config": {"workload": f"endo-synth P={args.P} {W}x{H} SH3 m={args.m} seed0, fused render fwd+bwd, "
                                    f"1 frame/GPU/step", "l2": "256 MiB flush before every timed step (outside the events)",
                        "tile_instances": R_inst, "tile_instances_reference_rect": R_rect,
-                       "parallelism": f"frame-dp{world}" + ("+nccl allreduce(grads)" if world > 1 else "")},
+                       "parallelism": f"frame-dp{world}" + ("" if world == 1 else
+                                                             "+nccl allreduce(grads, 236 B/Gaussian)" if args.exchange == "full"
+                                                             else "+nccl allreduce(compact grads, 56 B/Gaussian, in backward)")},
             "pose_grad_ms_per_frame": ms_track,
             "api_two_pass_ms_per_step": ms_two_pass,      # rank 0's; un-fused GaussianRasterizer drop-in path
             "ms_per_step_median": sorted(ms)[len(ms) // 2],
@@ -414,7 +420,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(G_host.numel() * 4),
                     "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e,
                     "note": "H2D of step k+1 prefetched on a side stream during step k; includes the 256 MiB L2 flush"},
-            "gpu_launches": 9 * args.steps,     # pose fwd, 5 forward kernels, 2 backward kernels, pose bwd
+            # pose fwd, 5 forward kernels, 2 backward kernels, pose bwd (+ the SH-gradient expansion when N > 1)
+            "gpu_launches": (9 + (1 if world > 1 and args.exchange == "compact" else 0)) * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(out))
@@ -431,6 +438,8 @@ def main():
     ap.add_argument("--m", type=float, default=2.0, help="splat size multiplier of the synthetic scene")
     ap.add_argument("--P", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="compact", choices=["compact", "full"],
+                    help="N>1: gradient exchange -- compact (56 B/Gaussian inside the backward) or full (236 B/Gaussian after it)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else args.steps

@@ -74,7 +74,7 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
                        float *__restrict__ dL_dfdc, float *__restrict__ dL_dfrest, float *__restrict__ dL_dopacity_raw,
                        float *__restrict__ dL_dscaling_raw, float *__restrict__ dL_drotation_raw,
                        float *__restrict__ dL_dpose, float *__restrict__ dL_dmeans2D, int use_tma,
-                       unsigned long long *__restrict__ err) {
+                       unsigned long long *__restrict__ err, float *__restrict__ dL_dsh_rgb) {
     // SH coefficients in, SH gradients out through ONE shared-memory buffer: bulk TMA load of the CTA's
     // 256 x 180 B slice, each thread turns its 45 coefficients into their gradients in place, bulk TMA
     // store to dL/dfeatures_rest (the plain path does 45 scalar loads + 45 scalar stores at a 180 B stride).
@@ -84,7 +84,9 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int base = blockIdx.x * blockDim.x, count = min((int)blockDim.x, P - base);
-    const bool staged = dL_dfrest != nullptr && (reinterpret_cast<uintptr_t>(f_rest) & 15u) == 0 &&
+    // (without dL_dfrest -- the frame-parallel compact mode -- the coefficients are still staged: the SH
+    // view-direction gradient needs them; nothing is stored back)
+    const bool staged = (reinterpret_cast<uintptr_t>(f_rest) & 15u) == 0 &&
                         (reinterpret_cast<uintptr_t>(dL_dfrest) & 15u) == 0 && use_tma;
     if (threadIdx.x < 16) s_pose[threadIdx.x] = 0.f;
     if (staged) stage_rows_tma<45>(s_rest, f_rest, base, count, &s_bar, err);
@@ -96,8 +98,8 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
         const size_t n = (size_t)i;
         const int radius = __float_as_int(records[n * 3 + 2].z);
         float dxyz[3] = {0.f, 0.f, 0.f}, ds_raw[3] = {0.f, 0.f, 0.f}, dq_raw[4] = {0.f, 0.f, 0.f, 0.f};
-        float dop_raw = 0.f, dfdc[3] = {0.f, 0.f, 0.f}, m2d[2] = {0.f, 0.f};
-        float *drest = staged ? s_rest + 45 * threadIdx.x : (dL_dfrest ? dL_dfrest + 45 * n : nullptr);
+        float dop_raw = 0.f, dfdc[3] = {0.f, 0.f, 0.f}, m2d[2] = {0.f, 0.f}, gc[3] = {0.f, 0.f, 0.f};
+        float *drest = !dL_dfrest ? nullptr : (staged ? s_rest + 45 * threadIdx.x : dL_dfrest + 45 * n);
         const float *rest = staged ? s_rest + 45 * threadIdx.x : f_rest + 45 * n;
         if (radius > 0) {
             float a[ACC_F];
@@ -113,18 +115,19 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
             const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
             const float q[4] = {q4.x, q4.y, q4.z, q4.w};
             fused_backward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, rest, opacity_raw[i], sc, q, clamped[i], a,
-                               gs_grad, cam_grad, dxyz, dfdc, drest, dop_raw, ds_raw, dq_raw, pg, m2d);
+                               gs_grad, cam_grad, dxyz, dfdc, drest, dop_raw, ds_raw, dq_raw, pg, m2d, gc);
         } else if (drest) {
             for (int k = 0; k < 45; ++k) drest[k] = 0.f;
         }
         if (dL_dxyz) { dL_dxyz[3 * n] = dxyz[0]; dL_dxyz[3 * n + 1] = dxyz[1]; dL_dxyz[3 * n + 2] = dxyz[2]; }
         if (dL_dfdc) { dL_dfdc[3 * n] = dfdc[0]; dL_dfdc[3 * n + 1] = dfdc[1]; dL_dfdc[3 * n + 2] = dfdc[2]; }
+        if (dL_dsh_rgb) { dL_dsh_rgb[3 * n] = gc[0]; dL_dsh_rgb[3 * n + 1] = gc[1]; dL_dsh_rgb[3 * n + 2] = gc[2]; }
         if (dL_dopacity_raw) dL_dopacity_raw[i] = dop_raw;
         if (dL_dscaling_raw) { dL_dscaling_raw[3 * n] = ds_raw[0]; dL_dscaling_raw[3 * n + 1] = ds_raw[1]; dL_dscaling_raw[3 * n + 2] = ds_raw[2]; }
         if (dL_drotation_raw) *reinterpret_cast<float4 *>(dL_drotation_raw + 4 * n) = make_float4(dq_raw[0], dq_raw[1], dq_raw[2], dq_raw[3]);
         if (dL_dmeans2D) { dL_dmeans2D[3 * n] = m2d[0]; dL_dmeans2D[3 * n + 1] = m2d[1]; dL_dmeans2D[3 * n + 2] = 0.f; }
     }
-    if (staged) {
+    if (staged && dL_dfrest) {
         // gradients -> global: bulk store for the 16-byte-multiple prefix, plain stores for <= 3 rows
         fence_proxy_async_smem();
         __syncthreads();
@@ -140,6 +143,49 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
         if ((lane & 1) == 0 && idx < 12 && pg[0] != 0.f) atomicAdd(&s_pose[idx], pg[0]);
         __syncthreads();
         if (threadIdx.x < 12 && s_pose[threadIdx.x] != 0.f) atomicAdd(&dL_dpose[threadIdx.x], s_pose[threadIdx.x]);
+    }
+}
+
+// Frame-parallel exchange, second half: after the masked colour gradients gc[P,3] have been summed over the
+// ranks, every SH-coefficient gradient is basis_k(dir) * gc (zero beyond the active degree), with
+// dir = normalize(xyz - cam_center) identical on all ranks.  Pure write kernel: 192 B/Gaussian, staged in
+// shared memory and written with one bulk TMA store per CTA like the backward above.
+__global__ void __launch_bounds__(CTA)
+k_sh_grad_expand(int P, int sh_deg, const float *__restrict__ xyz, const float *__restrict__ cam_center,
+                 const float *__restrict__ gc, float *__restrict__ dL_dfdc, float *__restrict__ dL_dfrest, int use_tma) {
+    __shared__ __align__(128) float s_rest[CTA * 45];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int base = blockIdx.x * blockDim.x, count = min((int)blockDim.x, P - base);
+    const bool staged = (reinterpret_cast<uintptr_t>(dL_dfrest) & 15u) == 0 && use_tma;
+    if (i < P) {
+        const size_t n = (size_t)i;
+        const float g0 = gc[3 * n], g1 = gc[3 * n + 1], g2 = gc[3 * n + 2];
+        float d[3] = {xyz[3 * n] - __ldg(cam_center), xyz[3 * n + 1] - __ldg(cam_center + 1),
+                      xyz[3 * n + 2] - __ldg(cam_center + 2)};
+        const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        d[0] *= inv; d[1] *= inv; d[2] *= inv;
+        float B[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) B[k] = 0.f;
+        sh_basis(sh_deg, d[0], d[1], d[2], B);
+        const bool any = (g0 != 0.f) | (g1 != 0.f) | (g2 != 0.f);     // untouched Gaussians: exact zeros, also for NaN-free dir
+        dL_dfdc[3 * n] = any ? B[0] * g0 : 0.f; dL_dfdc[3 * n + 1] = any ? B[0] * g1 : 0.f; dL_dfdc[3 * n + 2] = any ? B[0] * g2 : 0.f;
+        float *o = staged ? s_rest + 45 * threadIdx.x : dL_dfrest + 45 * n;
+        const int nb = (sh_deg + 1) * (sh_deg + 1);
+#pragma unroll
+        for (int k = 1; k < 16; ++k) {
+            const float b = (any && k < nb) ? B[k] : 0.f;
+            o[3 * (k - 1)] = b * g0; o[3 * (k - 1) + 1] = b * g1; o[3 * (k - 1) + 2] = b * g2;
+        }
+    }
+    if (staged) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        const int rows_tma = count & ~3;
+        float *gdst = dL_dfrest + (size_t)base * 45;
+        if (threadIdx.x == 0 && rows_tma > 0) tma_store_1d(gdst, s_rest, (uint32_t)rows_tma * 180u);
+        for (int q = rows_tma * 45 + threadIdx.x; q < count * 45; q += blockDim.x) gdst[q] = s_rest[q];
+        if (threadIdx.x == 0 && rows_tma > 0) tma_store_commit_and_wait();
     }
 }
 

@@ -444,7 +444,7 @@ FSGS_HD void fused_backward_one(const CamConst &cc, const float *V, const float 
                                 const float *cam_center, const float *xyz, const float *dc, const float *rest,
                                 float op_raw, const float *sc_raw, const float *rot_raw, uint8_t clamp,
                                 const float *acc, int gs_grad, int cam_grad, float *dxyz, float *dfdc, float *drest,
-                                float &dop_raw, float *ds_raw, float *dq_raw, float *pg, float *m2d) {
+                                float &dop_raw, float *ds_raw, float *dq_raw, float *pg, float *m2d, float *gc = nullptr) {
     float mean[3];
     for (int r = 0; r < 3; ++r)
         mean[r] = pose[4 * r] * xyz[0] + pose[4 * r + 1] * xyz[1] + pose[4 * r + 2] * xyz[2] + pose[4 * r + 3];
@@ -469,6 +469,9 @@ FSGS_HD void fused_backward_one(const CamConst &cc, const float *V, const float 
     const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     d[0] *= inv; d[1] *= inv; d[2] *= inv;
     const float grgb[3] = {acc[6], acc[7], acc[8]};
+    // gc = the colour gradient after the clamp mask: every SH-coefficient gradient is basis(dir) x gc, and
+    // dir / the mask do not depend on the frame (quirk iii) -- what the frame-parallel exchange reduces
+    if (gc) { gc[0] = (clamp & 1) ? 0.f : grgb[0]; gc[1] = (clamp & 2) ? 0.f : grgb[1]; gc[2] = (clamp & 4) ? 0.f : grgb[2]; }
     sh_to_rgb_backward(
         cc.sh_deg, 16, d, inv, [&](int k, int ch) { return k == 0 ? dc[ch] : rest[3 * (k - 1) + ch]; }, clamp, grgb,
         [&](int k, int ch, float v) {

@@ -73,7 +73,7 @@ inline int blocks(int n) { return (n + CTA - 1) / CTA; }
 // Off by default.  bench.py switches it on for a separate profiling pass (never for the timed
 // steps) to obtain the per-launch duration of each kernel for the roofline line.
 enum KernelId { K_PRE_API = 0, K_PRE_FUSED, K_SCAN, K_SCATTER, K_SORT, K_COMP_FWD, K_COMP_BWD, K_PRE_API_BWD,
-                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_COUNT };
+                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_COUNT };
 struct Profiler {
     bool on = false;
     static constexpr int MAXREC = 8192;
@@ -314,7 +314,8 @@ const char *fsgs_error_string(int code) {
 
 const char *fsgs_kernel_names(void) {
     return "k_preprocess_api,k_preprocess_fused,k_tile_scan,k_scatter,k_tile_sort,k_composite_fwd,"
-           "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible,k_pose_forward,k_pose_backward";
+           "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible,k_pose_forward,k_pose_backward,"
+           "k_sh_grad_expand";
 }
 
 size_t fsgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
@@ -535,7 +536,7 @@ int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendere
                                    rotation_raw, pose, cam_center, viewmatrix, projmatrix, geom, binning, img, dL_dplanes,
                                    dL_dplanes + 3 * HW, dL_dplanes + 4 * HW, dL_dplanes + 5 * HW, grad_scratch, gs_grad,
                                    cam_grad, dL_dxyz, dL_dfeatures_dc, dL_dfeatures_rest, dL_dopacity_raw, dL_dscaling_raw,
-                                   dL_drotation_raw, dL_dpose, dL_dmeans2D, stream_);
+                                   dL_drotation_raw, dL_dpose, dL_dmeans2D, nullptr, stream_);
 }
 
 int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg, const float *xyz,
@@ -546,7 +547,7 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
                             const float *dL_dsil, const float *dL_ddepth_sq, void *grad_scratch, int32_t gs_grad,
                             int32_t cam_grad, float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
                             float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw, float *dL_dpose,
-                            float *dL_dmeans2D, void *stream_) {
+                            float *dL_dmeans2D, float *dL_dsh_rgb, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CamConst cc;
     int rc = make_cam(st, cc);
@@ -582,9 +583,26 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
         projmatrix, reinterpret_cast<const float4 *>(g + gl.records), reinterpret_cast<const uint8_t *>(g + gl.clamped),
         acc, gs_grad, cam_grad, dL_dxyz, dL_dfeatures_dc, dL_dfeatures_rest, dL_dopacity_raw, dL_dscaling_raw,
         dL_drotation_raw, dL_dpose, dL_dmeans2D, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1,
-        const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
+        const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR,
+        dL_dsh_rgb);
     prof_end(K_PRE_FUSED_BWD, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused_bwd");
+    return FSGS_OK;
+}
+
+int fsgs_sh_grad_expand(const fsgs_settings *st, int32_t P, const float *xyz, const float *cam_center,
+                        const float *dL_dsh_rgb, float *dL_dfeatures_dc, float *dL_dfeatures_rest, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!st || st->sh_degree < 0 || st->sh_degree > 3 || P < 0) return FSGS_E_INVALID;
+    if (P == 0) return FSGS_OK;
+    if (!xyz || !cam_center || !dL_dsh_rgb || !dL_dfeatures_dc || !dL_dfeatures_rest) return FSGS_E_INVALID;
+    int rc = check_arch();
+    if (rc) return rc;
+    prof_begin(K_SH_EXPAND, stream);
+    k_sh_grad_expand<<<blocks(P), CTA, 0, stream>>>(P, st->sh_degree, xyz, cam_center, dL_dsh_rgb, dL_dfeatures_dc,
+                                                    dL_dfeatures_rest, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1);
+    prof_end(K_SH_EXPAND, stream);
+    FSGS_LAUNCH_OK("k_sh_grad_expand");
     return FSGS_OK;
 }
 

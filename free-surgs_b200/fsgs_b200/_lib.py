@@ -71,7 +71,8 @@ _SIGNATURES = {
     "fsgs_render_backward": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 16 +
                              [_i32, _i32] + [_vp] * 9),
     "fsgs_render_backward_ex": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 19 +
-                                [_i32, _i32] + [_vp] * 9),
+                                [_i32, _i32] + [_vp] * 10),
+    "fsgs_sh_grad_expand": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 6),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -82,6 +82,50 @@ def allreduce_gaussian_grads(params: dict, group=None, bucket: bool = True) -> i
     return nbytes
 
 
+def enable_frame_parallel(group=None, check_cam_center: torch.Tensor = None) -> None:
+    """Fold the gradient exchange into the fused render's backward (the fast path; replaces a later call to
+    ``allreduce_gaussian_grads``).  In Free-SurGS every SH-coefficient gradient of a Gaussian is
+    ``basis_k(dir) * gc`` with ``gc`` the clamp-masked colour gradient, and neither ``dir = normalize(xyz -
+    cam_center)`` nor the mask depends on the frame (the SH view origin is frozen at the first camera,
+    gaussian_model.py:317 / pose_optimizer.py:603).  The ranks therefore SUM-reduce 14 floats per Gaussian
+    (xyz, opacity, scaling, rotation, gc: 56 B) instead of 59 (236 B) and expand the SH gradients locally from the
+    reduced ``gc`` (``fsgs_sh_grad_expand``).  After ``loss.backward()`` every rank holds the summed gradients of all
+    frames; pose gradients stay local.  ``check_cam_center``: if given, asserts that all ranks use the same SH view
+    origin (the precondition)."""
+    from . import frame_render
+    if not _is_dist(group):
+        frame_render.set_grad_reducer(None)
+        return
+    if check_cam_center is not None:
+        c = check_cam_center.detach().float().reshape(-1).clone()
+        ref = c.clone()
+        dist.broadcast(ref, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if not torch.equal(c, ref):
+            raise ValueError("frame-parallel SH-gradient exchange needs the same cam_center (SH view origin) on every rank")
+    frame_render.set_grad_reducer(lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group))
+
+
+def disable_frame_parallel() -> None:
+    from . import frame_render
+    frame_render.set_grad_reducer(None)
+
+
+COMPACT_LAYOUT = (("_rotation", 4), ("_xyz", 3), ("_scaling", 3), ("_opacity", 1), ("gc", 3))   # 14 floats / Gaussian
+
+
+def expand_sh_grads_reference(gc: torch.Tensor, xyz: torch.Tensor, cam_center: torch.Tensor, sh_degree: int, eval_basis):
+    """Plain-torch statement of what ``fsgs_sh_grad_expand`` computes (used by the CPU tests of the protocol):
+    dL/dfeatures[P,16,3] = basis(dir)[P,16,1] * gc[P,1,3], zero above the active degree.
+    ``eval_basis(deg, dirs) -> [P,16]`` supplies the real SH basis."""
+    d = xyz - cam_center.reshape(1, 3)
+    d = d / d.norm(dim=1, keepdim=True)
+    B = eval_basis(sh_degree, d)
+    nb = (sh_degree + 1) ** 2
+    B = torch.cat([B[:, :nb], torch.zeros(B.shape[0], 16 - nb, dtype=B.dtype)], dim=1) if B.shape[1] >= nb else B
+    full = B[:, :, None] * gc[:, None, :]
+    return full[:, :1, :], full[:, 1:, :]
+
+
 def allreduce_densification_stats(variables: dict, group=None) -> None:
     """``xyz_gradient_accum`` and ``denom`` are sums over the frames seen, ``max_radii2D`` a max."""
     if not _is_dist(group):
@@ -95,6 +139,19 @@ def dp_render_step(render_fn, poses, pc, frames: Iterable[int], loss_fn, group=N
     """One data-parallel step: render this rank's frames, sum their losses, one backward, then the
     gradient all-reduce.  ``render_fn(poses, frame, pc, gs_grad, cam_grad)`` is ``fsgs_b200.render``;
     ``loss_fn(frame, render_pkg) -> scalar``.  Returns (local loss or None, list of render packages)."""
+    from . import frame_render
+    folded = frame_render._GRAD_REDUCER["fn"] is not None    # enable_frame_parallel: the exchange happens in backward
+    frames = list(frames)
+    if folded and _is_dist(group):
+        n = torch.tensor([len(frames)], dtype=torch.int64)
+        lo, hi = n.clone(), n.clone()
+        if dist.get_backend(group) == "nccl":
+            lo, hi = lo.cuda(), hi.cuda()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+        if int(lo) != int(hi):
+            raise ValueError("frame-parallel mode runs one collective per rendered frame: every rank needs the same "
+                             f"number of frames per step (got between {int(lo)} and {int(hi)})")
     pkgs, loss = [], None
     for f in frames:
         pkg = render_fn(poses, f, pc, gs_grad=True, cam_grad=True)
@@ -103,5 +160,6 @@ def dp_render_step(render_fn, poses, pc, frames: Iterable[int], loss_fn, group=N
         pkgs.append(pkg)
     if loss is not None:
         loss.backward()
-    allreduce_gaussian_grads(pc.params, group=group)
+    if not folded:
+        allreduce_gaussian_grads(pc.params, group=group)
     return loss, pkgs

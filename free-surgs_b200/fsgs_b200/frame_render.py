@@ -25,6 +25,14 @@ from .rasterizer import GaussianRasterizer, _Arena, _f32, _ptr, _require_cuda, _
 
 _IDENTITY_OK: Dict[tuple, bool] = {}
 
+# Frame-parallel gradient exchange hook (set through fsgs_b200.dist.enable_frame_parallel): a callable that
+# sum-all-reduces a flat float32 CUDA tensor in place, ordered on the current stream; None = single GPU.
+_GRAD_REDUCER = {"fn": None}
+
+
+def set_grad_reducer(fn) -> None:
+    _GRAD_REDUCER["fn"] = fn
+
 
 def _check_identity_view(rs) -> None:
     """The fused path composites the depth planes from the view-space z of the (single) projection,
@@ -97,19 +105,32 @@ class _RenderFused(torch.autograd.Function):
         gs_grad, cam_grad = ctx.flags
         # every output is fully overwritten by the library (zeros where a Gaussian is not visible)
         z = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        # The six Gaussian-parameter gradients are carved out of ONE flat buffer (59 floats/Gaussian, in the
-        # order of fsgs_b200.dist.PARAM_KEYS): autograd adopts the views as .grad, and the frame-parallel path
-        # can then sum-all-reduce the whole model gradient with a single collective and no packing copies.
+        # The six Gaussian-parameter gradients are carved out of ONE flat buffer (59 floats/Gaussian): autograd
+        # adopts the views as .grad, and fsgs_b200.dist.allreduce_gaussian_grads can then sum-all-reduce the whole
+        # model gradient with a single collective and no packing copies.
         # (rotation and f_rest first: their float4 / bulk-TMA stores need 16-byte alignment for any P)
-        flat = z(P * 59)
-        g, off = {}, 0
-        for name, shape in (("rotation", (P, 4)), ("f_rest", (P, 15, 3)), ("xyz", (P, 3)), ("f_dc", (P, 1, 3)),
-                            ("scaling", (P, 3)), ("opacity", (P, 1))):
-            n = 1
-            for s_ in shape:
-                n *= s_
-            g[name] = flat[off:off + n].view(*shape)
-            off += n
+        reducer = _GRAD_REDUCER["fn"]
+        g = {}
+
+        def carve(flat, layout):
+            off = 0
+            for name, shape in layout:
+                n = 1
+                for s_ in shape:
+                    n *= s_
+                g[name] = flat[off:off + n].view(*shape)
+                off += n
+
+        if reducer is None:
+            carve(z(P * 59), (("rotation", (P, 4)), ("f_rest", (P, 15, 3)), ("xyz", (P, 3)), ("f_dc", (P, 1, 3)),
+                             ("scaling", (P, 3)), ("opacity", (P, 1))))
+        else:
+            # frame-parallel mode (fsgs_b200.dist.enable_frame_parallel): the library emits the masked colour
+            # gradient gc[P,3] instead of the 48 SH-coefficient gradients; 14 floats/Gaussian are reduced over the
+            # ranks inside this backward and the SH gradients are expanded from the reduced gc afterwards
+            compact = z(P * 14)
+            carve(compact, (("rotation", (P, 4)), ("xyz", (P, 3)), ("scaling", (P, 3)), ("opacity", (P, 1)), ("gc", (P, 3))))
+            carve(z(P * 48), (("f_rest", (P, 15, 3)), ("f_dc", (P, 1, 3))))
         g["pose"], g["means2D"] = z(4, 4), z(P, 3)
         if P == 0:
             g["pose"].zero_()
@@ -121,11 +142,17 @@ class _RenderFused(torch.autograd.Function):
                 rc = _lib.lib().fsgs_render_backward_ex(
                     ctypes.byref(ctx.st), P, ctx.num_rendered, *[_ptr(x) for x in t], _ptr(geom), _ptr(binning),
                     _ptr(img), *[None if x is None else _ptr(x) for x in gp], _ptr(scratch), int(gs_grad), int(cam_grad),
-                    _ptr(g["xyz"]), _ptr(g["f_dc"]),
-                    _ptr(g["f_rest"]), _ptr(g["opacity"]), _ptr(g["scaling"]), _ptr(g["rotation"]), _ptr(g["pose"]),
-                    _ptr(g["means2D"]), _stream(dev))
+                    _ptr(g["xyz"]), None if reducer else _ptr(g["f_dc"]), None if reducer else _ptr(g["f_rest"]),
+                    _ptr(g["opacity"]), _ptr(g["scaling"]), _ptr(g["rotation"]), _ptr(g["pose"]), _ptr(g["means2D"]),
+                    _ptr(g["gc"]) if reducer else None, _stream(dev))
             arena.finish().release()           # kernels are enqueued; reuse is ordered on this stream
             _lib.check(rc)
+            if reducer is not None:
+                reducer(compact)               # SUM over the ranks, in place, ordered on this stream
+                with torch.cuda.device(dev):
+                    rc = _lib.lib().fsgs_sh_grad_expand(ctypes.byref(ctx.st), P, _ptr(t[1]), _ptr(t[8]), _ptr(g["gc"]),
+                                                        _ptr(g["f_dc"]), _ptr(g["f_rest"]), _stream(dev))
+                _lib.check(rc)
         return (g["xyz"], g["f_dc"], g["f_rest"], g["opacity"], g["scaling"], g["rotation"],
                 g["pose"] if cam_grad else None, g["means2D"], None, None, None, None, None, None, None)
 

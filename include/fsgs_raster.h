@@ -184,7 +184,21 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
                             const float *dL_ddepth_sq, void *grad_scratch, int32_t gs_grad, int32_t cam_grad,
                             float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
                             float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw,
-                            float *dL_dpose, float *dL_dmeans2D, void *stream);
+                            float *dL_dpose, float *dL_dmeans2D, float *dL_dsh_rgb, void *stream);
+
+/* Frame-parallel gradient exchange (one frame per GPU, shared Gaussian model).
+ * Every SH-coefficient gradient of a Gaussian is  basis_k(dir) * gc[ch]  with gc = the colour gradient after
+ * the clamp mask, and in Free-SurGS neither dir = normalize(xyz - cam_center) nor the mask depends on the frame
+ * (the SH view origin is frozen, gaussian_model.py:317 / pose_optimizer.py:603).  So instead of all-reducing
+ * 48 SH-gradient floats per Gaussian the ranks reduce the 3 floats of gc:
+ *   1. fsgs_render_backward_ex with dL_dfeatures_dc = dL_dfeatures_rest = NULL and dL_dsh_rgb[P,3] set:
+ *      the other gradients as usual (dL_dxyz includes the SH view-direction term, which is linear in gc);
+ *   2. the caller sum-all-reduces xyz | opacity | scaling | rotation | gc  (14 floats = 56 B per Gaussian
+ *      instead of 59 floats = 236 B);
+ *   3. fsgs_sh_grad_expand turns the reduced gc into dL_dfeatures_dc[P,1,3] and dL_dfeatures_rest[P,15,3]
+ *      (st->sh_degree = active degree; coefficients above it get zeros). */
+int fsgs_sh_grad_expand(const fsgs_settings *st, int32_t P, const float *xyz, const float *cam_center,
+                        const float *dL_dsh_rgb, float *dL_dfeatures_dc, float *dL_dfeatures_rest, void *stream);
 
 /* Per-frame pose, LearnPose.forward (scene/pose_optimizer.py:822-877): r[1,4,N] raw quaternion
  * (w,x,y,z) and t[3,N] as the reference stores them; column `cam` -> Rt[4,4] row-major

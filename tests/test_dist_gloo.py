@@ -94,6 +94,85 @@ def test_frame_dp_host_logic_world2_gloo(bucket):
     assert res == {0: "ok", 1: "ok"}, res
 
 
+def _compact_worker(rank, world, port, sh_deg, q):
+    """The frame-parallel exchange protocol (fsgs_b200.dist.enable_frame_parallel) on the float64 oracle:
+    rank r renders frame r; all-reducing the 14-float compact gradient and expanding the SH gradients from the
+    reduced masked colour gradient must equal all-reducing the full 59-float gradient."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fsgs_b200.synth import frame_pose_params, make_scene
+        from oracle import raster_oracle as ro
+        from oracle import render_oracle as R
+        dt = torch.float64
+        sc = make_scene(300, 96, 64, size_mult=2.0, seed=5)
+        params = {k: v.to(dt).requires_grad_(True) for k, v in sc.params.items()}
+        qf, tf = frame_pose_params(rank)
+        r = torch.tensor(qf, dtype=dt, requires_grad=True)
+        t = torch.tensor(tf, dtype=dt, requires_grad=True)
+        out = R.render(params, r, t, sc.camera, sh_deg, sc.camera.campos, True, True, backend="c")
+        gen = torch.Generator().manual_seed(77 + rank)          # every frame has its own target
+        G = torch.randn(4, sc.height, sc.width, generator=gen, dtype=dt)
+        ((out["render"] * G[:3]).sum() + (out["render_dep"] * G[3]).sum()).backward()
+        g = {k: p.grad.clone() for k, p in params.items()}
+        assert g["_features_dc"].abs().max() > 0
+        gc = g["_features_dc"][:, 0, :] / ro.SH_C0                  # dL/df_dc = basis_0 * gc, basis_0 = SH_C0
+        compact = torch.cat([g[k].reshape(sc.P, w) if k != "gc" else gc for k, w in fd.COMPACT_LAYOUT], dim=1)
+        assert compact.shape == (sc.P, 14)
+        dist.all_reduce(compact)
+        for k in g:
+            dist.all_reduce(g[k])
+        basis = lambda deg, dirs: ro.eval_sh(deg, torch.eye(16, dtype=dt).expand(dirs.shape[0], 16, 16), dirs)
+        f_dc, f_rest = fd.expand_sh_grads_reference(compact[:, 11:14], params["_xyz"].detach(), sc.camera.campos.to(dt),
+                                                    sh_deg, basis)
+        off = 0
+        for k, w in fd.COMPACT_LAYOUT:
+            if k != "gc":
+                assert torch.equal(compact[:, off:off + w].reshape(g[k].shape), g[k]), k
+            off += w
+        scale = g["_features_rest"].abs().max()
+        assert (f_dc - g["_features_dc"]).abs().max() <= 1e-12 * scale
+        assert (f_rest - g["_features_rest"]).abs().max() <= 1e-12 * scale, (f_rest - g["_features_rest"]).abs().max()
+        if sh_deg < 3:
+            assert g["_features_rest"][:, (sh_deg + 1) ** 2 - 1:, :].abs().max() == 0
+        # dp_render_step refuses uneven frame counts once the exchange is folded into the backward
+        from fsgs_b200 import frame_render
+        frame_render.set_grad_reducer(lambda flat: dist.all_reduce(flat))
+        try:
+            pc = type("PC", (), {})()
+            pc.params = {"_xyz": torch.ones(3, 3, requires_grad=True)}
+            render = lambda poses, f, pc, gs_grad, cam_grad: {"x": pc.params["_xyz"].sum()}
+            try:
+                fd.dp_render_step(render, None, pc, fd.shard_frames([0, 1, 2], world, rank), lambda f, pkg: pkg["x"])
+                raise AssertionError("uneven frame counts must be rejected")
+            except ValueError:
+                pass
+            fd.dp_render_step(render, None, pc, fd.shard_frames([0, 1], world, rank), lambda f, pkg: pkg["x"])
+            assert torch.equal(pc.params["_xyz"].grad, torch.ones(3, 3))      # no second reduction on top
+        finally:
+            frame_render.set_grad_reducer(None)
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, repr(e) + traceback.format_exc()[-600:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sh_deg", [3, 1])
+def test_compact_gradient_exchange_world2_gloo(sh_deg):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_compact_worker, args=(r, 2, port, sh_deg, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: "ok", 1: "ok"}, res
+
+
 def test_shard_frames():
     assert fd.shard_frames(list(range(8)), 8, 3) == [3]
     assert fd.shard_frames(list(range(5)), 2, 0) == [0, 2, 4] and fd.shard_frames(list(range(5)), 2, 1) == [1, 3]

@@ -151,3 +151,40 @@ def test_concurrent_threads_and_side_stream_give_identical_frames():
         grads[name] = {k: v.grad.detach().clone() for k, v in pc.params.items()}
     for k in grads["default"]:
         assert rel_err(grads["side"][k], grads["default"][k]) < 1e-5, k
+
+
+def test_frame_parallel_compact_exchange_equals_full_gradient_sum():
+    """Two 'ranks' simulated on one GPU: the compact exchange (14 floats/Gaussian reduced inside the backward, SH
+    gradients expanded from the reduced masked colour gradient by fsgs_sh_grad_expand) must give the same
+    gradients as summing the two frames' full gradients."""
+    from fsgs_b200 import frame_render as render
+    from fsgs_b200 import model
+    from fsgs_b200.synth import frame_pose_params, make_scene
+    sc = make_scene(20000, 320, 256, size_mult=2.0, seed=3)
+    G = [torch.randn(4, sc.height, sc.width, generator=torch.Generator().manual_seed(10 + k)).cuda() for k in range(2)]
+
+    def run(frame, sh_deg):
+        poses, pc = model.scene_to_device(sc, "cuda")
+        pc.active_sh_degree = sh_deg
+        poses.set_pose(0, *frame_pose_params(frame))
+        out = render.render(poses, 0, pc, gs_grad=True, cam_grad=True)
+        ((out["render"] * G[frame][:3]).sum() + (out["render_dep"] * G[frame][3]).sum()).backward()
+        return {k: p.grad.detach().clone() for k, p in pc.params.items()}, poses.pose_param_net.r.grad.clone()
+
+    for sh_deg in (3, 2):
+        full = [run(f, sh_deg) for f in range(2)]
+        want = {k: full[0][0][k] + full[1][0][k] for k in full[0][0]}
+        other = {}
+        try:
+            render.set_grad_reducer(lambda flat: other.__setitem__("compact", flat.clone()))   # rank 1: just record
+            run(1, sh_deg)
+            render.set_grad_reducer(lambda flat: flat.add_(other["compact"]))                  # rank 0: SUM with rank 1
+            got, r_grad = run(0, sh_deg)
+        finally:
+            render.set_grad_reducer(None)
+        for k, v in want.items():
+            err = (got[k] - v).norm() / v.norm()
+            assert err < 1e-5, (sh_deg, k, float(err))
+        if sh_deg < 3:
+            assert got["_features_rest"][:, (sh_deg + 1) ** 2 - 1:, :].abs().max().item() == 0
+        assert torch.allclose(r_grad, full[0][1], rtol=1e-5, atol=1e-9), "pose gradients stay local"
