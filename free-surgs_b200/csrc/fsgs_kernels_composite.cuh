@@ -387,25 +387,30 @@ __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int war
     for (int c0 = ((nrel - 1) / PCHUNK) * PCHUNK; c0 >= 0; c0 -= PCHUNK) {
         const int cn = min(PCHUNK, nrel - c0);                 // this chunk: list positions c0 .. c0+cn-1
         const uint2 packed = *reinterpret_cast<const uint2 *>(&sm.list[warp][c0]);
+        auto slot = [&](int s) __attribute__((always_inline)) {
+            const int j = list_byte(packed, s);
+            const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
+            const float2 q2 = *reinterpret_cast<const float2 *>(&sb[j * 3 + 2]);   // (b, depth)
+            const float dx = q0.x - pxf, dy = q0.y - pyf;
+            const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
+            const float G = fast_exp2(p2);
+            const float alpha = fminf(ALPHA_MAX, q1.y * G);
+            const bool valid = (j < last_rel) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
+            float q, w, q_rgb;
+            bwd_pair_weights<FUSED, LEVEL>(ps, valid ? G * q1.y : 0.f, valid ? alpha : 0.f, q1.z, q1.w, q2.x, q2.y,
+                                           g, T_final, bgdot_rgb, bgdot_dep, q, w, q_rgb);
+            const int px = lane ^ ((s & 1) << 2);
+            sm.pair[warp][0][s][px] = q;
+            sm.pair[warp][1][s][px] = w;
+            if (FUSED && LEVEL >= 1) sm.pair[warp][2][s][px] = q_rgb;
+        };
+        if (cn == PCHUNK) {                                       // all but the first-visited chunk of a batch
 #pragma unroll
-        for (int s = PCHUNK - 1; s >= 0; --s) {               // back to front
-            if (s < cn) {
-                const int j = list_byte(packed, s);
-                const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
-                const float2 q2 = *reinterpret_cast<const float2 *>(&sb[j * 3 + 2]);   // (b, depth)
-                const float dx = q0.x - pxf, dy = q0.y - pyf;
-                const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
-                const float G = fast_exp2(p2);
-                const float alpha = fminf(ALPHA_MAX, q1.y * G);
-                const bool valid = (j < last_rel) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
-                float q, w, q_rgb;
-                bwd_pair_weights<FUSED, LEVEL>(ps, valid ? G * q1.y : 0.f, valid ? alpha : 0.f, q1.z, q1.w, q2.x, q2.y,
-                                               g, T_final, bgdot_rgb, bgdot_dep, q, w, q_rgb);
-                const int px = lane ^ ((s & 1) << 2);
-                sm.pair[warp][0][s][px] = q;
-                sm.pair[warp][1][s][px] = w;
-                if (FUSED && LEVEL >= 1) sm.pair[warp][2][s][px] = q_rgb;
-            }
+            for (int s = PCHUNK - 1; s >= 0; --s) slot(s);        // back to front
+        } else {
+#pragma unroll
+            for (int s = PCHUNK - 1; s >= 0; --s)
+                if (s < cn) slot(s);
         }
         __syncwarp();
         bwd_phase_b<FUSED, LEVEL>(sm, sb, warp, lane, cn, packed, bx, by, kx, ky, grad_acc);

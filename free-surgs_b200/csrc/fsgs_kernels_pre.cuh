@@ -11,6 +11,7 @@ namespace fsgs {
 __device__ __noinline__ bool tile_hit_ni(float px, float py, float A, float B, float C, float tau, int tx, int ty) {
     CullEllipse e;
     e.px = px; e.py = py; e.A = A; e.B = B; e.C = C; e.tau = tau; e.hx = 0.f; e.hy = 0.f;
+    e.nBC = -B * fast_rcp(C); e.nBA = -B * fast_rcp(A);     // two MUFU.RCP instead of four IEEE divisions
     return tile_hit(e, tx, ty);
 }
 
@@ -172,7 +173,9 @@ k_preprocess_api(CamConst cc, int P, const float *__restrict__ means3D, const fl
 
 // ---- K1, fused flavour: gaussian_renderer.render's pre-processing folded in -----------------------
 // pose is ROW-major [4,4] (LearnPose.forward output); features_dc [P,1,3], features_rest [P,15,3].
-__global__ void __launch_bounds__(CTA)
+// (4 resident CTAs = 64 registers: with the 46 KB SH staging buffer that is also the shared-memory limit; an
+// unconstrained build takes 74 registers, drops to 3 CTAs/SM and runs 10 % slower)
+__global__ void __launch_bounds__(CTA, 4)
 k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const float *__restrict__ f_dc,
                    const float *__restrict__ f_rest, const float *__restrict__ opacity_raw,
                    const float *__restrict__ scaling_raw, const float *__restrict__ rotation_raw,

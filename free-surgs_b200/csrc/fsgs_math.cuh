@@ -156,7 +156,19 @@ FSGS_HD bool project_gaussian(const CamConst &cc, const float *V, const float *P
 struct CullEllipse {
     float px, py, A, B, C, tau;   // tau already padded; tau < 0 => Gaussian can never contribute
     float hx, hy;                 // half extents of the ellipse's axis-aligned bounding box
+    float nBC, nBA;               // -B/C, -B/A: argmin slope of q along a vertical / horizontal line
 };
+
+// 1/x: MUFU.RCP + one Newton step (avoids the ~10-instruction IEEE division in hot loops)
+FSGS_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return __fmaf_rn(r, __fmaf_rn(-x, r, 1.0f), r);
+#else
+    return 1.0f / x;
+#endif
+}
 
 FSGS_HD CullEllipse make_cull_ellipse(float px, float py, float conx, float cony, float conz, float opacity) {
     CullEllipse e;
@@ -168,6 +180,8 @@ FSGS_HD CullEllipse make_cull_ellipse(float px, float py, float conx, float cony
     const float tt = fmaxf(e.tau, 0.f) * 2.0f;
     e.hx = sqrtf(tt * conz / det) * 1.0005f + 0.01f;
     e.hy = sqrtf(tt * conx / det) * 1.0005f + 0.01f;
+    e.nBC = -cony * fast_rcp(conz);
+    e.nBA = -cony * fast_rcp(conx);
     return e;
 }
 
@@ -175,6 +189,12 @@ FSGS_HD CullEllipse make_cull_ellipse(float px, float py, float conx, float cony
 FSGS_HD float edge_min(float A, float B, float C, float dx, float lo, float hi) {
     float dy = -B * dx / C;
     dy = fminf(hi, fmaxf(lo, dy));
+    return 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
+}
+// the same with the slope nBC = -B/C of the unconstrained minimiser precomputed (evaluating q a rounding
+// error away from the exact minimiser changes it only to second order -- far inside the padding of tau)
+FSGS_HD float edge_min_s(float A, float B, float C, float nBC, float dx, float lo, float hi) {
+    const float dy = fminf(hi, fmaxf(lo, nBC * dx));
     return 0.5f * (A * dx * dx + C * dy * dy) + B * dx * dy;
 }
 
@@ -186,10 +206,10 @@ FSGS_HD bool tile_hit(const CullEllipse &e, int tx, int ty) {
     // d = centre - pixel, so dx ranges over [px - x1, px - x0]
     const float dxl = e.px - x1, dxh = e.px - x0, dyl = e.py - y1, dyh = e.py - y0;
     if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return true;   // centre inside the square
-    float q = edge_min(e.A, e.B, e.C, dxl, dyl, dyh);
-    q = fminf(q, edge_min(e.A, e.B, e.C, dxh, dyl, dyh));
-    q = fminf(q, edge_min(e.C, e.B, e.A, dyl, dxl, dxh));
-    q = fminf(q, edge_min(e.C, e.B, e.A, dyh, dxl, dxh));
+    float q = edge_min_s(e.A, e.B, e.C, e.nBC, dxl, dyl, dyh);
+    q = fminf(q, edge_min_s(e.A, e.B, e.C, e.nBC, dxh, dyl, dyh));
+    q = fminf(q, edge_min_s(e.C, e.B, e.A, e.nBA, dyl, dxl, dxh));
+    q = fminf(q, edge_min_s(e.C, e.B, e.A, e.nBA, dyh, dxl, dxh));
     return q <= e.tau;
 }
 
@@ -370,11 +390,19 @@ struct BwdPixel {
 // k-th coefficient of channel ch.
 template <typename Coef>
 FSGS_HD void sh_to_rgb(int deg, const float *dir, Coef coef, float *rgb, uint8_t &clamp) {
+    // B stays in registers: fixed trip count, basis values above the active degree are exact zeros
+    // (their products add +0 and leave the sums bit-identical to a loop over the active coefficients only)
     float B[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 16; ++k) B[k] = 0.f;
     sh_basis(deg, dir[0], dir[1], dir[2], B);
-    const int nb = (deg + 1) * (deg + 1);
     rgb[0] = rgb[1] = rgb[2] = 0.f;
-    for (int k = 0; k < nb; ++k) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 16; ++k) {
         rgb[0] += B[k] * coef(k, 0); rgb[1] += B[k] * coef(k, 1); rgb[2] += B[k] * coef(k, 2);
     }
     clamp = 0;
@@ -512,7 +540,8 @@ FSGS_HD bool api_forward_one(const CamConst &cc, const float *V, const float *PM
         float d[3] = {mean[0] - campos[0], mean[1] - campos[1], mean[2] - campos[2]};
         const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
         d[0] *= inv; d[1] *= inv; d[2] *= inv;
-        sh_to_rgb(cc.sh_deg, d, [&](int k, int ch) { return sh_i[3 * k + ch]; }, rgb, clamp);
+        // (sh_to_rgb visits all 16 basis slots; a tensor with fewer stored coefficients reads as zero there)
+        sh_to_rgb(cc.sh_deg, d, [&](int k, int ch) { return k < cc.n_coeffs ? sh_i[3 * k + ch] : 0.f; }, rgb, clamp);
     } else {
         rgb[0] = color_i[0]; rgb[1] = color_i[1]; rgb[2] = color_i[2];
     }
@@ -614,17 +643,6 @@ FSGS_HD float fast_exp2(float x) {
     return exp2f(x);
 #endif
 }
-// 1/x: MUFU.RCP + one Newton step (avoids the ~10-instruction IEEE division in the hot loop)
-FSGS_HD float fast_rcp(float x) {
-#if defined(__CUDA_ARCH__)
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return __fmaf_rn(r, __fmaf_rn(-x, r, 1.0f), r);
-#else
-    return 1.0f / x;
-#endif
-}
-
 // Conservative test: can the rectangle of pixel centres [x0,x1]x[y0,y1] contain a pixel with
 // q <= tau?  (tile_hit generalised; used for the per-instance 8x4-block masks.)
 FSGS_HD bool rect_hit(float px, float py, float A, float B, float C, float tau, float x0, float x1, float y0,

@@ -187,4 +187,5 @@ def test_frame_parallel_compact_exchange_equals_full_gradient_sum():
             assert err < 1e-5, (sh_deg, k, float(err))
         if sh_deg < 3:
             assert got["_features_rest"][:, (sh_deg + 1) ** 2 - 1:, :].abs().max().item() == 0
-        assert torch.allclose(r_grad, full[0][1], rtol=1e-5, atol=1e-9), "pose gradients stay local"
+        # pose gradients stay local (same frame rendered twice: float atomics order only)
+        assert rel_err(r_grad, full[0][1]) < 1e-5
