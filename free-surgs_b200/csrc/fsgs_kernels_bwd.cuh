@@ -63,7 +63,17 @@ k_preprocess_api_bwd(CamConst cc, int P, const float *__restrict__ means3D, cons
     if (dL_drot) *reinterpret_cast<float4 *>(dL_drot + 4 * n) = make_float4(dq[0], dq[1], dq[2], dq[3]);
 }
 
-__global__ void __launch_bounds__(CTA)
+#ifndef FSGS_PREBWD_MINB
+#define FSGS_PREBWD_MINB 1
+#endif
+#ifndef FSGS_PREBWD_CTA
+#define FSGS_PREBWD_CTA 64
+#endif
+// threads per CTA of the fused per-Gaussian backward.  A/B on B200: 256 -> 0.074 / 0.273 ms, 128 -> 0.072 / 0.268,
+// 64 -> 0.070 / 0.256 (P = 500k / 2M): at 128 registers only 512 threads fit an SM, and smaller CTAs interleave
+// their load -> compute -> store phases better
+constexpr int PREBWD_CTA = FSGS_PREBWD_CTA;
+__global__ void __launch_bounds__(PREBWD_CTA, FSGS_PREBWD_MINB)
 k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const float *__restrict__ f_dc,
                        const float *__restrict__ f_rest, const float *__restrict__ opacity_raw,
                        const float *__restrict__ scaling_raw, const float *__restrict__ rotation_raw,
@@ -78,7 +88,7 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
     // SH coefficients in, SH gradients out through ONE shared-memory buffer: bulk TMA load of the CTA's
     // 256 x 180 B slice, each thread turns its 45 coefficients into their gradients in place, bulk TMA
     // store to dL/dfeatures_rest (the plain path does 45 scalar loads + 45 scalar stores at a 180 B stride).
-    __shared__ __align__(128) float s_rest[CTA * 45];
+    __shared__ __align__(128) float s_rest[PREBWD_CTA * 45];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ float s_pose[16];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

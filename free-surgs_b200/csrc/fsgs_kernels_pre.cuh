@@ -175,7 +175,11 @@ k_preprocess_api(CamConst cc, int P, const float *__restrict__ means3D, const fl
 // pose is ROW-major [4,4] (LearnPose.forward output); features_dc [P,1,3], features_rest [P,15,3].
 // (4 resident CTAs = 64 registers: with the 46 KB SH staging buffer that is also the shared-memory limit; an
 // unconstrained build takes 74 registers, drops to 3 CTAs/SM and runs 10 % slower)
-__global__ void __launch_bounds__(CTA, 4)
+#ifndef FSGS_PRE_CTA
+#define FSGS_PRE_CTA 128
+#endif
+constexpr int PRE_CTA = FSGS_PRE_CTA;   // A/B on B200: 256 -> 0.063 / 0.157 ms, 128 -> 0.060 / 0.150, 64 -> 0.061 / 0.150 (500k / 2M)
+__global__ void __launch_bounds__(PRE_CTA, 1024 / PRE_CTA)
 k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const float *__restrict__ f_dc,
                    const float *__restrict__ f_rest, const float *__restrict__ opacity_raw,
                    const float *__restrict__ scaling_raw, const float *__restrict__ rotation_raw,
@@ -187,7 +191,7 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
     // The 180 B/Gaussian of higher-order SH coefficients (76 % of the input bytes) are contiguous per
     // CTA: one bulk TMA copy stages them; threads then read their own 45 floats at a conflict-free
     // stride.  FSGS_FLAG_NO_TMA (or a mis-aligned tensor) reads them straight from global memory.
-    __shared__ __align__(128) float s_rest[CTA * 45];
+    __shared__ __align__(128) float s_rest[PRE_CTA * 45];
     __shared__ __align__(8) uint64_t s_bar;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int base = blockIdx.x * blockDim.x;

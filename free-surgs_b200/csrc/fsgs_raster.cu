@@ -511,7 +511,7 @@ int fsgs_render_forward_ex(const fsgs_settings *st, int32_t P, const float *bg, 
     Buffers B;
     if ((rc = alloc_fixed(P, cc, geom_alloc, geom_user, img_alloc, img_user, B, stream))) return rc;
     prof_begin(K_PRE_FUSED, stream);
-    k_preprocess_fused<<<blocks(P), CTA, 0, stream>>>(
+    k_preprocess_fused<<<(P + PRE_CTA - 1) / PRE_CTA, PRE_CTA, 0, stream>>>(
         cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
         projmatrix, reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped),
         radii, reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
@@ -578,7 +578,7 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
         FSGS_LAUNCH_OK("k_composite_bwd");
     }
     prof_begin(K_PRE_FUSED_BWD, stream);
-    k_preprocess_fused_bwd<<<blocks(P), CTA, 0, stream>>>(
+    k_preprocess_fused_bwd<<<(P + PREBWD_CTA - 1) / PREBWD_CTA, PREBWD_CTA, 0, stream>>>(
         cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
         projmatrix, reinterpret_cast<const float4 *>(g + gl.records), reinterpret_cast<const uint8_t *>(g + gl.clamped),
         acc, gs_grad, cam_grad, dL_dxyz, dL_dfeatures_dc, dL_dfeatures_rest, dL_dopacity_raw, dL_dscaling_raw,
