@@ -399,6 +399,7 @@ def run_ours(args):
             "pose_grad_ms_per_frame": ms_track,
             "api_two_pass_ms_per_step": ms_two_pass,      # rank 0's; un-fused GaussianRasterizer drop-in path
             "ms_per_step_median": sorted(ms)[len(ms) // 2],
+            "ms_per_step_p10_p90": [sorted(ms)[int(0.1 * (len(ms) - 1))], sorted(ms)[int(round(0.9 * (len(ms) - 1)))]],
             "ms_steps": [round(x, 3) for x in ms],
             "wall_ms_per_step_incl_flush": t_wall * 1e3 / args.steps,
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
