@@ -489,7 +489,7 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 
     BwdPixel ps;
     ps.T = T_final;
-    ps.acc_r = ps.acc_g = ps.acc_b = ps.acc_d = ps.acc_s = ps.acc_d2 = 0.f;
+    ps.ag_rgb = ps.ag_dep = 0.f;
 
     const float4 *src = sorted_rec + (size_t)start * REC_F4;
     auto batch_cnt = [&](int k) { return min(BWD_BATCH, maxlast - k * BWD_BATCH); };

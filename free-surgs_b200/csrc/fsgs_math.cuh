@@ -382,7 +382,11 @@ FSGS_HD float gauss_power(float A, float B, float C, float dx, float dy) {
 // Per-pixel state of the back-to-front replay (K7).
 struct BwdPixel {
     float T;
-    float acc_r, acc_g, acc_b, acc_d, acc_s, acc_d2;   // per plane: the colour seen behind the current entry
+    // the colour seen BEHIND the current entry, already contracted with this pixel's upstream gradient:
+    // ag_rgb = sum over the RGB planes of acc_plane * g_plane, ag_dep the same over depth | silhouette | depth^2.
+    // (Everything the replay needs from the per-plane accumulators is linear in them, so two scalars replace
+    // four to six accumulators and their subtract / multiply / update chains.)
+    float ag_rgb, ag_dep;
 };
 
 // ---- whole-Gaussian forward / backward bodies (shared by the CUDA kernels and the CPU emulation) --
@@ -713,26 +717,20 @@ template <bool FUSED, int LEVEL>
 FSGS_HD void bwd_pair_weights(BwdPixel &s, float Go, float alpha, float cr, float cg, float cb, float z,
                               const float *g, float T_final, float bgdot_rgb, float bgdot_dep, float &q, float &w,
                               float &q_rgb) {
-    // s.acc_* hold, for the entry being replayed, the colour seen BEHIND it (upstream's accum_rec after
-    // its "last_alpha * last_color + (1 - last_alpha) * accum_rec" update).  The update for the next
-    // (nearer) entry is applied here, right after use, in the algebraically identical form
-    // acc + alpha * (c - acc): one FMA per plane, and no last_alpha / last_colour state to carry.
+    // upstream: accum_rec = last_alpha * last_color + (1 - last_alpha) * accum_rec per plane, then
+    // dL/dalpha += (c - accum_rec) * dL/dC.  With e = c - acc the update for the next (nearer) entry is
+    // acc + alpha * e; contracting with g first gives  da = c.g - ag,  ag <- ag + alpha * da.
     const float inv = fast_rcp(1.f - alpha);
     s.T = s.T * inv;
     w = alpha * s.T;
-    const float er = cr - s.acc_r, eg = cg - s.acc_g, eb = cb - s.acc_b;
-    float da_rgb = er * g[0] + eg * g[1] + eb * g[2];
-    s.acc_r = fmaf(alpha, er, s.acc_r); s.acc_g = fmaf(alpha, eg, s.acc_g); s.acc_b = fmaf(alpha, eb, s.acc_b);
+    float da_rgb = fmaf(cb, g[2], fmaf(cg, g[1], cr * g[0])) - s.ag_rgb;
+    s.ag_rgb = fmaf(alpha, da_rgb, s.ag_rgb);
     float da_dep = 0.f;
     if (LEVEL >= 1) {
-        const float ed = z - s.acc_d;
-        da_dep = ed * g[3];
-        s.acc_d = fmaf(alpha, ed, s.acc_d);
-        if (FUSED && LEVEL >= 2) {
-            const float es = 1.f - s.acc_s, e2 = z * z - s.acc_d2;
-            da_dep += es * g[4] + e2 * g[5];
-            s.acc_s = fmaf(alpha, es, s.acc_s); s.acc_d2 = fmaf(alpha, e2, s.acc_d2);
-        }
+        float cgd = z * g[3];
+        if (FUSED && LEVEL >= 2) cgd = fmaf(z * z, g[5], cgd + g[4]);
+        da_dep = cgd - s.ag_dep;
+        s.ag_dep = fmaf(alpha, da_dep, s.ag_dep);
     }
     const float tf = -T_final * inv;
     da_rgb = da_rgb * s.T + tf * bgdot_rgb;

@@ -16,6 +16,7 @@ and dL/d(pose) directly (``fsgs_render_forward`` / ``fsgs_render_backward`` in
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import Dict
 
 import torch
@@ -24,6 +25,7 @@ from . import _lib
 from .rasterizer import GaussianRasterizer, _Arena, _f32, _ptr, _require_cuda, _stream, make_settings
 
 _IDENTITY_OK: Dict[tuple, bool] = {}
+_TLS = threading.local()
 
 # Frame-parallel gradient exchange hook (set through fsgs_b200.dist.enable_frame_parallel): a callable that
 # sum-all-reduces a flat float32 CUDA tensor in place, ordered on the current stream; None = single GPU.
@@ -50,7 +52,6 @@ def _check_identity_view(rs) -> None:
 
 
 class _RenderFused(torch.autograd.Function):
-    last_stats = (0, 0)
 
     @staticmethod
     def forward(ctx, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, rs, cam_center,
@@ -91,7 +92,7 @@ class _RenderFused(torch.autograd.Function):
         ctx.flags = (bool(gs_grad), bool(cam_grad))
         ctx.mark_non_differentiable(radii, *extras)
         ctx.set_materialize_grads(False)        # an output the loss does not use arrives as None, not as zeros
-        _RenderFused.last_stats = (int(nr.value), int(nrect.value))
+        _TLS.last_stats = (int(nr.value), int(nrect.value))     # per thread: the viewer thread renders too
         # one output per render() product, all views of the one [6,H,W] buffer the compositor writes: the upstream
         # gradients then arrive per product and go to the library as separate planes (fsgs_render_backward_ex) --
         # no zero-filled [6,H,W] gradient is assembled from slices by autograd
@@ -171,8 +172,8 @@ def render_planes(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pos
                                                 raster_settings, cam_center, active_sh_degree, gs_grad, cam_grad,
                                                 mr if fuse_mr else None, want_extras)
     if want_extras:
-        return (rgb, depth, sil, dsq), radii, _RenderFused.last_stats, (*extras, fuse_mr)
-    return (rgb, depth, sil, dsq), radii, _RenderFused.last_stats
+        return (rgb, depth, sil, dsq), radii, getattr(_TLS, "last_stats", (0, 0)), (*extras, fuse_mr)
+    return (rgb, depth, sil, dsq), radii, getattr(_TLS, "last_stats", (0, 0))
 
 
 def _pack_fused(pc, viewmatrix_cur, planes, radius, means2D, extras):

@@ -320,6 +320,23 @@ def test_long_tile_lists_and_depth_ties(n_stack, ties):
         check_grad(k, gpu[k].grad, ref[k].grad, tol=2e-4)
 
 
+def test_config4_size_runs_and_is_deterministic():
+    """Config 4 size (2M Gaussians, 1280x1024): finite, deterministic forward, silhouette + T == 1, longer lists."""
+    sc = make_scene(2_000_000, 1280, 1024, size_mult=2.0, seed=0)
+    G6 = torch.zeros(6, 1024, 1280)
+    G6[:3] = sc.grads_out["G_rgb"]
+    G6[3] = sc.grads_out["G_dep"]
+    out1, p1, g1 = _run_fused(sc, G6)
+    out2, p2, g2 = _run_fused(sc, G6)
+    assert torch.isfinite(p1).all() and torch.equal(p1, p2)
+    assert (p1[4] - 1.0).abs().max().item() < 1e-4
+    assert int(out1["num_rendered"][0]) > 4_000_000 and int(out1["num_rendered"][0]) < int(out1["num_rendered"][1])
+    for k, v in g1.items():
+        if v is not None:
+            assert torch.isfinite(v).all(), k
+            assert rel_err(g2[k], v) < 1e-5, k
+
+
 def test_full_size_properties():
     """Config 2 size (500k Gaussians, 1280x1024): properties that need no oracle."""
     sc = make_scene(500_000, 1280, 1024, size_mult=2.0, seed=0)
