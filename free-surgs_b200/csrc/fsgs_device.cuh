@@ -228,6 +228,14 @@ __device__ __forceinline__ int warp_reduce_scatter12(float (&v)[12], int lane) {
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 
+// 16-byte vector reduction into global memory (sm_90+): one L2 operation, no value returned.
+// (atomicAdd(float4*) compiles to ATOMG with a discarded result; this is the plain RED form.)
+__device__ __forceinline__ void red_add_v4(float4 *addr, float4 v) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
 #endif  // __CUDACC__
 
 }  // namespace fsgs

@@ -373,7 +373,7 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int w
         o.z = (r0.z + r1.z) + (r2.z + r3.z); o.w = (r0.w + r1.w) + (r2.w + r3.w);
         if ((o.x != 0.f) | (o.y != 0.f) | (o.z != 0.f) | (o.w != 0.f)) {
             const unsigned int gid = __float_as_uint(sb[j * 3 + 2].w);
-            atomicAdd(reinterpret_cast<float4 *>(grad_acc + (size_t)gid * ACC_F) + row, o);
+            red_add_v4(reinterpret_cast<float4 *>(grad_acc + (size_t)gid * ACC_F) + row, o);
         }
     }
 }
