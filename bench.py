@@ -339,7 +339,7 @@ def run_ours(args):
         poses.pose_param_net.zero_grad(set_to_none=True)
         out = render.render_two_pass(poses, 0, pc, gs_grad=True, cam_grad=True)
         ((out["render"] * G_dev[:3]).sum() + (out["render_dep"] * G_dev[3]).sum()).backward()
-    for _ in range(3):
+    for _ in range(5):
         two_pass_step()
     barrier()
     n2 = max(3, args.steps // 2)

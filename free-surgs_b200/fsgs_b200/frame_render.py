@@ -22,7 +22,7 @@ from typing import Dict
 import torch
 
 from . import _lib
-from .rasterizer import GaussianRasterizer, _Arena, _f32, _ptr, _require_cuda, _stream, make_settings
+from .rasterizer import GaussianRasterizer, _Arena, _f32, _on_device, _ptr, _require_cuda, make_settings
 
 _IDENTITY_OK: Dict[tuple, bool] = {}
 _TLS = threading.local()
@@ -41,7 +41,7 @@ def _check_identity_view(rs) -> None:
     which equals the reference's ``get_depth_and_silhouette`` only for the identity rasteriser view
     Free-SurGS always uses (train.py:41, gaussian_model.py:245-246).  Checked once per tensor."""
     vm = rs.viewmatrix
-    key = (vm.data_ptr(), vm._version, str(vm.device))
+    key = (vm.data_ptr(), vm._version, vm.device.index)
     ok = _IDENTITY_OK.get(key)
     if ok is None:
         ok = bool(torch.equal(vm.reshape(4, 4).float().cpu(), torch.eye(4)))
@@ -65,7 +65,8 @@ class _RenderFused(torch.autograd.Function):
                                     rs.viewmatrix, rs.projmatrix)]
         planes = torch.empty(6, H, W, dtype=torch.float32, device=dev)
         radii = torch.empty(P, dtype=torch.int32, device=dev)     # the projection kernel writes every entry
-        arena = _Arena(dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        arena = _Arena(dev, stream)
         nr, nrect = ctypes.c_int64(0), ctypes.c_int64(0)
         # render()'s derived maps come out of the same kernels (fsgs_render_extras): one byte buffer for the
         # three masks, the uncertainty map, and max_radii2D updated in place when it is a float32 tensor
@@ -79,11 +80,11 @@ class _RenderFused(torch.autograd.Function):
             ex_ptr = ctypes.cast(ctypes.pointer(ex), ctypes.c_void_p)
             mb = masks.view(torch.bool)
             extras = (unc, mb[:H * W].view(H, W), mb[H * W:2 * H * W].view(1, H, W), mb[2 * H * W:])
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             rc = _lib.lib().fsgs_render_forward_ex(
                 ctypes.byref(st), P, *[_ptr(x) for x in t], arena.callback("geom"), None, arena.callback("binning"),
                 None, arena.callback("img"), None, _ptr(planes), _ptr(radii), ctypes.byref(nr), ctypes.byref(nrect),
-                ex_ptr, _stream(dev))
+                ex_ptr, ctypes.c_void_p(stream))
         _lib.check(rc)
         empty = torch.empty(0, dtype=torch.uint8, device=dev)
         ctx.save_for_backward(*t, *[arena.tensors.get(k, empty) for k in ("geom", "binning", "img")])
@@ -137,22 +138,23 @@ class _RenderFused(torch.autograd.Function):
             g["pose"].zero_()
         if P > 0:
             gp = [None if x is None else _f32(x, dev) for x in (g_rgb, g_depth, g_sil, g_dsq)]
-            arena = _Arena(dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            arena = _Arena(dev, stream)
             scratch = arena.take("grad_scratch", _lib.lib().fsgs_grad_scratch_bytes(P))
-            with torch.cuda.device(dev):
+            with _on_device(dev):
                 rc = _lib.lib().fsgs_render_backward_ex(
                     ctypes.byref(ctx.st), P, ctx.num_rendered, *[_ptr(x) for x in t], _ptr(geom), _ptr(binning),
                     _ptr(img), *[None if x is None else _ptr(x) for x in gp], _ptr(scratch), int(gs_grad), int(cam_grad),
                     _ptr(g["xyz"]), None if reducer else _ptr(g["f_dc"]), None if reducer else _ptr(g["f_rest"]),
                     _ptr(g["opacity"]), _ptr(g["scaling"]), _ptr(g["rotation"]), _ptr(g["pose"]), _ptr(g["means2D"]),
-                    _ptr(g["gc"]) if reducer else None, _stream(dev))
+                    _ptr(g["gc"]) if reducer else None, ctypes.c_void_p(stream))
             arena.finish().release()           # kernels are enqueued; reuse is ordered on this stream
             _lib.check(rc)
             if reducer is not None:
                 reducer(compact)               # SUM over the ranks, in place, ordered on this stream
-                with torch.cuda.device(dev):
+                with _on_device(dev):
                     rc = _lib.lib().fsgs_sh_grad_expand(ctypes.byref(ctx.st), P, _ptr(t[1]), _ptr(t[8]), _ptr(g["gc"]),
-                                                        _ptr(g["f_dc"]), _ptr(g["f_rest"]), _stream(dev))
+                                                        _ptr(g["f_dc"]), _ptr(g["f_rest"]), ctypes.c_void_p(stream))
                 _lib.check(rc)
         return (g["xyz"], g["f_dc"], g["f_rest"], g["opacity"], g["scaling"], g["rotation"],
                 g["pose"] if cam_grad else None, g["means2D"], None, None, None, None, None, None, None)

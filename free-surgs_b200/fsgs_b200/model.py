@@ -69,11 +69,12 @@ class _PoseFn(torch.autograd.Function):
     def forward(ctx, r, t, cam_id):
         import ctypes
         from . import _lib
+        from .rasterizer import _on_device
         rc_, tc_ = r.detach().contiguous(), t.detach().contiguous()
         n = rc_.shape[-1]
         Rt = torch.empty(4, 4, dtype=torch.float32, device=r.device)
         s = ctypes.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)
-        with torch.cuda.device(r.device):
+        with _on_device(r.device):
             _lib.check(_lib.lib().fsgs_pose_forward(ctypes.c_void_p(rc_.data_ptr()), ctypes.c_void_p(tc_.data_ptr()),
                                                     int(cam_id), int(n), ctypes.c_void_p(Rt.data_ptr()), s))
         ctx.save_for_backward(rc_)
@@ -88,8 +89,9 @@ class _PoseFn(torch.autograd.Function):
         g = g.contiguous().float()
         dr = torch.empty(ctx.shapes[0], dtype=torch.float32, device=g.device)
         dt = torch.empty(ctx.shapes[1], dtype=torch.float32, device=g.device)
+        from .rasterizer import _on_device
         s = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
-        with torch.cuda.device(g.device):
+        with _on_device(g.device):
             _lib.check(_lib.lib().fsgs_pose_backward(ctypes.c_void_p(rc_.data_ptr()), ctx.cam_id, ctx.n,
                                                      ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(dr.data_ptr()),
                                                      ctypes.c_void_p(dt.data_ptr()), s))

@@ -113,9 +113,9 @@ class _Arena:
     """Serves the library's allocation callbacks from the workspace pool."""
     HEADROOM = {"binning": 1.25}
 
-    def __init__(self, device):
+    def __init__(self, device, stream: Optional[int] = None):
         self.device = device
-        self.stream = torch.cuda.current_stream(device).cuda_stream
+        self.stream = torch.cuda.current_stream(device).cuda_stream if stream is None else stream
         self.tensors = {}
         self.lease = _Lease()
         self._cbs = []
@@ -150,6 +150,8 @@ def _f32(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
         return None
     if t.device != device:
         raise ValueError(f"tensor on {t.device}, expected {device}")
+    if t.dtype == torch.float32 and t.is_contiguous():      # the usual case: no copies, one cheap op at most
+        return t.detach() if t.requires_grad else t
     return t.detach().contiguous().float()
 
 
@@ -170,6 +172,23 @@ def make_settings(rs, n_coeffs: int = 0, sh_degree: Optional[int] = None) -> _li
 
 def _stream(device) -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _on_device:
+    """``with torch.cuda.device(dev)`` only when ``dev`` is not already current (the context manager costs
+    several microseconds of host time per use, and the hot path enters it three times per frame)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -198,7 +217,7 @@ def rasterize_gaussians(bg, means3D, colors_precomp, opacities, scales, rotation
     radii = torch.empty(P, dtype=torch.int32, device=dev)       # every entry is written by the projection kernel
     arena = _Arena(dev)
     nr, nrect = ctypes.c_int64(0), ctypes.c_int64(0)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = _lib.lib().fsgs_rasterize_forward(
             ctypes.byref(st), P, _ptr(t["bg"]), _ptr(t["means3D"]), _ptr(t["colors"]), _ptr(t["sh"]), _ptr(t["opac"]),
             _ptr(t["scales"]), _ptr(t["rots"]), _ptr(t["cov"]), _ptr(t["view"]), _ptr(t["proj"]), _ptr(t["campos"]),
@@ -206,10 +225,14 @@ def rasterize_gaussians(bg, means3D, colors_precomp, opacities, scales, rotation
             _ptr(color), _ptr(depth), _ptr(radii), ctypes.byref(nr), ctypes.byref(nrect), _stream(dev))
     _lib.check(rc)
     empty = torch.empty(0, dtype=torch.uint8, device=dev)
-    bufs = [arena.tensors.get(k, empty) for k in ("geom", "binning", "img")]
+    # The caller gets ALIASES of the pooled buffers, and the aliases carry the lease: when the caller drops all
+    # three, the lease dies (plain reference counting) and the pooled tensors go back to the workspace pool.
+    # (Tagging the pooled tensors themselves would close a cycle tensor -> lease -> tensor that only the cyclic
+    # GC can break -- the buffers then come back late and every frame allocates ~400 MB of fresh scratch.)
+    bufs = [arena.tensors[k][:] if k in arena.tensors else empty for k in ("geom", "binning", "img")]
     rasterize_gaussians.last_num_rect = int(nrect.value)
     lease = arena.finish()
-    for b in bufs:                  # the buffers return to the workspace pool once the caller drops all three
+    for b in bufs:
         b._fsgs_lease = lease
     return int(nr.value), color, depth, radii, bufs[0], bufs[1], bufs[2]
 
@@ -243,7 +266,7 @@ def rasterize_gaussians_backward(bg, means3D, radii, colors_precomp, scales, rot
              campos=_f32(campos, dev), gc=_f32(grad_out_color, dev), gd=_f32(grad_out_depth, dev))
     arena = _Arena(dev)
     scratch = arena.take("grad_scratch", _lib.lib().fsgs_grad_scratch_bytes(P))
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = _lib.lib().fsgs_rasterize_backward(
             ctypes.byref(st), P, int(num_rendered), _ptr(t["bg"]), _ptr(t["means3D"]), _ptr(t["colors"]), _ptr(t["sh"]),
             _ptr(t["opac"]), _ptr(t["scales"]), _ptr(t["rots"]), _ptr(t["cov"]), _ptr(t["view"]), _ptr(t["proj"]),

@@ -189,3 +189,38 @@ def test_frame_parallel_compact_exchange_equals_full_gradient_sum():
             assert got["_features_rest"][:, (sh_deg + 1) ** 2 - 1:, :].abs().max().item() == 0
         # pose gradients stay local (same frame rendered twice: float atomics order only)
         assert rel_err(r_grad, full[0][1]) < 1e-5
+
+
+def test_scratch_returns_to_the_pool_without_the_cyclic_gc():
+    """The API path hands its geometry / binning / image-state buffers to the caller (as the reference's pybind
+    module does); they must return to the workspace pool by plain reference counting when the autograd graph
+    dies, so steady-state frames allocate nothing new (a reference cycle here once leaked ~400 MB per frame
+    until the cyclic collector ran)."""
+    import gc
+    from fsgs_b200 import frame_render as render
+    from fsgs_b200 import model
+    sc = make_scene(50_000, 640, 512, size_mult=2.0, seed=1)
+    poses, pc = model.scene_to_device(sc, "cuda")
+    G = torch.randn(4, sc.height, sc.width, generator=torch.Generator().manual_seed(0)).cuda()
+
+    def step(fn):
+        pc.zero_grad()
+        poses.pose_param_net.zero_grad(set_to_none=True)
+        out = fn(poses, 0, pc, gs_grad=True, cam_grad=True)
+        ((out["render"] * G[:3]).sum() + (out["render_dep"] * G[3]).sum()).backward()
+
+    gc.collect()
+    gc.disable()
+    try:
+        for fn in (render.render_two_pass, render.render):
+            for _ in range(3):
+                step(fn)
+            torch.cuda.synchronize()
+            base = torch.cuda.memory_allocated()
+            for _ in range(6):
+                step(fn)
+            torch.cuda.synchronize()
+            grown = torch.cuda.memory_allocated() - base
+            assert grown < (8 << 20), (fn.__name__, grown >> 20)
+    finally:
+        gc.enable()
