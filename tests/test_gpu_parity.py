@@ -225,6 +225,31 @@ def test_tma_and_culling_do_not_change_results():
                 assert rel_err(res[name][1][k], v) < tol, (name, k)
 
 
+def test_optimistic_tail_relaunches_when_the_instance_count_outgrows_the_hint():
+    """The forward launches scatter/sort/composite into a buffer sized from the PREVIOUS frame's instance count
+    before the host knows the current one; when the count outgrows it (densification, a new scene) the kernels
+    must bail out on the device-side guard and the host must relaunch them into an exact-size buffer."""
+    _, _, rasterizer, _ = _gpu_modules()
+    small = make_scene(1500, 320, 256, size_mult=1.0, seed=7)
+    big = make_scene(30000, 320, 256, size_mult=2.0, seed=8)
+    G6 = torch.randn(6, 256, 320, generator=torch.Generator().manual_seed(3))
+    try:
+        rasterizer.set_debug_flags(no_optimistic=True)
+        out_ref, p_ref, g_ref = _run_fused(big, G6)
+    finally:
+        rasterizer.set_debug_flags()
+    out_s, _, _ = _run_fused(small, G6)                       # leaves a small hint behind
+    out_b, p_b, g_b = _run_fused(big, G6)                     # ~7x more instances than the hint
+    assert int(out_b["num_rendered"][0]) > 3 * int(out_s["num_rendered"][0])     # far beyond hint * 1.125
+    assert tuple(out_b["num_rendered"]) == tuple(out_ref["num_rendered"])
+    assert torch.equal(p_b, p_ref)
+    for k, v in g_ref.items():
+        if v is not None:
+            assert rel_err(g_b[k], v) < 2e-6, k
+    out_s2, p_s2, _ = _run_fused(small, G6)                   # and back down: hint far too large is fine too
+    assert torch.isfinite(p_s2).all() and tuple(out_s2["num_rendered"]) == tuple(out_s["num_rendered"])
+
+
 def test_render_derived_outputs_match_the_elementwise_formulation():
     """uncertainty / presence_mask / nan_mask / visibility_filter / max_radii2D are written by the forward
     kernels (fsgs_render_extras); they must equal the reference's torch expressions
