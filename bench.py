@@ -314,7 +314,59 @@ def run_ours(args):
         return t0.elapsed_time(t1) / n_steps
 
     run_e2e(3)                                            # warm the side stream / pinned mailbox path
-    ms_e2e = run_e2e(args.steps)
+    ms_e2e_eager = run_e2e(args.steps)
+    ms_e2e, e2e_mode = ms_e2e_eager, "eager"
+
+    # The same loop with the step (forward + loss + backward + packing of the result) captured once in a CUDA
+    # graph (fsgs_b200.GraphedStep: the library runs in fixed-capacity mode, no host read-back inside the step)
+    # and replayed: after each per-step synchronisation the host has one launch to issue instead of ~25 kernels
+    # plus the PyTorch / autograd dispatch of a frame.  Per step still: H2D of the inputs (prefetched), a
+    # device-to-device copy into the graph's static input, replay, D2H of loss + pose gradient, host wait.
+    if world == 1 and not args.no_graph:
+        from fsgs_b200 import GraphedStep
+        G_static = torch.empty_like(G_dev)
+        G_static.copy_(G_dev)
+
+        def graph_body():
+            loss = step(G_static)
+            return torch.cat([loss.detach().reshape(1), poses.pose_param_net.r.grad.reshape(-1),
+                              poses.pose_param_net.t.grad.reshape(-1)])
+
+        gstep = GraphedStep(graph_body, warmup=3)
+
+        def run_e2e_graph(n_steps):
+            for e in consumed:
+                e.record(main)
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(main)
+            copy_stream.wait_event(t0)
+            prefetch(0)
+            for k in range(n_steps):
+                b = k & 1
+                flush.zero_()
+                main.wait_event(copied[b])
+                if k + 1 < n_steps:
+                    prefetch(k + 1)
+                G_static.copy_(G_in[b], non_blocking=True)
+                consumed[b].record(main)
+                packed = gstep.replay()
+                result_host.copy_(packed, non_blocking=True)
+                result_ready.record(main)
+                result_ready.synchronize()
+                _ = float(result_host[0])
+            t1.record(main)
+            barrier()
+            return t0.elapsed_time(t1) / n_steps
+
+        run_e2e_graph(3)
+        ms_e2e, e2e_mode = run_e2e_graph(args.steps), "cuda-graph"
+        if gstep.overflowed():
+            raise SystemExit("bench: the captured step overflowed its instance capacity")
+        loss_graph = float(result_host[0])
+        loss_eager = float(step(G_dev))
+        if abs(loss_graph - loss_eager) > 1e-4 * abs(loss_eager):
+            raise SystemExit(f"bench: graph replay disagrees with the eager step ({loss_graph} vs {loss_eager})")
 
     # ---- pose-gradient latency: tracking-mode step (gs_grad=False, cam_grad=True), RGB loss only ----
     def track_step():
@@ -362,10 +414,10 @@ def run_ours(args):
     _lib.profile_enable(False)
 
     # max over ranks
-    t = torch.tensor([ms_step, ms_e2e, ms_track], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_step, ms_e2e, ms_track, ms_e2e_eager], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_e2e, ms_track = t.tolist()
+    ms_step, ms_e2e, ms_track, ms_e2e_eager = t.tolist()
 
     if rank == 0:
         R_inst, R_rect = int(last["stats"][0]), int(last["stats"][1])
@@ -419,8 +471,12 @@ def run_ours(args):
             "kernel_ms": {k: round(v, 4) for k, v in kern.items() if v > 0},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(G_host.numel() * 4),
-                    "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e,
-                    "note": "H2D of step k+1 prefetched on a side stream during step k; includes the 256 MiB L2 flush"},
+                    "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e, "mode": e2e_mode,
+                    "ms_per_step_eager": ms_e2e_eager,
+                    "note": "per step: H2D of the inputs (step k+1 prefetched on a side stream during step k), the frame, "
+                            "D2H of loss + pose gradient and a host wait on it; includes the 256 MiB L2 flush.  mode "
+                            "cuda-graph: the frame (forward+loss+backward) is one fsgs_b200.GraphedStep replay; "
+                            "ms_per_step_eager: the same loop issuing the frame from Python every step"},
             # pose fwd, 5 forward kernels, 2 backward kernels, pose bwd (+ the SH-gradient expansion when N > 1)
             "gpu_launches": (9 + (1 if world > 1 and args.exchange == "compact" else 0)) * args.steps,
             "clocks": clocks,
@@ -439,6 +495,7 @@ def main():
     ap.add_argument("--m", type=float, default=2.0, help="splat size multiplier of the synthetic scene")
     ap.add_argument("--P", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="e2e: issue every frame from Python (no CUDA-graph replay)")
     ap.add_argument("--exchange", default="compact", choices=["compact", "full"],
                     help="N>1: gradient exchange -- compact (56 B/Gaussian inside the backward) or full (236 B/Gaussian after it)")
     args = ap.parse_args()

@@ -122,6 +122,7 @@ struct HostMailbox {
 };
 thread_local HostMailbox g_mail;
 unsigned long long g_hint[64] = {};         // last R per device (benign race: performance hint only)
+unsigned long long g_fixed_cap[64] = {};    // FSGS_FLAG_FIXED_CAPACITY: instance capacity per device (fsgs_set_instance_capacity)
 
 int mailbox(int dev, unsigned long long **pinned, cudaEvent_t *ev) {
     if (!g_mail.pinned) FSGS_CUDA(cudaHostAlloc((void **)&g_mail.pinned, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -148,17 +149,20 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
     int dev = 0;
     FSGS_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return FSGS_E_INVALID;
+    const bool fixed = (st->flags & FSGS_FLAG_FIXED_CAPACITY) != 0;
     unsigned long long *h_cnt = nullptr;
-    cudaEvent_t landed;
-    int rc = mailbox(dev, &h_cnt, &landed);
-    if (rc != FSGS_OK) return rc;
+    cudaEvent_t landed = nullptr;
+    int rc = FSGS_OK;
+    if (!fixed && (rc = mailbox(dev, &h_cnt, &landed)) != FSGS_OK) return rc;
 
     prof_begin(K_SCAN, stream);
     k_tile_scan<<<1, 1024, 0, stream>>>(tiles, tile_count, tile_offset, cursor, counters);
     prof_end(K_SCAN, stream);
     FSGS_LAUNCH_OK("k_tile_scan");
-    FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-    FSGS_CUDA(cudaEventRecord(landed, stream));
+    if (!fixed) {
+        FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        FSGS_CUDA(cudaEventRecord(landed, stream));
+    }
 
     // launches scatter -> sort -> composite into a buffer of `capacity` instances
     auto launch_tail = [&](unsigned long long capacity, bool have_instances) -> int {
@@ -186,6 +190,20 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
         return FSGS_OK;
     };
 
+    if (fixed) {
+        // Stream-capture mode (CUDA graphs): nothing here may touch the host.  The binning buffer is sized for the
+        // capacity the caller declared; if the frame has more instances, every tail kernel (and the backward
+        // compositor) returns at once on the device-side guard and the caller finds counters[0] > capacity.
+        const unsigned long long cap = g_fixed_cap[dev];
+        if (cap == 0 || st->debug) return FSGS_E_INVALID;
+        B.bl = bin_layout((int64_t)cap);
+        B.bin = static_cast<char *>(binning_alloc(binning_user, B.bl.total));
+        if (!B.bin) return FSGS_E_ALLOC;
+        if ((rc = launch_tail(cap, true)) != FSGS_OK) return rc;
+        if (num_rendered_host) *num_rendered_host = (int64_t)cap;     // an upper bound; the backward only needs > 0
+        if (num_rect_host) *num_rect_host = 0;
+        return FSGS_OK;
+    }
     const unsigned long long hint = g_hint[dev];
     unsigned long long capacity = 0;
     bool launched = false;
@@ -407,7 +425,8 @@ int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rend
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_dout_color, dL_dout_depth, nullptr, nullptr, acc, (unsigned)st->flags,
-            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
+            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR,
+            (unsigned long long)num_rendered);
         prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");
     }
@@ -573,7 +592,8 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_drgb, dL_ddepth, dL_dsil, dL_ddepth_sq, acc, (unsigned)st->flags,
-            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR);
+            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR,
+            (unsigned long long)num_rendered);
         prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");
     }
@@ -587,6 +607,12 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
         dL_dsh_rgb);
     prof_end(K_PRE_FUSED_BWD, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused_bwd");
+    return FSGS_OK;
+}
+
+int fsgs_set_instance_capacity(int32_t device, int64_t capacity) {
+    if (device < 0 || device >= 64 || capacity < 0) return FSGS_E_INVALID;
+    g_fixed_cap[device] = (unsigned long long)capacity;
     return FSGS_OK;
 }
 

@@ -19,6 +19,7 @@ FLAG_NO_TMA = 1
 FLAG_NO_TILE_CULL = 2
 FLAG_NO_OPTIMISTIC = 8
 FLAG_SORT_NETWORK = 16
+FLAG_FIXED_CAPACITY = 32
 
 
 class FsgsError(RuntimeError):
@@ -72,6 +73,7 @@ _SIGNATURES = {
                              [_i32, _i32] + [_vp] * 9),
     "fsgs_render_backward_ex": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 19 +
                                 [_i32, _i32] + [_vp] * 10),
+    "fsgs_set_instance_capacity": (ctypes.c_int, [_i32, _i64]),
     "fsgs_sh_grad_expand": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 6),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

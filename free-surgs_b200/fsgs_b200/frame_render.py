@@ -26,6 +26,7 @@ from .rasterizer import GaussianRasterizer, _Arena, _f32, _on_device, _ptr, _req
 
 _IDENTITY_OK: Dict[tuple, bool] = {}
 _TLS = threading.local()
+_CAPTURED = []      # (image-state buffer, capacity, W, H) of every fused forward recorded during a graph capture
 
 # Frame-parallel gradient exchange hook (set through fsgs_b200.dist.enable_frame_parallel): a callable that
 # sum-all-reduces a flat float32 CUDA tensor in place, ordered on the current stream; None = single GPU.
@@ -61,6 +62,12 @@ class _RenderFused(torch.autograd.Function):
         P = xyz.shape[0]
         H, W = int(rs.image_height), int(rs.image_width)
         st = make_settings(rs, n_coeffs=16, sh_degree=int(active_sh_degree))
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing:
+            # CUDA-graph capture (fsgs_b200.graphs): no host read-back of the instance count; the binning buffer is
+            # sized by the capacity fsgs_b200.graphs declared for this device
+            st.flags |= _lib.FLAG_FIXED_CAPACITY
+            st.debug = 0
         t = [_f32(x, dev) for x in (rs.bg, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center,
                                     rs.viewmatrix, rs.projmatrix)]
         planes = torch.empty(6, H, W, dtype=torch.float32, device=dev)
@@ -91,6 +98,8 @@ class _RenderFused(torch.autograd.Function):
         ctx.lease = arena.finish()             # scratch goes back to the workspace pool when this node dies
         ctx.st, ctx.P, ctx.num_rendered, ctx.num_rect = st, P, int(nr.value), int(nrect.value)
         ctx.flags = (bool(gs_grad), bool(cam_grad))
+        if capturing:
+            _CAPTURED.append((arena.tensors["img"], int(nr.value), W, H))      # for GraphedStep.overflowed()
         ctx.mark_non_differentiable(radii, *extras)
         ctx.set_materialize_grads(False)        # an output the loss does not use arrives as None, not as zeros
         _TLS.last_stats = (int(nr.value), int(nrect.value))     # per thread: the viewer thread renders too

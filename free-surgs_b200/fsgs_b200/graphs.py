@@ -1,0 +1,80 @@
+"""CUDA-graph capture of a whole render step (forward + loss + backward).
+
+The host side of one fused frame -- PyTorch dispatch, autograd, ctypes marshalling, ~25 kernel launches -- costs
+about as much wall time as the GPU needs for the frame (~0.8 ms vs ~1.1 ms at 500k Gaussians).  Free-SurGS' loops
+read a scalar back every iteration (loss for the progress bar / early stopping: train.py:166-210), so after every
+synchronisation the GPU idles until the host has issued the next frame's first kernels.  The tracking loop runs
+50 iterations per frame with identical shapes: the classic case for a CUDA graph.
+
+    step = GraphedStep(lambda: my_step(static_inputs))    # runs my_step eagerly a few times, then captures it
+    out = step.replay()                                   # re-launches the captured kernels: no Python in between
+
+``my_step`` must be a pure function of tensors that live at fixed addresses (update them in place between replays:
+``static_target.copy_(new_target)``; parameters updated in place by the optimiser qualify) and must set the
+gradients it produces to ``None`` at its start (so that the backward allocates them from the graph's memory pool,
+the usual whole-network-capture recipe).  It may call ``fsgs_b200.render`` any number of times.
+
+What cannot be captured is the read-back of the per-frame instance count that sizes the binning buffer; in
+capture the library runs in fixed-capacity mode (``FSGS_FLAG_FIXED_CAPACITY``): the buffer is sized from the
+instance count seen during the eager warm-up times ``headroom``.  If a later replay produces more instances (the
+pose moved a lot, Gaussians were added) the binning / compositing kernels skip themselves; ``overflowed()``
+detects that (one small device->host read) and ``recapture()`` rebuilds the graph with a larger capacity.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, List
+
+import torch
+
+from . import _lib
+from . import frame_render
+
+
+class GraphedStep:
+    def __init__(self, fn: Callable[[], object], warmup: int = 3, headroom: float = 1.25, device=None):
+        self.fn, self.warmup, self.headroom = fn, int(warmup), float(headroom)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.graph, self.outputs, self._captured, self.capacity = None, None, [], 0
+        self._capture()
+
+    def _capture(self) -> None:
+        dev = self.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        most = 0
+        with torch.cuda.stream(side):                      # warm-up off the default stream, as graph capture requires
+            for _ in range(max(self.warmup, 1)):
+                self.fn()
+                most = max(most, int(getattr(frame_render._TLS, "last_stats", (0, 0))[0]))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.capacity = max(int(most * self.headroom) + 4096, int(self.capacity * self.headroom))
+        _lib.check(_lib.lib().fsgs_set_instance_capacity(dev.index, self.capacity))
+        del frame_render._CAPTURED[:]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.outputs = self.fn()
+        self._captured = list(frame_render._CAPTURED)
+        del frame_render._CAPTURED[:]
+
+    def replay(self):
+        self.graph.replay()
+        return self.outputs
+
+    def instance_counts(self) -> List[int]:
+        """Instance count of every captured fused forward in the LAST replay (synchronises)."""
+        out = []
+        for img, _cap, W, H in self._captured:
+            off = (ctypes.c_size_t * 6)()
+            _lib.lib().fsgs_img_offsets(W, H, off)
+            out.append(int(img[off[5]:off[5] + 8].view(torch.int64).item()))
+        return out
+
+    def overflowed(self) -> bool:
+        return any(n > cap for n, (_img, cap, _w, _h) in zip(self.instance_counts(), self._captured))
+
+    def recapture(self) -> None:
+        """Rebuild the graph (after ``overflowed()``, or when tensor shapes changed)."""
+        self.capacity = max(self.capacity, max(self.instance_counts(), default=0))
+        self._capture()

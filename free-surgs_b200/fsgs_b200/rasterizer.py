@@ -59,6 +59,10 @@ class _WorkspacePool:
         self._free = {}
 
     def acquire(self, key, nbytes: int, device, headroom: float = 1.0) -> torch.Tensor:
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture: the buffer must belong to the graph (its private memory pool keeps it alive
+            # and at a fixed address for every replay); never a pooled tensor another call could be handed
+            return torch.empty(max(int(nbytes * headroom), 256), dtype=torch.uint8, device=device)
         with self._lock:
             lst = self._free.get(key)
             if lst:
@@ -93,12 +97,15 @@ class _Lease:
 
     def __init__(self):
         self.items = []
+        self.pooled = not torch.cuda.is_current_stream_capturing()   # graph-owned buffers never enter the pool
 
     def add(self, key, t):
         self.items.append((key, t))
 
     def release(self):
         items, self.items = self.items, []
+        if not self.pooled:
+            return
         for key, t in items:
             _POOL.release(key, t)
 

@@ -74,6 +74,8 @@ typedef struct fsgs_settings {
 #define FSGS_FLAG_RESERVED_4 4u    /* (was: first backward formulation, removed; ignored)          */
 #define FSGS_FLAG_NO_OPTIMISTIC 8u /* forward: always wait for the instance count before binning   */
 #define FSGS_FLAG_SORT_NETWORK 16u /* per-tile sort: always the compare-exchange network (A/B, tests) */
+#define FSGS_FLAG_FIXED_CAPACITY 32u /* forward: no host read-back of the instance count (CUDA-graph capture);
+                                        the binning buffer is sized by fsgs_set_instance_capacity()     */
 
 /* ------------------------------------------------------------------------------------------
  * API-level rasteriser (one GaussianRasterizer call).
@@ -185,6 +187,15 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
                             float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
                             float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw,
                             float *dL_dpose, float *dL_dmeans2D, float *dL_dsh_rgb, void *stream);
+
+/* CUDA-graph capture support.  A forward normally reads the number of (tile, Gaussian) instances back to size
+ * the binning buffer -- a host synchronisation that cannot be captured.  With FSGS_FLAG_FIXED_CAPACITY in
+ * st->flags the forward sizes that buffer for `capacity` instances (declared here, per device), touches
+ * the host nowhere (st->debug must be 0) and reports *num_rendered_host = capacity; pass that value on to the
+ * backward.  If a frame has more instances than the capacity, the binning / compositing kernels of both
+ * directions return immediately (outputs undefined) and counters[0] (see fsgs_img_offsets) > capacity tells
+ * the caller to re-capture with a larger capacity. */
+int fsgs_set_instance_capacity(int32_t device, int64_t capacity);
 
 /* Frame-parallel gradient exchange (one frame per GPU, shared Gaussian model).
  * Every SH-coefficient gradient of a Gaussian is  basis_k(dir) * gc[ch]  with gc = the colour gradient after

@@ -224,3 +224,57 @@ def test_scratch_returns_to_the_pool_without_the_cyclic_gc():
             assert grown < (8 << 20), (fn.__name__, grown >> 20)
     finally:
         gc.enable()
+
+
+def test_cuda_graph_capture_of_a_whole_step_matches_eager():
+    """fsgs_b200.GraphedStep: forward + loss + backward captured once (fixed-capacity mode, no host read-back) and
+    replayed; parameters / pose / targets are updated in place between replays.  Also the overflow protocol: more
+    instances than the captured capacity -> kernels skip themselves, overflowed() says so, recapture() fixes it."""
+    import fsgs_b200
+    from fsgs_b200 import frame_render as render
+    from fsgs_b200 import model
+    sc = make_scene(20000, 320, 256, size_mult=1.5, seed=11)
+    poses, pc = model.scene_to_device(sc, "cuda")
+    G = torch.randn(4, sc.height, sc.width, generator=torch.Generator().manual_seed(5)).cuda()
+    keys = list(pc.params)
+
+    def step():
+        pc.zero_grad()
+        poses.pose_param_net.zero_grad(set_to_none=True)
+        out = render.render(poses, 0, pc, gs_grad=True, cam_grad=True)
+        loss = (out["render"] * G[:3]).sum() + (out["render_dep"] * G[3]).sum()
+        loss.backward()
+        return loss.detach(), out["render"].detach(), poses.pose_param_net.r.grad, [pc.params[k].grad for k in keys]
+
+    def eager():
+        loss, img, rg, pg = step()
+        return loss.clone(), img.clone(), rg.clone(), [g.clone() for g in pg]
+
+    def check(got, want, tag):
+        assert torch.equal(got[1], want[1]), tag + ": image"
+        assert abs(float(got[0]) - float(want[0])) <= 1e-5 * abs(float(want[0])), tag
+        assert rel_err(got[2], want[2]) < 1e-5, tag + ": pose grad"
+        for k, a, b in zip(keys, got[3], want[3]):
+            assert rel_err(a, b) < 1e-5, (tag, k)
+
+    want0 = eager()
+    gs = fsgs_b200.GraphedStep(step, warmup=2, headroom=1.25)
+    check(gs.replay(), want0, "first replay")
+    assert not gs.overflowed() and gs.instance_counts()[0] > 10000
+    # new pose and new target, written in place; replay must follow
+    with torch.no_grad():
+        poses.pose_param_net.t[:, 0] += torch.tensor([0.004, -0.003, 0.01], device="cuda")
+        G.mul_(0.5)
+    got = gs.replay()
+    got = (got[0].clone(), got[1].clone(), got[2].clone(), [g.clone() for g in got[3]])
+    check(got, eager(), "after in-place update")
+    # grow the splats: far more instances than the captured capacity
+    with torch.no_grad():
+        pc.params["_scaling"] += 0.9
+    gs.replay()
+    assert gs.overflowed()
+    gs.recapture()
+    got = gs.replay()
+    assert not gs.overflowed()
+    got = (got[0].clone(), got[1].clone(), got[2].clone(), [g.clone() for g in got[3]])
+    check(got, eager(), "after recapture")
