@@ -2,7 +2,7 @@
 
 The host side of one fused frame -- PyTorch dispatch, autograd, ctypes marshalling, ~25 kernel launches -- costs
 about as much wall time as the GPU needs for the frame (~0.8 ms vs ~1.1 ms at 500k Gaussians).  Free-SurGS' loops
-read a scalar back every iteration (loss for the progress bar / early stopping: train.py:166-210), so after every
+read a scalar back every iteration (`rgb_loss.item()` / `flow_loss.item()`, train.py:191-192), so after every
 synchronisation the GPU idles until the host has issued the next frame's first kernels.  The tracking loop runs
 50 iterations per frame with identical shapes: the classic case for a CUDA graph.
 
