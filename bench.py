@@ -136,6 +136,14 @@ def cpu_port_step(sc, dtype=torch.float32):
     return float(loss)
 
 
+def use_all_host_threads(c_oracle):
+    """The CPU arm uses every host thread it can get, however the process was launched (torchrun sets
+    OMP_NUM_THREADS=1 for its children, which would slow the reference arm ~13x at N > 1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    c_oracle.set_num_threads(n)
+    torch.set_num_threads(n)
+
+
 def cpu_sample(args, budget_s, steps):
     """Pick the largest area fraction f in {1, 1/4, 1/16, 1/64} of the workload whose `steps` CPU frames fit
     the budget.  The fractional sample is the same generator at P*f Gaussians and (W*sqrt f)x(H*sqrt f)
@@ -164,6 +172,7 @@ def run_reference(args):
     if rank != 0:
         return
     c_oracle.build()
+    use_all_host_threads(c_oracle)
     cores = c_oracle.num_threads()
     sc, desc = cpu_sample(args, budget_s=150.0, steps=args.steps + args.warmup)
     for _ in range(args.warmup):
@@ -435,6 +444,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             from oracle import c_oracle
             c_oracle.build()
+            use_all_host_threads(c_oracle)
             sc_cpu, desc = cpu_sample(args, budget_s=25.0, steps=1)
             t0 = time.perf_counter()
             cpu_port_step(sc_cpu)

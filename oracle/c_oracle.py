@@ -59,6 +59,15 @@ def num_threads() -> int:
     return int(_lib(torch.float32)[4]())
 
 
+def set_num_threads(n: int) -> None:
+    """Use ``n`` OpenMP threads in both builds (overrides an inherited OMP_NUM_THREADS, e.g. torchrun's 1)."""
+    for dt, sfx in ((torch.float32, "f32"), (torch.float64, "f64")):
+        lib = _lib(dt)[0]
+        fn = getattr(lib, f"fsgs_oracle_set_num_threads_{sfx}")
+        fn.restype, fn.argtypes = None, [ctypes.c_int]
+        fn(int(n))
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 

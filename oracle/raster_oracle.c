@@ -581,6 +581,15 @@ void FN(fsgs_oracle_backward)(void *vctx, const real *dL_dcolor, const real *dL_
     free(dL_ddepth);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the timed CPU arm asks for all host threads explicitly */
+void FN(fsgs_oracle_set_num_threads)(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int FN(fsgs_oracle_num_threads)(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
