@@ -100,6 +100,7 @@ class _RenderFused(torch.autograd.Function):
         ctx.flags = (bool(gs_grad), bool(cam_grad))
         if capturing:
             _CAPTURED.append((arena.tensors["img"], int(nr.value), W, H))      # for GraphedStep.overflowed()
+            del _CAPTURED[:-64]                                                 # (bounded, whoever does the capturing)
         ctx.mark_non_differentiable(radii, *extras)
         ctx.set_materialize_grads(False)        # an output the loss does not use arrives as None, not as zeros
         _TLS.last_stats = (int(nr.value), int(nrect.value))     # per thread: the viewer thread renders too
