@@ -71,7 +71,9 @@ k_preprocess_api_bwd(CamConst cc, int P, const float *__restrict__ means3D, cons
 #endif
 // threads per CTA of the fused per-Gaussian backward.  A/B on B200: 256 -> 0.074 / 0.273 ms, 128 -> 0.072 / 0.268,
 // 64 -> 0.070 / 0.256 (P = 500k / 2M): at 128 registers only 512 threads fit an SM, and smaller CTAs interleave
-// their load -> compute -> store phases better
+// their load -> compute -> store phases better.  (A persistent variant with a two-stage bulk-TMA ring per CTA --
+// next chunk's coefficients in flight while the current one is computed -- was tried and was slower: 0.072 / 0.275 ms;
+// 140 registers, 7 CTAs/SM and a store-read wait per chunk.)
 constexpr int PREBWD_CTA = FSGS_PREBWD_CTA;
 __global__ void __launch_bounds__(PREBWD_CTA, FSGS_PREBWD_MINB)
 k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const float *__restrict__ f_dc,
