@@ -158,6 +158,49 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
     }
 }
 
+// Pose-only flavour of the fused per-Gaussian backward (tracking with a frozen Gaussian model: the caller
+// wants dL/dpose and nothing else).  Reads 48 B accumulator row + 12 B xyz + 28 B scale / rotation + the radius
+// word per Gaussian, writes nothing per Gaussian: no SH staging, no 236 B/Gaussian of parameter gradients.
+// The block reduction of dL/dRt is the one of k_preprocess_fused_bwd.
+__global__ void __launch_bounds__(CTA)
+k_preprocess_pose_bwd(CamConst cc, int P, const float *__restrict__ xyz, const float *__restrict__ scaling_raw,
+                      const float *__restrict__ rotation_raw, const float *__restrict__ pose,
+                      const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
+                      const float4 *__restrict__ records, const float *__restrict__ grad_acc,
+                      float *__restrict__ dL_dpose) {
+    __shared__ float s_pose[16];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 16) s_pose[threadIdx.x] = 0.f;
+    __syncthreads();
+    float pg[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) pg[k] = 0.f;
+    if (i < P) {
+        const size_t n = (size_t)i;
+        const int radius = __float_as_int(records[n * 3 + 2].z);
+        if (radius > 0) {
+            float a[ACC_F];
+            load_acc(grad_acc, i, a);
+            float V[16], PM[16], Rt[12];
+            load16(viewmatrix, V);
+            load16(projmatrix, PM);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose + k);
+            const float w[3] = {xyz[3 * n], xyz[3 * n + 1], xyz[3 * n + 2]};
+            const float sc[3] = {scaling_raw[3 * n], scaling_raw[3 * n + 1], scaling_raw[3 * n + 2]};
+            const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
+            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+            fused_backward_pose_one(cc, V, PM, Rt, w, sc, q, a, pg);
+        }
+    }
+    warp_reduce_scatter16(pg, lane);
+    const int idx = lane >> 1;
+    if ((lane & 1) == 0 && idx < 12 && pg[0] != 0.f) atomicAdd(&s_pose[idx], pg[0]);
+    __syncthreads();
+    if (threadIdx.x < 12 && s_pose[threadIdx.x] != 0.f) atomicAdd(&dL_dpose[threadIdx.x], s_pose[threadIdx.x]);
+}
+
 // Frame-parallel exchange, second half: after the masked colour gradients gc[P,3] have been summed over the
 // ranks, every SH-coefficient gradient is basis_k(dir) * gc (zero beyond the active degree), with
 // dir = normalize(xyz - cam_center) identical on all ranks.  Pure write kernel: 192 B/Gaussian, staged in

@@ -309,7 +309,12 @@ struct BwdSmem {
 //      3 x float4 into the (now consumed) pair buffer of its warp, then lane (e, k < 3) adds the four rows
 //      of float4 k and issues ONE red.global.add.v4.f32 -- 48 B per entry in 3 lanes.
 //      (A shuffle reduce-scatter + regroup of 12 values over 4 lanes cost ~60 instructions here; this is ~25.)
-template <bool FUSED, int LEVEL>
+//
+// POSE_ONLY (fused flavour, tracking with a frozen Gaussian model: only dL/dpose is wanted): the colour, opacity
+// and RGB-only screen-space columns of the accumulator row are not needed -- the pose reaches a splat only through
+// its mean (2-D mean, conic via the Jacobian, view depth) -- so their sums, the w / q_rgb planes of the pair buffer
+// (w is still needed for the depth column when a depth-side gradient is present) and the third flush are dropped.
+template <bool FUSED, int LEVEL, bool POSE_ONLY>
 __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int warp, int lane,
                                             int cn, uint2 packed, float bx, float by, float kx, float ky,
                                             float *__restrict__ grad_acc) {
@@ -330,21 +335,26 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int w
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int c = (row * 2 + h) ^ sw;
-            const float4 qv = pq[c], wv = pw[c];
-            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (FUSED && LEVEL >= 1) rv = pr[c];
+            const float4 qv = pq[c];
+            float4 wv = make_float4(0.f, 0.f, 0.f, 0.f), rv = wv;
+            if (!POSE_ONLY || LEVEL >= 1) wv = pw[c];
+            if (FUSED && LEVEL >= 1 && !POSE_ONLY) rv = pr[c];
             const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, wa[4] = {wv.x, wv.y, wv.z, wv.w},
                         ra[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int i = h * 4 + k;
                 const float fi = (float)i, fi2 = (float)(i * i);
-                const float4 g4 = pg[i];
                 S0 += qa[k];
                 if (i > 0) { S1 = fmaf(qa[k], fi, S1); S2 = fmaf(qa[k], fi2, S2); }
-                if (FUSED && LEVEL >= 1) { R0 += ra[k]; if (i > 0) R1 = fmaf(ra[k], fi, R1); }
-                cr = fmaf(wa[k], g4.x, cr); cg = fmaf(wa[k], g4.y, cg); cb = fmaf(wa[k], g4.z, cb);
-                if (LEVEL >= 1) cz = fmaf(wa[k], g4.w, cz);
+                if (POSE_ONLY) {
+                    if (LEVEL >= 1) cz = fmaf(wa[k], pg[i].w, cz);
+                } else {
+                    const float4 g4 = pg[i];
+                    if (FUSED && LEVEL >= 1) { R0 += ra[k]; if (i > 0) R1 = fmaf(ra[k], fi, R1); }
+                    cr = fmaf(wa[k], g4.x, cr); cg = fmaf(wa[k], g4.y, cg); cb = fmaf(wa[k], g4.z, cb);
+                    if (LEVEL >= 1) cz = fmaf(wa[k], g4.w, cz);
+                }
                 if (FUSED && LEVEL >= 2) cz2 = fmaf(wa[k], pg2[i].y, cz2);
             }
         }
@@ -358,14 +368,22 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int w
         float A, B, C;
         unscale_conic(q0.z, q0.w, q1.x, A, B, C);
         o0 = make_float4(-kx * (A * Sx + B * Sy), -ky * (C * Sy + B * Sx), -0.5f * Sxx, -0.5f * Sxy);
-        o1 = make_float4(-0.5f * Syy, S0 * fast_rcp(q1.y), cr, cg);
-        o2 = make_float4(cb, cz, -kx * (A * Rx + B * Ry), -ky * (C * Ry + B * Rx));
+        if (POSE_ONLY) {
+            o1 = make_float4(-0.5f * Syy, 0.f, 0.f, 0.f);
+            o2 = make_float4(0.f, cz, 0.f, 0.f);
+        } else {
+            o1 = make_float4(-0.5f * Syy, S0 * fast_rcp(q1.y), cr, cg);
+            o2 = make_float4(cb, cz, -kx * (A * Rx + B * Ry), -ky * (C * Ry + B * Rx));
+        }
     }
     __syncwarp();                                   // every lane is done reading the pair buffer
     float4 *tp = reinterpret_cast<float4 *>(&sm.pair[warp][0][0][0]);   // [entry][row][3] float4 = 1536 B of 3072
-    if (act) { tp[lane * 3] = o0; tp[lane * 3 + 1] = o1; tp[lane * 3 + 2] = o2; }
+    if (act) {
+        tp[lane * 3] = o0; tp[lane * 3 + 1] = o1;
+        if (!POSE_ONLY || LEVEL >= 1) tp[lane * 3 + 2] = o2;
+    }
     __syncwarp();
-    if (act && row < 3) {
+    if (act && row < ((POSE_ONLY && LEVEL == 0) ? 2 : 3)) {
         const float4 r0 = tp[(e * 4) * 3 + row], r1 = tp[(e * 4 + 1) * 3 + row], r2 = tp[(e * 4 + 2) * 3 + row],
                      r3 = tp[(e * 4 + 3) * 3 + row];
         float4 o;
@@ -379,7 +397,7 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int w
 }
 
 // One staged batch, back to front, for one warp (phase A + embedded phase B).
-template <bool FUSED, int LEVEL>
+template <bool FUSED, int LEVEL, bool POSE_ONLY>
 __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int warp, int lane,
                                           int nrel, int last_rel, float pxf, float pyf, float bx, float by,
                                           float kx, float ky, const float *g, float T_final, float bgdot_rgb,
@@ -401,8 +419,8 @@ __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int war
                                            g, T_final, bgdot_rgb, bgdot_dep, q, w, q_rgb);
             const int px = lane ^ ((s & 1) << 2);
             sm.pair[warp][0][s][px] = q;
-            sm.pair[warp][1][s][px] = w;
-            if (FUSED && LEVEL >= 1) sm.pair[warp][2][s][px] = q_rgb;
+            if (!POSE_ONLY || LEVEL >= 1) sm.pair[warp][1][s][px] = w;
+            if (FUSED && LEVEL >= 1 && !POSE_ONLY) sm.pair[warp][2][s][px] = q_rgb;
         };
         if (cn == PCHUNK) {                                       // all but the first-visited chunk of a batch
 #pragma unroll
@@ -413,12 +431,12 @@ __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int war
                 if (s < cn) slot(s);
         }
         __syncwarp();
-        bwd_phase_b<FUSED, LEVEL>(sm, sb, warp, lane, cn, packed, bx, by, kx, ky, grad_acc);
+        bwd_phase_b<FUSED, LEVEL, POSE_ONLY>(sm, sb, warp, lane, cn, packed, bx, by, kx, ky, grad_acc);
         __syncwarp();
     }
 }
 
-template <bool FUSED>
+template <bool FUSED, bool POSE_ONLY = false>
 __global__ void __launch_bounds__(FSGS_BWD_LB)
 k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const float4 *__restrict__ sorted_rec,
                 const float *__restrict__ bg, const float *__restrict__ final_T,
@@ -505,13 +523,13 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
         const int nrel = limit > 0 ? compact_entries(sb, limit, warp_bit, lane, sm.list[warp]) : 0;
         if (nrel > 0) {
             if (level == 0)
-                bwd_batch<FUSED, 0>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 0, POSE_ONLY>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
             else if (!FUSED || level == 1)
-                bwd_batch<FUSED, 1>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 1, POSE_ONLY>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
             else
-                bwd_batch<FUSED, 2>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 2, POSE_ONLY>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
         }
     };

@@ -469,6 +469,40 @@ FSGS_HD bool fused_forward_one(const CamConst &cc, const float *V, const float *
     return true;
 }
 
+// Geometry half of the fused backward, shared by the full and the pose-only bodies: camera-frame mean,
+// activated scale / rotation, then dL/d(camera-frame mean) and dL/d(Sigma) from the accumulator row.
+FSGS_HD void fused_backward_geometry(const CamConst &cc, const float *V, const float *PM, const float *pose,
+                                     const float *xyz, const float *sc_raw, const float *rot_raw, const float *acc,
+                                     float *s, float *q, float &qi, float *dmean, float *dc6) {
+    float mean[3];
+    for (int r = 0; r < 3; ++r)
+        mean[r] = pose[4 * r] * xyz[0] + pose[4 * r + 1] * xyz[1] + pose[4 * r + 2] * xyz[2] + pose[4 * r + 3];
+    s[0] = cc.mod * expf(sc_raw[0]); s[1] = cc.mod * expf(sc_raw[1]); s[2] = cc.mod * expf(sc_raw[2]);
+    const float qn = fmaxf(sqrtf(rot_raw[0] * rot_raw[0] + rot_raw[1] * rot_raw[1] + rot_raw[2] * rot_raw[2] +
+                                 rot_raw[3] * rot_raw[3]), 1e-12f);
+    qi = 1.0f / qn;
+    q[0] = rot_raw[0] * qi; q[1] = rot_raw[1] * qi; q[2] = rot_raw[2] * qi; q[3] = rot_raw[3] * qi;
+    float c6[6];
+    cov3d_from_scale_rot(s, q, c6);
+    // acc[9] = dL/d(view z) through the depth / depth^2 colour planes
+    project_backward(cc, V, PM, mean, c6, acc[2], acc[3], acc[4], acc[0], acc[1], acc[9], dmean, dc6);
+}
+
+// Pose-only backward for Gaussian i (radius > 0): pg[12] = this Gaussian's contribution to dL/d(pose[:3,:]),
+// i.e. the transform_to_frame matmul backward (reference scene/pose_optimizer.py:987) for one row.  The pose reaches
+// a splat only through its camera-frame mean (colours use the world position and a frozen camera centre, quirk iii),
+// so the accumulator's colour / opacity columns and the SH coefficients are not read.
+FSGS_HD void fused_backward_pose_one(const CamConst &cc, const float *V, const float *PM, const float *pose,
+                                     const float *xyz, const float *sc_raw, const float *rot_raw, const float *acc,
+                                     float *pg) {
+    float s[3], q[4], qi, dmean[3], dc6[6];
+    fused_backward_geometry(cc, V, PM, pose, xyz, sc_raw, rot_raw, acc, s, q, qi, dmean, dc6);
+    for (int r = 0; r < 3; ++r) {
+        pg[4 * r] = dmean[r] * xyz[0]; pg[4 * r + 1] = dmean[r] * xyz[1]; pg[4 * r + 2] = dmean[r] * xyz[2];
+        pg[4 * r + 3] = dmean[r];
+    }
+}
+
 // Fused flavour, backward for Gaussian i (radius > 0).  acc = the compositor's 12-float row.
 // Outputs: dxyz[3], dfdc[3], drest[45] (may be null), dop_raw, ds_raw[3], dq_raw[4],
 // pg[12] = this Gaussian's contribution to dL/d(pose[:3,:]) (zeros unless cam_grad), m2d[2].
@@ -477,18 +511,8 @@ FSGS_HD void fused_backward_one(const CamConst &cc, const float *V, const float 
                                 float op_raw, const float *sc_raw, const float *rot_raw, uint8_t clamp,
                                 const float *acc, int gs_grad, int cam_grad, float *dxyz, float *dfdc, float *drest,
                                 float &dop_raw, float *ds_raw, float *dq_raw, float *pg, float *m2d, float *gc = nullptr) {
-    float mean[3];
-    for (int r = 0; r < 3; ++r)
-        mean[r] = pose[4 * r] * xyz[0] + pose[4 * r + 1] * xyz[1] + pose[4 * r + 2] * xyz[2] + pose[4 * r + 3];
-    const float s[3] = {cc.mod * expf(sc_raw[0]), cc.mod * expf(sc_raw[1]), cc.mod * expf(sc_raw[2])};
-    const float qn = fmaxf(sqrtf(rot_raw[0] * rot_raw[0] + rot_raw[1] * rot_raw[1] + rot_raw[2] * rot_raw[2] +
-                                 rot_raw[3] * rot_raw[3]), 1e-12f);
-    const float qi = 1.0f / qn;
-    const float q[4] = {rot_raw[0] * qi, rot_raw[1] * qi, rot_raw[2] * qi, rot_raw[3] * qi};
-    float c6[6], dmean[3], dc6[6], ds[3], dq[4];
-    cov3d_from_scale_rot(s, q, c6);
-    // acc[9] = dL/d(view z) through the depth / depth^2 colour planes
-    project_backward(cc, V, PM, mean, c6, acc[2], acc[3], acc[4], acc[0], acc[1], acc[9], dmean, dc6);
+    float s[3], q[4], qi, dmean[3], dc6[6], ds[3], dq[4];
+    fused_backward_geometry(cc, V, PM, pose, xyz, sc_raw, rot_raw, acc, s, q, qi, dmean, dc6);
     cov3d_backward(s, q, dc6, ds, dq);
     // exp / normalize / sigmoid
     ds_raw[0] = ds[0] * s[0]; ds_raw[1] = ds[1] * s[1]; ds_raw[2] = ds[2] * s[2];

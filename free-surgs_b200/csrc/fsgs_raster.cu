@@ -73,7 +73,7 @@ inline int blocks(int n) { return (n + CTA - 1) / CTA; }
 // Off by default.  bench.py switches it on for a separate profiling pass (never for the timed
 // steps) to obtain the per-launch duration of each kernel for the roofline line.
 enum KernelId { K_PRE_API = 0, K_PRE_FUSED, K_SCAN, K_SCATTER, K_SORT, K_COMP_FWD, K_COMP_BWD, K_PRE_API_BWD,
-                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_COUNT };
+                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_PRE_POSE_BWD, K_COUNT };
 struct Profiler {
     bool on = false;
     static constexpr int MAXREC = 8192;
@@ -261,6 +261,10 @@ int one_time_setup() {
                                        (int)sizeof(BwdSmem)));
         FSGS_CUDA(cudaFuncSetAttribute(k_composite_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(BwdSmem)));
+        FSGS_CUDA((cudaFuncSetAttribute(k_composite_bwd<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(BwdSmem))));
+        FSGS_CUDA((cudaFuncSetAttribute(k_composite_bwd<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        (int)cudaSharedmemCarveoutMaxShared)));
         // 4 resident CTAs x ~48 KB: ask for the large shared-memory carve-out
         FSGS_CUDA(cudaFuncSetAttribute(k_composite_bwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        (int)cudaSharedmemCarveoutMaxShared));
@@ -333,7 +337,7 @@ const char *fsgs_error_string(int code) {
 const char *fsgs_kernel_names(void) {
     return "k_preprocess_api,k_preprocess_fused,k_tile_scan,k_scatter,k_tile_sort,k_composite_fwd,"
            "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible,k_pose_forward,k_pose_backward,"
-           "k_sh_grad_expand";
+           "k_sh_grad_expand,k_preprocess_pose_bwd";
 }
 
 size_t fsgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
@@ -586,9 +590,16 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
                *bn = static_cast<const char *>(binning);
     float *acc = static_cast<float *>(grad_scratch);
     FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
+    // Pose-only request (tracking against a frozen Gaussian model): dL/dpose is the only output asked for.
+    // The compositor then skips the colour / opacity / RGB-only columns and a lean per-Gaussian kernel
+    // reduces dL/dRt without touching the SH coefficients or writing per-Gaussian gradients.
+    const bool pose_only = cam_grad && dL_dpose && !dL_dxyz && !dL_dfeatures_dc && !dL_dfeatures_rest &&
+                           !dL_dopacity_raw && !dL_dscaling_raw && !dL_drotation_raw && !dL_dmeans2D && !dL_dsh_rgb &&
+                           !(st->flags & FSGS_FLAG_NO_POSE_ONLY);
     if (num_rendered > 0) {
         prof_begin(K_COMP_BWD, stream);
-        k_composite_bwd<true><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
+        auto kern = pose_only ? k_composite_bwd<true, true> : k_composite_bwd<true, false>;
+        kern<<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_drgb, dL_ddepth, dL_dsil, dL_ddepth_sq, acc, (unsigned)st->flags,
@@ -596,6 +607,15 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
             (unsigned long long)num_rendered);
         prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");
+    }
+    if (pose_only) {
+        prof_begin(K_PRE_POSE_BWD, stream);
+        k_preprocess_pose_bwd<<<blocks(P), CTA, 0, stream>>>(
+            cc, P, xyz, scaling_raw, rotation_raw, pose, viewmatrix, projmatrix,
+            reinterpret_cast<const float4 *>(g + gl.records), acc, dL_dpose);
+        prof_end(K_PRE_POSE_BWD, stream);
+        FSGS_LAUNCH_OK("k_preprocess_pose_bwd");
+        return FSGS_OK;
     }
     prof_begin(K_PRE_FUSED_BWD, stream);
     k_preprocess_fused_bwd<<<(P + PREBWD_CTA - 1) / PREBWD_CTA, PREBWD_CTA, 0, stream>>>(

@@ -20,6 +20,7 @@ FLAG_NO_TILE_CULL = 2
 FLAG_NO_OPTIMISTIC = 8
 FLAG_SORT_NETWORK = 16
 FLAG_FIXED_CAPACITY = 32
+FLAG_NO_POSE_ONLY = 64
 
 
 class FsgsError(RuntimeError):

@@ -123,6 +123,24 @@ class _RenderFused(torch.autograd.Function):
         # (rotation and f_rest first: their float4 / bulk-TMA stores need 16-byte alignment for any P)
         reducer = _GRAD_REDUCER["fn"]
         g = {}
+        # Pose tracking against a frozen Gaussian model (no Gaussian parameter and not means2D requires grad):
+        # ask the library for dL/dpose only -- it then runs its pose-only backward (no colour / opacity sums in the
+        # compositor, no SH reads, no 236 B/Gaussian of gradient writes).
+        need = ctx.needs_input_grad
+        if cam_grad and need[6] and not any(need[k] for k in (0, 1, 2, 3, 4, 5, 7)) and P > 0:
+            gp = [None if x is None else _f32(x, dev) for x in (g_rgb, g_depth, g_sil, g_dsq)]
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            arena = _Arena(dev, stream)
+            scratch = arena.take("grad_scratch", _lib.lib().fsgs_grad_scratch_bytes(P))
+            g_pose = z(4, 4)
+            with _on_device(dev):
+                rc = _lib.lib().fsgs_render_backward_ex(
+                    ctypes.byref(ctx.st), P, ctx.num_rendered, *[_ptr(x) for x in t], _ptr(geom), _ptr(binning),
+                    _ptr(img), *[None if x is None else _ptr(x) for x in gp], _ptr(scratch), int(gs_grad), 1,
+                    None, None, None, None, None, None, _ptr(g_pose), None, None, ctypes.c_void_p(stream))
+            arena.finish().release()
+            _lib.check(rc)
+            return (None, None, None, None, None, None, g_pose, None, None, None, None, None, None, None, None)
 
         def carve(flat, layout):
             off = 0
@@ -224,7 +242,14 @@ def _pack(pc, viewmatrix_cur, im, depth_sil, radius, means2D):
 def render(viewpoint_camera, index, pc, gs_grad=True, cam_grad=True):
     """Same signature, return dict and side effects as the reference's ``render``."""
     xyz = pc.params['_xyz']
-    means2D = torch.zeros_like(xyz, requires_grad=True, device=xyz.device) + 0
+    frozen = (not gs_grad) and not any(v.requires_grad for v in pc.params.values())
+    if frozen:
+        # Pose tracking against a frozen model: the reference's screen-space tensor could only hand its gradient to
+        # a temporary nobody holds (it is retained under gs_grad only), so it is created without grad here and the
+        # backward takes the library's pose-only path.  With trainable parameters nothing changes.
+        means2D = torch.zeros_like(xyz)
+    else:
+        means2D = torch.zeros_like(xyz, requires_grad=True, device=xyz.device) + 0
     if gs_grad and means2D.requires_grad:        # (under torch.no_grad() there is nothing to retain)
         means2D.retain_grad()
     viewmatrix_cur = viewpoint_camera.get_pose(index)

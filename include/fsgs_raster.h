@@ -74,6 +74,7 @@ typedef struct fsgs_settings {
 #define FSGS_FLAG_RESERVED_4 4u    /* (was: first backward formulation, removed; ignored)          */
 #define FSGS_FLAG_NO_OPTIMISTIC 8u /* forward: always wait for the instance count before binning   */
 #define FSGS_FLAG_SORT_NETWORK 16u /* per-tile sort: always the compare-exchange network (A/B, tests) */
+#define FSGS_FLAG_NO_POSE_ONLY 64u /* fused backward: never take the pose-only specialisation (A/B, tests) */
 #define FSGS_FLAG_FIXED_CAPACITY 32u /* forward: no host read-back of the instance count (CUDA-graph capture);
                                         the binning buffer is sized by fsgs_set_instance_capacity()     */
 
@@ -162,7 +163,11 @@ int fsgs_render_forward_ex(const fsgs_settings *st, int32_t P, const float *bg, 
  * dL_dmeans2D[P,3] (screen-space gradient of the RGB planes only, as the reference's
  * `viewspace_points.grad`).  gs_grad / cam_grad mirror transform_to_frame's detach flags:
  * gs_grad=0 drops the pose path from dL_dxyz (the SH view-direction path stays, as in the
- * reference); cam_grad=0 leaves dL_dpose zero. */
+ * reference); cam_grad=0 leaves dL_dpose zero.
+ * Pose-only request: when every per-Gaussian output pointer is NULL and only dL_dpose is asked for (pose tracking
+ * against a frozen Gaussian model) the backward runs a specialisation that skips the colour / opacity columns in the
+ * compositor and neither reads the SH coefficients nor writes per-Gaussian gradients; dL_dpose is the same sum
+ * (different float summation order only).  FSGS_FLAG_NO_POSE_ONLY forces the general path. */
 int fsgs_render_backward(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg,
                          const float *xyz, const float *features_dc, const float *features_rest,
                          const float *opacity_raw, const float *scaling_raw, const float *rotation_raw,

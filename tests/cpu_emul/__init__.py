@@ -44,14 +44,15 @@ def render_fused(params, pose, cam, cam_center, sh_deg, dplanes=None, gs_grad=Tr
     radii = torch.zeros(P, dtype=torch.int32)
     R, Rr = ctypes.c_int64(0), ctypes.c_int64(0)
     g = dict(xyz=torch.zeros(P, 3), f_dc=torch.zeros(P, 1, 3), f_rest=torch.zeros(P, 15, 3), opacity=torch.zeros(P, 1),
-             scaling=torch.zeros(P, 3), rotation=torch.zeros(P, 4), pose=torch.zeros(4, 4), means2D=torch.zeros(P, 3))
+             scaling=torch.zeros(P, 3), rotation=torch.zeros(P, 4), pose=torch.zeros(4, 4), means2D=torch.zeros(P, 3),
+             pose_only=torch.zeros(4, 4))
     dp = _c(dplanes)
     lib().emul_render_fused(
         P, W, H, ctypes.c_float(cam.tanfovx), ctypes.c_float(cam.tanfovy), ctypes.c_float(cam.scale_modifier), int(sh_deg),
         _p(t[0]), _p(t[1]), _p(t[2]), _p(t[3]), _p(t[4]), _p(t[5]), _p(t[6]), _p(t[7]), _p(t[8]), _p(t[9]), _p(t[10]),
         int(no_cull), _p(planes), _p(radii), ctypes.byref(R), ctypes.byref(Rr), _p(dp), int(gs_grad), int(cam_grad),
         _p(g["xyz"]), _p(g["f_dc"]), _p(g["f_rest"]), _p(g["opacity"]), _p(g["scaling"]), _p(g["rotation"]), _p(g["pose"]),
-        _p(g["means2D"]))
+        _p(g["means2D"]), _p(g["pose_only"]))
     return planes, radii, int(R.value), int(Rr.value), g
 
 

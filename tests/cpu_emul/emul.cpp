@@ -219,7 +219,8 @@ int emul_render_fused(int P, int W, int H, float tanfovx, float tanfovy, float m
                       const float *sc_raw, const float *rot_raw, const float *pose, const float *cam_center,
                       const float *V, const float *PM, int no_cull, float *planes, int *radii, int64_t *R,
                       int64_t *Rrect, const float *dplanes, int gs_grad, int cam_grad, float *dxyz, float *dfdc,
-                      float *dfrest, float *dop, float *dsc, float *drot, float *dpose, float *dm2d) {
+                      float *dfrest, float *dop, float *dsc, float *drot, float *dpose, float *dm2d,
+                      float *dpose_only) {
     const CamConst cc = make_cc(W, H, tanfovx, tanfovy, mod, sh_deg, 16);
     std::vector<Rec> recs((size_t)P);
     std::vector<uint8_t> clamp((size_t)P, 0);
@@ -243,8 +244,16 @@ int emul_render_fused(int P, int W, int H, float tanfovx, float tanfovy, float m
     if (!dplanes) return 0;
     std::vector<float> acc;
     composite_bwd<true>(cc, (size_t)P, SR, bg, final_T, n_contrib, dplanes, nullptr, acc);
-    double pose_acc[12] = {0};
+    double pose_acc[12] = {0}, pose_only_acc[12] = {0};
     for (int i = 0; i < P; ++i) {
+        if (dpose_only && cam_grad && recs[i].radius > 0) {
+            // what the POSE_ONLY compositor leaves in the row: mean2D, conic and view-depth columns only
+            float a[12] = {0}, pg1[12] = {0};
+            const float *full = acc.data() + 12 * (size_t)i;
+            a[0] = full[0]; a[1] = full[1]; a[2] = full[2]; a[3] = full[3]; a[4] = full[4]; a[9] = full[9];
+            fused_backward_pose_one(cc, V, PM, pose, xyz + 3 * i, sc_raw + 3 * i, rot_raw + 4 * i, a, pg1);
+            for (int k = 0; k < 12; ++k) pose_only_acc[k] += pg1[k];
+        }
         float dx3[3] = {0, 0, 0}, dd[3] = {0, 0, 0}, ds3[3] = {0, 0, 0}, dq4[4] = {0, 0, 0, 0}, pg[12] = {0}, m2[2] = {0, 0};
         float dopv = 0.f;
         float *drest = dfrest + 45 * i;
@@ -260,6 +269,7 @@ int emul_render_fused(int P, int W, int H, float tanfovx, float tanfovy, float m
         for (int k = 0; k < 12; ++k) pose_acc[k] += pg[k];
     }
     for (int k = 0; k < 16; ++k) dpose[k] = k < 12 ? (float)pose_acc[k] : 0.f;
+    if (dpose_only) for (int k = 0; k < 16; ++k) dpose_only[k] = k < 12 ? (float)pose_only_acc[k] : 0.f;
     return 0;
 }
 

@@ -43,10 +43,13 @@ def _settings_to_cuda(cam, rasterizer):
         debug=True)
 
 
-def _run_fused(sc, G6, gs_grad=True, cam_grad=True, sh_deg=3, which="fused"):
+def _run_fused(sc, G6, gs_grad=True, cam_grad=True, sh_deg=3, which="fused", frozen=False):
     _, model, _, render = _gpu_modules()
     poses, pc = model.scene_to_device(sc, DEV)
     pc.active_sh_degree = sh_deg
+    if frozen:
+        for v in pc.params.values():
+            v.requires_grad_(False)
     pc.cam = pc.cam._replace(debug=True)
     fn = render.render if which == "fused" else render.render_two_pass
     out = fn(poses, 0, pc, gs_grad=gs_grad, cam_grad=cam_grad)
@@ -116,6 +119,47 @@ def test_fused_render_small_vs_autograd_oracle(gs_grad, cam_grad, sh_deg, which)
     *ref, G6m = _oracle_fused(sc, G6, gs_grad, cam_grad, sh_deg, "py")
     got = _run_fused(sc, G6m, gs_grad, cam_grad, sh_deg, which)
     _compare_fused(sc, *got, *ref, gs_grad, cam_grad)
+
+
+@pytest.mark.parametrize("n_planes", [3, 4, 5])
+def test_pose_only_backward_for_a_frozen_model(n_planes):
+    """Pose tracking against a frozen Gaussian model takes the library's pose-only backward (compositor without the
+    colour / opacity columns, lean per-Gaussian kernel, no per-Gaussian gradient writes).  dL/dpose, dL/dr, dL/dt
+    must match the float64 oracle and the general path; n_planes = 3 / 4 / 5 walks the compositor's gradient
+    levels (colour only | + depth | + silhouette)."""
+    _, _, rasterizer, _ = _gpu_modules()
+    sc = make_scene(1500, 200, 152, size_mult=2.0, seed=6)
+    G6 = torch.randn(6, sc.height, sc.width, generator=torch.Generator().manual_seed(3))
+    G6[n_planes:] = 0
+    *ref, G6m = _oracle_fused(sc, G6, False, True, 3, "py")
+    _lib.profile_enable(True)
+    try:
+        got = _run_fused(sc, G6m, False, True, 3, "fused", frozen=True)
+        prof = _lib.profile_collect()
+    finally:
+        _lib.profile_enable(False)
+    assert prof["k_preprocess_pose_bwd"][1] == 1 and prof["k_preprocess_fused_bwd"][1] == 0, "pose-only path not taken"
+    assert all(got[2][k] is None for k in ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation"))
+    ref_g = ref[2]
+    check_grad("pose", got[2]["pose"][:3], ref_g["pose"][:3])
+    check_grad("dL/dr", got[2]["r"][0, :, 0], ref_g["r"])
+    check_grad("dL/dt", got[2]["t"][:, 0], ref_g["t"])
+    assert torch.equal(got[2]["pose"][3], torch.zeros(4))
+    # against the general path (trainable model, same upstream gradient): float summation order only
+    gen = _run_fused(sc, G6m, False, True, 3, "fused", frozen=False)
+    assert torch.equal(gen[1], got[1])
+    assert rel_err(got[2]["pose"], gen[2]["pose"]) < 1e-5
+    # FSGS_FLAG_NO_POSE_ONLY sends the frozen model down the general kernels too
+    try:
+        rasterizer.set_debug_flags(no_pose_only=True)
+        _lib.profile_enable(True)
+        forced = _run_fused(sc, G6m, False, True, 3, "fused", frozen=True)
+        prof = _lib.profile_collect()
+    finally:
+        _lib.profile_enable(False)
+        rasterizer.set_debug_flags()
+    assert prof["k_preprocess_pose_bwd"][1] == 0 and prof["k_preprocess_fused_bwd"][1] == 1
+    assert rel_err(forced[2]["pose"], gen[2]["pose"]) < 1e-5
 
 
 @pytest.mark.parametrize("P", [1203, 257, 5])

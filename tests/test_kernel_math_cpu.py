@@ -51,6 +51,10 @@ def test_fused_render_emulation_matches_oracle(gs_grad, cam_grad, sh_deg, n_grad
             check_grad(k, g[k], v)
         if cam_grad:
             check_grad("pose", g["pose"][:3], out["render_w2c"].grad[:3])
+            # the pose-only body (tracking against a frozen model) sees only the mean2D / conic / view-depth
+            # columns of the accumulator row and must give the same dL/dRt
+            check_grad("pose_only", g["pose_only"][:3], out["render_w2c"].grad[:3])
+            assert (g["pose_only"] - g["pose"]).abs().max().item() <= 1e-6 * max(1.0, g["pose"].abs().max().item())
         else:
             assert g["pose"].abs().max().item() == 0
         results[no_cull] = (planes, g, Rn)
