@@ -333,10 +333,10 @@ def run_ours(args):
     # plus the PyTorch / autograd dispatch of a frame.  Per step still: H2D of the inputs (prefetched), a
     # device-to-device copy into the graph's static input, replay, D2H of loss + pose gradient, host wait.
     gstep = None
-    if world == 1 and not args.no_graph:
-        # (N > 1: capturing the frame-parallel step with its NCCL all-reduce inside works -- measured 1.58 -> 1.29 ms at
-        # N = 2 -- but tearing the process group down with a captured collective alive hung; left eager until that
-        # is understood)
+    if not args.no_graph and (world == 1 or args.exchange == "compact"):
+        # (N > 1: the frame-parallel step is captured with its NCCL all-reduce inside.  NCCL keeps the communicator
+        # alive while a captured graph references it, so the graph is released before the process group is torn down
+        # -- see the end of this function; destroying the group first hangs.)
         from fsgs_b200 import GraphedStep
         G_static = torch.empty_like(G_dev)
         G_static.copy_(G_dev)
@@ -516,9 +516,20 @@ def run_ours(args):
             "gpu_launches": (9 + (1 if world > 1 and args.exchange == "compact" else 0)) * args.steps,
             "clocks": clocks,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    if gstep is not None:
+        gstep.release()
     if world > 1:
+        # the result line is out; never let the teardown of the process group keep the job alive
+        import threading
+        sys.stdout.flush()
+        guard = threading.Timer(30.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        guard.cancel()
 
 
 def main():

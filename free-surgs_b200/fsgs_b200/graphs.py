@@ -62,6 +62,16 @@ class GraphedStep:
         self.graph.replay()
         return self.outputs
 
+    def release(self) -> None:
+        """Destroy the captured graph (and drop its outputs / private memory pool).  Call this before
+        ``torch.distributed.destroy_process_group()`` when the step contains a collective: NCCL keeps a
+        communicator alive for as long as a captured graph references it, and tearing the process group down
+        first waits on that reference forever."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.device)
+            self.graph.reset()
+        self.graph, self.outputs, self._captured = None, None, []
+
     def instance_counts(self) -> List[int]:
         """Instance count of every captured fused forward in the LAST replay (synchronises)."""
         out = []
