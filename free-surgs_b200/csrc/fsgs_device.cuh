@@ -162,6 +162,32 @@ __device__ __forceinline__ void stage_rows_tma(float *s_dst, const float *__rest
     if (rows_tma > 0) mbar_wait(bar, 0u, err);
 }
 
+// The same in two halves, so that a kernel can put its own (independent) global loads in flight between issuing the
+// bulk copy and waiting for it instead of serialising two DRAM latencies:
+//   stage_rows_issue: thread 0 arms the barrier and issues the copy; every thread loads its share of the remainder.
+//   stage_rows_wait : block barrier (mbarrier initialised + remainder visible), then the wait for the bulk copy.
+// Both must be called by all threads of the CTA, outside divergent code.
+template <int ROW_FLOATS>
+__device__ __forceinline__ void stage_rows_issue(float *s_dst, const float *__restrict__ src, int base, int count,
+                                                 uint64_t *bar) {
+    const int rows_tma = count & ~3;
+    const float *g = src + (size_t)base * ROW_FLOATS;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        if (rows_tma > 0) {
+            const uint32_t bytes = (uint32_t)rows_tma * ROW_FLOATS * 4u;
+            mbar_arrive_expect_tx(bar, bytes);
+            tma_load_1d(s_dst, g, bytes, bar);
+        }
+    }
+    for (int q = rows_tma * ROW_FLOATS + threadIdx.x; q < count * ROW_FLOATS; q += blockDim.x) s_dst[q] = __ldg(g + q);
+}
+__device__ __forceinline__ void stage_rows_wait(int count, uint64_t *bar, unsigned long long *err) {
+    __syncthreads();
+    if ((count & ~3) > 0) mbar_wait(bar, 0u, err);
+}
+
 // gauss_power (pinned operation order) lives in fsgs_math.cuh so the CPU emulation shares it.
 __device__ __forceinline__ float gauss_weight(float power) {
 #ifdef FSGS_PRECISE_EXP

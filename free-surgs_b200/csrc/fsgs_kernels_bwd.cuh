@@ -101,32 +101,49 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
     const bool staged = (reinterpret_cast<uintptr_t>(f_rest) & 15u) == 0 &&
                         (reinterpret_cast<uintptr_t>(dL_dfrest) & 15u) == 0 && use_tma;
     if (threadIdx.x < 16) s_pose[threadIdx.x] = 0.f;
-    if (staged) stage_rows_tma<45>(s_rest, f_rest, base, count, &s_bar, err);
-    else __syncthreads();
+    if (staged) stage_rows_issue<45>(s_rest, f_rest, base, count, &s_bar);
     float pg[16];   // pose-gradient contributions of this Gaussian: g_r * [x y z 1]_c at [4r + c]
 #pragma unroll
     for (int k = 0; k < 16; ++k) pg[k] = 0.f;
+    // this thread's own inputs (radius word, then the 48 B accumulator row + 56 B of parameters) go in flight while
+    // the bulk copy of the SH rows is under way: the wait for the copy, the radius load and the loads it gates were
+    // three serialised DRAM latencies (ncu: 37 % of the kernel's stall samples on those three instructions)
+    int radius = 0;
+    float a[ACC_F], w[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, dcv[3] = {0.f, 0.f, 0.f};
+    float op_raw = 0.f;
+    uint8_t cl = 0;
+#pragma unroll
+    for (int k = 0; k < ACC_F; ++k) a[k] = 0.f;
     if (i < P) {
         const size_t n = (size_t)i;
-        const int radius = __float_as_int(records[n * 3 + 2].z);
+        radius = __float_as_int(records[n * 3 + 2].z);
+        if (radius > 0) {
+            load_acc(grad_acc, i, a);
+            w[0] = xyz[3 * n]; w[1] = xyz[3 * n + 1]; w[2] = xyz[3 * n + 2];
+            sc[0] = scaling_raw[3 * n]; sc[1] = scaling_raw[3 * n + 1]; sc[2] = scaling_raw[3 * n + 2];
+            const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
+            q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+            dcv[0] = f_dc[3 * n]; dcv[1] = f_dc[3 * n + 1]; dcv[2] = f_dc[3 * n + 2];
+            op_raw = opacity_raw[i];
+            cl = clamped[i];
+        }
+    }
+    if (staged) stage_rows_wait(count, &s_bar, err);
+    else __syncthreads();
+    if (i < P) {
+        const size_t n = (size_t)i;
         float dxyz[3] = {0.f, 0.f, 0.f}, ds_raw[3] = {0.f, 0.f, 0.f}, dq_raw[4] = {0.f, 0.f, 0.f, 0.f};
         float dop_raw = 0.f, dfdc[3] = {0.f, 0.f, 0.f}, m2d[2] = {0.f, 0.f}, gc[3] = {0.f, 0.f, 0.f};
         float *drest = !dL_dfrest ? nullptr : (staged ? s_rest + 45 * threadIdx.x : dL_dfrest + 45 * n);
         const float *rest = staged ? s_rest + 45 * threadIdx.x : f_rest + 45 * n;
         if (radius > 0) {
-            float a[ACC_F];
-            load_acc(grad_acc, i, a);
             float V[16], PM[16], Rt[12], cp[3];
             load16(viewmatrix, V);
             load16(projmatrix, PM);
 #pragma unroll
             for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose + k);
             cp[0] = __ldg(cam_center); cp[1] = __ldg(cam_center + 1); cp[2] = __ldg(cam_center + 2);
-            const float w[3] = {xyz[3 * n], xyz[3 * n + 1], xyz[3 * n + 2]};
-            const float sc[3] = {scaling_raw[3 * n], scaling_raw[3 * n + 1], scaling_raw[3 * n + 2]};
-            const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
-            const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-            fused_backward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, rest, opacity_raw[i], sc, q, clamped[i], a,
+            fused_backward_one(cc, V, PM, Rt, cp, w, dcv, rest, op_raw, sc, q, cl, a,
                                gs_grad, cam_grad, dxyz, dfdc, drest, dop_raw, ds_raw, dq_raw, pg, m2d, gc);
         } else if (drest) {
             for (int k = 0; k < 45; ++k) drest[k] = 0.f;

@@ -196,13 +196,29 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int base = blockIdx.x * blockDim.x;
     const bool staged = (flags & 1u) == 0 && (reinterpret_cast<uintptr_t>(f_rest) & 15u) == 0;
-    if (staged) stage_rows_tma<45>(s_rest, f_rest, base, min((int)blockDim.x, P - base), &s_bar, counters + CNT_ERR);
+    const int count = min((int)blockDim.x, P - base);
+    if (staged) stage_rows_issue<45>(s_rest, f_rest, base, count, &s_bar);
     const int lane = threadIdx.x & 31;
     unsigned int rect_tiles = 0;
     Splat sp;
     sp.px = sp.py = sp.conx = sp.cony = sp.conz = 0.f; sp.radius = 0;
     float opacity = 0.f;
     bool vis = false;
+    // this thread's own 56 B go in flight while the bulk copy of the SH rows is under way (ncu: the wait for the
+    // copy and the first use of these loads were two serialised DRAM latencies, 20 % of the kernel's stall samples;
+    // 0.061 -> 0.056 ms)
+    float w[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, dcv[3] = {0.f, 0.f, 0.f};
+    float op_raw = 0.f;
+    if (i < P) {
+        const size_t n = (size_t)i;
+        w[0] = xyz[3 * n]; w[1] = xyz[3 * n + 1]; w[2] = xyz[3 * n + 2];
+        sc[0] = scaling_raw[3 * n]; sc[1] = scaling_raw[3 * n + 1]; sc[2] = scaling_raw[3 * n + 2];
+        const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
+        q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+        dcv[0] = f_dc[3 * n]; dcv[1] = f_dc[3 * n + 1]; dcv[2] = f_dc[3 * n + 2];
+        op_raw = opacity_raw[i];
+    }
+    if (staged) stage_rows_wait(count, &s_bar, counters + CNT_ERR);
     if (i < P) {
         float V[16], PM[16], Rt[12], cp[3];
         load16(viewmatrix, V);
@@ -211,14 +227,10 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
         for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose + k);
         cp[0] = __ldg(cam_center); cp[1] = __ldg(cam_center + 1); cp[2] = __ldg(cam_center + 2);
         const size_t n = (size_t)i;
-        const float w[3] = {xyz[3 * n], xyz[3 * n + 1], xyz[3 * n + 2]};
-        const float sc[3] = {scaling_raw[3 * n], scaling_raw[3 * n + 1], scaling_raw[3 * n + 2]};
-        const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
-        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
         float rgb[3];
         uint8_t cl = 0;
         const float *rest = staged ? s_rest + 45 * threadIdx.x : f_rest + 45 * n;
-        vis = fused_forward_one(cc, V, PM, Rt, cp, w, f_dc + 3 * n, rest, opacity_raw[i], sc, q, sp, opacity, rgb, cl);
+        vis = fused_forward_one(cc, V, PM, Rt, cp, w, dcv, rest, op_raw, sc, q, sp, opacity, rgb, cl);
         if (vis) {
             rect_tiles = (unsigned int)((sp.rmaxx - sp.rminx) * (sp.rmaxy - sp.rminy));
             store_record(records, i, sp, opacity, rgb[0], rgb[1], rgb[2], 1);
@@ -285,6 +297,11 @@ k_tile_scan(int tiles, const unsigned int *__restrict__ tile_count, unsigned int
 }
 
 // ---- K3: scatter (depth, id) keys into the per-tile segments ----------------------------------------
+// (ncu shows 2/3 of this kernel's stall samples on the instruction that consumes the slot returned by the cursor
+// atomic.  Putting 2 or 4 rounds of atomics in flight before the first key store was tried and changed nothing
+// (0.053 ms either way): per instance the kernel issues one L2 atomic, one scattered 8-byte store and one offset
+// load, ~7 M sector operations in ~50 us -- it sits on the L2's sector-operation rate, not on latency.  The way
+// down is fewer scattered operations per instance, e.g. taking the slot from the counting pass's atomic.)
 __global__ void __launch_bounds__(CTA)
 k_scatter(CamConst cc, int P, const float4 *__restrict__ records, const unsigned int *__restrict__ tile_offset,
           unsigned int *__restrict__ cursor, unsigned long long *__restrict__ keys, unsigned int flags,
@@ -475,6 +492,8 @@ __device__ __forceinline__ bool tile_sort_bucket(int n, const unsigned long long
     }
     __syncthreads();
 
+    // (gathering the 48-byte records of 2 or 4 entries per thread before using the first was tried: 0.095 ms either
+    // way with 2, slower with 4 -- the gather is not latency-bound at 24 resident warps per SM)
     for (int p = tid; p < n; p += CTA) {
         const unsigned long long k = s_out[p];
         const int b = depth_bucket(k, zmin, inv, nb);
