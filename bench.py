@@ -263,17 +263,51 @@ def run_ours(args):
         sampler.lines.clear()
 
     # ---- timed region: K steps, device time, L2 flushed between steps (flush outside the events) ----
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()
-        ev[k][0].record()
-        step(G_dev)
-        ev[k][1].record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    ms = [a.elapsed_time(b) for a, b in ev]
+    # Two ways of issuing the same step are timed:
+    #   eager : every frame issued from Python (PyTorch dispatch + autograd + ctypes, ~25 launches, ~0.8 ms of host
+    #           time per frame on an idle box -- with 4-8 ranks sharing the host's cores it exceeds the ~1.1 ms the
+    #           GPU needs and the step becomes HOST-bound: measured 1.09 ms at N = 1 but 1.71 ms at N = 4);
+    #   graph : the step captured once (fsgs_b200.GraphedStep, the library in fixed-capacity mode, the NCCL exchange
+    #           of N > 1 inside the capture) and replayed -- what DESIGN.md / INTEGRATION.md recommend for Free-SurGS'
+    #           iteration loops.  This is the headline `value`; the eager figure is reported next to it.
+    def timed(fn):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            flush.zero_()
+            ev[k][0].record()
+            fn()
+            ev[k][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        return [a.elapsed_time(b) for a, b in ev], wall
+
+    ms_eager_steps, t_wall = timed(lambda: step(G_dev))
+    ms_eager = sum(ms_eager_steps) / len(ms_eager_steps)
+    ms, value_mode = ms_eager_steps, "eager"
+    gstep = None
+    if not args.no_graph and (world == 1 or args.exchange == "compact"):
+        # (N > 1: the frame-parallel step is captured with its NCCL all-reduce inside.  NCCL keeps the communicator
+        # alive while a captured graph references it, so the graph is released before the process group is torn down
+        # -- see the end of this function; destroying the group first hangs.)
+        from fsgs_b200 import GraphedStep
+        G_static = torch.empty_like(G_dev)
+        G_static.copy_(G_dev)
+
+        def graph_body():
+            loss = step(G_static)
+            return torch.cat([loss.detach().reshape(1), poses.pose_param_net.r.grad.reshape(-1),
+                              poses.pose_param_net.t.grad.reshape(-1)])
+
+        gstep = GraphedStep(graph_body, warmup=3)
+    if gstep is not None:
+        for _ in range(3):
+            gstep.replay()
+        ms, t_wall = timed(gstep.replay)
+        value_mode = "cuda-graph"
+        if gstep.overflowed():
+            raise SystemExit("bench: the captured step overflowed its instance capacity")
     ms_step = sum(ms) / len(ms)
     # (the sampler keeps running through the end-to-end and pose-tracking loops below -- all of them keep the GPU
     # busy with the same kernels -- so that the clocks line rests on more than one 200 ms sample)
@@ -332,21 +366,6 @@ def run_ours(args):
     # and replayed: after each per-step synchronisation the host has one launch to issue instead of ~25 kernels
     # plus the PyTorch / autograd dispatch of a frame.  Per step still: H2D of the inputs (prefetched), a
     # device-to-device copy into the graph's static input, replay, D2H of loss + pose gradient, host wait.
-    gstep = None
-    if not args.no_graph and (world == 1 or args.exchange == "compact"):
-        # (N > 1: the frame-parallel step is captured with its NCCL all-reduce inside.  NCCL keeps the communicator
-        # alive while a captured graph references it, so the graph is released before the process group is torn down
-        # -- see the end of this function; destroying the group first hangs.)
-        from fsgs_b200 import GraphedStep
-        G_static = torch.empty_like(G_dev)
-        G_static.copy_(G_dev)
-
-        def graph_body():
-            loss = step(G_static)
-            return torch.cat([loss.detach().reshape(1), poses.pose_param_net.r.grad.reshape(-1),
-                              poses.pose_param_net.t.grad.reshape(-1)])
-
-        gstep = GraphedStep(graph_body, warmup=3)
     if gstep is not None:
 
         def run_e2e_graph(n_steps):
@@ -474,7 +493,7 @@ def run_ours(args):
                    "sample": f"{desc}; {dt_cpu:.1f} s"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "value_mode": value_mode, "ms_per_step_eager_issue": ms_eager, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"endo-synth P={args.P} {W}x{H} SH3 m={args.m} seed0, fused render fwd+bwd, "
                                    f"1 frame/GPU/step", "l2": "256 MiB flush before every timed step (outside the events)",
