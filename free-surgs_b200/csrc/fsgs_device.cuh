@@ -142,28 +142,8 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 // Stage the CTA's slice of a [P, row_floats] float array into shared memory: one bulk TMA copy for the
 // largest 16-byte-multiple prefix, plain loads for the (at most 3-row) remainder.  `count` rows starting at
-// row `base`.  Call from all threads; returns after the data has landed.  Requires src 16-B aligned.
-template <int ROW_FLOATS>
-__device__ __forceinline__ void stage_rows_tma(float *s_dst, const float *__restrict__ src, int base, int count,
-                                               uint64_t *bar, unsigned long long *err) {
-    const int rows_tma = count & ~3;                                 // rows*ROW_FLOATS*4 B multiple of 16
-    const float *g = src + (size_t)base * ROW_FLOATS;
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-        if (rows_tma > 0) {
-            const uint32_t bytes = (uint32_t)rows_tma * ROW_FLOATS * 4u;
-            mbar_arrive_expect_tx(bar, bytes);
-            tma_load_1d(s_dst, g, bytes, bar);
-        }
-    }
-    for (int q = rows_tma * ROW_FLOATS + threadIdx.x; q < count * ROW_FLOATS; q += blockDim.x) s_dst[q] = __ldg(g + q);
-    __syncthreads();                                                  // barrier initialised + remainder visible
-    if (rows_tma > 0) mbar_wait(bar, 0u, err);
-}
-
-// The same in two halves, so that a kernel can put its own (independent) global loads in flight between issuing the
-// bulk copy and waiting for it instead of serialising two DRAM latencies:
+// row `base`.  Requires src 16-B aligned.  In two halves, so that a kernel can put its own (independent) global
+// loads in flight between issuing the bulk copy and waiting for it instead of serialising two DRAM latencies:
 //   stage_rows_issue: thread 0 arms the barrier and issues the copy; every thread loads its share of the remainder.
 //   stage_rows_wait : block barrier (mbarrier initialised + remainder visible), then the wait for the bulk copy.
 // Both must be called by all threads of the CTA, outside divergent code.
@@ -188,15 +168,6 @@ __device__ __forceinline__ void stage_rows_wait(int count, uint64_t *bar, unsign
     if ((count & ~3) > 0) mbar_wait(bar, 0u, err);
 }
 
-// gauss_power (pinned operation order) lives in fsgs_math.cuh so the CPU emulation shares it.
-__device__ __forceinline__ float gauss_weight(float power) {
-#ifdef FSGS_PRECISE_EXP
-    return expf(power);
-#else
-    return __expf(power);
-#endif
-}
-
 // ---- warp reduce-scatter of 16 values ----------------------------------------------------------
 // After the call lane L holds in v[0] the warp-wide sum of input index (L >> 1) & 15.
 // 16 shuffles instead of 16 * 5.
@@ -212,44 +183,6 @@ __device__ __forceinline__ void warp_reduce_scatter16(float (&v)[16], int lane) 
         }
     }
     v[0] += __shfl_xor_sync(FULL, v[0], 1);
-}
-
-// ---- warp reduce-scatter of 12 values (13 shuffles) -------------------------------------------
-// Halving tree 12 -> 6 -> 3 -> (2 + pad) -> 1.  Returns the index of the input whose warp-wide sum
-// this lane now holds in v[0], or -1 (odd lanes duplicate their neighbour, and the lanes with bits
-// 2 and 1 both set hold the padding slot).  idx = 6*bit4 + 3*bit3 + 2*bit2 + bit1.
-__device__ __forceinline__ int warp_reduce_scatter12(float (&v)[12], int lane) {
-    {
-        const bool up = (lane & 16) != 0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const float keep = up ? v[i + 6] : v[i], send = up ? v[i] : v[i + 6];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
-        }
-    }
-    {
-        const bool up = (lane & 8) != 0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float keep = up ? v[i + 3] : v[i], send = up ? v[i] : v[i + 3];
-            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
-        }
-    }
-    {
-        const bool up = (lane & 4) != 0;
-        const float keep0 = up ? v[2] : v[0], send0 = up ? v[0] : v[2];
-        const float keep1 = up ? 0.f : v[1], send1 = up ? v[1] : 0.f;
-        v[0] = keep0 + __shfl_xor_sync(FULL, send0, 4);
-        v[1] = keep1 + __shfl_xor_sync(FULL, send1, 4);
-    }
-    {
-        const bool up = (lane & 2) != 0;
-        const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
-        v[0] = keep + __shfl_xor_sync(FULL, send, 2);
-    }
-    v[0] += __shfl_xor_sync(FULL, v[0], 1);
-    if ((lane & 1) || ((lane & 6) == 6)) return -1;
-    return ((lane >> 4) & 1) * 6 + ((lane >> 3) & 1) * 3 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }

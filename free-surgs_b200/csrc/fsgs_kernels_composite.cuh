@@ -120,54 +120,6 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
         if (threadIdx.x == 0 && nb > 0) stage_issue_tma(s_rec[0], src, min(BATCH, n), &s_full[0]);
     }
 
-#ifdef FSGS_FWD_LEGACY
-    bool done = !pix.inside;
-    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f, S = 0.f, D2 = 0.f;
-    unsigned int last = 0;
-
-    for (int k = 0; k < nb; ++k) {
-        const int all_done = __syncthreads_and(done ? 1 : 0);   // everyone is also past batch k-1
-        const int buf = k & 1;
-        const int cnt = min(BATCH, n - k * BATCH);
-        if (use_tma) {
-            if (threadIdx.x == 0 && !all_done && k + 1 < nb)
-                stage_issue_tma(s_rec[buf ^ 1], src + (size_t)(k + 1) * BATCH * REC_F4, min(BATCH, n - (k + 1) * BATCH),
-                                &s_full[buf ^ 1]);
-            mbar_wait(&s_full[buf], (uint32_t)(k >> 1) & 1u, err);   // drain even when leaving
-            if (all_done) break;
-        } else {
-            if (all_done) break;
-            stage_plain(s_rec[buf], src + (size_t)k * BATCH * REC_F4, cnt);
-            __syncthreads();
-        }
-        if (__all_sync(FULL, done)) continue;                       // this warp's pixels are finished
-        const float4 *sb = s_rec[buf];
-        const int nrel = compact_entries(sb, cnt, warp_bit, lane, s_list[warp]);
-        for (int i = 0; i < nrel; ++i) {
-            if ((i & 7) == 0 && __all_sync(FULL, done)) break;
-            if (done) continue;
-            const int j = s_list[warp][i];
-            const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
-            const float dx = q0.x - pxf, dy = q0.y - pyf;
-            const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
-            const float alpha = fminf(ALPHA_MAX, q1.y * fast_exp2(p2));
-            if (p2 <= 0.f && alpha >= ALPHA_MIN) {
-                const float test_T = T * (1.f - alpha);
-                if (test_T < T_MIN) {
-                    done = true;
-                } else {
-                    const float4 q2 = sb[j * 3 + 2];
-                    const float w = alpha * T;
-                    C0 += q1.z * w; C1 += q1.w * w; C2 += q2.x * w; D += q2.y * w;
-                    if (FUSED) { S += w; D2 += q2.y * q2.y * w; }
-                    T = test_T;
-                    last = (unsigned int)(k * BATCH + j + 1);
-                }
-            }
-        }
-    }
-
-#else
     // A finished pixel (T would drop below 1e-4, or outside the image) is marked by the SIGN of T: the next
     // entry's test_T = T * (1 - alpha) is then negative, fails `test_T >= T_MIN` and re-marks the pixel --
     // no separate flag, no per-entry "done" branch.  The body is branch-free (selects), entries are taken in
@@ -223,7 +175,6 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
         if (lj >= 0) last = (unsigned int)(k * BATCH + lj + 1);
     }
     T = fabsf(T);
-#endif
 
     if (pix.inside) {
         const size_t HW = (size_t)cc.W * cc.H, p = (size_t)pix.py * cc.W + pix.px;
