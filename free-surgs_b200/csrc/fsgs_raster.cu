@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include "fsgs_kernels_bwd.cuh"
+#include "fsgs_kernels_loss.cuh"
 #include "fsgs_kernels_composite.cuh"
 #include "fsgs_kernels_pre.cuh"
 
@@ -73,7 +74,7 @@ inline int blocks(int n) { return (n + CTA - 1) / CTA; }
 // Off by default.  bench.py switches it on for a separate profiling pass (never for the timed
 // steps) to obtain the per-launch duration of each kernel for the roofline line.
 enum KernelId { K_PRE_API = 0, K_PRE_FUSED, K_SCAN, K_SCATTER, K_SORT, K_COMP_FWD, K_COMP_BWD, K_PRE_API_BWD,
-                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_PRE_POSE_BWD, K_COUNT };
+                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_PRE_POSE_BWD, K_LOSS_FWD, K_LOSS_BWD, K_COUNT };
 struct Profiler {
     bool on = false;
     static constexpr int MAXREC = 8192;
@@ -337,7 +338,7 @@ const char *fsgs_error_string(int code) {
 const char *fsgs_kernel_names(void) {
     return "k_preprocess_api,k_preprocess_fused,k_tile_scan,k_scatter,k_tile_sort,k_composite_fwd,"
            "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible,k_pose_forward,k_pose_backward,"
-           "k_sh_grad_expand,k_preprocess_pose_bwd";
+           "k_sh_grad_expand,k_preprocess_pose_bwd,k_rgb_loss_fwd,k_rgb_loss_bwd";
 }
 
 size_t fsgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
@@ -649,6 +650,77 @@ int fsgs_sh_grad_expand(const fsgs_settings *st, int32_t P, const float *xyz, co
                                                     dL_dfeatures_rest, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1);
     prof_end(K_SH_EXPAND, stream);
     FSGS_LAUNCH_OK("k_sh_grad_expand");
+    return FSGS_OK;
+}
+
+// ---- fused image loss --------------------------------------------------------------
+static LossWindow make_loss_window() {
+    // the reference's 1-D window: exp(-(i - 5)^2 / (2 * 1.5^2)) normalised, float32 (utils/loss_utils.py:56-58)
+    LossWindow w;
+    float sum = 0.f;
+    for (int i = 0; i < 2 * LOSS_R + 1; ++i) {
+        const float d = (float)(i - LOSS_R);
+        w.g[i] = expf(-(d * d) / (2.0f * 1.5f * 1.5f));
+        sum += w.g[i];
+    }
+    for (int i = 0; i < 2 * LOSS_R + 1; ++i) w.g[i] /= sum;
+    return w;
+}
+static inline size_t loss_blocks(int C, int H, int W) {
+    return (size_t)C * (size_t)((H + LOSS_T - 1) / LOSS_T) * (size_t)((W + LOSS_T - 1) / LOSS_T);
+}
+
+size_t fsgs_rgb_loss_scratch_bytes(int32_t C, int32_t H, int32_t W) {
+    if (C <= 0 || H <= 0 || W <= 0) return 256;
+    return align_up(loss_blocks(C, H, W) * 2 * sizeof(double), 256);
+}
+
+static int loss_args_ok(int32_t C, int32_t H, int32_t W, const float *img, const float *gt, const unsigned char *mask_u8,
+                        const float *mask_f32, int64_t mask_cstride) {
+    if (C <= 0 || C > 65535 || H <= 0 || W <= 0 || !img || !gt) return FSGS_E_INVALID;
+    if (mask_u8 && mask_f32) return FSGS_E_INVALID;
+    if (mask_cstride != 0 && mask_cstride != (int64_t)H * W) return FSGS_E_INVALID;
+    if ((H + LOSS_T - 1) / LOSS_T > 65535) return FSGS_E_INVALID;
+    return FSGS_OK;
+}
+
+int fsgs_rgb_loss_forward(int32_t C, int32_t H, int32_t W, const float *img, const float *gt, const unsigned char *mask_u8,
+                          const float *mask_f32, int64_t mask_cstride, float lambda_dssim, float *maps, void *scratch,
+                          float *out, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = loss_args_ok(C, H, W, img, gt, mask_u8, mask_f32, mask_cstride);
+    if (rc) return rc;
+    if (!scratch || !out) return FSGS_E_INVALID;
+    if ((rc = check_arch())) return rc;
+    const LossMask mask{mask_u8, mask_f32, (long long)mask_cstride};
+    const LossWindow win = make_loss_window();
+    const dim3 grid((W + LOSS_T - 1) / LOSS_T, (H + LOSS_T - 1) / LOSS_T, C);
+    double *partial = static_cast<double *>(scratch);
+    prof_begin(K_LOSS_FWD, stream);
+    k_rgb_loss_fwd<<<grid, CTA, 0, stream>>>(H, W, img, gt, mask, win, maps, partial);
+    k_rgb_loss_reduce<<<1, CTA, 0, stream>>>((long long)loss_blocks(C, H, W), partial, 1.0 / ((double)C * H * W),
+                                             lambda_dssim, out);
+    prof_end(K_LOSS_FWD, stream);
+    FSGS_CUDA(cudaGetLastError());
+    return FSGS_OK;
+}
+
+int fsgs_rgb_loss_backward(int32_t C, int32_t H, int32_t W, const float *img, const float *gt, const unsigned char *mask_u8,
+                           const float *mask_f32, int64_t mask_cstride, float lambda_dssim, const float *maps,
+                           const float *upstream, float *dimg, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = loss_args_ok(C, H, W, img, gt, mask_u8, mask_f32, mask_cstride);
+    if (rc) return rc;
+    if (!maps || !dimg) return FSGS_E_INVALID;
+    if ((rc = check_arch())) return rc;
+    const LossMask mask{mask_u8, mask_f32, (long long)mask_cstride};
+    const LossWindow win = make_loss_window();
+    const dim3 grid((W + LOSS_T - 1) / LOSS_T, (H + LOSS_T - 1) / LOSS_T, C);
+    prof_begin(K_LOSS_BWD, stream);
+    k_rgb_loss_bwd<<<grid, CTA, 0, stream>>>(H, W, img, gt, mask, win, maps, upstream, lambda_dssim,
+                                             (float)(1.0 / ((double)C * H * W)), dimg);
+    prof_end(K_LOSS_BWD, stream);
+    FSGS_CUDA(cudaGetLastError());
     return FSGS_OK;
 }
 

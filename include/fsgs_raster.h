@@ -247,6 +247,25 @@ size_t fsgs_geom_record_offset(int32_t P);
 void fsgs_img_offsets(int32_t image_width, int32_t image_height, size_t *out6);
 void fsgs_binning_offsets(int64_t num_rendered, size_t *out2);
 
+/* Fused image loss of Free-SurGS (reference utils/loss_utils.py:47-96, rgb_loss_func):
+ *   loss = (1 - lambda_dssim) * mean|x - y| + lambda_dssim * (1 - mean SSIM(x, y)),  x = img * mask, y = gt * mask,
+ * SSIM with the reference's 11x11 Gaussian window (sigma 1.5), zero padding, C1 = 0.01^2, C2 = 0.03^2.
+ * img, gt: float32 [C,H,W] device pointers.  Mask (optional): mask_u8 (one byte per element, non-zero = 1) or
+ * mask_f32, at most one non-NULL; mask_cstride = 0 for one [H,W] plane shared by the channels, H*W for [C,H,W].
+ * forward : out[3] = (loss, mean|x-y|, mean SSIM) (device); maps[3,C,H,W] (device, NULL = no gradient wanted)
+ *           receives the per-pixel partial derivatives the backward needs; scratch = fsgs_rgb_loss_scratch_bytes().
+ * backward: dimg[C,H,W] = d(upstream * loss)/d(img); `upstream` is a DEVICE scalar (NULL = 1) so that no host
+ *           synchronisation is needed between the caller's loss arithmetic and this call.
+ * One forward kernel + a one-CTA reduction, one backward kernel; the sums are taken in a fixed order
+ * (deterministic). */
+size_t fsgs_rgb_loss_scratch_bytes(int32_t C, int32_t H, int32_t W);
+int fsgs_rgb_loss_forward(int32_t C, int32_t H, int32_t W, const float *img, const float *gt,
+                          const unsigned char *mask_u8, const float *mask_f32, int64_t mask_cstride,
+                          float lambda_dssim, float *maps, void *scratch, float *out, void *stream);
+int fsgs_rgb_loss_backward(int32_t C, int32_t H, int32_t W, const float *img, const float *gt,
+                           const unsigned char *mask_u8, const float *mask_f32, int64_t mask_cstride,
+                           float lambda_dssim, const float *maps, const float *upstream, float *dimg, void *stream);
+
 /* Optional per-kernel timing with CUDA events on the launching stream (single-threaded use; off
  * by default).  fsgs_profile_collect synchronises the device and returns, per kernel in the
  * order of fsgs_kernel_names(), the summed duration in ms and the launch count since enable. */

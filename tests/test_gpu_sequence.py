@@ -37,7 +37,7 @@ def _cam_centre(Rt):
 def test_progressive_tracking_and_mapping_on_a_synthetic_sequence():
     from fsgs_b200 import frame_render as render
     from fsgs_b200 import model
-    from fsgs_b200.losses import rgb_loss_func
+    from fsgs_b200.losses import rgb_loss_func_fused as rgb_loss_func
 
     N, P, W, H = 4, 20000, 320, 256
     sc = make_scene(P, W, H, size_mult=2.0, seed=7)
