@@ -6,8 +6,9 @@
 //
 // The PyTorch formulation runs five depthwise 11x11 convolutions forward (and their transposes backward) plus a
 // dozen element-wise kernels per call -- several milliseconds at 1280x1024, i.e. more than the whole render.
-// Here one forward kernel and one backward kernel do it, both tiled 16x16 with a 5-pixel halo staged in shared
-// memory and the window applied separably (11 + 11 taps instead of 121):
+// Here one forward kernel and one backward kernel do it, both tiled 32x16 with a 5-pixel halo staged in shared
+// memory and the window applied separably (11 + 11 taps instead of 121), each thread producing 4 adjacent outputs of
+// the horizontal pass (128-bit shared-memory loads, products formed once per input) and 2 of the vertical pass:
 //
 //   forward : a = G*x, b = G*y, p = G*x^2, q = G*y^2, r = G*xy per pixel ->
 //               A1 = 2ab + C1, A2 = 2(r - ab) + C2, B1 = a^2 + b^2 + C1, B2 = (p - a^2) + (q - b^2) + C2,
@@ -27,14 +28,18 @@
 
 namespace fsgs {
 
-constexpr int LOSS_T = 16;             // output tile edge
-constexpr int LOSS_R = 5;              // window radius (11 taps)
-constexpr int LOSS_H = LOSS_T + 2 * LOSS_R;   // halo tile edge (26)
-constexpr int LOSS_HS = 48;            // row stride of the halo tiles: two consecutive rows 16 banks apart
+constexpr int LOSS_TW = 32, LOSS_TH = 16;      // output tile
+constexpr int LOSS_R = 5;                      // window radius (11 taps)
+constexpr int LOSS_K = 2 * LOSS_R + 1;
+constexpr int LOSS_HW = LOSS_TW + 2 * LOSS_R;  // halo tile width  (42)
+constexpr int LOSS_HH = LOSS_TH + 2 * LOSS_R;  // halo tile height (26)
+constexpr int LOSS_HS = 48;                    // row stride of the halo tiles (16-byte aligned rows, >= 4*7+16 = 44)
+constexpr int LOSS_ITEMS = LOSS_HH * (LOSS_TW / 4);   // horizontal-pass work items: (halo row, group of 4 columns)
 constexpr float SSIM_C1 = 0.01f * 0.01f, SSIM_C2 = 0.03f * 0.03f;
+static_assert(LOSS_ITEMS <= CTA && LOSS_TW * LOSS_TH == 2 * CTA, "thread mapping of the loss kernels");
 
 struct LossWindow {
-    float g[2 * LOSS_R + 1];
+    float g[LOSS_K];
 };
 
 struct LossMask {
@@ -49,67 +54,110 @@ __device__ __forceinline__ float loss_mask_at(const LossMask &m, int c, size_t p
     return 1.f;
 }
 
-// Forward.  grid (ceil(W/16), ceil(H/16), C), 256 threads.  partial[2 * block] = (sum S, sum |x-y|) of the block.
+// 16 consecutive floats of a halo row starting at a multiple-of-4 column (four 128-bit loads)
+__device__ __forceinline__ void loss_load16(const float *row, float *v) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 q = *reinterpret_cast<const float4 *>(row + 4 * k);
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+}
+
+// Forward.  grid (ceil(W/32), ceil(H/16), C), 256 threads.  partial[2 * block] = (sum S, sum |x-y|) of the block.
 __global__ void __launch_bounds__(CTA)
 k_rgb_loss_fwd(int H, int W, const float *__restrict__ img, const float *__restrict__ gt, LossMask mask, LossWindow win,
                float *__restrict__ maps, double *__restrict__ partial) {
-    __shared__ float sx[LOSS_H][LOSS_HS], sy[LOSS_H][LOSS_HS];
-    __shared__ float sh[5][LOSS_H][LOSS_T + 1];
+    __shared__ __align__(16) float sx[LOSS_HH][LOSS_HS], sy[LOSS_HH][LOSS_HS];
+    __shared__ __align__(16) float sh[5][LOSS_HH][LOSS_TW];
     __shared__ double s_red[2][CTA / 32];
     const int c = blockIdx.z;
-    const int x0 = blockIdx.x * LOSS_T, y0 = blockIdx.y * LOSS_T;
+    const int x0 = blockIdx.x * LOSS_TW, y0 = blockIdx.y * LOSS_TH;
     const size_t HW = (size_t)H * W;
     const float *ic = img + (size_t)c * HW, *gc = gt + (size_t)c * HW;
-    for (int e = threadIdx.x; e < LOSS_H * LOSS_H; e += CTA) {
-        const int ry = e / LOSS_H, rx = e - ry * LOSS_H;
+    for (int e = threadIdx.x; e < LOSS_HH * LOSS_HS; e += CTA) {
+        const int ry = e / LOSS_HS, rx = e - ry * LOSS_HS;
         const int py = y0 + ry - LOSS_R, px = x0 + rx - LOSS_R;
         float vx = 0.f, vy = 0.f;
-        if (py >= 0 && py < H && px >= 0 && px < W) {
+        if (rx < LOSS_HW && py >= 0 && py < H && px >= 0 && px < W) {
             const size_t pix = (size_t)py * W + px;
             const float m = loss_mask_at(mask, c, pix);
             vx = ic[pix] * m; vy = gc[pix] * m;
         }
-        sx[ry][rx] = vx; sy[ry][rx] = vy;
+        sx[ry][rx] = vx; sy[ry][rx] = vy;      // (columns 42..47 are zero padding the 128-bit loads may touch)
     }
     __syncthreads();
-    // horizontal pass: LOSS_H rows x LOSS_T columns x 5 quantities
-    for (int e = threadIdx.x; e < LOSS_H * LOSS_T; e += CTA) {
-        const int ry = e / LOSS_T, cx = e - ry * LOSS_T;
-        float a = 0.f, b = 0.f, p = 0.f, q = 0.f, r = 0.f;
+    // horizontal pass: one (halo row, 4 adjacent columns) item per thread
+    if (threadIdx.x < LOSS_ITEMS) {
+        const int ry = threadIdx.x >> 3, cg = (threadIdx.x & 7) * 4;
+        float vx[16], vy[16];
+        loss_load16(&sx[ry][cg], vx);
+        loss_load16(&sy[ry][cg], vy);
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f}, p[4] = {0.f, 0.f, 0.f, 0.f},
+              q[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int t = 0; t < 2 * LOSS_R + 1; ++t) {
-            const float w = win.g[t], vx = sx[ry][cx + t], vy = sy[ry][cx + t];
-            const float wx = w * vx, wy = w * vy;
-            a += wx; b += wy; p = fmaf(wx, vx, p); q = fmaf(wy, vy, q); r = fmaf(wx, vy, r);
+        for (int i = 0; i < LOSS_K + 3; ++i) {
+            const float xx = vx[i] * vx[i], yy = vy[i] * vy[i], xy = vx[i] * vy[i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = i - j;                  // tap index of input i for output j
+                if (t >= 0 && t < LOSS_K) {
+                    const float w = win.g[t];
+                    a[j] = fmaf(w, vx[i], a[j]); b[j] = fmaf(w, vy[i], b[j]); p[j] = fmaf(w, xx, p[j]);
+                    q[j] = fmaf(w, yy, q[j]); r[j] = fmaf(w, xy, r[j]);
+                }
+            }
         }
-        sh[0][ry][cx] = a; sh[1][ry][cx] = b; sh[2][ry][cx] = p; sh[3][ry][cx] = q; sh[4][ry][cx] = r;
+        *reinterpret_cast<float4 *>(&sh[0][ry][cg]) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4 *>(&sh[1][ry][cg]) = make_float4(b[0], b[1], b[2], b[3]);
+        *reinterpret_cast<float4 *>(&sh[2][ry][cg]) = make_float4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<float4 *>(&sh[3][ry][cg]) = make_float4(q[0], q[1], q[2], q[3]);
+        *reinterpret_cast<float4 *>(&sh[4][ry][cg]) = make_float4(r[0], r[1], r[2], r[3]);
     }
     __syncthreads();
-    const int tx = threadIdx.x & (LOSS_T - 1), ty = threadIdx.x >> 4;
-    const int px = x0 + tx, py = y0 + ty;
+    // vertical pass: column tx, output rows 2*tg and 2*tg + 1
+    const int tx = threadIdx.x & 31, tg = threadIdx.x >> 5;
+    const int px = x0 + tx;
+    float acc[2][5];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc[j][k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < LOSS_K + 1; ++i) {
+        float v[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = sh[k][2 * tg + i][tx];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int t = i - j;
+            if (t >= 0 && t < LOSS_K) {
+                const float w = win.g[t];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) acc[j][k] = fmaf(w, v[k], acc[j][k]);
+            }
+        }
+    }
     double sumS = 0.0, sumL1 = 0.0;
-    if (px < W && py < H) {
-        float a = 0.f, b = 0.f, p = 0.f, q = 0.f, r = 0.f;
 #pragma unroll
-        for (int t = 0; t < 2 * LOSS_R + 1; ++t) {
-            const float w = win.g[t];
-            a = fmaf(w, sh[0][ty + t][tx], a); b = fmaf(w, sh[1][ty + t][tx], b); p = fmaf(w, sh[2][ty + t][tx], p);
-            q = fmaf(w, sh[3][ty + t][tx], q); r = fmaf(w, sh[4][ty + t][tx], r);
-        }
-        const float ab = a * b, aa = a * a, bb = b * b;
-        const float A1 = 2.f * ab + SSIM_C1, A2 = 2.f * (r - ab) + SSIM_C2;
-        const float B1 = aa + bb + SSIM_C1, B2 = (p - aa) + (q - bb) + SSIM_C2;
-        const float iB1 = 1.f / B1, iB2 = 1.f / B2;
-        const float S = A1 * A2 * iB1 * iB2;
-        sumS = (double)S;
-        sumL1 = (double)fabsf(sx[ty + LOSS_R][tx + LOSS_R] - sy[ty + LOSS_R][tx + LOSS_R]);
-        if (maps) {
-            // dS/da with sigma's expanded: d(A1 A2)/da = 2b (A2 - A1), d(B1 B2)/da = 2a (B2 - B1)
-            const float Da = (2.f * b * (A2 - A1) - S * 2.f * a * (B2 - B1)) * iB1 * iB2;
-            const float Dp = -S * iB2;
-            const float Dr = 2.f * A1 * iB1 * iB2;
-            const size_t CHW = (size_t)gridDim.z * HW, o = (size_t)c * HW + (size_t)py * W + px;
-            maps[o] = Da; maps[CHW + o] = Dp; maps[2 * CHW + o] = Dr;
+    for (int j = 0; j < 2; ++j) {
+        const int ty = 2 * tg + j, py = y0 + ty;
+        if (px < W && py < H) {
+            const float a = acc[j][0], b = acc[j][1], p = acc[j][2], q = acc[j][3], r = acc[j][4];
+            const float ab = a * b, aa = a * a, bb = b * b;
+            const float A1 = 2.f * ab + SSIM_C1, A2 = 2.f * (r - ab) + SSIM_C2;
+            const float B1 = aa + bb + SSIM_C1, B2 = (p - aa) + (q - bb) + SSIM_C2;
+            const float iB1 = 1.f / B1, iB2 = 1.f / B2;
+            const float S = A1 * A2 * iB1 * iB2;
+            sumS += (double)S;
+            sumL1 += (double)fabsf(sx[ty + LOSS_R][tx + LOSS_R] - sy[ty + LOSS_R][tx + LOSS_R]);
+            if (maps) {
+                // dS/da with sigma's expanded: d(A1 A2)/da = 2b (A2 - A1), d(B1 B2)/da = 2a (B2 - B1)
+                const float Da = (2.f * b * (A2 - A1) - S * 2.f * a * (B2 - B1)) * iB1 * iB2;
+                const float Dp = -S * iB2;
+                const float Dr = 2.f * A1 * iB1 * iB2;
+                const size_t CHW = (size_t)gridDim.z * HW, o = (size_t)c * HW + (size_t)py * W + px;
+                maps[o] = Da; maps[CHW + o] = Dp; maps[2 * CHW + o] = Dr;
+            }
         }
     }
     // block sums (fixed order: lanes by shuffle tree, warps serially -> deterministic)
@@ -157,51 +205,76 @@ __global__ void __launch_bounds__(CTA)
 k_rgb_loss_bwd(int H, int W, const float *__restrict__ img, const float *__restrict__ gt, LossMask mask, LossWindow win,
                const float *__restrict__ maps, const float *__restrict__ upstream, float lambda_dssim, float inv_n,
                float *__restrict__ dimg) {
-    __shared__ float sm[3][LOSS_H][LOSS_HS];
-    __shared__ float sh[3][LOSS_H][LOSS_T + 1];
+    __shared__ __align__(16) float sm[3][LOSS_HH][LOSS_HS];
+    __shared__ __align__(16) float sh[3][LOSS_HH][LOSS_TW];
     const int c = blockIdx.z;
-    const int x0 = blockIdx.x * LOSS_T, y0 = blockIdx.y * LOSS_T;
+    const int x0 = blockIdx.x * LOSS_TW, y0 = blockIdx.y * LOSS_TH;
     const size_t HW = (size_t)H * W, CHW = (size_t)gridDim.z * HW;
     const float *mc = maps + (size_t)c * HW;
-    for (int e = threadIdx.x; e < LOSS_H * LOSS_H; e += CTA) {
-        const int ry = e / LOSS_H, rx = e - ry * LOSS_H;
+    for (int e = threadIdx.x; e < LOSS_HH * LOSS_HS; e += CTA) {
+        const int ry = e / LOSS_HS, rx = e - ry * LOSS_HS;
         const int py = y0 + ry - LOSS_R, px = x0 + rx - LOSS_R;
         float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-        if (py >= 0 && py < H && px >= 0 && px < W) {
+        if (rx < LOSS_HW && py >= 0 && py < H && px >= 0 && px < W) {
             const size_t pix = (size_t)py * W + px;
             v0 = mc[pix]; v1 = mc[CHW + pix]; v2 = mc[2 * CHW + pix];
         }
         sm[0][ry][rx] = v0; sm[1][ry][rx] = v1; sm[2][ry][rx] = v2;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < LOSS_H * LOSS_T; e += CTA) {
-        const int ry = e / LOSS_T, cx = e - ry * LOSS_T;
-        float a = 0.f, p = 0.f, r = 0.f;
+    if (threadIdx.x < LOSS_ITEMS) {
+        const int ry = threadIdx.x >> 3, cg = (threadIdx.x & 7) * 4;
 #pragma unroll
-        for (int t = 0; t < 2 * LOSS_R + 1; ++t) {
-            const float w = win.g[t];
-            a = fmaf(w, sm[0][ry][cx + t], a); p = fmaf(w, sm[1][ry][cx + t], p); r = fmaf(w, sm[2][ry][cx + t], r);
+        for (int k = 0; k < 3; ++k) {
+            float v[16], o[4] = {0.f, 0.f, 0.f, 0.f};
+            loss_load16(&sm[k][ry][cg], v);
+#pragma unroll
+            for (int i = 0; i < LOSS_K + 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = i - j;
+                    if (t >= 0 && t < LOSS_K) o[j] = fmaf(win.g[t], v[i], o[j]);
+                }
+            *reinterpret_cast<float4 *>(&sh[k][ry][cg]) = make_float4(o[0], o[1], o[2], o[3]);
         }
-        sh[0][ry][cx] = a; sh[1][ry][cx] = p; sh[2][ry][cx] = r;
     }
     __syncthreads();
-    const int tx = threadIdx.x & (LOSS_T - 1), ty = threadIdx.x >> 4;
-    const int px = x0 + tx, py = y0 + ty;
-    if (px >= W || py >= H) return;
-    float ga = 0.f, gp = 0.f, gr = 0.f;
+    const int tx = threadIdx.x & 31, tg = threadIdx.x >> 5;
+    const int px = x0 + tx;
+    float acc[2][3];
 #pragma unroll
-    for (int t = 0; t < 2 * LOSS_R + 1; ++t) {
-        const float w = win.g[t];
-        ga = fmaf(w, sh[0][ty + t][tx], ga); gp = fmaf(w, sh[1][ty + t][tx], gp); gr = fmaf(w, sh[2][ty + t][tx], gr);
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[j][k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < LOSS_K + 1; ++i) {
+        float v[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = sh[k][2 * tg + i][tx];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int t = i - j;
+            if (t >= 0 && t < LOSS_K) {
+                const float w = win.g[t];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc[j][k] = fmaf(w, v[k], acc[j][k]);
+            }
+        }
     }
-    const size_t pix = (size_t)py * W + px, o = (size_t)c * HW + pix;
-    const float m = loss_mask_at(mask, c, pix);
-    const float x = img[o] * m, y = gt[o] * m;
-    const float d = x - y;
-    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
     const float up = upstream ? __ldg(upstream) : 1.f;
-    const float gx = (1.f - lambda_dssim) * inv_n * sgn - lambda_dssim * inv_n * (ga + 2.f * x * gp + y * gr);
-    dimg[o] = m * gx * up;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int py = y0 + 2 * tg + j;
+        if (px >= W || py >= H) continue;
+        const size_t pix = (size_t)py * W + px, o = (size_t)c * HW + pix;
+        const float m = loss_mask_at(mask, c, pix);
+        const float x = img[o] * m, y = gt[o] * m;
+        const float d = x - y;
+        const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        const float gx = (1.f - lambda_dssim) * inv_n * sgn -
+                         lambda_dssim * inv_n * (acc[j][0] + 2.f * x * acc[j][1] + y * acc[j][2]);
+        dimg[o] = m * gx * up;
+    }
 }
 
 }  // namespace fsgs

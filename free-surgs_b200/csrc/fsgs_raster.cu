@@ -667,7 +667,7 @@ static LossWindow make_loss_window() {
     return w;
 }
 static inline size_t loss_blocks(int C, int H, int W) {
-    return (size_t)C * (size_t)((H + LOSS_T - 1) / LOSS_T) * (size_t)((W + LOSS_T - 1) / LOSS_T);
+    return (size_t)C * (size_t)((H + LOSS_TH - 1) / LOSS_TH) * (size_t)((W + LOSS_TW - 1) / LOSS_TW);
 }
 
 size_t fsgs_rgb_loss_scratch_bytes(int32_t C, int32_t H, int32_t W) {
@@ -680,7 +680,7 @@ static int loss_args_ok(int32_t C, int32_t H, int32_t W, const float *img, const
     if (C <= 0 || C > 65535 || H <= 0 || W <= 0 || !img || !gt) return FSGS_E_INVALID;
     if (mask_u8 && mask_f32) return FSGS_E_INVALID;
     if (mask_cstride != 0 && mask_cstride != (int64_t)H * W) return FSGS_E_INVALID;
-    if ((H + LOSS_T - 1) / LOSS_T > 65535) return FSGS_E_INVALID;
+    if ((H + LOSS_TH - 1) / LOSS_TH > 65535) return FSGS_E_INVALID;
     return FSGS_OK;
 }
 
@@ -694,7 +694,7 @@ int fsgs_rgb_loss_forward(int32_t C, int32_t H, int32_t W, const float *img, con
     if ((rc = check_arch())) return rc;
     const LossMask mask{mask_u8, mask_f32, (long long)mask_cstride};
     const LossWindow win = make_loss_window();
-    const dim3 grid((W + LOSS_T - 1) / LOSS_T, (H + LOSS_T - 1) / LOSS_T, C);
+    const dim3 grid((W + LOSS_TW - 1) / LOSS_TW, (H + LOSS_TH - 1) / LOSS_TH, C);
     double *partial = static_cast<double *>(scratch);
     prof_begin(K_LOSS_FWD, stream);
     k_rgb_loss_fwd<<<grid, CTA, 0, stream>>>(H, W, img, gt, mask, win, maps, partial);
@@ -715,7 +715,7 @@ int fsgs_rgb_loss_backward(int32_t C, int32_t H, int32_t W, const float *img, co
     if ((rc = check_arch())) return rc;
     const LossMask mask{mask_u8, mask_f32, (long long)mask_cstride};
     const LossWindow win = make_loss_window();
-    const dim3 grid((W + LOSS_T - 1) / LOSS_T, (H + LOSS_T - 1) / LOSS_T, C);
+    const dim3 grid((W + LOSS_TW - 1) / LOSS_TW, (H + LOSS_TH - 1) / LOSS_TH, C);
     prof_begin(K_LOSS_BWD, stream);
     k_rgb_loss_bwd<<<grid, CTA, 0, stream>>>(H, W, img, gt, mask, win, maps, upstream, lambda_dssim,
                                              (float)(1.0 / ((double)C * H * W)), dimg);
