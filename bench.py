@@ -431,6 +431,46 @@ def run_ours(args):
         tr[k][0].record(); track_step(); tr[k][1].record()
     barrier()
     ms_track_frozen = sum(a.elapsed_time(b) for a, b in tr) / args.steps
+
+    # ---- one whole tracking iteration as train.py:166-188 runs it: render, mask = depth > 0, L1 + SSIM image loss
+    # against a target frame, backward to the pose.  "reference_style" = Gaussian parameters trainable + the PyTorch
+    # formulation of the loss; "fused" = frozen model (pose-only backward) + the library's fused loss kernels.
+    # Informational (never the headline); a failure here must not take the bench line down.
+    track_iter = None
+    try:
+        if world > 1:
+            raise RuntimeError("single-GPU only (informational)")
+        from fsgs_b200 import losses as fsgs_losses
+        target = torch.rand(3, H, W, generator=torch.Generator().manual_seed(5)).to(dev)
+
+        def make_iter(loss_fn):
+            def it():
+                pc.zero_grad()
+                poses.pose_param_net.zero_grad(set_to_none=True)
+                out = render.render(poses, 0, pc, gs_grad=False, cam_grad=True)
+                mask = (out["render_dep"] > 0).unsqueeze(0)
+                loss_fn(out["render"], target, mask=mask).backward()
+            return it
+
+        def time_iter(it):
+            for _ in range(3):
+                it()
+            barrier()
+            for k in range(args.steps):
+                flush.zero_()
+                tr[k][0].record(); it(); tr[k][1].record()
+            barrier()
+            return sum(a.elapsed_time(b) for a, b in tr) / args.steps
+
+        t_fused = time_iter(make_iter(fsgs_losses.rgb_loss_func_fused))           # (model still frozen here)
+        for v in pc.params.values():
+            v.requires_grad_(True)
+        t_ref_style = time_iter(make_iter(fsgs_losses.rgb_loss_func))
+        track_iter = {"fused_loss_frozen_model": t_fused, "pytorch_loss_trainable_model": t_ref_style,
+                      "what": "render(gs_grad=False, cam_grad=True) + mask + rgb_loss_func (L1 + SSIM) + backward, "
+                              "issued from Python, device time per iteration"}
+    except Exception as exc:  # noqa: BLE001
+        track_iter = {"error": repr(exc)[:200]}
     for v in pc.params.values():
         v.requires_grad_(True)
 
@@ -503,6 +543,7 @@ def run_ours(args):
                                                              else "+nccl allreduce(compact grads, 56 B/Gaussian, in backward)")},
             "pose_grad_ms_per_frame": ms_track,
             "pose_grad_ms_per_frame_frozen_model": ms_track_frozen,
+            "tracking_iteration_ms": track_iter,
             "api_two_pass_ms_per_step": ms_two_pass,      # rank 0's; un-fused GaussianRasterizer drop-in path
             "ms_per_step_median": sorted(ms)[len(ms) // 2],
             "ms_per_step_p10_p90": [sorted(ms)[int(0.1 * (len(ms) - 1))], sorted(ms)[int(round(0.9 * (len(ms) - 1)))]],
