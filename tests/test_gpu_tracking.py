@@ -278,3 +278,8 @@ def test_cuda_graph_capture_of_a_whole_step_matches_eager():
     assert not gs.overflowed()
     got = (got[0].clone(), got[1].clone(), got[2].clone(), [g.clone() for g in got[3]])
     check(got, eager(), "after recapture")
+    # release(): the graph is destroyed (what a frame-parallel job does before tearing its process group down --
+    # NCCL keeps a communicator alive while a captured graph references it); eager steps keep working
+    gs.release()
+    assert gs.graph is None and gs.outputs is None
+    check(eager(), got, "eager after release")
