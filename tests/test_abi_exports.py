@@ -54,6 +54,15 @@ def test_invalid_arguments_are_rejected_before_any_cuda_call():
     st = _lib.Settings(64, 64, 1.0, 1.0, 1.0, 7, 0, 0, 0)      # unsupported SH degree
     rc = L.fsgs_render_backward(ctypes.byref(st), 1, 0, *([None] * 16), 1, 1, *([None] * 9))
     assert rc == -1
+    # fused image loss: argument checks come before any device call
+    one = ctypes.c_void_p(256)                                 # a non-NULL placeholder; never dereferenced
+    assert L.fsgs_rgb_loss_forward(0, 8, 8, one, one, None, None, 0, 0.2, None, one, one, None) == -1      # C = 0
+    assert L.fsgs_rgb_loss_forward(3, 8, 8, None, one, None, None, 0, 0.2, None, one, one, None) == -1     # img NULL
+    assert L.fsgs_rgb_loss_forward(3, 8, 8, one, one, one, one, 0, 0.2, None, one, one, None) == -1        # two masks
+    assert L.fsgs_rgb_loss_forward(3, 8, 8, one, one, one, None, 7, 0.2, None, one, one, None) == -1       # bad stride
+    assert L.fsgs_rgb_loss_forward(3, 8, 8, one, one, None, None, 0, 0.2, None, None, one, None) == -1     # no scratch
+    assert L.fsgs_rgb_loss_backward(3, 8, 8, one, one, None, None, 0, 0.2, None, None, one, None) == -1    # no maps
+    assert L.fsgs_rgb_loss_scratch_bytes(3, 1024, 1280) >= 3 * 64 * 40 * 16
 
 
 def test_no_cpu_fallback():
