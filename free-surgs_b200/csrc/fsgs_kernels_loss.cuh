@@ -277,4 +277,76 @@ k_rgb_loss_bwd(int H, int W, const float *__restrict__ img, const float *__restr
     }
 }
 
+// ---- Pearson depth loss (reference utils/loss_utils.py:98-109) ------------------------------------------
+//   loss = 1 - mean( (x - mean x) / (std x + 1e-6) * (y - mean y) / (std y + 1e-6) ),  std = unbiased (n - 1)
+// The PyTorch formulation is ~12 element-wise / reduction launches forward and ~20 backward over the depth plane.
+// Here: one pass accumulates the five raw sums (double), a one-CTA kernel turns them into the statistics
+//   stats = (mean x, mean y, sqrt var x, sqrt var y, c = sum (x - mx)(y - my), n)  and the loss,
+// and the backward is one element-wise kernel:
+//   dL/dy_i = -[ (x_i - mx) / (n sx sy) - c / (n sx sy^2) * (y_i - my) / ((n - 1) sqrt var y) ],  s = sqrt var + 1e-6
+// (symmetric for x).  Fixed grid and summation order: deterministic.
+constexpr int PEARSON_MAX_BLOCKS = 1184;     // 148 SMs x 8
+
+__global__ void __launch_bounds__(CTA)
+k_pearson_sums(long long n, const float *__restrict__ x, const float *__restrict__ y, double *__restrict__ partial) {
+    __shared__ double s_red[5][CTA / 32];
+    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * CTA + threadIdx.x; i < n; i += (long long)gridDim.x * CTA) {
+        const double xv = (double)x[i], yv = (double)y[i];
+        a[0] += xv; a[1] += yv; a[2] += xv * xv; a[3] += yv * yv; a[4] += xv * yv;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) a[k] += __shfl_xor_sync(FULL, a[k], d);
+        if ((threadIdx.x & 31) == 0) s_red[k][threadIdx.x >> 5] = a[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0.0;
+        for (int w = 0; w < CTA / 32; ++w) t += s_red[threadIdx.x][w];
+        partial[5 * (size_t)blockIdx.x + threadIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_pearson_finish(long long n, int n_blocks, const double *__restrict__ partial, double *__restrict__ stats,
+                 float *__restrict__ out) {
+    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int b = threadIdx.x; b < n_blocks; b += 32)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) a[k] += partial[5 * (size_t)b + k];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) a[k] += __shfl_xor_sync(FULL, a[k], d);
+    if (threadIdx.x == 0) {
+        const double N = (double)n, mx = a[0] / N, my = a[1] / N;
+        const double den = N > 1.0 ? N - 1.0 : 1.0;
+        const double vx = fmax(a[2] - N * mx * mx, 0.0) / den, vy = fmax(a[3] - N * my * my, 0.0) / den;
+        const double qx = sqrt(vx), qy = sqrt(vy);
+        const double c = a[4] - N * mx * my;
+        stats[0] = mx; stats[1] = my; stats[2] = qx; stats[3] = qy; stats[4] = c; stats[5] = N;
+        out[0] = (float)(1.0 - c / (N * (qx + 1e-6) * (qy + 1e-6)));
+    }
+}
+
+__global__ void __launch_bounds__(CTA)
+k_pearson_bwd(long long n, const float *__restrict__ x, const float *__restrict__ y, const double *__restrict__ stats,
+              const float *__restrict__ upstream, float *__restrict__ dx, float *__restrict__ dy) {
+    const double mx = stats[0], my = stats[1], qx = stats[2], qy = stats[3], c = stats[4], N = stats[5];
+    const double sx = qx + 1e-6, sy = qy + 1e-6, den = N > 1.0 ? N - 1.0 : 1.0;
+    const double up = upstream ? (double)__ldg(upstream) : 1.0;
+    // dL/dy_i = -(k1 (x_i - mx) - ky (y_i - my)),  dL/dx_i = -(k1 (y_i - my) - kx (x_i - mx))
+    const float k1 = (float)(up / (N * sx * sy));
+    const float ky = qy > 0.0 ? (float)(up * c / (N * sx * sy * sy * den * qy)) : 0.f;
+    const float kx = qx > 0.0 ? (float)(up * c / (N * sx * sx * sy * den * qx)) : 0.f;
+    for (long long i = (long long)blockIdx.x * CTA + threadIdx.x; i < n; i += (long long)gridDim.x * CTA) {
+        // (centre in double: x - mean cancels leading digits)
+        const float xc = (float)((double)x[i] - mx), yc = (float)((double)y[i] - my);
+        if (dy) dy[i] = -(k1 * xc - ky * yc);
+        if (dx) dx[i] = -(k1 * yc - kx * xc);
+    }
+}
+
 }  // namespace fsgs

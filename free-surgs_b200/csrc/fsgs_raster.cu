@@ -74,7 +74,7 @@ inline int blocks(int n) { return (n + CTA - 1) / CTA; }
 // Off by default.  bench.py switches it on for a separate profiling pass (never for the timed
 // steps) to obtain the per-launch duration of each kernel for the roofline line.
 enum KernelId { K_PRE_API = 0, K_PRE_FUSED, K_SCAN, K_SCATTER, K_SORT, K_COMP_FWD, K_COMP_BWD, K_PRE_API_BWD,
-                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_PRE_POSE_BWD, K_LOSS_FWD, K_LOSS_BWD, K_COUNT };
+                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_PRE_POSE_BWD, K_LOSS_FWD, K_LOSS_BWD, K_PEARSON_FWD, K_PEARSON_BWD, K_COUNT };
 struct Profiler {
     bool on = false;
     static constexpr int MAXREC = 8192;
@@ -338,7 +338,7 @@ const char *fsgs_error_string(int code) {
 const char *fsgs_kernel_names(void) {
     return "k_preprocess_api,k_preprocess_fused,k_tile_scan,k_scatter,k_tile_sort,k_composite_fwd,"
            "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible,k_pose_forward,k_pose_backward,"
-           "k_sh_grad_expand,k_preprocess_pose_bwd,k_rgb_loss_fwd,k_rgb_loss_bwd";
+           "k_sh_grad_expand,k_preprocess_pose_bwd,k_rgb_loss_fwd,k_rgb_loss_bwd,k_pearson_sums,k_pearson_bwd";
 }
 
 size_t fsgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
@@ -720,6 +720,43 @@ int fsgs_rgb_loss_backward(int32_t C, int32_t H, int32_t W, const float *img, co
     k_rgb_loss_bwd<<<grid, CTA, 0, stream>>>(H, W, img, gt, mask, win, maps, upstream, lambda_dssim,
                                              (float)(1.0 / ((double)C * H * W)), dimg);
     prof_end(K_LOSS_BWD, stream);
+    FSGS_CUDA(cudaGetLastError());
+    return FSGS_OK;
+}
+
+// ---- fused Pearson depth loss ---------------------------------------------------------------------------
+static inline int pearson_blocks(int64_t n) {
+    const int64_t b = (n + (int64_t)CTA * 4 - 1) / ((int64_t)CTA * 4);
+    return (int)(b < 1 ? 1 : (b > PEARSON_MAX_BLOCKS ? PEARSON_MAX_BLOCKS : b));
+}
+
+size_t fsgs_pearson_scratch_bytes(void) { return align_up((size_t)PEARSON_MAX_BLOCKS * 5 * sizeof(double), 256); }
+
+int fsgs_pearson_forward(int64_t n, const float *src, const float *target, void *scratch, double *stats, float *out,
+                         void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n <= 0 || !src || !target || !scratch || !stats || !out) return FSGS_E_INVALID;
+    int rc = check_arch();
+    if (rc) return rc;
+    const int nb = pearson_blocks(n);
+    double *partial = static_cast<double *>(scratch);
+    prof_begin(K_PEARSON_FWD, stream);
+    k_pearson_sums<<<nb, CTA, 0, stream>>>((long long)n, src, target, partial);
+    k_pearson_finish<<<1, 32, 0, stream>>>((long long)n, nb, partial, stats, out);
+    prof_end(K_PEARSON_FWD, stream);
+    FSGS_CUDA(cudaGetLastError());
+    return FSGS_OK;
+}
+
+int fsgs_pearson_backward(int64_t n, const float *src, const float *target, const double *stats, const float *upstream,
+                          float *dsrc, float *dtarget, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n <= 0 || !src || !target || !stats || (!dsrc && !dtarget)) return FSGS_E_INVALID;
+    int rc = check_arch();
+    if (rc) return rc;
+    prof_begin(K_PEARSON_BWD, stream);
+    k_pearson_bwd<<<pearson_blocks(n), CTA, 0, stream>>>((long long)n, src, target, stats, upstream, dsrc, dtarget);
+    prof_end(K_PEARSON_BWD, stream);
     FSGS_CUDA(cudaGetLastError());
     return FSGS_OK;
 }

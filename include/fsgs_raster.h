@@ -266,6 +266,18 @@ int fsgs_rgb_loss_backward(int32_t C, int32_t H, int32_t W, const float *img, co
                            const unsigned char *mask_u8, const float *mask_f32, int64_t mask_cstride,
                            float lambda_dssim, const float *maps, const float *upstream, float *dimg, void *stream);
 
+/* Fused Pearson depth loss (reference utils/loss_utils.py:98-109, pearson_depth_loss):
+ *   loss = 1 - mean( (x - mean x)/(std x + 1e-6) * (y - mean y)/(std y + 1e-6) ),  unbiased std, over n elements.
+ * forward : out[1] (device float) = loss; stats[8] (device doubles) = the statistics the backward needs;
+ *           scratch = fsgs_pearson_scratch_bytes().
+ * backward: dsrc / dtarget [n] (either may be NULL) = d(upstream * loss)/d(src | target); upstream is a DEVICE
+ *           scalar (NULL = 1).  Sums are taken in double in a fixed order (deterministic). */
+size_t fsgs_pearson_scratch_bytes(void);
+int fsgs_pearson_forward(int64_t n, const float *src, const float *target, void *scratch, double *stats, float *out,
+                         void *stream);
+int fsgs_pearson_backward(int64_t n, const float *src, const float *target, const double *stats, const float *upstream,
+                          float *dsrc, float *dtarget, void *stream);
+
 /* Optional per-kernel timing with CUDA events on the launching stream (single-threaded use; off
  * by default).  fsgs_profile_collect synchronises the device and returns, per kernel in the
  * order of fsgs_kernel_names(), the summed duration in ms and the launch count since enable. */
