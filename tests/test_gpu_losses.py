@@ -134,29 +134,3 @@ def test_fused_rgb_loss_full_frame_and_speed():
     print(f"rgb_loss fwd+bwd at 1280x1024: PyTorch {t_torch:.3f} ms, fused {t_fused:.3f} ms "
           f"(kernels: forward+reduce {k_f:.3f} ms, backward {k_b:.3f} ms)")
     assert t_fused < 0.5 * t_torch
-
-
-@pytest.mark.parametrize("shape", [(256, 384), (1024, 1280), (37, 5), (3, 7)])      # (n = 2 is degenerate: |corr| = 1, zero gradient)
-@pytest.mark.parametrize("which", ["target", "both"])
-def test_fused_pearson_depth_loss_matches_the_pytorch_formulation(shape, which):
-    g = torch.Generator().manual_seed(shape[0] + shape[1])
-    a = (0.5 + torch.rand(*shape, generator=g)).to(DEV)
-    b = (0.8 * a.cpu() + 0.4 * torch.rand(*shape, generator=g) + 0.3).to(DEV)
-    x64, y64 = a.double().requires_grad_(which == "both"), b.double().requires_grad_(True)
-    (L.pearson_depth_loss(x64, y64) * 0.05).backward()
-    x, y = a.clone().requires_grad_(which == "both"), b.clone().requires_grad_(True)
-    loss = L.pearson_depth_loss_fused(x, y)
-    (loss * 0.05).backward()
-    assert abs(float(loss) - float(L.pearson_depth_loss(a.double(), b.double()))) <= 1e-5
-    assert rel_err(y.grad.double(), y64.grad) <= 1e-4
-    if which == "both":
-        assert rel_err(x.grad.double(), x64.grad) <= 1e-4
-    else:
-        assert x.grad is None
-
-
-def test_fused_pearson_matches_the_reference_golden_value_and_is_deterministic():
-    a, b = torch.from_numpy(GOLD["loss_dep_a"]).to(DEV), torch.from_numpy(GOLD["loss_dep_b"]).to(DEV)
-    v = [float(L.pearson_depth_loss_fused(a, b)) for _ in range(3)]
-    assert v[0] == v[1] == v[2]
-    assert abs(v[0] - float(GOLD["loss_pearson"])) <= 1e-5
