@@ -394,10 +394,10 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
                 const unsigned int *__restrict__ n_contrib, const float *__restrict__ g_rgb,
                 const float *__restrict__ g_depth, const float *__restrict__ g_sil, const float *__restrict__ g_dsq,
                 float *__restrict__ grad_acc, unsigned int flags, unsigned long long *__restrict__ err,
-                unsigned long long capacity) {
+                const unsigned long long *__restrict__ counters, unsigned long long capacity) {
     // (the forward's tail did not run if the frame had more instances than the buffer it was given: see
-    // FSGS_FLAG_FIXED_CAPACITY; err points at counters[CNT_ERR])
-    if (*(err - CNT_ERR + CNT_R) > capacity) return;
+    // FSGS_FLAG_FIXED_CAPACITY; err = the device's sticky watchdog word)
+    if (counters[CNT_R] > capacity) return;
     // upstream gradients: g_rgb[3,H,W] and one [H,W] plane each for depth | silhouette | depth^2 (fused
     // flavour; the API flavour has the package's depth output in g_depth).  A NULL plane is all zeros.
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -187,7 +187,8 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
                    const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                    float4 *__restrict__ records, uint8_t *__restrict__ clamped, int *__restrict__ radii,
                    unsigned int *__restrict__ tile_count, unsigned long long *__restrict__ counters,
-                   unsigned int flags, unsigned char *__restrict__ visibility, float *__restrict__ max_radii2D) {
+                   unsigned int flags, unsigned char *__restrict__ visibility, float *__restrict__ max_radii2D,
+                   unsigned long long *__restrict__ err) {
     // The 180 B/Gaussian of higher-order SH coefficients (76 % of the input bytes) are contiguous per
     // CTA: one bulk TMA copy stages them; threads then read their own 45 floats at a conflict-free
     // stride.  FSGS_FLAG_NO_TMA (or a mis-aligned tensor) reads them straight from global memory.
@@ -218,7 +219,7 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
         dcv[0] = f_dc[3 * n]; dcv[1] = f_dc[3 * n + 1]; dcv[2] = f_dc[3 * n + 2];
         op_raw = opacity_raw[i];
     }
-    if (staged) stage_rows_wait(count, &s_bar, counters + CNT_ERR);
+    if (staged) stage_rows_wait(count, &s_bar, err);
     if (i < P) {
         float V[16], PM[16], Rt[12], cp[3];
         load16(viewmatrix, V);

@@ -123,10 +123,15 @@ struct HostMailbox {
 };
 thread_local HostMailbox g_mail;
 unsigned long long g_hint[64] = {};         // last R per device (benign race: performance hint only)
+// Device watchdog: one sticky 64-bit word per device (allocated once, never freed).  A bounded device-side wait that
+// gives up (mbar_wait) sets it; every forward reads it back together with the instance count -- the read-back it
+// performs anyway -- and fails with FSGS_E_WATCHDOG, so a stuck barrier is reported by the NEXT forward on that
+// device (like an asynchronous CUDA error), in release mode too.  fsgs_watchdog_flag() reads it on demand.
+unsigned long long *g_sticky[64] = {};
 unsigned long long g_fixed_cap[64] = {};    // FSGS_FLAG_FIXED_CAPACITY: instance capacity per device (fsgs_set_instance_capacity)
 
 int mailbox(int dev, unsigned long long **pinned, cudaEvent_t *ev) {
-    if (!g_mail.pinned) FSGS_CUDA(cudaHostAlloc((void **)&g_mail.pinned, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    if (!g_mail.pinned) FSGS_CUDA(cudaHostAlloc((void **)&g_mail.pinned, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     if (!g_mail.have_ev[dev]) {
         FSGS_CUDA(cudaEventCreateWithFlags(&g_mail.ev[dev], cudaEventDisableTiming));
         g_mail.have_ev[dev] = true;
@@ -160,8 +165,10 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
     k_tile_scan<<<1, 1024, 0, stream>>>(tiles, tile_count, tile_offset, cursor, counters);
     prof_end(K_SCAN, stream);
     FSGS_LAUNCH_OK("k_tile_scan");
+    unsigned long long *sticky = g_sticky[dev];
     if (!fixed) {
         FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        FSGS_CUDA(cudaMemcpyAsync(h_cnt + 4, sticky, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         FSGS_CUDA(cudaEventRecord(landed, stream));
     }
 
@@ -184,7 +191,7 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
         prof_begin(K_COMP_FWD, stream);
         k_composite_fwd<FUSED><<<tiles, CTA, 0, stream>>>(
             cc, tile_offset, sorted_rec, bg, out_planes, out_depth, reinterpret_cast<float *>(B.img + B.il.final_T),
-            reinterpret_cast<unsigned int *>(B.img + B.il.n_contrib), (unsigned)st->flags, counters + CNT_ERR, counters,
+            reinterpret_cast<unsigned int *>(B.img + B.il.n_contrib), (unsigned)st->flags, sticky, counters,
             capacity, ex);
         prof_end(K_COMP_FWD, stream);
         FSGS_LAUNCH_OK("k_composite_fwd");
@@ -217,6 +224,11 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
         launched = true;
     }
     FSGS_CUDA(cudaEventSynchronize(landed));
+    if (h_cnt[4]) {
+        // a device-side wait of an EARLIER launch on this device gave up: its results are not to be trusted
+        FSGS_CUDA(cudaMemsetAsync(sticky, 0, sizeof(unsigned long long), stream));
+        return FSGS_E_WATCHDOG;
+    }
     const int64_t R = (int64_t)h_cnt[CNT_R];
     if (num_rendered_host) *num_rendered_host = R;
     if (num_rect_host) *num_rect_host = (int64_t)h_cnt[CNT_RECT];
@@ -230,9 +242,12 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
         if ((rc = launch_tail((unsigned long long)(R > 0 ? R : 1), R > 0)) != FSGS_OK) return rc;
     }
     if (st->debug) {
-        FSGS_CUDA(cudaMemcpyAsync(h_cnt, counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        FSGS_CUDA(cudaMemcpyAsync(h_cnt + 4, sticky, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         FSGS_CUDA(cudaStreamSynchronize(stream));
-        if (h_cnt[CNT_ERR]) return FSGS_E_WATCHDOG;
+        if (h_cnt[4]) {
+            FSGS_CUDA(cudaMemsetAsync(sticky, 0, sizeof(unsigned long long), stream));
+            return FSGS_E_WATCHDOG;
+        }
     }
     return FSGS_OK;
 }
@@ -271,9 +286,19 @@ int one_time_setup() {
                                        (int)cudaSharedmemCarveoutMaxShared));
         FSGS_CUDA(cudaFuncSetAttribute(k_composite_bwd<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        (int)cudaSharedmemCarveoutMaxShared));
+        if (dev >= 0 && dev < 64 && !g_sticky[dev]) {
+            FSGS_CUDA(cudaMalloc((void **)&g_sticky[dev], 256));
+            FSGS_CUDA(cudaMemset(g_sticky[dev], 0, 256));
+        }
         if (dev >= 0 && dev < 64) done[dev] = true;
     }
     return FSGS_OK;
+}
+
+unsigned long long *sticky_flag() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    return g_sticky[dev];
 }
 
 // fills the whole image with the background (P == 0 or nothing visible is handled by the kernels,
@@ -429,9 +454,8 @@ int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rend
         k_composite_bwd<false><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
-            dL_dout_color, dL_dout_depth, nullptr, nullptr, acc, (unsigned)st->flags,
-            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR,
-            (unsigned long long)num_rendered);
+            dL_dout_color, dL_dout_depth, nullptr, nullptr, acc, (unsigned)st->flags, sticky_flag(),
+            reinterpret_cast<const unsigned long long *>(im + il.counters), (unsigned long long)num_rendered);
         prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");
     }
@@ -539,7 +563,8 @@ int fsgs_render_forward_ex(const fsgs_settings *st, int32_t P, const float *bg, 
         cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
         projmatrix, reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped),
         radii, reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
-        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags, ex.visibility, ex.max_radii2D);
+        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags, ex.visibility, ex.max_radii2D,
+        sticky_flag());
     prof_end(K_PRE_FUSED, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused");
     return forward_tail<true>(st, cc, P, bg, B, binning_alloc, binning_user, out_planes, nullptr, num_rendered_host,
@@ -603,9 +628,8 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
         kern<<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
-            dL_drgb, dL_ddepth, dL_dsil, dL_ddepth_sq, acc, (unsigned)st->flags,
-            const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR,
-            (unsigned long long)num_rendered);
+            dL_drgb, dL_ddepth, dL_dsil, dL_ddepth_sq, acc, (unsigned)st->flags, sticky_flag(),
+            reinterpret_cast<const unsigned long long *>(im + il.counters), (unsigned long long)num_rendered);
         prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");
     }
@@ -623,12 +647,27 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
         cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
         projmatrix, reinterpret_cast<const float4 *>(g + gl.records), reinterpret_cast<const uint8_t *>(g + gl.clamped),
         acc, gs_grad, cam_grad, dL_dxyz, dL_dfeatures_dc, dL_dfeatures_rest, dL_dopacity_raw, dL_dscaling_raw,
-        dL_drotation_raw, dL_dpose, dL_dmeans2D, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1,
-        const_cast<unsigned long long *>(reinterpret_cast<const unsigned long long *>(im + il.counters)) + CNT_ERR,
-        dL_dsh_rgb);
+        dL_drotation_raw, dL_dpose, dL_dmeans2D, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1, sticky_flag(), dL_dsh_rgb);
     prof_end(K_PRE_FUSED_BWD, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused_bwd");
     return FSGS_OK;
+}
+
+int fsgs_watchdog_flag(int32_t device, int32_t reset) {
+    if (device < 0 || device >= 64) return FSGS_E_INVALID;
+    if (!g_sticky[device]) return 0;      // no launch on this device yet
+    int cur = 0;
+    FSGS_CUDA(cudaGetDevice(&cur));
+    if (cur != device) FSGS_CUDA(cudaSetDevice(device));
+    unsigned long long v = 0;
+    cudaError_t e = cudaMemcpy(&v, g_sticky[device], sizeof(v), cudaMemcpyDeviceToHost);     // synchronises
+    if (e == cudaSuccess && v && reset) e = cudaMemset(g_sticky[device], 0, sizeof(v));
+    if (cur != device) cudaSetDevice(cur);
+    if (e != cudaSuccess) {
+        snprintf(g_cuda_msg, sizeof(g_cuda_msg), "fsgs_watchdog_flag: %s", cudaGetErrorString(e));
+        return FSGS_E_CUDA;
+    }
+    return v ? 1 : 0;
 }
 
 int fsgs_set_instance_capacity(int32_t device, int64_t capacity) {

@@ -75,6 +75,7 @@ _SIGNATURES = {
     "fsgs_render_backward_ex": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 19 +
                                 [_i32, _i32] + [_vp] * 10),
     "fsgs_set_instance_capacity": (ctypes.c_int, [_i32, _i64]),
+    "fsgs_watchdog_flag": (ctypes.c_int, [_i32, _i32]),
     "fsgs_sh_grad_expand": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 6),
     "fsgs_rgb_loss_scratch_bytes": (ctypes.c_size_t, [_i32, _i32, _i32]),
     "fsgs_rgb_loss_forward": (ctypes.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp, _vp, _vp]),

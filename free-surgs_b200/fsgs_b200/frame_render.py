@@ -52,6 +52,23 @@ def _check_identity_view(rs) -> None:
                                   "use render_two_pass / GaussianRasterizer for a general view matrix")
 
 
+def _check_fused_shapes(P, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center) -> None:
+    """The fused kernels address the parameter tensors with fixed row widths (3 / 3 / 45 / 1 / 3 / 4 floats per
+    Gaussian: SH degree 3 storage as Free-SurGS allocates it, gaussian_model.py:66-67 with max_sh_degree = 3) and
+    write gradients of the same widths -- a tensor of another shape would be read and written out of bounds."""
+    want = (("_xyz", xyz, (P, 3)), ("_features_dc", f_dc, (P, 1, 3)), ("_features_rest", f_rest, (P, 15, 3)),
+            ("_opacity", opacity_raw, (P, 1)), ("_scaling", scaling_raw, (P, 3)), ("_rotation", rotation_raw, (P, 4)))
+    for name, t, shape in want:
+        if tuple(t.shape) != shape:
+            hint = (" (the fused render needs max_sh_degree = 3 storage; use render_two_pass / GaussianRasterizer "
+                    "for other SH layouts)") if name == "_features_rest" else ""
+            raise ValueError(f"fused render: {name} has shape {tuple(t.shape)}, expected {shape}{hint}")
+    if pose.numel() != 16:
+        raise ValueError(f"fused render: the pose must be a 4x4 matrix, got shape {tuple(pose.shape)}")
+    if cam_center.numel() != 3:
+        raise ValueError(f"fused render: cam_center must have 3 elements, got shape {tuple(cam_center.shape)}")
+
+
 class _RenderFused(torch.autograd.Function):
 
     @staticmethod
@@ -60,6 +77,7 @@ class _RenderFused(torch.autograd.Function):
         _require_cuda(xyz)
         dev = xyz.device
         P = xyz.shape[0]
+        _check_fused_shapes(P, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center)
         H, W = int(rs.image_height), int(rs.image_width)
         st = make_settings(rs, n_coeffs=16, sh_degree=int(active_sh_degree))
         capturing = torch.cuda.is_current_stream_capturing()
@@ -96,7 +114,7 @@ class _RenderFused(torch.autograd.Function):
         empty = torch.empty(0, dtype=torch.uint8, device=dev)
         ctx.save_for_backward(*t, *[arena.tensors.get(k, empty) for k in ("geom", "binning", "img")])
         ctx.lease = arena.finish()             # scratch goes back to the workspace pool when this node dies
-        ctx.st, ctx.P, ctx.num_rendered, ctx.num_rect = st, P, int(nr.value), int(nrect.value)
+        ctx.st, ctx.P, ctx.num_rendered, ctx.num_rect, ctx.dev = st, P, int(nr.value), int(nrect.value), dev
         ctx.flags = (bool(gs_grad), bool(cam_grad))
         if capturing:
             _CAPTURED.append((arena.tensors["img"], int(nr.value), W, H))      # for GraphedStep.overflowed()
@@ -104,6 +122,9 @@ class _RenderFused(torch.autograd.Function):
         ctx.mark_non_differentiable(radii, *extras)
         ctx.set_materialize_grads(False)        # an output the loss does not use arrives as None, not as zeros
         _TLS.last_stats = (int(nr.value), int(nrect.value))     # per thread: the viewer thread renders too
+        # the largest instance count of ANY fused forward since the caller last reset it (GraphedStep sizes the
+        # fixed binning capacity of a captured step from it: a step may render several frames)
+        _TLS.max_instances = max(int(nr.value), int(getattr(_TLS, "max_instances", 0)))
         # one output per render() product, all views of the one [6,H,W] buffer the compositor writes: the upstream
         # gradients then arrive per product and go to the library as separate planes (fsgs_render_backward_ex) --
         # no zero-filled [6,H,W] gradient is assembled from slices by autograd
@@ -112,7 +133,7 @@ class _RenderFused(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_sil, g_dsq, _g_radii=None, *_g_extras):
         *t, geom, binning, img = ctx.saved_tensors
-        dev = t[1].device
+        dev = ctx.dev          # (an empty model saves None for its parameter tensors)
         P = ctx.P
         gs_grad, cam_grad = ctx.flags
         # every output is fully overwritten by the library (zeros where a Gaussian is not visible)

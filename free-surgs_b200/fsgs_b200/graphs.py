@@ -29,6 +29,7 @@ import torch
 
 from . import _lib
 from . import frame_render
+from .rasterizer import _POOL
 
 
 class GraphedStep:
@@ -42,13 +43,18 @@ class GraphedStep:
         dev = self.device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        most = 0
+        # the capacity must hold the LARGEST frame of the step (fn may render several frames; every fused forward
+        # records its instance count in the per-thread maximum, reset here)
+        frame_render._TLS.max_instances = 0
         with torch.cuda.stream(side):                      # warm-up off the default stream, as graph capture requires
             for _ in range(max(self.warmup, 1)):
                 self.fn()
-                most = max(most, int(getattr(frame_render._TLS, "last_stats", (0, 0))[0]))
+        most = int(getattr(frame_render._TLS, "max_instances", 0))
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # the warm-up ran on a stream nobody will use again: its scratch buffers (~300 MB at 500k Gaussians) sit in
+        # the workspace pool under that stream's key -- hand them back to the allocator instead of stranding them
+        _POOL.drop_stream(dev.index, side.cuda_stream)
         self.capacity = max(int(most * self.headroom) + 4096, int(self.capacity * self.headroom))
         _lib.check(_lib.lib().fsgs_set_instance_capacity(dev.index, self.capacity))
         del frame_render._CAPTURED[:]
@@ -82,7 +88,16 @@ class GraphedStep:
         return out
 
     def overflowed(self) -> bool:
-        return any(n > cap for n, (_img, cap, _w, _h) in zip(self.instance_counts(), self._captured))
+        """True if the last replay produced more instances than the captured capacity (its binning / compositing
+        kernels then skipped themselves).  Also raises if the device watchdog fired (a captured forward cannot
+        read that flag back itself)."""
+        over = any(n > cap for n, (_img, cap, _w, _h) in zip(self.instance_counts(), self._captured))
+        rc = _lib.lib().fsgs_watchdog_flag(self.device.index, 1)
+        if rc < 0:
+            _lib.check(rc)
+        if rc == 1:
+            _lib.check(-5)
+        return over
 
     def recapture(self) -> None:
         """Rebuild the graph (after ``overflowed()``, or when tensor shapes changed)."""

@@ -89,6 +89,12 @@ class _WorkspacePool:
         with self._lock:
             self._free.clear()
 
+    def drop_stream(self, device_index, stream_handle) -> None:
+        """Forget the buffers cached for one (device, stream): for streams that will not be used again."""
+        with self._lock:
+            for key in [k for k in self._free if k[0] == device_index and k[1] == stream_handle]:
+                del self._free[key]
+
 
 _POOL = _WorkspacePool()
 

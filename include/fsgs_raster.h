@@ -48,7 +48,8 @@ enum {
     FSGS_E_CUDA = -2,      /* a CUDA runtime call failed; see fsgs_error_string(code)            */
     FSGS_E_ALLOC = -3,     /* an allocation callback returned NULL                               */
     FSGS_E_ARCH = -4,      /* device is not sm_100                                               */
-    FSGS_E_WATCHDOG = -5   /* debug builds only: a device-side wait exceeded its spin budget      */
+    FSGS_E_WATCHDOG = -5   /* a device-side wait of an earlier launch on this device exceeded its spin
+                              budget (reported by the next forward, or by fsgs_watchdog_flag)          */
 };
 
 /* Returns a device pointer to at least `bytes` bytes, 256-byte aligned, valid until the caller
@@ -192,6 +193,12 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
                             float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
                             float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw,
                             float *dL_dpose, float *dL_dmeans2D, float *dL_dsh_rgb, void *stream);
+
+/* Device watchdog.  Every device-side wait in the library is bounded; one that gives up sets a sticky per-device
+ * word instead of hanging the GPU.  Each (non-captured) forward reads the word back together with the instance
+ * count and returns FSGS_E_WATCHDOG if an EARLIER launch on the device set it.  This call reads it on demand
+ * (synchronises the device): returns 1 if set, 0 if clear, a negative FSGS_E_* code on failure; `reset` clears it. */
+int fsgs_watchdog_flag(int32_t device, int32_t reset);
 
 /* CUDA-graph capture support.  A forward normally reads the number of (tile, Gaussian) instances back to size
  * the binning buffer -- a host synchronisation that cannot be captured.  With FSGS_FLAG_FIXED_CAPACITY in

@@ -213,7 +213,9 @@ def preprocess(means3D, means2D, opacities, scales, rotations, cov3D_precomp, st
     out = dict(p_view=p_view, depth=p_view[:, 2], xy=xy, conic=conic, cov2d=torch.stack([a, b, c2], 1),
                radii=radii, rect=torch.stack([rmin_x, rmin_y, rmax_x, rmax_y], 1), visible=visible,
                tiles_touched=torch.where(visible, area, torch.zeros_like(area)), margin=margin,
-               margin_edges=m_edges, margin_z=m_z)
+               margin_edges=m_edges, margin_z=m_z, margin_radius=m_rad, rad_f=rad_f)
+    if opacities is not None:
+        out["opacity"] = opacities.reshape(-1).detach()
 
     if shs is not None:
         # shs [P,K,3]; dir from campos (Appendix A K1 colour branch)
@@ -367,15 +369,19 @@ def rasterize(means3D, means2D, opacities, st, colors_precomp=None, shs=None, sc
     return color, pre["radii"], depth, aux
 
 
-def fragile_pixel_mask(aux, H: int, W: int, eps_pix: float = 1e-4, eps_gauss: float = 2e-6) -> torch.Tensor:
+def fragile_pixel_mask(aux, H: int, W: int, eps_pix: float = 1e-4, eps_gauss: float = 2e-6,
+                       refine: bool = True) -> torch.Tensor:
     """Pixels where a float32 implementation may legitimately flip a threshold decision relative to
     this oracle.  Needs ``want_aux=True``.  ``eps_*`` are relative distances to the threshold
     (float32 epsilon is 6e-8).
       * per pixel: some evaluated entry has alpha within eps_pix of 1/255, or T within eps_pix of 1e-4;
       * per Gaussian: a tile-rectangle edge within eps_gauss of a tile boundary (directly, or through
         an integer radius about to round the other way) can add/remove one line of tiles at that
-        edge -- the two tile lines either side of the edge are marked; a near-plane decision within
-        eps_gauss marks the whole rectangle.
+        edge -- the two tile lines either side of the edge are candidates; a near-plane decision within
+        eps_gauss makes the whole rectangle a candidate.  With ``refine`` (default) a candidate pixel is
+        only marked if that Gaussian could change it at all, i.e. its alpha there reaches 1/255 (a tile
+        line beyond the 3-sigma radius mostly holds pixels the splat skips anyway); ``refine=False`` marks
+        every candidate pixel (the round-1 behaviour, ~8 % of config 1).
     """
     mask = aux["pix_margin"] < eps_pix
     pre = aux["pre"]
@@ -384,21 +390,79 @@ def fragile_pixel_mask(aux, H: int, W: int, eps_pix: float = 1e-4, eps_gauss: fl
     me, mz = pre["margin_edges"], pre["margin_z"]
     frag = ((me.min(dim=1).values < eps_gauss) | (pre["visible"] & (mz < eps_gauss)) |
             (~pre["visible"] & (mz < eps_gauss))).nonzero().flatten()
+    refine = refine and ("opacity" in pre) and ("rad_f" in pre)
+    ys = torch.arange(H, dtype=torch.float64)[:, None]
+    xs = torch.arange(W, dtype=torch.float64)[None, :]
+
+    def rect_of(x, y, r, d):
+        # the reference's tile rectangle with every edge coordinate moved by d * (|edge| + 1)
+        e = [x - r, y - r, x + r + BLOCK - 1, y + r + BLOCK - 1]
+        e = [v + d * (abs(v) + 1.0) for v in e]
+        lim = [gx, gy, gx, gy]
+        return [min(max(int(v / BLOCK), 0), lim[k]) for k, v in enumerate(e)]    # int(): truncation toward zero
+
     for i in frag.tolist():
         x0, y0, x1, y1 = pre["rect"][i].tolist()
         ox0, oy0, ox1, oy1 = max(0, x0 - 1), max(0, y0 - 1), min(gx, x1 + 1), min(gy, y1 + 1)
-        if mz[i] < eps_gauss:
-            tile_mask[oy0:oy1, ox0:ox1] = True
+        if not refine:
+            if mz[i] < eps_gauss:
+                tile_mask[oy0:oy1, ox0:ox1] = True
+                continue
+            e = me[i] < eps_gauss
+            if e[0]:
+                tile_mask[oy0:oy1, max(0, x0 - 1):min(gx, x0 + 1)] = True
+            if e[1]:
+                tile_mask[max(0, y0 - 1):min(gy, y0 + 1), ox0:ox1] = True
+            if e[2]:
+                tile_mask[oy0:oy1, max(0, x1 - 1):min(gx, x1 + 1)] = True
+            if e[3]:
+                tile_mask[max(0, y1 - 1):min(gy, y1 + 1), ox0:ox1] = True
             continue
-        e = me[i] < eps_gauss
-        if e[0]:
-            tile_mask[oy0:oy1, max(0, x0 - 1):min(gx, x0 + 1)] = True
-        if e[1]:
-            tile_mask[max(0, y0 - 1):min(gy, y0 + 1), ox0:ox1] = True
-        if e[2]:
-            tile_mask[oy0:oy1, max(0, x1 - 1):min(gx, x1 + 1)] = True
-        if e[3]:
-            tile_mask[max(0, y1 - 1):min(gy, y1 + 1), ox0:ox1] = True
-    if frag.numel():
+        # candidate tiles: those a float32 implementation may add to / drop from this Gaussian's rectangle, i.e.
+        # the tiles not common to every variant of the rectangle under the perturbations that are in question
+        # (edge coordinates moved by +-eps, the integer radius rounding the other way); a near-plane flip
+        # puts the whole rectangle in question
+        tm = torch.zeros(gy, gx, dtype=torch.bool)
+        if mz[i] < eps_gauss:
+            tm[oy0:oy1, ox0:ox1] = True
+        else:
+            x, y = float(pre["xy"][i, 0]), float(pre["xy"][i, 1])
+            rf = float(pre["rad_f"][i])
+            rad = float(math.ceil(rf))
+            rads = [rad]
+            if float(pre["margin_radius"][i]) < eps_gauss:
+                rads.append(rad - 1.0 if rf - math.floor(rf) < 0.5 else rad + 1.0)
+            union = torch.zeros(gy, gx, dtype=torch.bool)
+            inter = torch.ones(gy, gx, dtype=torch.bool)
+            for r_ in rads:
+                for d in (0.0, -eps_gauss, eps_gauss):
+                    a0, b0, a1, b1 = rect_of(x, y, r_, d)
+                    v = torch.zeros(gy, gx, dtype=torch.bool)
+                    v[b0:b1, a0:a1] = True
+                    union |= v
+                    inter &= v
+            tm = union & ~inter
+        if tm.any():
+            rows = tm.any(dim=1).nonzero().flatten()
+            cols = tm.any(dim=0).nonzero().flatten()
+            ya, yb = int(rows[0]) * BLOCK, min(H, (int(rows[-1]) + 1) * BLOCK)
+            xa, xb = int(cols[0]) * BLOCK, min(W, (int(cols[-1]) + 1) * BLOCK)
+            dx = float(pre["xy"][i, 0]) - xs[:, xa:xb]
+            dy = float(pre["xy"][i, 1]) - ys[ya:yb]
+            con = pre["conic"][i].double()
+            power = -0.5 * (con[0] * dx * dx + con[2] * dy * dy) - con[1] * dx * dy
+            alpha = float(pre["opacity"][i]) * torch.exp(power)
+            hit = (power <= 1e-9) & (alpha >= ALPHA_MIN * (1.0 - 1e-3))
+            cand = tm.repeat_interleave(BLOCK, 0).repeat_interleave(BLOCK, 1)[ya:yb, xa:xb]
+            mask[ya:yb, xa:xb] |= hit & cand
+    if frag.numel() and not refine:
         mask = mask | tile_mask.repeat_interleave(BLOCK, 0).repeat_interleave(BLOCK, 1)[:H, :W]
     return mask
+
+
+def fragile_radii(aux, eps: float = 1e-5) -> torch.Tensor:
+    """Gaussians whose integer screen radius ceil(3 sqrt(lambda)) or near-plane decision sits within a relative
+    ``eps`` of rounding the other way in float32 -- the only ones whose ``radii`` entry may differ from this
+    oracle's.  Needs ``want_aux=True``."""
+    pre = aux["pre"]
+    return (pre["margin_radius"] < eps) | (pre["margin_z"] < eps)

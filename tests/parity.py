@@ -1,4 +1,19 @@
-"""Shared parity metrics for the tests (CPU emulation and GPU)."""
+"""Shared parity metrics for the tests (CPU emulation and GPU).
+
+Gates (north star): <= 1e-5 abs on RGB / depth planes, <= 1e-4 rel on every gradient.  The algorithm is
+discontinuous (alpha < 1/255 skip, T < 1e-4 stop, integer radius / tile rectangle, z <= 0.2 cull); a pixel
+the float64 oracle puts within float32 noise of such a threshold may legitimately take the other branch in
+any float32 implementation -- the reference's included.  Those pixels ("fragile", oracle.fragile_pixel_mask)
+are handled explicitly and every number about them is printed, bounded and written to the parity report:
+
+  * mask fraction      -- fragile pixels / all pixels, asserted <= MASK_FRACTION_MAX (1 %);
+  * flips              -- pixels whose value actually differs by more than the gate; every flip must lie
+                          inside the mask (no unmasked pixel may exceed 1e-5) and flips are counted;
+  * gradients          -- compared with the upstream gradient zeroed on the mask on BOTH sides.
+"""
+import json
+import os
+
 import torch
 
 from oracle import raster_oracle as ro
@@ -7,10 +22,34 @@ IMG_ABS_TOL = 1e-5        # north-star: <= 1e-5 abs on RGB / depth
 GRAD_REL_TOL = 1e-4       # north-star: <= 1e-4 rel on all gradients
 FLIP_ABS_BOUND = 2e-2     # a flipped alpha<1/255 / T<1e-4 decision moves a pixel by at most ~alpha*T*c
 FLIP_FRACTION = 2e-3      # at most 0.2 % of the pixels may sit on a flipped decision
+MASK_FRACTION_MAX = 1e-2  # the fragile-pixel mask may cover at most 1 % of the image
+EPS_PIX = 1e-4            # relative distance of alpha to 1/255 (T to 1e-4) below which a pixel is fragile
+EPS_GAUSS = 2e-6          # relative distance of a tile-rectangle edge / the near plane to its threshold
+EPS_RADII = 1e-4          # relative distance of 3 sqrt(lambda) to an integer below which radii may differ
+
+_REPORT = os.environ.get("FSGS_PARITY_REPORT") or os.path.join(
+    os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
 
 
-def check_image(name, got, ref, aux, scale=1.0):
-    """got/ref [C,H,W]; ref is the float64 oracle; aux from want_aux=True (or None)."""
+def report(case, **fields):
+    """Print one line of parity statistics and append it to the parity report (gpurun_out/parity_report.jsonl
+    on the GPU box; copied to profiles/ when it is to be judged)."""
+    rec = {"case": case}
+    rec.update({k: (float(v) if isinstance(v, float) else v) for k, v in fields.items()})
+    line = json.dumps(rec)
+    print("[parity]", line)
+    try:
+        if os.path.isdir(os.path.dirname(_REPORT)):
+            with open(_REPORT, "a") as f:
+                f.write(line + "\n")
+    except OSError:
+        pass
+    return rec
+
+
+def check_image(name, got, ref, aux, scale=1.0, mask=None):
+    """got/ref [C,H,W]; ref is the float64 oracle; aux from want_aux=True (or None); mask overrides
+    the fragile-pixel mask derived from aux.  Returns (max err, number of flipped pixels)."""
     got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
     assert got.shape == ref.shape, (name, got.shape, ref.shape)
     assert torch.isfinite(got).all(), name
@@ -20,9 +59,10 @@ def check_image(name, got, ref, aux, scale=1.0):
     n_bad = int((err > tol).sum())
     assert n_bad <= FLIP_FRACTION * H * W, f"{name}: {n_bad} pixels above {tol:g} (max {err.max():.3g})"
     assert err.max().item() <= FLIP_ABS_BOUND * scale, f"{name}: max abs err {err.max():.3g}"
-    if aux is not None:
-        fm = ro.fragile_pixel_mask(aux, H, W)
-        solid = err[~fm]
+    if mask is None and aux is not None:
+        mask = fragile_mask(aux, H, W)
+    if mask is not None:
+        solid = err[~mask]
         if solid.numel():
             assert solid.max().item() <= tol, f"{name}: {solid.max():.3g} on a pixel with no near-threshold decision"
     return err.max().item(), n_bad
@@ -34,13 +74,32 @@ def rel_err(got, ref):
     return ((got - ref).norm() / ref.norm().clamp(min=1e-30)).item()
 
 
-def fragile_mask(aux, H, W, eps_pix=1e-4, eps_gauss=2e-6):
+def fragile_mask(aux, H, W, eps_pix=EPS_PIX, eps_gauss=EPS_GAUSS):
     """Pixels whose value may legitimately differ by a flipped threshold decision (see
     oracle/raster_oracle.fragile_pixel_mask).  Gradient comparisons zero the upstream gradient on
     these pixels on BOTH sides, so that a flip (an O(1/255) discontinuity that any float32
     implementation -- the reference included -- takes at its own rounding) cannot masquerade as a
     gradient error; the image checks count and bound the flips separately."""
     return ro.fragile_pixel_mask(aux, H, W, eps_pix=eps_pix, eps_gauss=eps_gauss)
+
+
+def check_mask_fraction(name, mask):
+    frac = float(mask.float().mean())
+    assert frac <= MASK_FRACTION_MAX, f"{name}: the fragile-pixel mask covers {frac:.2%} of the image (> {MASK_FRACTION_MAX:.0%})"
+    return frac
+
+
+def check_radii(name, got, ref, aux):
+    """Integer screen radii: equal everywhere except on Gaussians whose 3 sqrt(lambda) sits within EPS_RADII
+    (relative) of an integer or whose depth sits on the near plane.  Returns (mismatches, fragile count)."""
+    got, ref = got.detach().cpu().to(torch.int64), ref.detach().cpu().to(torch.int64)
+    diff = got != ref
+    frag = ro.fragile_radii(aux, EPS_RADII)
+    n_diff, n_frag = int(diff.sum()), int(frag.sum())
+    stray = int((diff & ~frag).sum())
+    assert stray == 0, f"{name}: {stray} radii differ on Gaussians that are not near an integer radius"
+    assert int((got[diff] - ref[diff]).abs().max()) <= 1 if n_diff else True, f"{name}: a radius differs by more than 1"
+    return n_diff, n_frag
 
 
 def check_grad(name, got, ref, tol=GRAD_REL_TOL):
