@@ -37,6 +37,24 @@ def set_grad_reducer(fn) -> None:
     _GRAD_REDUCER["fn"] = fn
 
 
+class keep_geometry:
+    """Test / debugging hook: inside ``with keep_geometry() as g:`` the per-Gaussian projection records of every fused
+    forward on this thread are copied out (``g.records``: list of float32 [P,12] tensors, layout in
+    csrc/fsgs_device.cuh -- x, y, conic xyz, opacity, r, g, b, view depth, radius bits, tiles).  The parity tests
+    feed the view depths to the oracle as sort keys, so that both sides composite near-equal depths in the same
+    (float32-rounding dependent) order."""
+
+    def __enter__(self):
+        self.records = []
+        self._prev = getattr(_TLS, "keep_geom", None)
+        _TLS.keep_geom = self.records
+        return self
+
+    def __exit__(self, *a):
+        _TLS.keep_geom = self._prev
+        return False
+
+
 def _check_identity_view(rs) -> None:
     """The fused path composites the depth planes from the view-space z of the (single) projection,
     which equals the reference's ``get_depth_and_silhouette`` only for the identity rasteriser view
@@ -112,6 +130,10 @@ class _RenderFused(torch.autograd.Function):
                 ex_ptr, ctypes.c_void_p(stream))
         _lib.check(rc)
         empty = torch.empty(0, dtype=torch.uint8, device=dev)
+        keep = getattr(_TLS, "keep_geom", None)
+        if keep is not None and P > 0:
+            off = int(_lib.lib().fsgs_geom_record_offset(P))
+            keep.append(arena.tensors["geom"][off:off + 48 * P].view(torch.float32).view(P, 12).clone())
         ctx.save_for_backward(*t, *[arena.tensors.get(k, empty) for k in ("geom", "binning", "img")])
         ctx.lease = arena.finish()             # scratch goes back to the workspace pool when this node dies
         ctx.st, ctx.P, ctx.num_rendered, ctx.num_rect, ctx.dev = st, P, int(nr.value), int(nrect.value), dev

@@ -219,7 +219,13 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
                               real scale_modifier, const real *rotations, const real *cov3D_precomp,
                               const real *viewmatrix, const real *projmatrix, const real *campos, int W,
                               int H, real tanfovx, real tanfovy, const real *bg, real *out_color,
-                              real *out_depth, int *radii_out, int64_t *num_rendered, real *pix_margin) {
+                              real *out_depth, int *radii_out, int64_t *num_rendered, real *pix_margin,
+                              const float *sort_depth) {
+    /* sort_depth (optional, P floats): float32 view depths to take the SORT KEYS from instead of rounding this
+       build's own depths.  The list order of near-equal depths is decided by float32 rounding and therefore differs
+       between float32 implementations; a test that checks compositing against this oracle passes the depths of the
+       implementation under test here (and checks separately that they are within float32 rounding of the truth),
+       so the two composite every tile in the same order.  Only the keys change, never a composited value. */
     Ctx *c = (Ctx *)calloc(1, sizeof(Ctx));
     c->P = P; c->sh_deg = sh_deg; c->n_coeffs = n_coeffs; c->W = W; c->H = H;
     c->means3D = means3D; c->shs = shs; c->colors_precomp = colors_precomp; c->opacities = opacities;
@@ -309,7 +315,8 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
     for (int i = 0; i < P; ++i) {
         if (c->radii[i] <= 0) continue;
         int64_t off = offsets[i];
-        float df = (float)c->depth[i];
+        /* (a NaN entry = no override for that Gaussian) */
+        float df = (sort_depth && sort_depth[i] == sort_depth[i]) ? sort_depth[i] : (float)c->depth[i];
         uint32_t dbits;
         memcpy(&dbits, &df, 4);
         for (int y = c->rect[4 * i + 1]; y < c->rect[4 * i + 3]; ++y)
@@ -343,6 +350,9 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
             for (int px = tx0; px < tx0 + BLOCK && px < W; ++px) {
                 real T = 1, C[NCH] = {0, 0, 0}, D = 0;
                 real margin = (real)1e30;   /* relative distance of the closest threshold decision */
+                /* relative depth gap of the closest pair of consecutive entries that both reach alpha >= 1/255
+                   here: a float32 implementation whose depths round differently may composite them in the other order */
+                real order_margin = (real)1e30, prev_depth = (real)-1;
                 int contributor = 0, last = 0;
                 for (int64_t k = s; k < e; ++k) {
                     contributor++;
@@ -355,6 +365,8 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
                     real alpha = fmin((real)0.99, opacities[id] * R_EXP(power));
                     margin = fmin(margin, fabs(alpha - (real)(1.0 / 255.0)) * 255);
                     if (alpha < (real)(1.0 / 255.0)) continue;
+                    if (prev_depth >= 0) order_margin = fmin(order_margin, (c->depth[id] - prev_depth) / c->depth[id]);
+                    prev_depth = c->depth[id];
                     real test_T = T * (1 - alpha);
                     margin = fmin(margin, fabs(test_T - (real)0.0001) * 10000);
                     if (test_T < (real)0.0001) break;
@@ -366,7 +378,7 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
                 int64_t pix = (int64_t)py * W + px;
                 c->final_T[pix] = T;
                 c->n_contrib[pix] = last;
-                if (pix_margin) pix_margin[pix] = margin;
+                if (pix_margin) { pix_margin[pix] = margin; pix_margin[(int64_t)W * H + pix] = order_margin; }
                 for (int ch = 0; ch < NCH; ++ch) out_color[(int64_t)ch * H * W + pix] = C[ch] + T * c->bg[ch];
                 out_depth[pix] = D;
             }

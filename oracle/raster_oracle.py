@@ -229,12 +229,16 @@ def preprocess(means3D, means2D, opacities, scales, rotations, cov3D_precomp, st
     return out
 
 
-def build_tile_lists(pre: Dict[str, torch.Tensor], H: int, W: int) -> Tuple[List[torch.Tensor], int]:
-    """Appendix A, K2-K5: per tile, Gaussian ids ordered by (depth float32 bits, id)."""
+def build_tile_lists(pre: Dict[str, torch.Tensor], H: int, W: int, sort_depth=None) -> Tuple[List[torch.Tensor], int]:
+    """Appendix A, K2-K5: per tile, Gaussian ids ordered by (depth float32 bits, id).  ``sort_depth`` (optional,
+    float32 [P]): take the sort keys from these depths instead (see raster_oracle.c, fsgs_oracle_forward)."""
     gx, gy = (W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK
     vis = pre["visible"].nonzero().flatten()
     rect = pre["rect"][vis]
     depth32 = pre["depth"].detach().to(torch.float32)
+    if sort_depth is not None:        # (a NaN entry = no override for that Gaussian)
+        sd = sort_depth.detach().to(torch.float32)
+        depth32 = torch.where(torch.isnan(sd), depth32, sd)
     ids_l, tiles_l = [], []
     # expand rect -> (tile, id) instances, row-major inside the rect like duplicateWithKeys
     w = (rect[:, 2] - rect[:, 0])
@@ -274,6 +278,7 @@ def composite(pre: Dict[str, torch.Tensor], lists: List[torch.Tensor], st: Raste
     n_contrib = torch.zeros(H, W, dtype=torch.int32)
     final_T = torch.ones(H, W, dtype=dt)
     pix_margin = torch.full((H, W), float("inf"), dtype=torch.float64)
+    order_margin = torch.full((H, W), float("inf"), dtype=torch.float64)
     color_tiles, depth_tiles = {}, {}
     for t, ids in enumerate(lists):
         if ids.numel() == 0:
@@ -324,6 +329,14 @@ def composite(pre: Dict[str, torch.Tensor], lists: List[torch.Tensor], st: Raste
                 m = torch.minimum(m_a, m_t).min(dim=0).values.double()
                 m = torch.where(m_p.any(dim=0), torch.zeros_like(m), m)
                 pix_margin[ty0:ty0 + ph, tx0:tx0 + pw] = m.view(ph, pw)
+                # depth-order margin: smallest relative depth gap between consecutive entries that both reach
+                # alpha >= 1/255 at the pixel (entries evaluated up to and including the stop entry)
+                reach = live & valid
+                dcol = depth[ids].detach()[:, None].expand_as(alpha)
+                seen_d = torch.where(reach, dcol, torch.full_like(dcol, -1.0))
+                prev = torch.cat([torch.full_like(seen_d[:1], -1.0), torch.cummax(seen_d, dim=0).values[:-1]], dim=0)
+                gap = torch.where(reach & (prev >= 0), (dcol - prev) / dcol, torch.full_like(dcol, float("inf")))
+                order_margin[ty0:ty0 + ph, tx0:tx0 + pw] = gap.min(dim=0).values.double().view(ph, pw)
     # assemble with autograd-friendly ops (index_put on views keeps the graph)
     if color_tiles:
         rows_c, rows_d, idx = [], [], []
@@ -339,12 +352,12 @@ def composite(pre: Dict[str, torch.Tensor], lists: List[torch.Tensor], st: Raste
         flat_d = flat_d.index_copy(1, idx, torch.cat(rows_d, 0)[None, :])
         out_color = flat_c.view(C, H, W)
         out_depth = flat_d.view(1, H, W)
-    aux = dict(n_contrib=n_contrib, final_T=final_T, pix_margin=pix_margin)
+    aux = dict(n_contrib=n_contrib, final_T=final_T, pix_margin=pix_margin, order_margin=order_margin)
     return out_color, out_depth, aux
 
 
 def rasterize(means3D, means2D, opacities, st, colors_precomp=None, shs=None, scales=None,
-              rotations=None, cov3D_precomp=None, want_aux: bool = False):
+              rotations=None, cov3D_precomp=None, want_aux: bool = False, sort_depth=None):
     """One ``GaussianRasterizer(raster_settings)(...)`` call.  Returns (color, radii, depth, aux)."""
     if (shs is None) == (colors_precomp is None):
         raise Exception('Please provide excatly one of either SHs or precomputed colors!')
@@ -363,18 +376,21 @@ def rasterize(means3D, means2D, opacities, st, colors_precomp=None, shs=None, sc
     pre = preprocess(means3D, means2D, opacities, scales, rotations, cov3D_precomp, st,
                      colors_precomp=colors_precomp, shs=shs)
     pre["opacity"] = opacities.reshape(-1)
-    lists, R = build_tile_lists(pre, H, W)
+    lists, R = build_tile_lists(pre, H, W, sort_depth=sort_depth)
     color, depth, aux = composite(pre, lists, st, want_aux=want_aux)
     aux.update(num_rendered=R, lists=lists, pre=pre)
     return color, pre["radii"], depth, aux
 
 
 def fragile_pixel_mask(aux, H: int, W: int, eps_pix: float = 1e-4, eps_gauss: float = 2e-6,
-                       refine: bool = True) -> torch.Tensor:
+                       refine: bool = True, eps_order: float = 1e-6) -> torch.Tensor:
     """Pixels where a float32 implementation may legitimately flip a threshold decision relative to
     this oracle.  Needs ``want_aux=True``.  ``eps_*`` are relative distances to the threshold
     (float32 epsilon is 6e-8).
       * per pixel: some evaluated entry has alpha within eps_pix of 1/255, or T within eps_pix of 1e-4;
+      * per pixel: two consecutive entries that both reach alpha >= 1/255 there have view depths within a relative
+        eps_order of each other -- the list is sorted by FLOAT32 depth bits, so an implementation whose depths
+        round differently composites the pair in the other order (an O(alpha^2) change over their overlap);
       * per Gaussian: a tile-rectangle edge within eps_gauss of a tile boundary (directly, or through
         an integer radius about to round the other way) can add/remove one line of tiles at that
         edge -- the two tile lines either side of the edge are candidates; a near-plane decision within
@@ -384,6 +400,8 @@ def fragile_pixel_mask(aux, H: int, W: int, eps_pix: float = 1e-4, eps_gauss: fl
         every candidate pixel (the round-1 behaviour, ~8 % of config 1).
     """
     mask = aux["pix_margin"] < eps_pix
+    if "order_margin" in aux and eps_order > 0:
+        mask = mask | (aux["order_margin"] < eps_order)
     pre = aux["pre"]
     gx, gy = (W + BLOCK - 1) // BLOCK, (H + BLOCK - 1) // BLOCK
     tile_mask = torch.zeros(gy, gx, dtype=torch.bool)

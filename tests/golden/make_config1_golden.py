@@ -28,7 +28,7 @@ def main():
     r, t = sc.pose_q.to(dt).requires_grad_(True), sc.pose_t.to(dt).requires_grad_(True)
     out = R.render(params, r, t, sc.camera, 3, sc.camera.campos, True, True, backend="c", want_aux=True)
     # pixels sitting on a threshold decision take no upstream gradient (tests/parity.py::fragile_mask)
-    mask = ro.fragile_pixel_mask(out["_aux"], 512, 640, eps_pix=1e-4, eps_gauss=2e-6)
+    mask = ro.fragile_pixel_mask(out["_aux"], 512, 640, eps_pix=1e-4, eps_gauss=2e-6, eps_order=0.0)
     keep = (~mask).to(dt)
     loss = (out["render"] * sc.grads_out["G_rgb"].to(dt) * keep).sum() + \
            (out["render_dep"] * sc.grads_out["G_dep"].to(dt) * keep).sum()
