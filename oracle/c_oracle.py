@@ -42,7 +42,7 @@ def _lib(dtype: torch.dtype):
         fwd = getattr(lib, f"fsgs_oracle_forward_{sfx}")
         fwd.restype = ctypes.c_void_p
         fwd.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, p, p, p, p, p, real, p, p, p, p, p,
-                        ctypes.c_int, ctypes.c_int, real, real, p, p, p, p, p, p, p]
+                        ctypes.c_int, ctypes.c_int, real, real, p, p, p, p, p, p, p, real]
         bwd = getattr(lib, f"fsgs_oracle_backward_{sfx}")
         bwd.restype = None
         bwd.argtypes = [p] * 11
@@ -83,7 +83,7 @@ class _Handle:
 
 
 def forward(means3D, opacities, st, colors_precomp=None, shs=None, scales=None, rotations=None,
-            cov3D_precomp=None, want_margin=False, sort_depth=None):
+            cov3D_precomp=None, want_margin=False, sort_depth=None, margin_kappa=0.0):
     """Raw forward.  ``st`` is anything with the GaussianRasterizationSettings fields.
     Returns (color[3,H,W], radii[P] int32, depth[1,H,W], handle, num_rendered)."""
     dt = means3D.dtype
@@ -110,7 +110,7 @@ def forward(means3D, opacities, st, colors_precomp=None, shs=None, scales=None, 
               _ptr(opacities), _ptr(scales), float(st.scale_modifier), _ptr(rotations),
               _ptr(cov3D_precomp), _ptr(view), _ptr(proj), _ptr(campos), W, H, float(st.tanfovx),
               float(st.tanfovy), _ptr(bg), _ptr(color), _ptr(depth), _ptr(radii), ctypes.byref(nr),
-              _ptr(margin), _ptr(sort_depth))
+              _ptr(margin), _ptr(sort_depth), float(margin_kappa))
     keep = (means3D, opacities, colors_precomp, shs, scales, rotations, cov3D_precomp)
     h = _Handle(ptr, fr, keep)
     h.pix_margin = margin
@@ -136,13 +136,14 @@ def backward(handle: _Handle, dL_dcolor, dL_ddepth, P: int, n_coeffs: int, dt):
 class _RasterizeC(torch.autograd.Function):
     want_margin = False     # tests flip this to also get the per-pixel threshold margins
     sort_depth = None       # optional float32 depths the sort keys are taken from (see raster_oracle.c)
+    margin_kappa = 0.0      # gradient weighting of the threshold margins (see raster_oracle.c)
     last_handle = None
 
     @staticmethod
     def forward(ctx, means3D, means2D, opacities, colors_precomp, shs, scales, rotations, cov3D_precomp, st):
         color, radii, depth, h, nr = forward(means3D, opacities, st, colors_precomp, shs, scales,
                                              rotations, cov3D_precomp, want_margin=_RasterizeC.want_margin,
-                                             sort_depth=_RasterizeC.sort_depth)
+                                             sort_depth=_RasterizeC.sort_depth, margin_kappa=_RasterizeC.margin_kappa)
         _RasterizeC.last_handle = h
         ctx.h, ctx.P, ctx.dt = h, means3D.shape[0], means3D.dtype
         ctx.n_coeffs = 0 if shs is None else shs.shape[1]
@@ -161,18 +162,20 @@ class _RasterizeC(torch.autograd.Function):
 
 
 def rasterize(means3D, means2D, opacities, st, colors_precomp=None, shs=None, scales=None,
-              rotations=None, cov3D_precomp=None, want_aux=False, sort_depth=None):
+              rotations=None, cov3D_precomp=None, want_aux=False, sort_depth=None, margin_kappa=0.0):
     """Differentiable ``GaussianRasterizer(st)(...)`` on the CPU through the C oracle.
     Returns (color, radii, depth, aux) like ``raster_oracle.rasterize``; with ``want_aux`` the aux
     dict carries what ``raster_oracle.fragile_pixel_mask`` needs."""
     _RasterizeC.want_margin = bool(want_aux)
     _RasterizeC.sort_depth = sort_depth
+    _RasterizeC.margin_kappa = float(margin_kappa)
     try:
         color, radii, depth = _RasterizeC.apply(means3D, means2D, opacities, colors_precomp, shs, scales,
                                                 rotations, cov3D_precomp, st)
     finally:
         _RasterizeC.want_margin = False
         _RasterizeC.sort_depth = None
+        _RasterizeC.margin_kappa = 0.0
     h = _RasterizeC.last_handle
     aux = {"num_rendered": getattr(h, "num_rendered", None)}
     if want_aux:

@@ -220,7 +220,12 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
                               const real *viewmatrix, const real *projmatrix, const real *campos, int W,
                               int H, real tanfovx, real tanfovy, const real *bg, real *out_color,
                               real *out_depth, int *radii_out, int64_t *num_rendered, real *pix_margin,
-                              const float *sort_depth) {
+                              const float *sort_depth, real margin_kappa) {
+    /* margin_kappa: the threshold margins written to pix_margin are relative distances divided by
+       (1 + margin_kappa * g), g = |d power / d centre| in 1/pixel (for the T test: the alpha-weighted sum of g over the
+       entries in front).  A splat centre is a float32 PIXEL coordinate, so any float32 implementation carries an
+       absolute error of a few ulp(W) in it, which moves log(alpha) by g times that -- steep (small) splats are
+       fragile over a wider band than flat ones.  0 = plain relative distances. */
     /* sort_depth (optional, P floats): float32 view depths to take the SORT KEYS from instead of rounding this
        build's own depths.  The list order of near-equal depths is decided by float32 rounding and therefore differs
        between float32 implementations; a test that checks compositing against this oracle passes the depths of the
@@ -352,7 +357,7 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
                 real margin = (real)1e30;   /* relative distance of the closest threshold decision */
                 /* relative depth gap of the closest pair of consecutive entries that both reach alpha >= 1/255
                    here: a float32 implementation whose depths round differently may composite them in the other order */
-                real order_margin = (real)1e30, prev_depth = (real)-1;
+                real order_margin = (real)1e30, prev_depth = (real)-1, gsum = 0;
                 int contributor = 0, last = 0;
                 for (int64_t k = s; k < e; ++k) {
                     contributor++;
@@ -363,12 +368,14 @@ void *FN(fsgs_oracle_forward)(int P, int sh_deg, int n_coeffs, const real *means
                     if (fabs(power) < (real)1e-12) margin = 0;
                     if (power > 0) continue;
                     real alpha = fmin((real)0.99, opacities[id] * R_EXP(power));
-                    margin = fmin(margin, fabs(alpha - (real)(1.0 / 255.0)) * 255);
+                    const real g = fabs(con[0] * dx + con[1] * dy) + fabs(con[2] * dy + con[1] * dx);
+                    margin = fmin(margin, fabs(alpha - (real)(1.0 / 255.0)) * 255 / (1 + margin_kappa * g));
                     if (alpha < (real)(1.0 / 255.0)) continue;
                     if (prev_depth >= 0) order_margin = fmin(order_margin, (c->depth[id] - prev_depth) / c->depth[id]);
                     prev_depth = c->depth[id];
                     real test_T = T * (1 - alpha);
-                    margin = fmin(margin, fabs(test_T - (real)0.0001) * 10000);
+                    gsum += g * alpha / (1 - alpha);
+                    margin = fmin(margin, fabs(test_T - (real)0.0001) * 10000 / (1 + margin_kappa * gsum));
                     if (test_T < (real)0.0001) break;
                     for (int ch = 0; ch < NCH; ++ch) C[ch] += c->rgb[3 * id + ch] * alpha * T;
                     D += c->depth[id] * alpha * T;

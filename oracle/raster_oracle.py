@@ -263,7 +263,7 @@ def build_tile_lists(pre: Dict[str, torch.Tensor], H: int, W: int, sort_depth=No
 
 
 def composite(pre: Dict[str, torch.Tensor], lists: List[torch.Tensor], st: RasterSettings,
-              extra_channels: Optional[torch.Tensor] = None, want_aux: bool = False):
+              extra_channels: Optional[torch.Tensor] = None, want_aux: bool = False, margin_kappa: float = 0.0):
     """Appendix A, K6, vectorised per tile.  Returns color [C,H,W], depth [1,H,W], aux."""
     xy, conic, colors, depth = pre["xy"], pre["conic"], pre["colors"], pre["depth"]
     dt = xy.dtype
@@ -321,9 +321,13 @@ def composite(pre: Dict[str, torch.Tensor], lists: List[torch.Tensor], st: Raste
                 # entries the kernel actually evaluates: everything up to and incl. the stop entry
                 first_stop = stop & (torch.cumsum(stop.to(torch.int32), 0) == 1)
                 live = (~stopped) | first_stop
-                m_a = torch.where(live & (power <= 0), (alpha - ALPHA_MIN).abs() / ALPHA_MIN,
+                # margin_kappa: relative distances are divided by (1 + kappa * g), g = |d power / d centre| per pixel
+                # of centre displacement (T test: alpha-weighted sum over the entries in front) -- see raster_oracle.c
+                gpx = (con[:, 0:1] * dx + con[:, 1:2] * dy).abs() + (con[:, 2:3] * dy + con[:, 1:2] * dx).abs()
+                gsum = torch.cumsum(gpx * a / (1.0 - a), dim=0)
+                m_a = torch.where(live & (power <= 0), (alpha - ALPHA_MIN).abs() / ALPHA_MIN / (1 + margin_kappa * gpx),
                                   torch.full_like(alpha, float("inf")))
-                m_t = torch.where(live & valid, (test_T - T_MIN).abs() / T_MIN,
+                m_t = torch.where(live & valid, (test_T - T_MIN).abs() / T_MIN / (1 + margin_kappa * gsum),
                                   torch.full_like(alpha, float("inf")))
                 m_p = torch.where(live, power.abs() < 1e-12, torch.zeros_like(valid))
                 m = torch.minimum(m_a, m_t).min(dim=0).values.double()
@@ -357,7 +361,7 @@ def composite(pre: Dict[str, torch.Tensor], lists: List[torch.Tensor], st: Raste
 
 
 def rasterize(means3D, means2D, opacities, st, colors_precomp=None, shs=None, scales=None,
-              rotations=None, cov3D_precomp=None, want_aux: bool = False, sort_depth=None):
+              rotations=None, cov3D_precomp=None, want_aux: bool = False, sort_depth=None, margin_kappa: float = 0.0):
     """One ``GaussianRasterizer(raster_settings)(...)`` call.  Returns (color, radii, depth, aux)."""
     if (shs is None) == (colors_precomp is None):
         raise Exception('Please provide excatly one of either SHs or precomputed colors!')
@@ -377,7 +381,7 @@ def rasterize(means3D, means2D, opacities, st, colors_precomp=None, shs=None, sc
                      colors_precomp=colors_precomp, shs=shs)
     pre["opacity"] = opacities.reshape(-1)
     lists, R = build_tile_lists(pre, H, W, sort_depth=sort_depth)
-    color, depth, aux = composite(pre, lists, st, want_aux=want_aux)
+    color, depth, aux = composite(pre, lists, st, want_aux=want_aux, margin_kappa=margin_kappa)
     aux.update(num_rendered=R, lists=lists, pre=pre)
     return color, pre["radii"], depth, aux
 
