@@ -90,8 +90,18 @@ def rigid_flow(depth, K, T_ab):
     return torch.stack([u.reshape(H, W) - xs, v.reshape(H, W) - ys], dim=0).float()
 
 
+def sequence_pose(k, motion_scale=4.0):
+    """World->camera of frame k: the test pose plus k * motion_scale * the per-frame increment of
+    fsgs_b200.synth (motion_scale 4: ~0.5 degree and 1.8 % of the scene depth per frame, a few pixels of flow at
+    320x256 -- the order of the SCARED sequences' inter-frame motion after the loader's depth normalisation)."""
+    from fsgs_b200.synth import DELTA_POSE_Q, DELTA_POSE_T, TEST_POSE_Q, TEST_POSE_T
+    q = tuple(a + k * motion_scale * b for a, b in zip(TEST_POSE_Q, DELTA_POSE_Q))
+    t = tuple(a + k * motion_scale * b for a, b in zip(TEST_POSE_T, DELTA_POSE_T))
+    return pose_matrix(q, t, dtype=torch.float64)
+
+
 def write_sequence(root, n_frames=8, W=320, H=256, P=20000, m=2.0, seed=0, device="cuda", renderer="fsgs",
-                   scene_id="1", data_id="1"):
+                   scene_id="1", data_id="1", motion_scale=4.0):
     """Returns a dict with the ground truth (w2c relative to frame 0 [N,4,4], K at image size, depths [N,H,W])."""
     from PIL import Image
     for sub in ("input", os.path.join("poses", f"{scene_id}_{data_id}"), "flow", "monodep"):
@@ -102,7 +112,7 @@ def write_sequence(root, n_frames=8, W=320, H=256, P=20000, m=2.0, seed=0, devic
     KL = K.clone()
     KL[0] *= 1280.0 / W
     KL[1] *= 1024.0 / H
-    Rts = [pose_matrix(*frame_pose_params(k), dtype=torch.float64) for k in range(n_frames)]
+    Rts = [sequence_pose(k, motion_scale) for k in range(n_frames)]
     rel = [Rt @ torch.inverse(Rts[0]) for Rt in Rts]                 # world := camera frame of frame 0
     names, depths = [], []
     for k in range(n_frames):

@@ -43,6 +43,40 @@ def find_reference(explicit=None):
     return None
 
 
+def _cpu_redirect():
+    """--cpu (plumbing tests in a container without a GPU; oracle backend only): the reference hard-codes 'cuda'
+    (``.cuda()``, ``device="cuda"``, CUDA events); send all of it to the host."""
+    import torch
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    for name in ("zeros", "ones", "eye", "tensor", "zeros_like", "ones_like", "empty", "arange", "full", "randint",
+                 "rand", "randn", "linspace"):
+        orig = getattr(torch, name)
+
+        def wrapped(*a, __orig=orig, **k):
+            if "device" in k and str(k["device"]).startswith("cuda"):
+                k["device"] = "cpu"
+            return __orig(*a, **k)
+        setattr(torch, name, wrapped)
+    orig_to = torch.nn.Module.to
+
+    def module_to(self, *a, **k):
+        a = tuple("cpu" if isinstance(x, str) and x.startswith("cuda") else x for x in a)
+        if "device" in k and str(k["device"]).startswith("cuda"):
+            k["device"] = "cpu"
+        return orig_to(self, *a, **k)
+    torch.nn.Module.to = module_to
+
+    class _Event:
+        def __init__(self, *a, **k):
+            pass
+
+        def record(self, *a, **k):
+            pass
+    torch.cuda.Event = _Event
+    torch.cuda.empty_cache = lambda: None
+
+
 def run(ref, backend, data_root, model_path, iterations, quiet=True):
     """Execute the reference's train.py in this process.  Returns (globals of train.py, wall seconds)."""
     import torch
@@ -129,7 +163,13 @@ def main():
     ap.add_argument("--renderer", default="fsgs", choices=["fsgs", "oracle"], help="what renders the ground-truth frames")
     ap.add_argument("--report", default=None)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--cpu", action="store_true", help="redirect the reference's hard-coded 'cuda' to the host "
+                    "(oracle backend + oracle renderer only: plumbing test without a GPU)")
     a = ap.parse_args()
+    if a.cpu:
+        if a.backend != "oracle" or a.renderer != "oracle":
+            raise SystemExit("--cpu needs --backend oracle --renderer oracle (the CUDA library has no CPU fallback)")
+        _cpu_redirect()
     ref = find_reference(a.ref)
     if ref is None:
         print(json.dumps({"config3": "skipped", "why": "no Free-SurGS checkout (baseline/_ref/Free-SurGS or /root/reference)"}))
