@@ -86,16 +86,25 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
                        float *__restrict__ dL_dfdc, float *__restrict__ dL_dfrest, float *__restrict__ dL_dopacity_raw,
                        float *__restrict__ dL_dscaling_raw, float *__restrict__ dL_drotation_raw,
                        float *__restrict__ dL_dpose, float *__restrict__ dL_dmeans2D, int use_tma,
-                       unsigned long long *__restrict__ err, float *__restrict__ dL_dsh_rgb) {
+                       unsigned long long *__restrict__ err, float *__restrict__ dL_dsh_rgb, int first, int end,
+                       float *__restrict__ stat_accum, float *__restrict__ stat_denom, float *__restrict__ compact) {
+    // [first, end): the Gaussians this launch covers (the frame-parallel exchange launches the kernel range by range
+    //   and reduces range k over the ranks while range k + 1 is computed); first % 4 == 0 keeps the bulk copies aligned.
+    // stat_accum / stat_denom [P,1] (optional): GaussianModel.add_densification_stats (scene/gaussian_model.py:678-681)
+    //   folded in -- accum[i] += ||dL/dmeans2D_i||, denom[i] += 1 for every visible Gaussian.
+    // compact [P,14] (optional): rotation | xyz | scaling | opacity | masked colour gradient as ONE 56-byte row per
+    //   Gaussian (the exchange unit of the frame-parallel mode: a Gaussian range is then one contiguous buffer);
+    //   replaces the separate xyz / opacity / scaling / rotation / dL_dsh_rgb outputs.
     // SH coefficients in, SH gradients out through ONE shared-memory buffer: bulk TMA load of the CTA's
     // 256 x 180 B slice, each thread turns its 45 coefficients into their gradients in place, bulk TMA
     // store to dL/dfeatures_rest (the plain path does 45 scalar loads + 45 scalar stores at a 180 B stride).
     __shared__ __align__(128) float s_rest[PREBWD_CTA * 45];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ float s_pose[16];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int base = blockIdx.x * blockDim.x, count = min((int)blockDim.x, P - base);
+    const int base = first + blockIdx.x * blockDim.x, count = min((int)blockDim.x, end - base);
+    P = end;
     // (without dL_dfrest -- the frame-parallel compact mode -- the coefficients are still staged: the SH
     // view-direction gradient needs them; nothing is stored back)
     const bool staged = (reinterpret_cast<uintptr_t>(f_rest) & 15u) == 0 &&
@@ -155,6 +164,17 @@ k_preprocess_fused_bwd(CamConst cc, int P, const float *__restrict__ xyz, const 
         if (dL_dscaling_raw) { dL_dscaling_raw[3 * n] = ds_raw[0]; dL_dscaling_raw[3 * n + 1] = ds_raw[1]; dL_dscaling_raw[3 * n + 2] = ds_raw[2]; }
         if (dL_drotation_raw) *reinterpret_cast<float4 *>(dL_drotation_raw + 4 * n) = make_float4(dq_raw[0], dq_raw[1], dq_raw[2], dq_raw[3]);
         if (dL_dmeans2D) { dL_dmeans2D[3 * n] = m2d[0]; dL_dmeans2D[3 * n + 1] = m2d[1]; dL_dmeans2D[3 * n + 2] = 0.f; }
+        if (stat_accum && radius > 0) {
+            stat_accum[i] += sqrtf(m2d[0] * m2d[0] + m2d[1] * m2d[1]);
+            stat_denom[i] += 1.0f;
+        }
+        if (compact) {
+            float2 *row = reinterpret_cast<float2 *>(compact + 14 * n);          // 56-byte rows: 8-byte aligned
+            row[0] = make_float2(dq_raw[0], dq_raw[1]); row[1] = make_float2(dq_raw[2], dq_raw[3]);
+            row[2] = make_float2(dxyz[0], dxyz[1]);     row[3] = make_float2(dxyz[2], ds_raw[0]);
+            row[4] = make_float2(ds_raw[1], ds_raw[2]); row[5] = make_float2(dop_raw, gc[0]);
+            row[6] = make_float2(gc[1], gc[2]);
+        }
     }
     if (staged && dL_dfrest) {
         // gradients -> global: bulk store for the 16-byte-multiple prefix, plain stores for <= 3 rows
@@ -224,14 +244,31 @@ k_preprocess_pose_bwd(CamConst cc, int P, const float *__restrict__ xyz, const f
 // shared memory and written with one bulk TMA store per CTA like the backward above.
 __global__ void __launch_bounds__(CTA)
 k_sh_grad_expand(int P, int sh_deg, const float *__restrict__ xyz, const float *__restrict__ cam_center,
-                 const float *__restrict__ gc, float *__restrict__ dL_dfdc, float *__restrict__ dL_dfrest, int use_tma) {
+                 const float *__restrict__ gc, float *__restrict__ dL_dfdc, float *__restrict__ dL_dfrest, int use_tma,
+                 int first, const float *__restrict__ compact, float *__restrict__ dL_dxyz,
+                 float *__restrict__ dL_dopacity_raw, float *__restrict__ dL_dscaling_raw,
+                 float *__restrict__ dL_drotation_raw) {
+    // [first, P): the Gaussian range of this launch (first % 4 == 0).  With `compact` [P,14] (the rank-summed rows of
+    // k_preprocess_fused_bwd) the colour gradient is taken from the row and the row's other 11 floats are unpacked
+    // into the per-parameter gradient tensors on the way.
     __shared__ __align__(128) float s_rest[CTA * 45];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int base = blockIdx.x * blockDim.x, count = min((int)blockDim.x, P - base);
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    const int base = first + blockIdx.x * blockDim.x, count = min((int)blockDim.x, P - base);
     const bool staged = (reinterpret_cast<uintptr_t>(dL_dfrest) & 15u) == 0 && use_tma;
     if (i < P) {
         const size_t n = (size_t)i;
-        const float g0 = gc[3 * n], g1 = gc[3 * n + 1], g2 = gc[3 * n + 2];
+        float g0, g1, g2;
+        if (compact) {
+            const float2 *row = reinterpret_cast<const float2 *>(compact + 14 * n);
+            const float2 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3], r4 = row[4], r5 = row[5], r6 = row[6];
+            *reinterpret_cast<float4 *>(dL_drotation_raw + 4 * n) = make_float4(r0.x, r0.y, r1.x, r1.y);
+            dL_dxyz[3 * n] = r2.x; dL_dxyz[3 * n + 1] = r2.y; dL_dxyz[3 * n + 2] = r3.x;
+            dL_dscaling_raw[3 * n] = r3.y; dL_dscaling_raw[3 * n + 1] = r4.x; dL_dscaling_raw[3 * n + 2] = r4.y;
+            dL_dopacity_raw[i] = r5.x;
+            g0 = r5.y; g1 = r6.x; g2 = r6.y;
+        } else {
+            g0 = gc[3 * n]; g1 = gc[3 * n + 1]; g2 = gc[3 * n + 2];
+        }
         float d[3] = {xyz[3 * n] - __ldg(cam_center), xyz[3 * n + 1] - __ldg(cam_center + 1),
                       xyz[3 * n + 2] - __ldg(cam_center + 2)};
         const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);

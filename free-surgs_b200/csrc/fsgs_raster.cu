@@ -597,12 +597,35 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
                             int32_t cam_grad, float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
                             float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw, float *dL_dpose,
                             float *dL_dmeans2D, float *dL_dsh_rgb, void *stream_) {
+    return fsgs_render_backward_v2(st, P, num_rendered, bg, xyz, features_dc, features_rest, opacity_raw, scaling_raw,
+                                   rotation_raw, pose, cam_center, viewmatrix, projmatrix, geom, binning, img, dL_drgb,
+                                   dL_ddepth, dL_dsil, dL_ddepth_sq, grad_scratch, gs_grad, cam_grad, dL_dxyz,
+                                   dL_dfeatures_dc, dL_dfeatures_rest, dL_dopacity_raw, dL_dscaling_raw, dL_drotation_raw,
+                                   dL_dpose, dL_dmeans2D, dL_dsh_rgb, nullptr, stream_);
+}
+
+int fsgs_render_backward_v2(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg, const float *xyz,
+                            const float *features_dc, const float *features_rest, const float *opacity_raw,
+                            const float *scaling_raw, const float *rotation_raw, const float *pose,
+                            const float *cam_center, const float *viewmatrix, const float *projmatrix, const void *geom,
+                            const void *binning, const void *img, const float *dL_drgb, const float *dL_ddepth,
+                            const float *dL_dsil, const float *dL_ddepth_sq, void *grad_scratch, int32_t gs_grad,
+                            int32_t cam_grad, float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
+                            float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw, float *dL_dpose,
+                            float *dL_dmeans2D, float *dL_dsh_rgb, const fsgs_backward_opts *opts, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CamConst cc;
     int rc = make_cam(st, cc);
     if (rc) return rc;
     cc.n_coeffs = 16;
-    if (dL_dpose) FSGS_CUDA(cudaMemsetAsync(dL_dpose, 0, 16 * sizeof(float), stream));
+    fsgs_backward_opts o{};
+    if (opts) o = *opts;
+    const bool ranged = o.count > 0;
+    if (ranged && (o.first < 0 || (o.first & 3) || (int64_t)o.first + o.count > P)) return FSGS_E_INVALID;
+    if ((o.xyz_gradient_accum == nullptr) != (o.denom == nullptr)) return FSGS_E_INVALID;
+    if (o.compact && (dL_dxyz || dL_dopacity_raw || dL_dscaling_raw || dL_drotation_raw || dL_dsh_rgb)) return FSGS_E_INVALID;
+    const int first = ranged ? o.first : 0, end = ranged ? o.first + o.count : P;
+    if (dL_dpose && !o.skip_composite) FSGS_CUDA(cudaMemsetAsync(dL_dpose, 0, 16 * sizeof(float), stream));
     if (P <= 0) return P == 0 ? FSGS_OK : FSGS_E_INVALID;
     if (!geom || !img || !binning || !grad_scratch || !xyz || !features_dc || !features_rest ||
         !opacity_raw || !scaling_raw || !rotation_raw || !pose || !cam_center || !viewmatrix || !projmatrix || !bg)
@@ -615,14 +638,14 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
     const char *g = static_cast<const char *>(geom), *im = static_cast<const char *>(img),
                *bn = static_cast<const char *>(binning);
     float *acc = static_cast<float *>(grad_scratch);
-    FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
+    if (!o.skip_composite) FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
     // Pose-only request (tracking against a frozen Gaussian model): dL/dpose is the only output asked for.
     // The compositor then skips the colour / opacity / RGB-only columns and a lean per-Gaussian kernel
     // reduces dL/dRt without touching the SH coefficients or writing per-Gaussian gradients.
     const bool pose_only = cam_grad && dL_dpose && !dL_dxyz && !dL_dfeatures_dc && !dL_dfeatures_rest &&
                            !dL_dopacity_raw && !dL_dscaling_raw && !dL_drotation_raw && !dL_dmeans2D && !dL_dsh_rgb &&
-                           !(st->flags & FSGS_FLAG_NO_POSE_ONLY);
-    if (num_rendered > 0) {
+                           !o.compact && !o.xyz_gradient_accum && !ranged && !(st->flags & FSGS_FLAG_NO_POSE_ONLY);
+    if (num_rendered > 0 && !o.skip_composite) {
         prof_begin(K_COMP_BWD, stream);
         auto kern = pose_only ? k_composite_bwd<true, true> : k_composite_bwd<true, false>;
         kern<<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
@@ -643,11 +666,12 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
         return FSGS_OK;
     }
     prof_begin(K_PRE_FUSED_BWD, stream);
-    k_preprocess_fused_bwd<<<(P + PREBWD_CTA - 1) / PREBWD_CTA, PREBWD_CTA, 0, stream>>>(
+    k_preprocess_fused_bwd<<<(end - first + PREBWD_CTA - 1) / PREBWD_CTA, PREBWD_CTA, 0, stream>>>(
         cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
         projmatrix, reinterpret_cast<const float4 *>(g + gl.records), reinterpret_cast<const uint8_t *>(g + gl.clamped),
         acc, gs_grad, cam_grad, dL_dxyz, dL_dfeatures_dc, dL_dfeatures_rest, dL_dopacity_raw, dL_dscaling_raw,
-        dL_drotation_raw, dL_dpose, dL_dmeans2D, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1, sticky_flag(), dL_dsh_rgb);
+        dL_drotation_raw, dL_dpose, dL_dmeans2D, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1, sticky_flag(), dL_dsh_rgb,
+        first, end, o.xyz_gradient_accum, o.denom, o.compact);
     prof_end(K_PRE_FUSED_BWD, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused_bwd");
     return FSGS_OK;
@@ -686,7 +710,32 @@ int fsgs_sh_grad_expand(const fsgs_settings *st, int32_t P, const float *xyz, co
     if (rc) return rc;
     prof_begin(K_SH_EXPAND, stream);
     k_sh_grad_expand<<<blocks(P), CTA, 0, stream>>>(P, st->sh_degree, xyz, cam_center, dL_dsh_rgb, dL_dfeatures_dc,
-                                                    dL_dfeatures_rest, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1);
+                                                    dL_dfeatures_rest, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1, 0, nullptr,
+                                                    nullptr, nullptr, nullptr, nullptr);
+    prof_end(K_SH_EXPAND, stream);
+    FSGS_LAUNCH_OK("k_sh_grad_expand");
+    return FSGS_OK;
+}
+
+int fsgs_compact_grad_expand(const fsgs_settings *st, int32_t P, int32_t first, int32_t count, const float *xyz,
+                             const float *cam_center, const float *compact, float *dL_dxyz, float *dL_dfeatures_dc,
+                             float *dL_dfeatures_rest, float *dL_dopacity_raw, float *dL_dscaling_raw,
+                             float *dL_drotation_raw, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!st || st->sh_degree < 0 || st->sh_degree > 3 || P < 0 || first < 0 || (first & 3) || count < 0 ||
+        (int64_t)first + count > P)
+        return FSGS_E_INVALID;
+    if (count == 0) return FSGS_OK;
+    if (!xyz || !cam_center || !compact || !dL_dxyz || !dL_dfeatures_dc || !dL_dfeatures_rest || !dL_dopacity_raw ||
+        !dL_dscaling_raw || !dL_drotation_raw)
+        return FSGS_E_INVALID;
+    int rc = check_arch();
+    if (rc) return rc;
+    prof_begin(K_SH_EXPAND, stream);
+    k_sh_grad_expand<<<blocks(count), CTA, 0, stream>>>(first + count, st->sh_degree, xyz, cam_center, nullptr,
+                                                        dL_dfeatures_dc, dL_dfeatures_rest,
+                                                        (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1, first, compact, dL_dxyz,
+                                                        dL_dopacity_raw, dL_dscaling_raw, dL_drotation_raw);
     prof_end(K_SH_EXPAND, stream);
     FSGS_LAUNCH_OK("k_sh_grad_expand");
     return FSGS_OK;

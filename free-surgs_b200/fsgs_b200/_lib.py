@@ -34,6 +34,13 @@ class Settings(ctypes.Structure):
                 ("n_coeffs", ctypes.c_int32), ("debug", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
+class BackwardOpts(ctypes.Structure):
+    """fsgs_backward_opts (include/fsgs_raster.h)."""
+    _fields_ = [("xyz_gradient_accum", ctypes.c_void_p), ("denom", ctypes.c_void_p), ("compact", ctypes.c_void_p),
+                ("first", ctypes.c_int32), ("count", ctypes.c_int32), ("skip_composite", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
 class RenderExtras(ctypes.Structure):
     """fsgs_render_extras: optional derived outputs of render() (device pointers, NULL = skip)."""
     _fields_ = [("uncertainty", ctypes.c_void_p), ("presence_mask", ctypes.c_void_p), ("nan_mask", ctypes.c_void_p),
@@ -74,6 +81,9 @@ _SIGNATURES = {
                              [_i32, _i32] + [_vp] * 9),
     "fsgs_render_backward_ex": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 19 +
                                 [_i32, _i32] + [_vp] * 10),
+    "fsgs_render_backward_v2": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i64] + [_vp] * 19 +
+                                [_i32, _i32] + [_vp] * 9 + [ctypes.POINTER(BackwardOpts), _vp]),
+    "fsgs_compact_grad_expand": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i32, _i32] + [_vp] * 10),
     "fsgs_set_instance_capacity": (ctypes.c_int, [_i32, _i64]),
     "fsgs_watchdog_flag": (ctypes.c_int, [_i32, _i32]),
     "fsgs_sh_grad_expand": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 6),

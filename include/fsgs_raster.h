@@ -194,6 +194,41 @@ int fsgs_render_backward_ex(const fsgs_settings *st, int32_t P, int64_t num_rend
                             float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw,
                             float *dL_dpose, float *dL_dmeans2D, float *dL_dsh_rgb, void *stream);
 
+/* Options of fsgs_render_backward_v2 (all optional; a zeroed struct or NULL = fsgs_render_backward_ex).
+ *   xyz_gradient_accum, denom [P,1]: GaussianModel.add_densification_stats (scene/gaussian_model.py:678-681, called
+ *       from train.py:298-303 after every mapping backward) folded into the per-Gaussian backward kernel:
+ *       accum[i] += ||dL/dmeans2D_i||_2 and denom[i] += 1 for every Gaussian the frame saw (radius > 0).  Both or none.
+ *   first, count: restrict the per-Gaussian kernel to Gaussians [first, first+count) (first % 4 == 0; count <= 0 = all).
+ *   skip_composite: the accumulator in grad_scratch already holds this frame's compositor output (an earlier call
+ *       with the same scratch buffer ran it): only the per-Gaussian kernel runs, dL_dpose is accumulated into, not
+ *       zeroed.  Lets a caller run the backward range by range and exchange range k over the GPUs while range k+1
+ *       is computed (frame-parallel mode).
+ *   compact [P,14]: rotation(4) | xyz(3) | scaling(3) | opacity(1) | clamp-masked colour gradient(3) written as one
+ *       56-byte row per Gaussian instead of the separate dL_dxyz / dL_dopacity_raw / dL_dscaling_raw /
+ *       dL_drotation_raw / dL_dsh_rgb outputs (which must then be NULL): the exchange unit of the frame-parallel
+ *       mode; fsgs_compact_grad_expand turns summed rows into the per-parameter gradients. */
+typedef struct fsgs_backward_opts {
+    float *xyz_gradient_accum;
+    float *denom;
+    float *compact;
+    int32_t first;
+    int32_t count;
+    int32_t skip_composite;
+    int32_t reserved;
+} fsgs_backward_opts;
+
+int fsgs_render_backward_v2(const fsgs_settings *st, int32_t P, int64_t num_rendered, const float *bg,
+                            const float *xyz, const float *features_dc, const float *features_rest,
+                            const float *opacity_raw, const float *scaling_raw, const float *rotation_raw,
+                            const float *pose, const float *cam_center, const float *viewmatrix,
+                            const float *projmatrix, const void *geom, const void *binning, const void *img,
+                            const float *dL_drgb, const float *dL_ddepth, const float *dL_dsil,
+                            const float *dL_ddepth_sq, void *grad_scratch, int32_t gs_grad, int32_t cam_grad,
+                            float *dL_dxyz, float *dL_dfeatures_dc, float *dL_dfeatures_rest,
+                            float *dL_dopacity_raw, float *dL_dscaling_raw, float *dL_drotation_raw,
+                            float *dL_dpose, float *dL_dmeans2D, float *dL_dsh_rgb,
+                            const fsgs_backward_opts *opts, void *stream);
+
 /* Device watchdog.  Every device-side wait in the library is bounded; one that gives up sets a sticky per-device
  * word instead of hanging the GPU.  Each (non-captured) forward reads the word back together with the instance
  * count and returns FSGS_E_WATCHDOG if an EARLIER launch on the device set it.  This call reads it on demand
@@ -222,6 +257,14 @@ int fsgs_set_instance_capacity(int32_t device, int64_t capacity);
  *      (st->sh_degree = active degree; coefficients above it get zeros). */
 int fsgs_sh_grad_expand(const fsgs_settings *st, int32_t P, const float *xyz, const float *cam_center,
                         const float *dL_dsh_rgb, float *dL_dfeatures_dc, float *dL_dfeatures_rest, void *stream);
+
+/* The same for the 56-byte rows of fsgs_backward_opts.compact, one Gaussian range [first, first+count) at a time
+ * (first % 4 == 0): unpacks rotation / xyz / scaling / opacity from the (rank-summed) rows into their gradient tensors
+ * and expands the colour gradient into the SH-coefficient gradients. */
+int fsgs_compact_grad_expand(const fsgs_settings *st, int32_t P, int32_t first, int32_t count, const float *xyz,
+                             const float *cam_center, const float *compact, float *dL_dxyz, float *dL_dfeatures_dc,
+                             float *dL_dfeatures_rest, float *dL_dopacity_raw, float *dL_dscaling_raw,
+                             float *dL_drotation_raw, void *stream);
 
 /* Per-frame pose, LearnPose.forward (scene/pose_optimizer.py:822-877): r[1,4,N] raw quaternion
  * (w,x,y,z) and t[3,N] as the reference stores them; column `cam` -> Rt[4,4] row-major

@@ -107,7 +107,11 @@ def _image_gate(case, planes_gpu, planes_ref, planes_f32, band, stats):
     n_out32 = int((e32[~band] > 1.0).sum())
     assert n_out <= max(SOFT_FRACTION * HW, 2 * n_out32), \
         f"{case}: {n_out} non-fragile pixels above the gate (float32 oracle build: {n_out32})"
-    stats.update(band_fraction=float(band.float().mean()), pixels_above_gate=int(flipped.sum()),
+    # the gradient mask: pixels where the CUDA path OR the float32 oracle build differs from the float64 oracle by more
+    # than the gate (the union, so that the float32 floor of step 4 is measured on the same footing)
+    gpu_flipped = int(flipped.sum())
+    flipped = flipped | (e32 > 1.0)
+    stats.update(band_fraction=float(band.float().mean()), pixels_above_gate=gpu_flipped,
                  pixels_above_gate_outside_band=n_out, max_gates_outside_band=float(out_band.max()),
                  max_abs_err_rgb=float((planes_gpu[:3].double() - planes_ref[:3].detach()).abs().max()),
                  f32_oracle_pixels_above_gate=int((e32 > 1.0).sum()), f32_oracle_pixels_above_gate_outside_band=n_out32,
