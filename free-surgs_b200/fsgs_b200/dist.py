@@ -82,7 +82,7 @@ def allreduce_gaussian_grads(params: dict, group=None, bucket: bool = True) -> i
     return nbytes
 
 
-def enable_frame_parallel(group=None, check_cam_center: torch.Tensor = None) -> None:
+def enable_frame_parallel(group=None, check_cam_center: torch.Tensor = None, chunks: int = 4) -> None:
     """Fold the gradient exchange into the fused render's backward (the fast path; replaces a later call to
     ``allreduce_gaussian_grads``).  In Free-SurGS every SH-coefficient gradient of a Gaussian is
     ``basis_k(dir) * gc`` with ``gc`` the clamp-masked colour gradient, and neither ``dir = normalize(xyz -
@@ -91,7 +91,9 @@ def enable_frame_parallel(group=None, check_cam_center: torch.Tensor = None) -> 
     (xyz, opacity, scaling, rotation, gc: 56 B) instead of 59 (236 B) and expand the SH gradients locally from the
     reduced ``gc`` (``fsgs_sh_grad_expand``).  After ``loss.backward()`` every rank holds the summed gradients of all
     frames; pose gradients stay local.  ``check_cam_center``: if given, asserts that all ranks use the same SH view
-    origin (the precondition)."""
+    origin (the precondition).  ``chunks``: the per-Gaussian backward kernel runs in that many Gaussian ranges and
+    range k is all-reduced + expanded on a side stream while range k+1 is computed (1 = one collective after the
+    kernel, as in round 1)."""
     from . import frame_render
     if not _is_dist(group):
         frame_render.set_grad_reducer(None)
@@ -102,7 +104,7 @@ def enable_frame_parallel(group=None, check_cam_center: torch.Tensor = None) -> 
         dist.broadcast(ref, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         if not torch.equal(c, ref):
             raise ValueError("frame-parallel SH-gradient exchange needs the same cam_center (SH view origin) on every rank")
-    frame_render.set_grad_reducer(lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group))
+    frame_render.set_grad_reducer(lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group), chunks=chunks)
 
 
 def disable_frame_parallel() -> None:

@@ -30,11 +30,31 @@ _CAPTURED = []      # (image-state buffer, capacity, W, H) of every fused forwar
 
 # Frame-parallel gradient exchange hook (set through fsgs_b200.dist.enable_frame_parallel): a callable that
 # sum-all-reduces a flat float32 CUDA tensor in place, ordered on the current stream; None = single GPU.
-_GRAD_REDUCER = {"fn": None}
+_GRAD_REDUCER = {"fn": None, "chunks": 1}
+_XCHG_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
-def set_grad_reducer(fn) -> None:
+def set_grad_reducer(fn, chunks: int = 1) -> None:
+    """``fn(flat)`` must SUM a flat float32 CUDA tensor over the ranks in place, ordered on the current stream.
+    ``chunks`` > 1: the fused backward runs its per-Gaussian kernel in that many Gaussian ranges and hands each
+    range's 56-byte rows to ``fn`` on a side stream while the next range is computed (``fn`` is then called
+    ``chunks`` times per backward, each time under ``torch.cuda.stream(side)``)."""
     _GRAD_REDUCER["fn"] = fn
+    _GRAD_REDUCER["chunks"] = max(1, int(chunks))
+
+
+def _exchange_stream(dev) -> "torch.cuda.Stream":
+    s = _XCHG_STREAMS.get(dev.index)
+    if s is None:
+        s = _XCHG_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def _chunk_bounds(P: int, n: int):
+    """Split [0, P) into <= n ranges whose starts are multiples of 256 (CTA-aligned for both kernels)."""
+    step = -(-P // n)
+    step = -(-step // 256) * 256
+    return [(a, min(P, a + step)) for a in range(0, P, step)]
 
 
 class keep_geometry:
@@ -91,7 +111,7 @@ class _RenderFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, rs, cam_center,
-                active_sh_degree, gs_grad, cam_grad, max_radii2D=None, want_extras=False):
+                active_sh_degree, gs_grad, cam_grad, max_radii2D=None, want_extras=False, stats=None):
         _require_cuda(xyz)
         dev = xyz.device
         P = xyz.shape[0]
@@ -138,6 +158,17 @@ class _RenderFused(torch.autograd.Function):
         ctx.lease = arena.finish()             # scratch goes back to the workspace pool when this node dies
         ctx.st, ctx.P, ctx.num_rendered, ctx.num_rect, ctx.dev = st, P, int(nr.value), int(nrect.value), dev
         ctx.flags = (bool(gs_grad), bool(cam_grad))
+        # densification statistics folded into the backward (xyz_gradient_accum [P,1], denom [P,1]; both float32,
+        # contiguous, on this device): updated in place by k_preprocess_fused_bwd
+        ctx.stats = None
+        if stats is not None and P > 0:
+            acc, den = stats
+            ok = all(torch.is_tensor(x) and x.dtype == torch.float32 and x.is_contiguous() and x.device == dev
+                     and x.numel() == P for x in (acc, den))
+            if not ok:
+                raise ValueError("densification statistics must be float32 contiguous tensors with one entry per "
+                                 "Gaussian on the model's device")
+            ctx.stats = (acc, den)
         if capturing:
             _CAPTURED.append((arena.tensors["img"], int(nr.value), W, H))      # for GraphedStep.overflowed()
             del _CAPTURED[:-64]                                                 # (bounded, whoever does the capturing)
@@ -170,7 +201,7 @@ class _RenderFused(torch.autograd.Function):
         # ask the library for dL/dpose only -- it then runs its pose-only backward (no colour / opacity sums in the
         # compositor, no SH reads, no 236 B/Gaussian of gradient writes).
         need = ctx.needs_input_grad
-        if cam_grad and need[6] and not any(need[k] for k in (0, 1, 2, 3, 4, 5, 7)) and P > 0:
+        if cam_grad and need[6] and not any(need[k] for k in (0, 1, 2, 3, 4, 5, 7)) and P > 0 and ctx.stats is None:
             gp = [None if x is None else _f32(x, dev) for x in (g_rgb, g_depth, g_sil, g_dsq)]
             stream = torch.cuda.current_stream(dev).cuda_stream
             arena = _Arena(dev, stream)
@@ -183,7 +214,7 @@ class _RenderFused(torch.autograd.Function):
                     None, None, None, None, None, None, _ptr(g_pose), None, None, ctypes.c_void_p(stream))
             arena.finish().release()
             _lib.check(rc)
-            return (None, None, None, None, None, None, g_pose, None, None, None, None, None, None, None, None)
+            return (None, None, None, None, None, None, g_pose, None, None, None, None, None, None, None, None, None)
 
         def carve(flat, layout):
             off = 0
@@ -194,45 +225,75 @@ class _RenderFused(torch.autograd.Function):
                 g[name] = flat[off:off + n].view(*shape)
                 off += n
 
-        if reducer is None:
-            carve(z(P * 59), (("rotation", (P, 4)), ("f_rest", (P, 15, 3)), ("xyz", (P, 3)), ("f_dc", (P, 1, 3)),
-                             ("scaling", (P, 3)), ("opacity", (P, 1))))
-        else:
-            # frame-parallel mode (fsgs_b200.dist.enable_frame_parallel): the library emits the masked colour
-            # gradient gc[P,3] instead of the 48 SH-coefficient gradients; 14 floats/Gaussian are reduced over the
-            # ranks inside this backward and the SH gradients are expanded from the reduced gc afterwards
-            compact = z(P * 14)
-            carve(compact, (("rotation", (P, 4)), ("xyz", (P, 3)), ("scaling", (P, 3)), ("opacity", (P, 1)), ("gc", (P, 3))))
-            carve(z(P * 48), (("f_rest", (P, 15, 3)), ("f_dc", (P, 1, 3))))
+        carve(z(P * 59), (("rotation", (P, 4)), ("f_rest", (P, 15, 3)), ("xyz", (P, 3)), ("f_dc", (P, 1, 3)),
+                         ("scaling", (P, 3)), ("opacity", (P, 1))))
         g["pose"], g["means2D"] = z(4, 4), z(P, 3)
         if P == 0:
             g["pose"].zero_()
         if P > 0:
+            L = _lib.lib()
             gp = [None if x is None else _f32(x, dev) for x in (g_rgb, g_depth, g_sil, g_dsq)]
-            stream = torch.cuda.current_stream(dev).cuda_stream
+            main = torch.cuda.current_stream(dev)
+            stream = main.cuda_stream
             arena = _Arena(dev, stream)
-            scratch = arena.take("grad_scratch", _lib.lib().fsgs_grad_scratch_bytes(P))
-            with _on_device(dev):
-                rc = _lib.lib().fsgs_render_backward_ex(
-                    ctypes.byref(ctx.st), P, ctx.num_rendered, *[_ptr(x) for x in t], _ptr(geom), _ptr(binning),
-                    _ptr(img), *[None if x is None else _ptr(x) for x in gp], _ptr(scratch), int(gs_grad), int(cam_grad),
-                    _ptr(g["xyz"]), None if reducer else _ptr(g["f_dc"]), None if reducer else _ptr(g["f_rest"]),
-                    _ptr(g["opacity"]), _ptr(g["scaling"]), _ptr(g["rotation"]), _ptr(g["pose"]), _ptr(g["means2D"]),
-                    _ptr(g["gc"]) if reducer else None, ctypes.c_void_p(stream))
-            arena.finish().release()           # kernels are enqueued; reuse is ordered on this stream
-            _lib.check(rc)
-            if reducer is not None:
-                reducer(compact)               # SUM over the ranks, in place, ordered on this stream
+            scratch = arena.take("grad_scratch", L.fsgs_grad_scratch_bytes(P))
+            acc_p, den_p = (None, None) if ctx.stats is None else (ctx.stats[0].data_ptr(), ctx.stats[1].data_ptr())
+
+            def launch(opts, outs):
                 with _on_device(dev):
-                    rc = _lib.lib().fsgs_sh_grad_expand(ctypes.byref(ctx.st), P, _ptr(t[1]), _ptr(t[8]), _ptr(g["gc"]),
-                                                        _ptr(g["f_dc"]), _ptr(g["f_rest"]), ctypes.c_void_p(stream))
+                    rc = L.fsgs_render_backward_v2(
+                        ctypes.byref(ctx.st), P, ctx.num_rendered, *[_ptr(x) for x in t], _ptr(geom), _ptr(binning),
+                        _ptr(img), *[None if x is None else _ptr(x) for x in gp], _ptr(scratch), int(gs_grad),
+                        int(cam_grad), *outs, _ptr(g["pose"]), _ptr(g["means2D"]), None, ctypes.byref(opts),
+                        ctypes.c_void_p(stream))
                 _lib.check(rc)
+
+            if reducer is None:
+                launch(_lib.BackwardOpts(acc_p, den_p, None, 0, 0, 0, 0),
+                       (_ptr(g["xyz"]), _ptr(g["f_dc"]), _ptr(g["f_rest"]), _ptr(g["opacity"]), _ptr(g["scaling"]),
+                        _ptr(g["rotation"])))
+                arena.finish().release()           # kernels are enqueued; reuse is ordered on this stream
+            else:
+                # frame-parallel mode (fsgs_b200.dist.enable_frame_parallel): per Gaussian the library emits ONE 56-byte
+                # row -- rotation | xyz | scaling | opacity | clamp-masked colour gradient -- instead of the 59 gradient
+                # floats; the rows are summed over the ranks and fsgs_compact_grad_expand unpacks them and expands
+                # the SH-coefficient gradients from the summed colour gradient.  With chunks > 1 the per-Gaussian
+                # kernel runs range by range and range k is exchanged + expanded on a side stream while range k+1
+                # is computed on this one.
+                compact = z(P * 14)
+                bounds = _chunk_bounds(P, _GRAD_REDUCER["chunks"])
+                side = _exchange_stream(dev) if len(bounds) > 1 else None
+                none6 = (None,) * 6
+
+                def exchange(a, b, on_stream):
+                    reducer(compact[a * 14:b * 14])            # SUM over the ranks, in place, ordered on the current stream
+                    with _on_device(dev):
+                        rc = L.fsgs_compact_grad_expand(
+                            ctypes.byref(ctx.st), P, a, b - a, _ptr(t[1]), _ptr(t[8]), _ptr(compact), _ptr(g["xyz"]),
+                            _ptr(g["f_dc"]), _ptr(g["f_rest"]), _ptr(g["opacity"]), _ptr(g["scaling"]),
+                            _ptr(g["rotation"]), ctypes.c_void_p(on_stream))
+                    _lib.check(rc)
+
+                for k, (a, b) in enumerate(bounds):
+                    launch(_lib.BackwardOpts(acc_p, den_p, compact.data_ptr(), a, b - a, 1 if k else 0, 0), none6)
+                    if side is None:
+                        exchange(a, b, stream)
+                    else:
+                        ready = torch.cuda.Event()
+                        ready.record(main)
+                        with torch.cuda.stream(side):
+                            side.wait_event(ready)
+                            exchange(a, b, side.cuda_stream)
+                arena.finish().release()
+                if side is not None:
+                    main.wait_stream(side)             # every gradient tensor is complete before autograd hands it on
         return (g["xyz"], g["f_dc"], g["f_rest"], g["opacity"], g["scaling"], g["rotation"],
-                g["pose"] if cam_grad else None, g["means2D"], None, None, None, None, None, None, None)
+                g["pose"] if cam_grad else None, g["means2D"], None, None, None, None, None, None, None, None)
 
 
 def render_planes(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, raster_settings,
-                  cam_center, active_sh_degree, gs_grad=True, cam_grad=True, max_radii2D=None, want_extras=False):
+                  cam_center, active_sh_degree, gs_grad=True, cam_grad=True, max_radii2D=None, want_extras=False,
+                  densification_stats=None):
     """Tensor-level entry: -> ((rgb[3,H,W], depth[H,W], silhouette[H,W], depth_sq[H,W]), radii[P] int32,
     (instances, reference-rectangle instances)); the four images are views of one [6,H,W] buffer.
     With ``want_extras`` a 4th element: (uncertainty[1,H,W], presence_mask[H,W], nan_mask[1,H,W],
@@ -243,7 +304,7 @@ def render_planes(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pos
                and mr.device == xyz.device and mr.numel() == xyz.shape[0])
     rgb, depth, sil, dsq, radii, *extras = _RenderFused.apply(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D,
                                                 raster_settings, cam_center, active_sh_degree, gs_grad, cam_grad,
-                                                mr if fuse_mr else None, want_extras)
+                                                mr if fuse_mr else None, want_extras, densification_stats)
     if want_extras:
         return (rgb, depth, sil, dsq), radii, getattr(_TLS, "last_stats", (0, 0)), (*extras, fuse_mr)
     return (rgb, depth, sil, dsq), radii, getattr(_TLS, "last_stats", (0, 0))
@@ -282,6 +343,17 @@ def _pack(pc, viewmatrix_cur, im, depth_sil, radius, means2D):
             "viewspace_points": means2D, "visibility_filter": radius > 0, "radii": radius}
 
 
+def _folded_stats(pc, gs_grad):
+    """``pc.fold_densification_stats = True`` (opt-in; the reference's objects do not have the attribute): the
+    backward of this render adds ||dL/dmeans2D|| and 1 to ``pc.variables['xyz_gradient_accum']`` / ``['denom']`` for
+    every visible Gaussian -- GaussianModel.add_densification_stats(viewspace_points, visibility_filter)
+    (scene/gaussian_model.py:678-681, train.py:298-303) without the [P,3] gradient round trip.  A caller that
+    sets it must not call add_densification_stats for the same render as well."""
+    if not (gs_grad and getattr(pc, "fold_densification_stats", False)):
+        return None
+    return pc.variables['xyz_gradient_accum'], pc.variables['denom']
+
+
 def render(viewpoint_camera, index, pc, gs_grad=True, cam_grad=True):
     """Same signature, return dict and side effects as the reference's ``render``."""
     xyz = pc.params['_xyz']
@@ -300,7 +372,8 @@ def render(viewpoint_camera, index, pc, gs_grad=True, cam_grad=True):
     planes, radius, stats, extras = render_planes(
         xyz, pc.params['_features_dc'], pc.params['_features_rest'], pc.params['_opacity'], pc.params['_scaling'],
         pc.params['_rotation'], pose, means2D, pc.cam, viewpoint_camera.cam_center, pc.active_sh_degree,
-        gs_grad=gs_grad, cam_grad=cam_grad, max_radii2D=pc.variables.get('max_radii2D'), want_extras=True)
+        gs_grad=gs_grad, cam_grad=cam_grad, max_radii2D=pc.variables.get('max_radii2D'), want_extras=True,
+        densification_stats=_folded_stats(pc, gs_grad))
     out = _pack_fused(pc, viewmatrix_cur, planes, radius, means2D, extras)
     out["num_rendered"] = stats
     return out
