@@ -221,7 +221,7 @@ def run_ours(args):
     if world > 1 and args.exchange == "compact":
         # gradient exchange folded into the backward: 56 B/Gaussian (xyz, opacity, scaling, rotation + the masked
         # colour gradient) all-reduced, SH gradients expanded locally afterwards (fsgs_b200/dist.py)
-        fsgs_dist.enable_frame_parallel(check_cam_center=poses.cam_center)
+        fsgs_dist.enable_frame_parallel(check_cam_center=poses.cam_center, chunks=args.exchange_chunks)
     HW = W * H
     # per-step host inputs (the reference copies the GT image to the GPU every iteration, train.py:174)
     G_host = torch.empty(4, H, W).pin_memory()
@@ -474,6 +474,92 @@ def run_ours(args):
     for v in pc.params.values():
         v.requires_grad_(True)
 
+    # ---- one whole MAPPING iteration as train.py:236-265 runs it for one view: render(gs_grad=True, cam_grad=False),
+    # 5 * rgb_loss_func (L1 + SSIM) + 0.05 * pearson_depth_loss + 0.15 * local_pearson_loss(128, 0.5), backward to the
+    # Gaussian parameters, densification statistics.  "pytorch_losses" = the reference's formulations on top of our
+    # rasteriser; "fused_losses" = the library's loss kernels + the statistics folded into the backward.
+    mapping_iter = None
+    try:
+        if world > 1 or args.no_variants:
+            raise RuntimeError("single-GPU only (informational)")
+        from fsgs_b200 import densify as fsgs_densify
+        from fsgs_b200 import losses as fsgs_losses
+        target = torch.rand(3, H, W, generator=torch.Generator().manual_seed(5)).to(dev)
+        mono = (1.0 + 0.3 * torch.rand(H, W, generator=torch.Generator().manual_seed(6))).to(dev)
+
+        def make_map_iter(fused):
+            rgb = fsgs_losses.rgb_loss_func_fused if fused else fsgs_losses.rgb_loss_func
+            pear = fsgs_losses.pearson_depth_loss_fused if fused else fsgs_losses.pearson_depth_loss
+            lpear = fsgs_losses.local_pearson_loss_fused if fused else fsgs_losses.local_pearson_loss
+
+            def it():
+                pc.zero_grad()
+                pc.fold_densification_stats = fused
+                out = render.render(poses, 0, pc, gs_grad=True, cam_grad=False)
+                loss = rgb(out["render"], target) * 5.0 + pear(mono, out["render_dep"]) * 0.05 + \
+                    lpear(mono, out["render_dep"], 128, 0.5) * 0.15
+                loss.backward()
+                if not fused:
+                    fsgs_densify.add_densification_stats(pc.variables, out["viewspace_points"], out["visibility_filter"])
+            return it
+
+        def time_map(it):
+            for _ in range(3):
+                it()
+            barrier()
+            for k in range(args.steps):
+                flush.zero_()
+                tr[k][0].record(); it(); tr[k][1].record()
+            barrier()
+            return sum(a.elapsed_time(b) for a, b in tr) / args.steps
+
+        last["map_iter"] = make_map_iter(True)
+        mapping_iter = {"fused_losses": time_map(last["map_iter"]), "pytorch_losses": time_map(make_map_iter(False)),
+                        "what": "render(gs_grad=True, cam_grad=False) + 5 rgb_loss_func + 0.05 pearson_depth_loss + 0.15 "
+                                "local_pearson_loss(128, 0.5) + backward + densification statistics, issued from Python, "
+                                "device time per iteration"}
+        pc.fold_densification_stats = False
+    except Exception as exc:  # noqa: BLE001
+        mapping_iter = {"error": repr(exc)[:200]}
+
+    # ---- the same fused step at the other splat sizes / seeds of SURVEY.md 8d (informational; graph replay) ----
+    variants = None
+    if world == 1 and not args.no_variants and not args.no_graph:
+        from fsgs_b200 import GraphedStep as _GS
+        variants = {}
+        for m_v, seed_v in ((1.0, 0), (4.0, 0), (args.m, 1), (args.m, 2)):
+            try:
+                sc_v = make_scene(args.P, W, H, size_mult=m_v, seed=seed_v)
+                poses_v, pc_v = model.scene_to_device(sc_v, dev)
+                Gv = torch.cat([sc_v.grads_out["G_rgb"], sc_v.grads_out["G_dep"][None]]).to(dev)
+                info = {}
+
+                def body():
+                    pc_v.zero_grad()
+                    poses_v.pose_param_net.zero_grad(set_to_none=True)
+                    o = render.render(poses_v, 0, pc_v, gs_grad=True, cam_grad=True)
+                    ((o["render"] * Gv[:3]).sum() + (o["render_dep"] * Gv[3]).sum()).backward()
+                    info["nr"] = o["num_rendered"]
+                gs_v = _GS(body, warmup=3)
+                for _ in range(3):
+                    gs_v.replay()
+                nv = max(5, args.steps // 2)
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nv)]
+                torch.cuda.synchronize()
+                for a_, b_ in evs:
+                    flush.zero_()
+                    a_.record(); gs_v.replay(); b_.record()
+                torch.cuda.synchronize()
+                ms_v = sum(a_.elapsed_time(b_) for a_, b_ in evs) / nv
+                over = gs_v.overflowed()
+                gs_v.release()
+                variants[f"m={m_v:g} seed{seed_v}"] = {
+                    "ms_per_step": ms_v, "value": args.P / (ms_v * 1e-3), "tile_instances_reference_rect": int(info["nr"][1]),
+                    "overflowed": bool(over)}
+                del gs_v, poses_v, pc_v, Gv, sc_v
+            except Exception as exc:  # noqa: BLE001
+                variants[f"m={m_v:g} seed{seed_v}"] = {"error": repr(exc)[:200]}
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the un-fused drop-in path: what an unmodified gaussian_renderer.render executes on top of our
@@ -502,7 +588,17 @@ def run_ours(args):
     for _ in range(nprof):
         flush.zero_()
         step(G_dev)
-    prof = _lib.profile_collect()
+    if "map_iter" in last:                     # the loss kernels of a mapping iteration (fused L1+SSIM, Pearson, local Pearson)
+        prof_step = _lib.profile_collect()
+        _lib.profile_enable(True)
+        for _ in range(3):
+            flush.zero_()
+            last["map_iter"]()
+        pc.fold_densification_stats = False
+        prof_map = _lib.profile_collect()
+        prof = {k: (prof_step[k] if prof_step[k][1] else prof_map[k]) for k in prof_step}
+    else:
+        prof = _lib.profile_collect()
     _lib.profile_enable(False)
 
     # max over ranks
@@ -540,10 +636,21 @@ def run_ours(args):
                        "tile_instances": R_inst, "tile_instances_reference_rect": R_rect,
                        "parallelism": f"frame-dp{world}" + ("" if world == 1 else
                                                              "+nccl allreduce(grads, 236 B/Gaussian)" if args.exchange == "full"
-                                                             else "+nccl allreduce(compact grads, 56 B/Gaussian, in backward)")},
+                                                             else f"+nccl allreduce(56 B/Gaussian rows, {args.exchange_chunks} "
+                                                                  "Gaussian ranges overlapped with the per-Gaussian backward)"),
+                       # which integration level each number of this line belongs to
+                       "integration_levels": {
+                           "value / ms_per_step": f"level 2 (fused fsgs_b200.render) + the step captured once and replayed "
+                                                  f"(fsgs_b200.GraphedStep): {value_mode}",
+                           "ms_per_step_eager_issue": "level 2, every frame issued from Python",
+                           "api_two_pass_ms_per_step": "level 1 (unmodified gaussian_renderer.render: PyTorch pre-processing + two "
+                                                       "GaussianRasterizer calls), issued from Python",
+                           "ms_per_step_eager_issue_value": ms_eager, "api_two_pass_ms_per_step_value": ms_two_pass}},
             "pose_grad_ms_per_frame": ms_track,
             "pose_grad_ms_per_frame_frozen_model": ms_track_frozen,
             "tracking_iteration_ms": track_iter,
+            "mapping_iteration_ms": mapping_iter,
+            "variants": variants,
             "api_two_pass_ms_per_step": ms_two_pass,      # rank 0's; un-fused GaussianRasterizer drop-in path
             "ms_per_step_median": sorted(ms)[len(ms) // 2],
             "ms_per_step_p10_p90": [sorted(ms)[int(0.1 * (len(ms) - 1))], sorted(ms)[int(round(0.9 * (len(ms) - 1)))]],
@@ -573,7 +680,8 @@ def run_ours(args):
                             "cuda-graph: the frame (forward+loss+backward) is one fsgs_b200.GraphedStep replay; "
                             "ms_per_step_eager: the same loop issuing the frame from Python every step"},
             # pose fwd, 5 forward kernels, 2 backward kernels, pose bwd (+ the SH-gradient expansion when N > 1)
-            "gpu_launches": (9 + (1 if world > 1 and args.exchange == "compact" else 0)) * args.steps,
+            "gpu_launches": (9 + ((2 * len(render._chunk_bounds(args.P, args.exchange_chunks)) - 1)
+                                  if world > 1 and args.exchange == "compact" else 0)) * args.steps,
             "clocks": clocks,
         }
         print(json.dumps(out), flush=True)
@@ -602,6 +710,10 @@ def main():
     ap.add_argument("--P", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="e2e: issue every frame from Python (no CUDA-graph replay)")
+    ap.add_argument("--exchange-chunks", type=int, default=4,
+                    help="N>1, compact exchange: Gaussian ranges of the per-Gaussian backward kernel; range k is all-reduced "
+                         "on a side stream while range k+1 is computed (1 = one collective after the kernel)")
+    ap.add_argument("--no-variants", action="store_true", help="skip the m=1 / m=4 / seed 1,2 timings and the mapping iteration")
     ap.add_argument("--exchange", default="compact", choices=["compact", "full"],
                     help="N>1: gradient exchange -- compact (56 B/Gaussian inside the backward) or full (236 B/Gaussian after it)")
     args = ap.parse_args()

@@ -349,4 +349,90 @@ k_pearson_bwd(long long n, const float *__restrict__ x, const float *__restrict_
     }
 }
 
+// ---- local Pearson loss (reference utils/loss_utils.py:112-127) ------------------------------------------------
+//   n random box x box patches (top-left corners (x0[i], y0[i]) = (row, column), drawn by the caller exactly as the
+//   reference draws them); loss = (1/n) sum_i pearson_depth_loss(src[patch_i], target[patch_i]).
+// The reference loops over the patches in Python, slicing with device-tensor indices (2 host syncs per patch, ~25
+// launches each).  Here: one launch accumulates the five raw sums of every patch (LP_BLOCKS CTAs per patch, double),
+// one small launch turns them into per-patch statistics + the loss, and the backward is one launch whose threads
+// add the per-patch Pearson derivative into the (overlapping) patches with float atomics.
+constexpr int LP_BLOCKS = 8;
+
+__global__ void __launch_bounds__(CTA)
+k_local_pearson_sums(int W, int box, const long long *__restrict__ x0, const long long *__restrict__ y0,
+                     const float *__restrict__ x, const float *__restrict__ y, double *__restrict__ partial) {
+    __shared__ double s_red[5][CTA / 32];
+    const int patch = blockIdx.y;
+    const long long r0 = x0[patch], c0 = y0[patch];
+    const int n = box * box;
+    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int e = blockIdx.x * CTA + threadIdx.x; e < n; e += LP_BLOCKS * CTA) {
+        const size_t p = (size_t)(r0 + e / box) * W + (size_t)(c0 + e % box);
+        const double xv = (double)x[p], yv = (double)y[p];
+        a[0] += xv; a[1] += yv; a[2] += xv * xv; a[3] += yv * yv; a[4] += xv * yv;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) a[k] += __shfl_xor_sync(FULL, a[k], d);
+        if ((threadIdx.x & 31) == 0) s_red[k][threadIdx.x >> 5] = a[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0.0;
+        for (int w = 0; w < CTA / 32; ++w) t += s_red[threadIdx.x][w];
+        partial[5 * ((size_t)patch * LP_BLOCKS + blockIdx.x) + threadIdx.x] = t;
+    }
+}
+
+// stats[i] = (mean x, mean y, sqrt var x, sqrt var y, c, n) per patch; out = mean over the patches of 1 - corr_i
+__global__ void __launch_bounds__(CTA)
+k_local_pearson_finish(int n_patches, int box, const double *__restrict__ partial, double *__restrict__ stats,
+                       float *__restrict__ out) {
+    __shared__ double s_loss[CTA];
+    double local = 0.0;
+    for (int i = threadIdx.x; i < n_patches; i += CTA) {
+        double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int b = 0; b < LP_BLOCKS; ++b)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) a[k] += partial[5 * ((size_t)i * LP_BLOCKS + b) + k];
+        const double N = (double)box * box, mx = a[0] / N, my = a[1] / N;
+        const double den = N > 1.0 ? N - 1.0 : 1.0;
+        const double vx = fmax(a[2] - N * mx * mx, 0.0) / den, vy = fmax(a[3] - N * my * my, 0.0) / den;
+        const double qx = sqrt(vx), qy = sqrt(vy), c = a[4] - N * mx * my;
+        double *st = stats + 6 * (size_t)i;
+        st[0] = mx; st[1] = my; st[2] = qx; st[3] = qy; st[4] = c; st[5] = N;
+        local += 1.0 - c / (N * (qx + 1e-6) * (qy + 1e-6));
+    }
+    s_loss[threadIdx.x] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < CTA; ++k) t += s_loss[k];          // fixed order
+        out[0] = (float)(t / (double)n_patches);
+    }
+}
+
+__global__ void __launch_bounds__(CTA)
+k_local_pearson_bwd(int W, int box, int n_patches, const long long *__restrict__ x0, const long long *__restrict__ y0,
+                    const float *__restrict__ x, const float *__restrict__ y, const double *__restrict__ stats,
+                    const float *__restrict__ upstream, float *__restrict__ dx, float *__restrict__ dy) {
+    const int patch = blockIdx.y;
+    const double *st = stats + 6 * (size_t)patch;
+    const double mx = st[0], my = st[1], qx = st[2], qy = st[3], c = st[4], N = st[5];
+    const double sx = qx + 1e-6, sy = qy + 1e-6, den = N > 1.0 ? N - 1.0 : 1.0;
+    const double up = (upstream ? (double)__ldg(upstream) : 1.0) / (double)n_patches;
+    const float k1 = (float)(up / (N * sx * sy));
+    const float ky = qy > 0.0 ? (float)(up * c / (N * sx * sy * sy * den * qy)) : 0.f;
+    const float kx = qx > 0.0 ? (float)(up * c / (N * sx * sx * sy * den * qx)) : 0.f;
+    const long long r0 = x0[patch], c0 = y0[patch];
+    const int n = box * box;
+    for (int e = blockIdx.x * CTA + threadIdx.x; e < n; e += LP_BLOCKS * CTA) {
+        const size_t p = (size_t)(r0 + e / box) * W + (size_t)(c0 + e % box);
+        const float xc = (float)((double)x[p] - mx), yc = (float)((double)y[p] - my);
+        if (dy) atomicAdd(dy + p, -(k1 * xc - ky * yc));
+        if (dx) atomicAdd(dx + p, -(k1 * yc - kx * xc));
+    }
+}
+
 }  // namespace fsgs

@@ -74,7 +74,8 @@ inline int blocks(int n) { return (n + CTA - 1) / CTA; }
 // Off by default.  bench.py switches it on for a separate profiling pass (never for the timed
 // steps) to obtain the per-launch duration of each kernel for the roofline line.
 enum KernelId { K_PRE_API = 0, K_PRE_FUSED, K_SCAN, K_SCATTER, K_SORT, K_COMP_FWD, K_COMP_BWD, K_PRE_API_BWD,
-                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_PRE_POSE_BWD, K_LOSS_FWD, K_LOSS_BWD, K_PEARSON_FWD, K_PEARSON_BWD, K_COUNT };
+                K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_PRE_POSE_BWD, K_LOSS_FWD, K_LOSS_BWD, K_PEARSON_FWD, K_PEARSON_BWD,
+                K_LOCAL_PEARSON_FWD, K_LOCAL_PEARSON_BWD, K_COUNT };
 struct Profiler {
     bool on = false;
     static constexpr int MAXREC = 8192;
@@ -363,7 +364,8 @@ const char *fsgs_error_string(int code) {
 const char *fsgs_kernel_names(void) {
     return "k_preprocess_api,k_preprocess_fused,k_tile_scan,k_scatter,k_tile_sort,k_composite_fwd,"
            "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible,k_pose_forward,k_pose_backward,"
-           "k_sh_grad_expand,k_preprocess_pose_bwd,k_rgb_loss_fwd,k_rgb_loss_bwd,k_pearson_sums,k_pearson_bwd";
+           "k_sh_grad_expand,k_preprocess_pose_bwd,k_rgb_loss_fwd,k_rgb_loss_bwd,k_pearson_sums,k_pearson_bwd,"
+           "k_local_pearson_sums,k_local_pearson_bwd";
 }
 
 size_t fsgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
@@ -845,6 +847,56 @@ int fsgs_pearson_backward(int64_t n, const float *src, const float *target, cons
     prof_begin(K_PEARSON_BWD, stream);
     k_pearson_bwd<<<pearson_blocks(n), CTA, 0, stream>>>((long long)n, src, target, stats, upstream, dsrc, dtarget);
     prof_end(K_PEARSON_BWD, stream);
+    FSGS_CUDA(cudaGetLastError());
+    return FSGS_OK;
+}
+
+// ---- fused local Pearson loss ------------------------------------------------------------------------------
+size_t fsgs_local_pearson_scratch_bytes(int32_t n_patches) {
+    return align_up((size_t)(n_patches > 0 ? n_patches : 1) * LP_BLOCKS * 5 * sizeof(double), 256);
+}
+
+static int local_pearson_args_ok(int32_t H, int32_t W, int32_t box, int32_t n, const void *x0, const void *y0,
+                                 const float *src, const float *target) {
+    if (H <= 0 || W <= 0 || box <= 0 || box > H || box > W || n <= 0 || n > 65535 || !x0 || !y0 || !src || !target)
+        return FSGS_E_INVALID;
+    return FSGS_OK;
+}
+
+int fsgs_local_pearson_forward(int32_t H, int32_t W, int32_t box, int32_t n_patches, const int64_t *x0, const int64_t *y0,
+                               const float *src, const float *target, void *scratch, double *stats, float *out,
+                               void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = local_pearson_args_ok(H, W, box, n_patches, x0, y0, src, target);
+    if (rc) return rc;
+    if (!scratch || !stats || !out) return FSGS_E_INVALID;
+    if ((rc = check_arch())) return rc;
+    prof_begin(K_LOCAL_PEARSON_FWD, stream);
+    k_local_pearson_sums<<<dim3(LP_BLOCKS, n_patches), CTA, 0, stream>>>(
+        W, box, reinterpret_cast<const long long *>(x0), reinterpret_cast<const long long *>(y0), src, target,
+        static_cast<double *>(scratch));
+    k_local_pearson_finish<<<1, CTA, 0, stream>>>(n_patches, box, static_cast<const double *>(scratch), stats, out);
+    prof_end(K_LOCAL_PEARSON_FWD, stream);
+    FSGS_CUDA(cudaGetLastError());
+    return FSGS_OK;
+}
+
+int fsgs_local_pearson_backward(int32_t H, int32_t W, int32_t box, int32_t n_patches, const int64_t *x0, const int64_t *y0,
+                                const float *src, const float *target, const double *stats, const float *upstream,
+                                float *dsrc, float *dtarget, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int rc = local_pearson_args_ok(H, W, box, n_patches, x0, y0, src, target);
+    if (rc) return rc;
+    if (!stats || (!dsrc && !dtarget)) return FSGS_E_INVALID;
+    if ((rc = check_arch())) return rc;
+    const size_t bytes = (size_t)H * W * sizeof(float);
+    if (dsrc) FSGS_CUDA(cudaMemsetAsync(dsrc, 0, bytes, stream));
+    if (dtarget) FSGS_CUDA(cudaMemsetAsync(dtarget, 0, bytes, stream));
+    prof_begin(K_LOCAL_PEARSON_BWD, stream);
+    k_local_pearson_bwd<<<dim3(LP_BLOCKS, n_patches), CTA, 0, stream>>>(
+        W, box, n_patches, reinterpret_cast<const long long *>(x0), reinterpret_cast<const long long *>(y0), src, target,
+        stats, upstream, dsrc, dtarget);
+    prof_end(K_LOCAL_PEARSON_BWD, stream);
     FSGS_CUDA(cudaGetLastError());
     return FSGS_OK;
 }

@@ -92,6 +92,9 @@ _SIGNATURES = {
     "fsgs_pearson_scratch_bytes": (ctypes.c_size_t, []),
     "fsgs_pearson_forward": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "fsgs_pearson_backward": (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "fsgs_local_pearson_scratch_bytes": (ctypes.c_size_t, [_i32]),
+    "fsgs_local_pearson_forward": (ctypes.c_int, [_i32, _i32, _i32, _i32] + [_vp] * 8),
+    "fsgs_local_pearson_backward": (ctypes.c_int, [_i32, _i32, _i32, _i32] + [_vp] * 9),
     "fsgs_rgb_loss_backward": (ctypes.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, ctypes.c_float, _vp, _vp, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

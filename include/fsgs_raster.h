@@ -328,6 +328,20 @@ int fsgs_pearson_forward(int64_t n, const float *src, const float *target, void 
 int fsgs_pearson_backward(int64_t n, const float *src, const float *target, const double *stats, const float *upstream,
                           float *dsrc, float *dtarget, void *stream);
 
+/* local_pearson_loss (utils/loss_utils.py:112-127; train.py:257 calls it with box 128, p_corr 0.5 on every mapping
+ * view): the mean over n_patches box x box patches of pearson_depth_loss(src[patch], target[patch]).  x0 / y0
+ * [n_patches] (int64, device): top-left ROW / COLUMN of each patch -- drawn by the caller with the reference's two
+ * torch.randint calls so that the patches are the reference's.  src / target [H,W]; scratch of
+ * fsgs_local_pearson_scratch_bytes(n_patches) bytes; stats [6 * n_patches] doubles (kept for the backward); out [1].
+ * The backward zero-fills and accumulates dsrc / dtarget [H,W] (either may be NULL); upstream [1] or NULL (= 1). */
+size_t fsgs_local_pearson_scratch_bytes(int32_t n_patches);
+int fsgs_local_pearson_forward(int32_t H, int32_t W, int32_t box, int32_t n_patches, const int64_t *x0,
+                               const int64_t *y0, const float *src, const float *target, void *scratch,
+                               double *stats, float *out, void *stream);
+int fsgs_local_pearson_backward(int32_t H, int32_t W, int32_t box, int32_t n_patches, const int64_t *x0,
+                                const int64_t *y0, const float *src, const float *target, const double *stats,
+                                const float *upstream, float *dsrc, float *dtarget, void *stream);
+
 /* Optional per-kernel timing with CUDA events on the launching stream (single-threaded use; off
  * by default).  fsgs_profile_collect synchronises the device and returns, per kernel in the
  * order of fsgs_kernel_names(), the summed duration in ms and the launch count since enable. */
