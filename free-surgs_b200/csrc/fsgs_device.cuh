@@ -163,6 +163,46 @@ __device__ __forceinline__ void stage_rows_issue(float *s_dst, const float *__re
     }
     for (int q = rows_tma * ROW_FLOATS + threadIdx.x; q < count * ROW_FLOATS; q += blockDim.x) s_dst[q] = __ldg(g + q);
 }
+// Several arrays staged behind ONE mbarrier (the per-Gaussian kernels stage every SoA attribute of their CTA's
+// Gaussians this way: xyz | scaling | f_dc | opacity | rotation | f_rest = six contiguous slices, six bulk copies,
+// one wait).  Call stage_multi_begin once (thread 0 initialises the barrier), stage_multi_add per array (thread 0
+// issues the 16-byte-multiple prefix, all threads load the remainder), stage_multi_wait once.
+struct StageMulti {
+    uint64_t *bar;
+    uint32_t bytes;     // thread 0: bytes expected so far
+};
+__device__ __forceinline__ StageMulti stage_multi_begin(uint64_t *bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    return StageMulti{bar, 0u};
+}
+template <int ROW_FLOATS>
+__device__ __forceinline__ void stage_multi_add(StageMulti &sm, float *s_dst, const float *__restrict__ src, int base,
+                                                int count) {
+    // rows whose byte length is a multiple of 16 from a 16-byte aligned start: count rounded down to a multiple of 4
+    const int rows_tma = count & ~3;
+    const float *g = src + (size_t)base * ROW_FLOATS;
+    if (threadIdx.x == 0 && rows_tma > 0) {
+        const uint32_t bytes = (uint32_t)rows_tma * ROW_FLOATS * 4u;
+        sm.bytes += bytes;
+        // (expect_tx may be raised in several steps before the single arrive: use the no-arrive form)
+        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(sm.bar)), "r"(bytes) : "memory");
+        tma_load_1d(s_dst, g, bytes, sm.bar);
+    }
+    for (int q = rows_tma * ROW_FLOATS + threadIdx.x; q < count * ROW_FLOATS; q += blockDim.x) s_dst[q] = __ldg(g + q);
+}
+__device__ __forceinline__ void stage_multi_wait(StageMulti &sm, unsigned long long *err) {
+    if (threadIdx.x == 0) {
+        uint64_t st;
+        asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(smem_u32(sm.bar)) : "memory");
+        (void)st;
+    }
+    __syncthreads();                 // barrier initialised + arrived, remainders visible
+    mbar_wait(sm.bar, 0u, err);
+}
+
 __device__ __forceinline__ void stage_rows_wait(int count, uint64_t *bar, unsigned long long *err) {
     __syncthreads();
     if ((count & ~3) > 0) mbar_wait(bar, 0u, err);

@@ -193,33 +193,55 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
     // CTA: one bulk TMA copy stages them; threads then read their own 45 floats at a conflict-free
     // stride.  FSGS_FLAG_NO_TMA (or a mis-aligned tensor) reads them straight from global memory.
     __shared__ __align__(128) float s_rest[PRE_CTA * 45];
+    __shared__ __align__(16) float s_xyz[PRE_CTA * 3], s_sc[PRE_CTA * 3], s_dc[PRE_CTA * 3], s_rot[PRE_CTA * 4], s_op[PRE_CTA];
     __shared__ __align__(8) uint64_t s_bar;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int base = blockIdx.x * blockDim.x;
-    const bool staged = (flags & 1u) == 0 && (reinterpret_cast<uintptr_t>(f_rest) & 15u) == 0;
+    // All six SoA attribute arrays of the CTA's Gaussians (236 B each) are contiguous slices: six bulk-TMA copies
+    // behind one mbarrier bring them into shared memory (16-byte vectorised, fully coalesced, no per-thread
+    // stride-3 scalar loads); threads then read their own rows at conflict-free strides (3, 4, 45 words).
+    const bool aligned = ((reinterpret_cast<uintptr_t>(f_rest) | reinterpret_cast<uintptr_t>(xyz) |
+                           reinterpret_cast<uintptr_t>(scaling_raw) | reinterpret_cast<uintptr_t>(f_dc) |
+                           reinterpret_cast<uintptr_t>(rotation_raw) | reinterpret_cast<uintptr_t>(opacity_raw)) & 15u) == 0;
+    const bool staged = (flags & 1u) == 0 && aligned;
     const int count = min((int)blockDim.x, P - base);
-    if (staged) stage_rows_issue<45>(s_rest, f_rest, base, count, &s_bar);
+    if (staged) {
+        StageMulti sm = stage_multi_begin(&s_bar);
+        stage_multi_add<3>(sm, s_xyz, xyz, base, count);
+        stage_multi_add<3>(sm, s_sc, scaling_raw, base, count);
+        stage_multi_add<4>(sm, s_rot, rotation_raw, base, count);
+        stage_multi_add<3>(sm, s_dc, f_dc, base, count);
+        stage_multi_add<1>(sm, s_op, opacity_raw, base, count);
+        stage_multi_add<45>(sm, s_rest, f_rest, base, count);
+        stage_multi_wait(sm, err);
+    }
     const int lane = threadIdx.x & 31;
     unsigned int rect_tiles = 0;
     Splat sp;
     sp.px = sp.py = sp.conx = sp.cony = sp.conz = 0.f; sp.radius = 0;
     float opacity = 0.f;
     bool vis = false;
-    // this thread's own 56 B go in flight while the bulk copy of the SH rows is under way (ncu: the wait for the
-    // copy and the first use of these loads were two serialised DRAM latencies, 20 % of the kernel's stall samples;
-    // 0.061 -> 0.056 ms)
     float w[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, dcv[3] = {0.f, 0.f, 0.f};
     float op_raw = 0.f;
     if (i < P) {
-        const size_t n = (size_t)i;
-        w[0] = xyz[3 * n]; w[1] = xyz[3 * n + 1]; w[2] = xyz[3 * n + 2];
-        sc[0] = scaling_raw[3 * n]; sc[1] = scaling_raw[3 * n + 1]; sc[2] = scaling_raw[3 * n + 2];
-        const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
-        q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
-        dcv[0] = f_dc[3 * n]; dcv[1] = f_dc[3 * n + 1]; dcv[2] = f_dc[3 * n + 2];
-        op_raw = opacity_raw[i];
+        if (staged) {
+            const int tl = threadIdx.x;
+            w[0] = s_xyz[3 * tl]; w[1] = s_xyz[3 * tl + 1]; w[2] = s_xyz[3 * tl + 2];
+            sc[0] = s_sc[3 * tl]; sc[1] = s_sc[3 * tl + 1]; sc[2] = s_sc[3 * tl + 2];
+            const float4 q4 = *reinterpret_cast<const float4 *>(s_rot + 4 * tl);
+            q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+            dcv[0] = s_dc[3 * tl]; dcv[1] = s_dc[3 * tl + 1]; dcv[2] = s_dc[3 * tl + 2];
+            op_raw = s_op[tl];
+        } else {
+            const size_t n = (size_t)i;
+            w[0] = xyz[3 * n]; w[1] = xyz[3 * n + 1]; w[2] = xyz[3 * n + 2];
+            sc[0] = scaling_raw[3 * n]; sc[1] = scaling_raw[3 * n + 1]; sc[2] = scaling_raw[3 * n + 2];
+            const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
+            q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+            dcv[0] = f_dc[3 * n]; dcv[1] = f_dc[3 * n + 1]; dcv[2] = f_dc[3 * n + 2];
+            op_raw = opacity_raw[i];
+        }
     }
-    if (staged) stage_rows_wait(count, &s_bar, err);
     if (i < P) {
         float V[16], PM[16], Rt[12], cp[3];
         load16(viewmatrix, V);

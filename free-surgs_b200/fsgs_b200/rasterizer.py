@@ -244,14 +244,16 @@ def rasterize_gaussians(bg, means3D, colors_precomp, opacities, scales, rotation
     # (Tagging the pooled tensors themselves would close a cycle tensor -> lease -> tensor that only the cyclic
     # GC can break -- the buffers then come back late and every frame allocates ~400 MB of fresh scratch.)
     bufs = [arena.tensors[k][:] if k in arena.tensors else empty for k in ("geom", "binning", "img")]
-    rasterize_gaussians.last_num_rect = int(nrect.value)
+    _CALL_TLS.last_num_rect = int(nrect.value)        # per thread: the viewer thread rasterises too (train.py:124-152)
     lease = arena.finish()
     for b in bufs:
         b._fsgs_lease = lease
     return int(nr.value), color, depth, radii, bufs[0], bufs[1], bufs[2]
 
 
-rasterize_gaussians.last_num_rect = 0
+import threading as _threading
+
+_CALL_TLS = _threading.local()
 
 
 def rasterize_gaussians_backward(bg, means3D, radii, colors_precomp, scales, rotations, scale_modifier, cov3D_precomp,
@@ -319,7 +321,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.raster_settings = rs
         ctx.lease = getattr(geomBuffer, "_fsgs_lease", None)
         ctx.num_rendered = num_rendered
-        ctx.num_rect = rasterize_gaussians.last_num_rect
+        ctx.num_rect = getattr(_CALL_TLS, "last_num_rect", 0)
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, opacities,
                               geomBuffer, binningBuffer, imgBuffer)
         ctx.mark_non_differentiable(radii)

@@ -50,9 +50,12 @@ def test_unmodified_train_py_on_the_library_vs_the_oracle_backed_boundary(tmp_pa
     for b, r in res.items():
         assert r["config3"] == "ok" and r["n_frames"] == 6, r
         assert len(r["checkpoints"]) >= 2, r            # chkpnt*.pth + poses*.pth written by the reference's own code
+        # the viewer path: render_fn -> setup_camera(I, visualize_data) -> render_custom at 2048x1200 from a second
+        # thread while the main thread runs mapping iterations (train.py:124-152)
+        assert r["viewer"]["ok"] and r["viewer"]["frames"] == 3, r["viewer"]
         report(f"config3 unmodified train.py, backend {b}", **{k: r[k] for k in (
             "psnr_test", "ssim_test", "psnr_train", "ssim_train", "ate", "rpe_trans", "rpe_rot_deg", "n_gaussians",
-            "iterations_run", "wall_s")})
+            "iterations_run", "wall_s", "viewer")})
     o = res["oracle"]
     for b in ("fsgs", "fsgs-fused"):
         r = res[b]

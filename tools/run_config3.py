@@ -145,10 +145,49 @@ def evaluate(g):
             pred_w2c = torch.from_numpy(slam.poses.record_data['pred_w2c'])[data_ind[i]:data_ind[i + 1]]
             _, m = align_pose(pred_w2c, gt_poses)
             metrics += np.array(m) * slam.poses.record_data['weights'][i]
-    return {"psnr_test": float(psnr), "ssim_test": float(ssim), "psnr_train": float(psnr_tr), "ssim_train": float(ssim_tr),
+    viewer = viewer_check(g)
+    return {"viewer": viewer,
+            "psnr_test": float(psnr), "ssim_test": float(ssim), "psnr_train": float(psnr_tr), "ssim_train": float(ssim_tr),
             "rpe_trans": float(metrics[0]), "rpe_rot_deg": float(metrics[1]), "ate": float(metrics[2]),
             "n_gaussians": int(slam.gaussians.params['_xyz'].shape[0]), "n_frames": int(slam.poses.num_cams),
             "iterations_run": int(slam.iteration)}
+
+
+def viewer_check(g, n_frames=3):
+    """The reference's viewer path (train.py:124-152): ``FreeSurGS.render_fn`` builds a 2048x1200 camera with
+    ``setup_camera(I, visualize_data)`` and calls ``render_custom`` (gaussian_renderer/__init__.py:112-135) from the
+    nerfview THREAD while the training thread keeps rendering.  Here: a second Python thread calls the unmodified
+    ``render_fn`` ``n_frames`` times while this thread runs mapping iterations on the same model."""
+    import threading
+    import types
+    import numpy as np
+    import torch
+    slam = g["slam"]
+    res = {"frames": 0, "errors": []}
+
+    def worker():
+        try:
+            for k in range(n_frames):
+                c2w = np.eye(4)
+                c2w[:3, 3] = [0.01 * k, 0.0, 0.0]
+                state = types.SimpleNamespace(fov=np.float64(0.9), c2w=c2w)
+                img = slam.render_fn(state, (2048, 1200))
+                assert img.shape == (1200, 2048, 3) and img.dtype == np.uint8, (img.shape, img.dtype)
+                res["frames"] += 1
+                res["mean_intensity"] = float(img.mean())
+        except Exception as exc:  # noqa: BLE001
+            res["errors"].append(repr(exc)[:300])
+
+    th = threading.Thread(target=worker)
+    th.start()
+    with contextlib.redirect_stdout(io.StringIO()):
+        slam.mapping(int(slam.poses.i_train[-1]), mapping_iter=3, progressive=False)
+    th.join(timeout=300)
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    res["ok"] = res["frames"] == n_frames and not res["errors"]
+    res["size"] = "2048x1200"
+    return res
 
 
 def main():

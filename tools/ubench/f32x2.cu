@@ -43,10 +43,27 @@ __global__ void k(float *out, float a, float b) {
             } else if (MODE == 6) {   // 4 FFMA + 4 FSEL-ish (alu pipe: FMNMX)
                 x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
                 x4 = fminf(x4, x0); x5 = fminf(x5, x1); x6 = fminf(x6, x2); x7 = fminf(x7, x3);
-            } else if (MODE == 7) {   // 2 FFMA2 + 4 FMNMX
+            } else if (MODE == 7) {   // 2 FFMA2 + 4 FMNMX (operands taken from the packed results: nothing to hoist or merge)
                 asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p0) : "l"(pa), "l"(pb));
                 asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p1) : "l"(pa), "l"(pb));
-                x4 = fminf(x4, a); x5 = fminf(x5, b); x6 = fminf(x6, a); x7 = fminf(x7, b);
+                float u0, u1, u2, u3;
+                asm volatile("mov.b64 {%0,%1}, %2;" : "=f"(u0), "=f"(u1) : "l"(p0));
+                asm volatile("mov.b64 {%0,%1}, %2;" : "=f"(u2), "=f"(u3) : "l"(p1));
+                x4 = fminf(x4, u0); x5 = fmaxf(x5, u1); x6 = fminf(x6, u2); x7 = fmaxf(x7, u3);
+            } else if (MODE == 10) {  // 2 FFMA2 + 2 FSETP/FSEL pairs + 2 MUFU.EX2 (the compositor's mix)
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p0) : "l"(pa), "l"(pb));
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p1) : "l"(pa), "l"(pb));
+                float u0, u1, u2, u3;
+                asm volatile("mov.b64 {%0,%1}, %2;" : "=f"(u0), "=f"(u1) : "l"(p0));
+                asm volatile("mov.b64 {%0,%1}, %2;" : "=f"(u2), "=f"(u3) : "l"(p1));
+                x4 = (u0 > x5) ? u1 : x4; x5 = (u2 > x4) ? u3 : x5;
+                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(x6) : "f"(u0 + x6));
+                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(x7) : "f"(u2 + x7));
+            } else if (MODE == 11) {  // the same work with scalar FFMA: 4 FFMA + 2 select pairs + 2 adds + 2 MUFU.EX2
+                x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+                x4 = (x0 > x5) ? x1 : x4; x5 = (x2 > x4) ? x3 : x5;
+                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(x6) : "f"(x0 + x6));
+                asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(x7) : "f"(x2 + x7));
             } else if (MODE == 8) {   // 8 SHFL
                 x0 = __shfl_xor_sync(~0u, x0, 1); x1 = __shfl_xor_sync(~0u, x1, 2); x2 = __shfl_xor_sync(~0u, x2, 4);
                 x3 = __shfl_xor_sync(~0u, x3, 8); x4 = __shfl_xor_sync(~0u, x4, 16); x5 = __shfl_xor_sync(~0u, x5, 1);
@@ -94,6 +111,8 @@ int main() {
     run<5>("4x FADD2", 4);
     run<6>("4 FFMA + 4 FMNMX", 8);
     run<7>("2 FFMA2 + 4 FMNMX", 6);
+    run<10>("2 FFMA2 + 2 sel + 2 add + 2 EX2", 10);
+    run<11>("4 FFMA  + 2 sel + 2 add + 2 EX2", 12);
     run<8>("8x SHFL", 8);
     run<9>("4 SHFL + 4 FFMA", 8);
     return 0;
