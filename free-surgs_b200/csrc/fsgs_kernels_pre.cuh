@@ -178,6 +178,15 @@ k_preprocess_api(CamConst cc, int P, const float *__restrict__ means3D, const fl
 #ifndef FSGS_PRE_CTA
 #define FSGS_PRE_CTA 128
 #endif
+// 1: all six SoA attribute arrays of the CTA's Gaussians through bulk-TMA staging (16-byte vectorised, no stride-3
+// scalar loads); 0: only the SH rows (76 % of the bytes) are staged and every thread puts its own 56 B of loads in
+// flight while that copy is under way.  A/B on B200 (round 2, tools/ab_variants.py, P = 500k / 2M):
+//   staged-all, 128 threads 0.0605 / 0.1435 ms   staged-all, 64 threads 0.0584 / 0.1411 ms   SH rows only 0.0548 / 0.1366 ms
+// -- the per-thread loads are already sector-efficient (a warp's stride-3 loads cover 384 contiguous bytes) and
+// overlapping them with the bulk copy beats waiting for six copies behind one barrier.  Default 0.
+#ifndef FSGS_PRE_STAGE_ALL
+#define FSGS_PRE_STAGE_ALL 0
+#endif
 constexpr int PRE_CTA = FSGS_PRE_CTA;   // A/B on B200: 256 -> 0.063 / 0.157 ms, 128 -> 0.060 / 0.150, 64 -> 0.061 / 0.150 (500k / 2M)
 __global__ void __launch_bounds__(PRE_CTA, 1024 / PRE_CTA)
 k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const float *__restrict__ f_dc,
@@ -205,15 +214,19 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
                            reinterpret_cast<uintptr_t>(rotation_raw) | reinterpret_cast<uintptr_t>(opacity_raw)) & 15u) == 0;
     const bool staged = (flags & 1u) == 0 && aligned;
     const int count = min((int)blockDim.x, P - base);
+    constexpr bool ALL = FSGS_PRE_STAGE_ALL != 0;
+    StageMulti sm{&s_bar, 0u};
     if (staged) {
-        StageMulti sm = stage_multi_begin(&s_bar);
-        stage_multi_add<3>(sm, s_xyz, xyz, base, count);
-        stage_multi_add<3>(sm, s_sc, scaling_raw, base, count);
-        stage_multi_add<4>(sm, s_rot, rotation_raw, base, count);
-        stage_multi_add<3>(sm, s_dc, f_dc, base, count);
-        stage_multi_add<1>(sm, s_op, opacity_raw, base, count);
+        sm = stage_multi_begin(&s_bar);
+        if (ALL) {
+            stage_multi_add<3>(sm, s_xyz, xyz, base, count);
+            stage_multi_add<3>(sm, s_sc, scaling_raw, base, count);
+            stage_multi_add<4>(sm, s_rot, rotation_raw, base, count);
+            stage_multi_add<3>(sm, s_dc, f_dc, base, count);
+            stage_multi_add<1>(sm, s_op, opacity_raw, base, count);
+        }
         stage_multi_add<45>(sm, s_rest, f_rest, base, count);
-        stage_multi_wait(sm, err);
+        if (ALL) stage_multi_wait(sm, err);
     }
     const int lane = threadIdx.x & 31;
     unsigned int rect_tiles = 0;
@@ -224,7 +237,7 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
     float w[3] = {0.f, 0.f, 0.f}, sc[3] = {0.f, 0.f, 0.f}, q[4] = {1.f, 0.f, 0.f, 0.f}, dcv[3] = {0.f, 0.f, 0.f};
     float op_raw = 0.f;
     if (i < P) {
-        if (staged) {
+        if (staged && ALL) {
             const int tl = threadIdx.x;
             w[0] = s_xyz[3 * tl]; w[1] = s_xyz[3 * tl + 1]; w[2] = s_xyz[3 * tl + 2];
             sc[0] = s_sc[3 * tl]; sc[1] = s_sc[3 * tl + 1]; sc[2] = s_sc[3 * tl + 2];
@@ -242,6 +255,7 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
             op_raw = opacity_raw[i];
         }
     }
+    if (staged && !ALL) stage_multi_wait(sm, err);      // own loads were put in flight while the SH rows were under way
     if (i < P) {
         float V[16], PM[16], Rt[12], cp[3];
         load16(viewmatrix, V);
