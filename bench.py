@@ -221,7 +221,8 @@ def run_ours(args):
     if world > 1 and args.exchange == "compact":
         # gradient exchange folded into the backward: 56 B/Gaussian (xyz, opacity, scaling, rotation + the masked
         # colour gradient) all-reduced, SH gradients expanded locally afterwards (fsgs_b200/dist.py)
-        fsgs_dist.enable_frame_parallel(check_cam_center=poses.cam_center, chunks=args.exchange_chunks)
+        fsgs_dist.enable_frame_parallel(check_cam_center=poses.cam_center, chunks=args.exchange_chunks,
+                                        exchange=args.exchange_transport)
     HW = W * H
     # per-step host inputs (the reference copies the GT image to the GPU every iteration, train.py:174)
     G_host = torch.empty(4, H, W).pin_memory()
@@ -636,8 +637,8 @@ def run_ours(args):
                        "tile_instances": R_inst, "tile_instances_reference_rect": R_rect,
                        "parallelism": f"frame-dp{world}" + ("" if world == 1 else
                                                              "+nccl allreduce(grads, 236 B/Gaussian)" if args.exchange == "full"
-                                                             else f"+nccl allreduce(56 B/Gaussian rows, {args.exchange_chunks} "
-                                                                  "Gaussian ranges overlapped with the per-Gaussian backward)"),
+                                                             else f"+{args.exchange_transport} allreduce(56 B/Gaussian rows, "
+                                                                  f"{args.exchange_chunks} Gaussian range(s), in backward)"),
                        # which integration level each number of this line belongs to
                        "integration_levels": {
                            "value / ms_per_step": f"level 2 (fused fsgs_b200.render) + the step captured once and replayed "
@@ -680,7 +681,10 @@ def run_ours(args):
                             "cuda-graph: the frame (forward+loss+backward) is one fsgs_b200.GraphedStep replay; "
                             "ms_per_step_eager: the same loop issuing the frame from Python every step"},
             # pose fwd, 5 forward kernels, 2 backward kernels, pose bwd (+ the SH-gradient expansion when N > 1)
-            "gpu_launches": (9 + ((2 * len(render._chunk_bounds(args.P, args.exchange_chunks)) - 1)
+            # pose fwd, 5 forward kernels, compositor bwd, per-Gaussian bwd, pose bwd; N > 1: + the row exchange kernel
+            # (nvlink transport) and the expansion kernel per Gaussian range
+            "gpu_launches": (9 + (((3 if args.exchange_transport == "nvlink" else 2)
+                                   * len(render._chunk_bounds(args.P, args.exchange_chunks)) - 1)
                                   if world > 1 and args.exchange == "compact" else 0)) * args.steps,
             "clocks": clocks,
         }
@@ -710,7 +714,10 @@ def main():
     ap.add_argument("--P", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="e2e: issue every frame from Python (no CUDA-graph replay)")
-    ap.add_argument("--exchange-chunks", type=int, default=4,
+    ap.add_argument("--exchange-transport", default="nvlink", choices=["nvlink", "nccl"],
+                    help="N>1, compact exchange: nvlink = the library's own two-shot all-reduce over NVLink/NVSwitch on a "
+                         "symmetric buffer (fsgs_exchange_rows); nccl = ncclAllReduce")
+    ap.add_argument("--exchange-chunks", type=int, default=1,
                     help="N>1, compact exchange: Gaussian ranges of the per-Gaussian backward kernel; range k is all-reduced "
                          "on a side stream while range k+1 is computed (1 = one collective after the kernel)")
     ap.add_argument("--no-variants", action="store_true", help="skip the m=1 / m=4 / seed 1,2 timings and the mapping iteration")

@@ -298,4 +298,49 @@ k_sh_grad_expand(int P, int sh_deg, const float *__restrict__ xyz, const float *
     }
 }
 
+// ---- frame-parallel exchange over NVLink / NVSwitch ------------------------------------------
+// Two-shot all-reduce of the 56-byte gradient rows, hand-written instead of ncclAllReduce.  Every rank holds the
+// rows of ITS frame in a symmetric buffer (same offset on every GPU, mapped into every peer's address space).
+// After a cross-GPU barrier (all rows written), rank g owns the g-th 1/N slice of the buffer:
+//   multicast path (NVSwitch, NVLS): ONE multimem.ld_reduce per 16 bytes makes the switch fetch the N copies and
+//     add them on the way, ONE multimem.st broadcasts the sum back into all N buffers -- per GPU 1/N of the
+//     payload crosses its links in each direction, whatever N is;
+//   peer path (no multicast object): the owner loads its slice from the N buffers through peer pointers, adds,
+//     and stores the sum to each of them.
+// After a second barrier every buffer holds the sum of all frames' rows, bit-identical on every rank (each 16-byte
+// word was summed exactly once, by its owner).  The barriers are the caller's (stream-ordered signal kernels).
+struct PeerPtrs {
+    float4 *p[8];
+};
+
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4 *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float4 *mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(CTA)
+k_exchange_rows(float4 *__restrict__ mc, PeerPtrs peers, int world, long long begin, long long end) {
+    // [begin, end): this rank's slice, in float4 units from the start of the symmetric buffer
+    const long long stride = (long long)gridDim.x * CTA;
+    if (mc) {
+        for (long long i = begin + (long long)blockIdx.x * CTA + threadIdx.x; i < end; i += stride)
+            multimem_st(mc + i, multimem_ld_reduce_add(mc + i));
+    } else {
+        for (long long i = begin + (long long)blockIdx.x * CTA + threadIdx.x; i < end; i += stride) {
+            float4 s = peers.p[0][i];
+            for (int r = 1; r < world; ++r) {
+                const float4 v = peers.p[r][i];
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            for (int r = 0; r < world; ++r) peers.p[r][i] = s;
+        }
+    }
+}
+
 }  // namespace fsgs

@@ -75,7 +75,7 @@ inline int blocks(int n) { return (n + CTA - 1) / CTA; }
 // steps) to obtain the per-launch duration of each kernel for the roofline line.
 enum KernelId { K_PRE_API = 0, K_PRE_FUSED, K_SCAN, K_SCATTER, K_SORT, K_COMP_FWD, K_COMP_BWD, K_PRE_API_BWD,
                 K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_PRE_POSE_BWD, K_LOSS_FWD, K_LOSS_BWD, K_PEARSON_FWD, K_PEARSON_BWD,
-                K_LOCAL_PEARSON_FWD, K_LOCAL_PEARSON_BWD, K_COUNT };
+                K_LOCAL_PEARSON_FWD, K_LOCAL_PEARSON_BWD, K_EXCHANGE, K_COUNT };
 struct Profiler {
     bool on = false;
     static constexpr int MAXREC = 8192;
@@ -365,7 +365,7 @@ const char *fsgs_kernel_names(void) {
     return "k_preprocess_api,k_preprocess_fused,k_tile_scan,k_scatter,k_tile_sort,k_composite_fwd,"
            "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible,k_pose_forward,k_pose_backward,"
            "k_sh_grad_expand,k_preprocess_pose_bwd,k_rgb_loss_fwd,k_rgb_loss_bwd,k_pearson_sums,k_pearson_bwd,"
-           "k_local_pearson_sums,k_local_pearson_bwd";
+           "k_local_pearson_sums,k_local_pearson_bwd,k_exchange_rows";
 }
 
 size_t fsgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
@@ -716,6 +716,35 @@ int fsgs_sh_grad_expand(const fsgs_settings *st, int32_t P, const float *xyz, co
                                                     nullptr, nullptr, nullptr, nullptr);
     prof_end(K_SH_EXPAND, stream);
     FSGS_LAUNCH_OK("k_sh_grad_expand");
+    return FSGS_OK;
+}
+
+int fsgs_exchange_rows(void *multicast_ptr, void *const *peer_ptrs_host, int32_t world, int32_t rank, int64_t first_vec4,
+                       int64_t n_vec4, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || first_vec4 < 0 || n_vec4 < 0) return FSGS_E_INVALID;
+    if (!multicast_ptr && !peer_ptrs_host) return FSGS_E_INVALID;
+    if (n_vec4 == 0 || world == 1) return FSGS_OK;
+    int rc = check_arch();
+    if (rc) return rc;
+    PeerPtrs pp{};
+    if (peer_ptrs_host)
+        for (int r = 0; r < world; ++r) {
+            if (!multicast_ptr && !peer_ptrs_host[r]) return FSGS_E_INVALID;
+            pp.p[r] = static_cast<float4 *>(peer_ptrs_host[r]);
+        }
+    // this rank's slice of [first, first + n): equal parts, the remainder to the last rank
+    const int64_t per = n_vec4 / world;
+    const int64_t begin = first_vec4 + per * rank;
+    const int64_t end = (rank == world - 1) ? first_vec4 + n_vec4 : begin + per;
+    if (end <= begin) return FSGS_OK;
+    int64_t nb = (end - begin + CTA - 1) / CTA;
+    if (nb > 148 * 8) nb = 148 * 8;
+    prof_begin(K_EXCHANGE, stream);
+    k_exchange_rows<<<(int)nb, CTA, 0, stream>>>(static_cast<float4 *>(multicast_ptr), pp, world, (long long)begin,
+                                                  (long long)end);
+    prof_end(K_EXCHANGE, stream);
+    if (cudaGetLastError() != cudaSuccess) return FSGS_E_CUDA;
     return FSGS_OK;
 }
 

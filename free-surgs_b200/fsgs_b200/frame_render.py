@@ -30,17 +30,20 @@ _CAPTURED = []      # (image-state buffer, capacity, W, H) of every fused forwar
 
 # Frame-parallel gradient exchange hook (set through fsgs_b200.dist.enable_frame_parallel): a callable that
 # sum-all-reduces a flat float32 CUDA tensor in place, ordered on the current stream; None = single GPU.
-_GRAD_REDUCER = {"fn": None, "chunks": 1}
+_GRAD_REDUCER = {"fn": None, "chunks": 1, "alloc": None}
 _XCHG_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
-def set_grad_reducer(fn, chunks: int = 1) -> None:
+def set_grad_reducer(fn, chunks: int = 1, alloc=None) -> None:
     """``fn(flat)`` must SUM a flat float32 CUDA tensor over the ranks in place, ordered on the current stream.
     ``chunks`` > 1: the fused backward runs its per-Gaussian kernel in that many Gaussian ranges and hands each
     range's 56-byte rows to ``fn`` on a side stream while the next range is computed (``fn`` is then called
-    ``chunks`` times per backward, each time under ``torch.cuda.stream(side)``)."""
+    ``chunks`` times per backward, each time under ``torch.cuda.stream(side)``).
+    ``alloc(n_floats, device) -> flat float32 tensor``: where the rows live (the NVLink exchange keeps them in a
+    symmetric buffer mapped into every rank); default: a fresh tensor per backward."""
     _GRAD_REDUCER["fn"] = fn
     _GRAD_REDUCER["chunks"] = max(1, int(chunks))
+    _GRAD_REDUCER["alloc"] = alloc
 
 
 def _exchange_stream(dev) -> "torch.cuda.Stream":
@@ -260,7 +263,7 @@ class _RenderFused(torch.autograd.Function):
                 # the SH-coefficient gradients from the summed colour gradient.  With chunks > 1 the per-Gaussian
                 # kernel runs range by range and range k is exchanged + expanded on a side stream while range k+1
                 # is computed on this one.
-                compact = z(P * 14)
+                compact = z(P * 14) if _GRAD_REDUCER["alloc"] is None else _GRAD_REDUCER["alloc"](P * 14, dev)
                 bounds = _chunk_bounds(P, _GRAD_REDUCER["chunks"])
                 side = _exchange_stream(dev) if len(bounds) > 1 else None
                 none6 = (None,) * 6

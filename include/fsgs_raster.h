@@ -258,6 +258,18 @@ int fsgs_set_instance_capacity(int32_t device, int64_t capacity);
 int fsgs_sh_grad_expand(const fsgs_settings *st, int32_t P, const float *xyz, const float *cam_center,
                         const float *dL_dsh_rgb, float *dL_dfeatures_dc, float *dL_dfeatures_rest, void *stream);
 
+/* Frame-parallel exchange over NVLink / NVSwitch, hand-written (two-shot all-reduce; replaces ncclAllReduce on this
+ * path).  The caller keeps the 56-byte rows of fsgs_backward_opts.compact in a SYMMETRIC buffer: the same allocation
+ * on every GPU, every copy mapped into every process (peer_ptrs_host[r] = rank r's copy as seen from this process,
+ * r = 0..world-1, host array of device pointers) and, where the fabric supports it, bound to one multicast address
+ * (multicast_ptr, else NULL).  Between two cross-GPU barriers of the caller's (1: every rank's rows are written,
+ * 2: every slice is summed), this call sums THIS rank's 1/world slice of float4 words [first_vec4, first_vec4 + n_vec4)
+ * over all copies and writes the sum back into all of them -- multimem.ld_reduce / multimem.st through the switch
+ * when multicast_ptr is given, peer loads and stores otherwise.  Every word is summed once, by its owner: all ranks end
+ * up with bit-identical sums.  world <= 8. */
+int fsgs_exchange_rows(void *multicast_ptr, void *const *peer_ptrs_host, int32_t world, int32_t rank, int64_t first_vec4,
+                       int64_t n_vec4, void *stream);
+
 /* The same for the 56-byte rows of fsgs_backward_opts.compact, one Gaussian range [first, first+count) at a time
  * (first % 4 == 0): unpacks rotation / xyz / scaling / opacity from the (rank-summed) rows into their gradient tensors
  * and expands the colour gradient into the SH-coefficient gradients. */
