@@ -325,20 +325,44 @@ __device__ __forceinline__ void multimem_st(float4 *mc, float4 v) {
 }
 
 __global__ void __launch_bounds__(CTA)
-k_exchange_rows(float4 *__restrict__ mc, PeerPtrs peers, int world, long long begin, long long end) {
-    // [begin, end): this rank's slice, in float4 units from the start of the symmetric buffer
-    const long long stride = (long long)gridDim.x * CTA;
+k_exchange_rows(float4 *__restrict__ mc, PeerPtrs peers, int world, int rank, long long begin, long long end) {
+    // [begin, end): this rank's slice, in float4 units from the start of the symmetric buffer.  Four independent
+    // 16-byte words per thread and iteration: the round trip through the switch is microseconds long, the links
+    // only fill up with a few MB in flight.
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * CTA * U;
+    const long long t0 = begin + (long long)blockIdx.x * CTA * U + threadIdx.x;
     if (mc) {
-        for (long long i = begin + (long long)blockIdx.x * CTA + threadIdx.x; i < end; i += stride)
-            multimem_st(mc + i, multimem_ld_reduce_add(mc + i));
+        for (long long i = t0; i < end; i += stride) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * CTA < end) v[u] = multimem_ld_reduce_add(mc + i + u * CTA);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * CTA < end) multimem_st(mc + i + u * CTA, v[u]);
+        }
     } else {
-        for (long long i = begin + (long long)blockIdx.x * CTA + threadIdx.x; i < end; i += stride) {
-            float4 s = peers.p[0][i];
-            for (int r = 1; r < world; ++r) {
-                const float4 v = peers.p[r][i];
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        for (long long i = t0; i < end; i += stride) {
+            float4 s[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * CTA < end) s[u] = peers.p[rank][i + u * CTA];
+            for (int d = 1; d < world; ++d) {               // peers in ring order from this rank: spreads the links
+                const float4 *src = peers.p[(rank + d) % world];
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (i + u * CTA < end) v[u] = src[i + u * CTA];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { s[u].x += v[u].x; s[u].y += v[u].y; s[u].z += v[u].z; s[u].w += v[u].w; }
             }
-            for (int r = 0; r < world; ++r) peers.p[r][i] = s;
+            for (int d = 0; d < world; ++d) {
+                float4 *dst = peers.p[(rank + d) % world];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (i + u * CTA < end) dst[i + u * CTA] = s[u];
+            }
         }
     }
 }

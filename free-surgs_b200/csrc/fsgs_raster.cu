@@ -738,10 +738,10 @@ int fsgs_exchange_rows(void *multicast_ptr, void *const *peer_ptrs_host, int32_t
     const int64_t begin = first_vec4 + per * rank;
     const int64_t end = (rank == world - 1) ? first_vec4 + n_vec4 : begin + per;
     if (end <= begin) return FSGS_OK;
-    int64_t nb = (end - begin + CTA - 1) / CTA;
+    int64_t nb = (end - begin + CTA * 4 - 1) / (CTA * 4);
     if (nb > 148 * 8) nb = 148 * 8;
     prof_begin(K_EXCHANGE, stream);
-    k_exchange_rows<<<(int)nb, CTA, 0, stream>>>(static_cast<float4 *>(multicast_ptr), pp, world, (long long)begin,
+    k_exchange_rows<<<(int)nb, CTA, 0, stream>>>(static_cast<float4 *>(multicast_ptr), pp, world, rank, (long long)begin,
                                                   (long long)end);
     prof_end(K_EXCHANGE, stream);
     if (cudaGetLastError() != cudaSuccess) return FSGS_E_CUDA;

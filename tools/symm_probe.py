@@ -30,7 +30,7 @@ for P in (1003, 500_000):
     err = float((buf - want).abs().max())
     same = buf.clone()
     dist.broadcast(same, src=0)
-    print(f"rank {rank} P {P}: multicast {'yes' if x.multicast else 'no'} max|nvlink - nccl| {err:.3e} "
+    print(f"rank {rank} P {P}: multicast path {'yes' if x.multicast else 'no (peer loads/stores)'} max|nvlink - nccl| {err:.3e} "
           f"bit-identical across ranks: {bool(torch.equal(same, buf))}", flush=True)
     assert err < 1e-5 * world
     for name, fn in (("nvlink", lambda: x.reduce(buf)), ("nccl", lambda: dist.all_reduce(want))):
