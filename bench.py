@@ -221,8 +221,28 @@ def run_ours(args):
     if world > 1 and args.exchange == "compact":
         # gradient exchange folded into the backward: 56 B/Gaussian (xyz, opacity, scaling, rotation + the masked
         # colour gradient) all-reduced, SH gradients expanded locally afterwards (fsgs_b200/dist.py)
-        fsgs_dist.enable_frame_parallel(check_cam_center=poses.cam_center, chunks=args.exchange_chunks,
-                                        exchange=args.exchange_transport)
+        # Preflight of the NVLink transport (symmetric memory + one exchange); every rank must come to the same
+        # verdict, else all fall back to ncclAllReduce (and the line says so in config.parallelism).
+        if args.exchange_transport == "nvlink":
+            ok = torch.ones(1, device=dev)
+            try:
+                fsgs_dist.enable_frame_parallel(check_cam_center=poses.cam_center, chunks=args.exchange_chunks,
+                                                exchange="nvlink")
+                xch = fsgs_dist._STATE["exchange"]
+                probe = xch.alloc(args.P * 14, dev)
+                probe.fill_(1.0)
+                xch.reduce(probe)
+                torch.cuda.synchronize()
+                if abs(float(probe[0]) - world) > 1e-6 or abs(float(probe[-1]) - world) > 1e-6:
+                    raise RuntimeError(f"exchange preflight: got {float(probe[0])}, want {world}")
+            except Exception as exc:  # noqa: BLE001
+                print(f"[bench] rank {rank}: NVLink exchange unavailable ({exc!r}); falling back to NCCL", file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok) == 0.0:
+                args.exchange_transport = "nccl"
+        if args.exchange_transport == "nccl":
+            fsgs_dist.enable_frame_parallel(check_cam_center=poses.cam_center, chunks=args.exchange_chunks, exchange="nccl")
     HW = W * H
     # per-step host inputs (the reference copies the GT image to the GPU every iteration, train.py:174)
     G_host = torch.empty(4, H, W).pin_memory()
