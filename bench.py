@@ -560,7 +560,8 @@ def run_ours(args):
                     poses_v.pose_param_net.zero_grad(set_to_none=True)
                     o = render.render(poses_v, 0, pc_v, gs_grad=True, cam_grad=True)
                     ((o["render"] * Gv[:3]).sum() + (o["render_dep"] * Gv[3]).sum()).backward()
-                    info["nr"] = o["num_rendered"]
+                    info["rect"] = max(info.get("rect", 0), int(o["num_rendered"][1]))      # (0 inside the capture)
+                    info["inst"] = int(o["num_rendered"][0]) if not torch.cuda.is_current_stream_capturing() else info.get("inst", 0)
                 gs_v = _GS(body, warmup=3)
                 for _ in range(3):
                     gs_v.replay()
@@ -575,7 +576,7 @@ def run_ours(args):
                 over = gs_v.overflowed()
                 gs_v.release()
                 variants[f"m={m_v:g} seed{seed_v}"] = {
-                    "ms_per_step": ms_v, "value": args.P / (ms_v * 1e-3), "tile_instances_reference_rect": int(info["nr"][1]),
+                    "ms_per_step": ms_v, "value": args.P / (ms_v * 1e-3), "tile_instances": info.get("inst", 0), "tile_instances_reference_rect": info.get("rect", 0),
                     "overflowed": bool(over)}
                 del gs_v, poses_v, pc_v, Gv, sc_v
             except Exception as exc:  # noqa: BLE001
