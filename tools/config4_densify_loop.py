@@ -2,7 +2,7 @@
 (render -> L1 image loss -> backward with the densification statistics folded in -> Adam step; densify_and_prune
 every `every` iterations).  For ncu captures on the GPU box:
 
-   ncu --set full --clock-control none -k regex:fsgs -c 40 -o gpurun_out/r2_config4 python tools/config4_densify_loop.py 7 3
+   ncu --set full --clock-control none -k regex:^k_ -c 40 -o gpurun_out/r2_config4 python tools/config4_densify_loop.py 7 3
 
    python tools/config4_densify_loop.py [iterations] [densify every]
 """
