@@ -88,9 +88,9 @@ class ClockSampler:
 
 
 def ncu_traffic(kernel, P, m):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r1_traffic.json),
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r2_traffic.json),
     only if that capture was taken on this workload; else None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         d = json.load(open(path))
         if int(d["workload"]["P"]) == int(P) and float(d["workload"]["m"]) == float(m):
@@ -102,7 +102,7 @@ def ncu_traffic(kernel, P, m):
 
 def ncu_instructions(kernel, P, m):
     """Executed warp-instructions per launch of `kernel` from the same committed capture (or None)."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         d = json.load(open(path))
         if int(d["workload"]["P"]) == int(P) and float(d["workload"]["m"]) == float(m):
