@@ -328,19 +328,19 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int w
         }
     }
     __syncwarp();                                   // every lane is done reading the pair buffer
-    // [entry][row][3] float4 with 13 float4 per entry (12 used): with a stride of 12 the four-row loads below put the
-    // eight entries of a quarter-warp on two 16-byte bank groups (ncu, round 1: 5.4 M bank conflicts per launch);
-    // 13 spreads them over all eight (the stores pay a 2-way conflict instead, 3 stores against 4 loads per lane)
-    constexpr int TPS = 13;
-    float4 *tp = reinterpret_cast<float4 *>(&sm.pair[warp][0][0][0]);   // 8 x 13 x 16 B = 1664 B of 3072
+    // [entry][row][3] float4 = 1536 B of 3072.  (The four-row loads below put the eight entries of a quarter-warp on two
+    // 16-byte bank groups -- ncu: 5.4 M shared-memory bank conflicts per launch.  Padding the entry stride to 13 float4
+    // removes them and was measured SLOWER, 0.511 vs 0.494 ms: the kernel is issue bound and the padded indexing costs
+    // more instructions than the conflicts cost cycles.  Round 2 A/B, tools/ab_variants.py.)
+    float4 *tp = reinterpret_cast<float4 *>(&sm.pair[warp][0][0][0]);
     if (act) {
-        tp[e * TPS + row * 3] = o0; tp[e * TPS + row * 3 + 1] = o1;
-        if (!POSE_ONLY || LEVEL >= 1) tp[e * TPS + row * 3 + 2] = o2;
+        tp[lane * 3] = o0; tp[lane * 3 + 1] = o1;
+        if (!POSE_ONLY || LEVEL >= 1) tp[lane * 3 + 2] = o2;
     }
     __syncwarp();
     if (act && row < ((POSE_ONLY && LEVEL == 0) ? 2 : 3)) {
-        const float4 r0 = tp[e * TPS + row], r1 = tp[e * TPS + 3 + row], r2 = tp[e * TPS + 6 + row],
-                     r3 = tp[e * TPS + 9 + row];
+        const float4 r0 = tp[(e * 4) * 3 + row], r1 = tp[(e * 4 + 1) * 3 + row], r2 = tp[(e * 4 + 2) * 3 + row],
+                     r3 = tp[(e * 4 + 3) * 3 + row];
         float4 o;
         o.x = (r0.x + r1.x) + (r2.x + r3.x); o.y = (r0.y + r1.y) + (r2.y + r3.y);
         o.z = (r0.z + r1.z) + (r2.z + r3.z); o.w = (r0.w + r1.w) + (r2.w + r3.w);
