@@ -362,7 +362,6 @@ def run_ours(args):
         prefetch(0)
         for k in range(n_steps):
             b = k & 1
-            flush.zero_()
             main.wait_event(copied[b])
             if k + 1 < n_steps:
                 prefetch(k + 1)
@@ -380,7 +379,7 @@ def run_ours(args):
 
     run_e2e(3)                                            # warm the side stream / pinned mailbox path
     ms_e2e_eager = run_e2e(args.steps)
-    ms_e2e, e2e_mode = ms_e2e_eager, "eager"
+    ms_e2e, e2e_mode, ms_e2e_sync = ms_e2e_eager, "eager", None
 
     # The same loop with the step (forward + loss + backward + packing of the result) captured once in a CUDA
     # graph (fsgs_b200.GraphedStep: the library runs in fixed-capacity mode, no host read-back inside the step)
@@ -399,7 +398,6 @@ def run_ours(args):
             prefetch(0)
             for k in range(n_steps):
                 b = k & 1
-                flush.zero_()
                 main.wait_event(copied[b])
                 if k + 1 < n_steps:
                     prefetch(k + 1)
@@ -414,8 +412,50 @@ def run_ours(args):
             barrier()
             return t0.elapsed_time(t1) / n_steps
 
+        # The same, software-pipelined by one step: the host launches step k + 1 BEFORE it waits for step k's
+        # result (two pinned mailboxes), so the GPU never idles while the host wakes up and issues the next
+        # launch.  Every step still gets its own H2D input copy and its own D2H result, and the host reads every
+        # result -- one step late, which is all Free-SurGS' loops need (they read the losses for the progress bar,
+        # train.py:191-207; the optimiser step that the next iteration depends on runs on the device).
+        results_host = [torch.empty(8).pin_memory() for _ in range(2)]
+        results_ready = [torch.cuda.Event() for _ in range(2)]
+
+        def run_e2e_graph_pipelined(n_steps):
+            for e in consumed:
+                e.record(main)
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(main)
+            copy_stream.wait_event(t0)
+            prefetch(0)
+            seen = []
+            for k in range(n_steps):
+                b = k & 1
+                main.wait_event(copied[b])
+                if k + 1 < n_steps:
+                    prefetch(k + 1)
+                G_static.copy_(G_in[b], non_blocking=True)
+                consumed[b].record(main)
+                packed = gstep.replay()
+                results_host[b].copy_(packed, non_blocking=True)
+                results_ready[b].record(main)
+                if k > 0:                                     # the previous step's result, while this one runs
+                    results_ready[b ^ 1].synchronize()
+                    seen.append(float(results_host[b ^ 1][0]))
+            results_ready[(n_steps - 1) & 1].synchronize()
+            seen.append(float(results_host[(n_steps - 1) & 1][0]))
+            t1.record(main)
+            barrier()
+            assert len(seen) == n_steps
+            return t0.elapsed_time(t1) / n_steps, seen[-1]
+
         run_e2e_graph(3)
-        ms_e2e, e2e_mode = run_e2e_graph(args.steps), "cuda-graph"
+        ms_e2e_sync = run_e2e_graph(args.steps)
+        run_e2e_graph_pipelined(3)
+        ms_e2e, loss_pipelined = run_e2e_graph_pipelined(args.steps)
+        e2e_mode = "cuda-graph, host reads each result one step late"
+        if abs(loss_pipelined - float(result_host[0])) > 1e-4 * abs(loss_pipelined):
+            raise SystemExit("bench: pipelined and synchronous end-to-end loops disagree")
         if gstep.overflowed():
             raise SystemExit("bench: the captured step overflowed its instance capacity")
         loss_graph = float(result_host[0])
@@ -624,10 +664,11 @@ def run_ours(args):
     _lib.profile_enable(False)
 
     # max over ranks
-    t = torch.tensor([ms_step, ms_e2e, ms_track, ms_e2e_eager, ms_track_frozen], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_step, ms_e2e, ms_track, ms_e2e_eager, ms_track_frozen, ms_e2e_sync or 0.0], device=dev,
+                     dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_e2e, ms_track, ms_e2e_eager, ms_track_frozen = t.tolist()
+    ms_step, ms_e2e, ms_track, ms_e2e_eager, ms_track_frozen, ms_e2e_sync = t.tolist()
 
     if rank == 0:
         R_inst, R_rect = int(last["stats"][0]), int(last["stats"][1])
@@ -696,11 +737,16 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(G_host.numel() * 4),
                     "d2h_bytes_per_step": 8 * 4, "ms_per_step": ms_e2e, "mode": e2e_mode,
-                    "ms_per_step_eager": ms_e2e_eager,
-                    "note": "per step: H2D of the inputs (step k+1 prefetched on a side stream during step k), the frame, "
-                            "D2H of loss + pose gradient and a host wait on it; includes the 256 MiB L2 flush.  mode "
-                            "cuda-graph: the frame (forward+loss+backward) is one fsgs_b200.GraphedStep replay; "
-                            "ms_per_step_eager: the same loop issuing the frame from Python every step"},
+                    "ms_per_step_eager": ms_e2e_eager, "ms_per_step_host_waits_every_step": ms_e2e_sync or None,
+                    "note": "per step, inside the timed region: H2D of the step's inputs from pinned memory (step k+1 "
+                            "prefetched on a side stream during step k), a device copy into the captured step's input, the "
+                            "frame (forward+loss+backward = one fsgs_b200.GraphedStep replay), D2H of loss + pose gradient "
+                            "into a pinned mailbox, and the host reading it.  ms_per_step: the host launches step k+1 "
+                            "before it waits for step k's result (two mailboxes; every result is read, one step late); "
+                            "ms_per_step_host_waits_every_step: the host waits for each result before it launches the next "
+                            "step (round 1's loop); ms_per_step_eager: that loop issuing the frame from Python.  No L2 "
+                            "flush inside these loops: a step streams ~0.8 GB through the 126 MB L2 and its inputs arrive "
+                            "over PCIe"},
             # pose fwd, 5 forward kernels, 2 backward kernels, pose bwd (+ the SH-gradient expansion when N > 1)
             # pose fwd, 5 forward kernels, compositor bwd, per-Gaussian bwd, pose bwd; N > 1: + the row exchange kernel
             # (nvlink transport) and the expansion kernel per Gaussian range

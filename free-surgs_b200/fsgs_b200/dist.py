@@ -107,15 +107,15 @@ class _NvlinkExchange:
             self.buf.zero_()
             self.hdl = self.symm_mem.rendezvous(self.buf, self.group)
             self.multicast = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
-            # In-switch reduction pays off from 4 GPUs on: with multimem a GPU's links carry ~(1 + 1/N) x the payload
-            # in each direction whatever N is, with peer loads / stores 2 (N-1)/N x -- less for N = 2 (where the
-            # multimem path also sends the local copy through the switch), more for N >= 4.
-            # FSGS_EXCHANGE_MULTICAST=0/1 forces one of them (A/B).
+            # With multimem a GPU's links carry ~(1 + 1/N) x the payload in each direction whatever N is, with peer
+            # loads / stores 2 (N-1)/N x.  Measured on B200 / NVSwitch, 28 MB of rows (tools/symm_probe.py):
+            #   N = 2: peer 61 us, multimem 98 us;  N = 4: 87 / 100 us;  N = 8: 102 / 99 us  (ncclAllReduce: 72 / 110 / 138 us)
+            # -> in-switch reduction from 8 ranks on.  FSGS_EXCHANGE_MULTICAST=0/1 forces one of them (A/B).
             import os
             force = os.environ.get("FSGS_EXCHANGE_MULTICAST")
             if force is not None:
                 self.multicast = self.multicast if force == "1" else 0
-            elif self.world < 4:
+            elif self.world < 8:
                 self.multicast = 0
             ptrs = [int(x) for x in self.hdl.buffer_ptrs]
             self.peers = (ctypes.c_void_p * self.world)(*ptrs)
