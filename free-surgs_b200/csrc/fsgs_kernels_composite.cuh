@@ -37,6 +37,14 @@
 
 namespace fsgs {
 
+#ifdef FSGS_PAIR_STATS
+// Instrumented A/B build only (tools/pair_stats.py): how full are the compositors' (warp, entry) visits?
+//   [0] backward visits  [1] valid (pixel, entry) pairs  [2] visits with no valid pixel
+//   [3] visits with exactly one of the two 4x4 halves of the 8x4 block populated
+//   [4] forward visits   [5] forward contributing pairs
+__device__ unsigned long long g_pair_stats[8];
+#endif
+
 // Derived per-pixel / per-Gaussian outputs of the reference's render() (fused flavour only; NULL = skip).
 struct RenderExtras {
     float *uncertainty;
@@ -155,6 +163,12 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
             const float test_T = T * (1.f - alpha);
             const bool pa = (p2 <= 0.f) & (alpha >= ALPHA_MIN);
             const bool ok = pa & (test_T >= T_MIN);
+#ifdef FSGS_PAIR_STATS
+            {
+                const unsigned int bv = __ballot_sync(FULL, ok);
+                if (lane == 0) { atomicAdd(&g_pair_stats[4], 1ull); atomicAdd(&g_pair_stats[5], (unsigned long long)__popc(bv)); }
+            }
+#endif
             const float w = ok ? alpha * T : 0.f;
             C0 = fmaf(q1.z, w, C0); C1 = fmaf(q1.w, w, C1); C2 = fmaf(q2.x, w, C2); D = fmaf(q2.y, w, D);
             if (FUSED) { S += w; D2 = fmaf(q2.y * q2.y, w, D2); }
@@ -369,6 +383,17 @@ __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int war
             const float G = fast_exp2(p2);
             const float alpha = fminf(ALPHA_MAX, q1.y * G);
             const bool valid = (j < last_rel) && (p2 <= 0.f) && (alpha >= ALPHA_MIN);
+#ifdef FSGS_PAIR_STATS
+            {
+                const unsigned int bv = __ballot_sync(FULL, valid);
+                if (lane == 0) {
+                    atomicAdd(&g_pair_stats[0], 1ull);
+                    atomicAdd(&g_pair_stats[1], (unsigned long long)__popc(bv));
+                    if (!bv) atomicAdd(&g_pair_stats[2], 1ull);
+                    else if (!(bv & 0x0f0f0f0fu) || !(bv & 0xf0f0f0f0u)) atomicAdd(&g_pair_stats[3], 1ull);
+                }
+            }
+#endif
             float q, w, q_rgb;
             bwd_pair_weights<FUSED, LEVEL>(ps, valid ? G * q1.y : 0.f, valid ? alpha : 0.f, q1.z, q1.w, q2.x, q2.y,
                                            g, T_final, bgdot_rgb, bgdot_dep, q, w, q_rgb);

@@ -696,6 +696,17 @@ int fsgs_watchdog_flag(int32_t device, int32_t reset) {
     return v ? 1 : 0;
 }
 
+#ifdef FSGS_PAIR_STATS
+// instrumented A/B build only (tools/pair_stats.py): read and clear the compositors' pair statistics
+extern "C" int fsgs_debug_pair_stats(unsigned long long *out8) {
+    FSGS_CUDA(cudaDeviceSynchronize());
+    FSGS_CUDA(cudaMemcpyFromSymbol(out8, g_pair_stats, 8 * sizeof(unsigned long long)));
+    unsigned long long z[8] = {};
+    FSGS_CUDA(cudaMemcpyToSymbol(g_pair_stats, z, sizeof(z)));
+    return FSGS_OK;
+}
+#endif
+
 int fsgs_set_instance_capacity(int32_t device, int64_t capacity) {
     if (device < 0 || device >= 64 || capacity < 0) return FSGS_E_INVALID;
     g_fixed_cap[device] = (unsigned long long)capacity;
