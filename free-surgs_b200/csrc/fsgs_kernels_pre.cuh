@@ -286,6 +286,82 @@ k_preprocess_fused(CamConst cc, int P, const float *__restrict__ xyz, const floa
     block_add_u64(&counters[CNT_RECT], rect_tiles);
 }
 
+// ---- K1, frozen-model flavour -------------------------------------------------------------------------
+// Free-SurGS' tracking loop renders the SAME Gaussian model from 50 successive pose estimates per frame
+// (train.py:154-210), and with the reference's quirks everything about a Gaussian except its
+// camera-frame mean is independent of the pose: the quaternions are not rotated into the camera frame, so
+// Sigma_3D = R S^2 R^T is a model constant, and the SH view direction is WORLD position minus a frozen camera
+// centre, so the colour and its clamp mask are too.  k_freeze_model evaluates those once into one 64-byte row per
+// Gaussian,
+//   f0 = (x, y, z, sigmoid(opacity))   f1 = (S00, S01, S02, S11)   f2 = (S12, S22, r, g)   f3 = (b, clamp bits, -, -)
+// and k_preprocess_frozen is k_preprocess_fused reading that row with four 128-bit loads (64 B instead of 236 B per
+// Gaussian, no SH evaluation, no exp / normalise / R S^2 R^T).  Both use the very functions the fused kernel uses, so
+// the records -- and with them the image and every gradient -- are bit-identical (tests/test_gpu_tracking.py).
+__global__ void __launch_bounds__(CTA)
+k_freeze_model(CamConst cc, int P, const float *__restrict__ xyz, const float *__restrict__ f_dc,
+               const float *__restrict__ f_rest, const float *__restrict__ opacity_raw,
+               const float *__restrict__ scaling_raw, const float *__restrict__ rotation_raw,
+               const float *__restrict__ cam_center, float4 *__restrict__ frozen) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const size_t n = (size_t)i;
+    const float w[3] = {xyz[3 * n], xyz[3 * n + 1], xyz[3 * n + 2]};
+    const float sc[3] = {scaling_raw[3 * n], scaling_raw[3 * n + 1], scaling_raw[3 * n + 2]};
+    const float4 q4 = *reinterpret_cast<const float4 *>(rotation_raw + 4 * n);
+    const float rot[4] = {q4.x, q4.y, q4.z, q4.w};
+    const float dcv[3] = {f_dc[3 * n], f_dc[3 * n + 1], f_dc[3 * n + 2]};
+    const float cp[3] = {__ldg(cam_center), __ldg(cam_center + 1), __ldg(cam_center + 2)};
+    float c6[6], rgb[3], opacity;
+    uint8_t cl = 0;
+    fused_frozen_one(cc, cp, w, dcv, f_rest + 45 * n, opacity_raw[i], sc, rot, c6, opacity, rgb, cl);
+    frozen[n * 4 + 0] = make_float4(w[0], w[1], w[2], opacity);
+    frozen[n * 4 + 1] = make_float4(c6[0], c6[1], c6[2], c6[3]);
+    frozen[n * 4 + 2] = make_float4(c6[4], c6[5], rgb[0], rgb[1]);
+    frozen[n * 4 + 3] = make_float4(rgb[2], __uint_as_float((unsigned int)cl), 0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(CTA)
+k_preprocess_frozen(CamConst cc, int P, const float4 *__restrict__ frozen, const float *__restrict__ pose,
+                    const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
+                    float4 *__restrict__ records, uint8_t *__restrict__ clamped, int *__restrict__ radii,
+                    unsigned int *__restrict__ tile_count, unsigned long long *__restrict__ counters,
+                    unsigned int flags, unsigned char *__restrict__ visibility, float *__restrict__ max_radii2D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    unsigned int rect_tiles = 0;
+    Splat sp;
+    sp.px = sp.py = sp.conx = sp.cony = sp.conz = 0.f; sp.radius = 0;
+    float opacity = 0.f;
+    bool vis = false;
+    if (i < P) {
+        const size_t n = (size_t)i;
+        const float4 f0 = ldg4(frozen + n * 4), f1 = ldg4(frozen + n * 4 + 1), f2 = ldg4(frozen + n * 4 + 2),
+                     f3 = ldg4(frozen + n * 4 + 3);
+        float V[16], PM[16], Rt[12];
+        load16(viewmatrix, V);
+        load16(projmatrix, PM);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) Rt[k] = __ldg(pose + k);
+        const float w[3] = {f0.x, f0.y, f0.z};
+        const float c6[6] = {f1.x, f1.y, f1.z, f1.w, f2.x, f2.y};
+        vis = fused_forward_frozen_one(cc, V, PM, Rt, w, c6, sp);
+        if (vis) {
+            opacity = f0.w;
+            rect_tiles = (unsigned int)((sp.rmaxx - sp.rminx) * (sp.rmaxy - sp.rminy));
+            store_record(records, i, sp, opacity, f2.z, f2.w, f3.x, 1);
+        } else {
+            store_empty_record(records, i);
+        }
+        clamped[i] = vis ? (uint8_t)__float_as_uint(f3.y) : (uint8_t)0;
+        radii[i] = vis ? sp.radius : 0;
+        if (visibility) visibility[i] = vis ? 1 : 0;
+        if (max_radii2D && vis) max_radii2D[i] = fmaxf(max_radii2D[i], (float)sp.radius);
+    }
+    warp_for_each_tile(cc.gx, cc.gy, vis, sp.px, sp.py, sp.conx, sp.cony, sp.conz, opacity, sp.radius, (flags & 2u) != 0,
+                       lane, [&](int, int t) { atomicAdd(&tile_count[t], 1u); });
+    block_add_u64(&counters[CNT_RECT], rect_tiles);
+}
+
 // ---- K2: exclusive scan of the per-tile counts (single CTA; a few thousand tiles) ------------------
 __global__ void __launch_bounds__(1024)
 k_tile_scan(int tiles, const unsigned int *__restrict__ tile_count, unsigned int *__restrict__ tile_offset,

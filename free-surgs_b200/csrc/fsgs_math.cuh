@@ -21,6 +21,20 @@
 
 namespace fsgs {
 
+// Pinned float32 operations: never contracted or re-associated by the compiler.  The forward projection is written
+// with them because it is inlined into several kernels (k_preprocess_fused, k_preprocess_frozen, k_preprocess_api)
+// that must produce the SAME bits from the same inputs, and ptxas picks which multiply of `a*b + c*d` joins the add
+// per kernel (measured: 4 % of the conics differed in the last bit between two inlinings of the same source).
+#if defined(__CUDA_ARCH__)
+#define FSGS_MUL(a, b) __fmul_rn((a), (b))
+#define FSGS_ADD(a, b) __fadd_rn((a), (b))
+#define FSGS_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#else
+#define FSGS_MUL(a, b) ((a) * (b))
+#define FSGS_ADD(a, b) ((a) + (b))
+#define FSGS_FMA(a, b, c) fmaf((a), (b), (c))
+#endif
+
 constexpr int TILE = 16;
 constexpr float NEAR_CULL = 0.2f;
 constexpr float ALPHA_MIN = 1.0f / 255.0f;
@@ -45,6 +59,13 @@ struct CamConst {
     int sh_deg, n_coeffs;
 };
 
+// a0 b0 + a1 b1 + a2 b2 (+ c), fixed evaluation order
+FSGS_HD float dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return FSGS_FMA(a2, b2, FSGS_FMA(a1, b1, FSGS_MUL(a0, b0)));
+}
+FSGS_HD float dot3p(float a0, float b0, float a1, float b1, float a2, float b2, float c) {
+    return FSGS_ADD(dot3(a0, b0, a1, b1, a2, b2), c);
+}
 // Result of projecting one Gaussian (K1).
 struct Splat {
     float px, py;          // pixel-space centre
@@ -56,30 +77,41 @@ struct Splat {
 };
 
 FSGS_HD void xf43(const float *M, float x, float y, float z, float &ox, float &oy, float &oz) {
-    ox = M[0] * x + M[4] * y + M[8] * z + M[12];
-    oy = M[1] * x + M[5] * y + M[9] * z + M[13];
-    oz = M[2] * x + M[6] * y + M[10] * z + M[14];
+    ox = dot3p(M[0], x, M[4], y, M[8], z, M[12]);
+    oy = dot3p(M[1], x, M[5], y, M[9], z, M[13]);
+    oz = dot3p(M[2], x, M[6], y, M[10], z, M[14]);
+}
+// camera-frame mean: rows of the row-major 3x4 pose times (xyz, 1)   (transform_to_frame)
+FSGS_HD void pose_mean(const float *pose, const float *xyz, float *mean) {
+    for (int r = 0; r < 3; ++r)
+        mean[r] = dot3p(pose[4 * r], xyz[0], pose[4 * r + 1], xyz[1], pose[4 * r + 2], xyz[2], pose[4 * r + 3]);
 }
 
 // Rotation matrix (row-major) of a quaternion (w,x,y,z) used as given.
 FSGS_HD void quat_to_R(const float *q, float *R) {
     const float r = q[0], x = q[1], y = q[2], z = q[3];
-    R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - r * z); R[2] = 2.f * (x * z + r * y);
-    R[3] = 2.f * (x * y + r * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - r * x);
-    R[6] = 2.f * (x * z - r * y); R[7] = 2.f * (y * z + r * x); R[8] = 1.f - 2.f * (x * x + y * y);
+    // (pinned evaluation order, see FSGS_MUL above: this feeds Sigma_3D, which two kernels must agree on bit for bit)
+    const float xx = FSGS_MUL(x, x), yy = FSGS_MUL(y, y), zz = FSGS_MUL(z, z);
+    const float xy = FSGS_MUL(x, y), xz = FSGS_MUL(x, z), yz = FSGS_MUL(y, z);
+    R[0] = FSGS_FMA(-2.f, FSGS_ADD(yy, zz), 1.f); R[1] = FSGS_MUL(2.f, FSGS_FMA(-r, z, xy)); R[2] = FSGS_MUL(2.f, FSGS_FMA(r, y, xz));
+    R[3] = FSGS_MUL(2.f, FSGS_FMA(r, z, xy)); R[4] = FSGS_FMA(-2.f, FSGS_ADD(xx, zz), 1.f); R[5] = FSGS_MUL(2.f, FSGS_FMA(-r, x, yz));
+    R[6] = FSGS_MUL(2.f, FSGS_FMA(-r, y, xz)); R[7] = FSGS_MUL(2.f, FSGS_FMA(r, x, yz)); R[8] = FSGS_FMA(-2.f, FSGS_ADD(xx, yy), 1.f);
 }
 
 // Sigma = R diag(s^2) R^T as (xx,xy,xz,yy,yz,zz); s already includes the scale modifier.
 FSGS_HD void cov3d_from_scale_rot(const float *s, const float *q, float *c6) {
     float R[9];
     quat_to_R(q, R);
-    const float s0 = s[0] * s[0], s1 = s[1] * s[1], s2 = s[2] * s[2];
-    c6[0] = R[0] * R[0] * s0 + R[1] * R[1] * s1 + R[2] * R[2] * s2;
-    c6[1] = R[0] * R[3] * s0 + R[1] * R[4] * s1 + R[2] * R[5] * s2;
-    c6[2] = R[0] * R[6] * s0 + R[1] * R[7] * s1 + R[2] * R[8] * s2;
-    c6[3] = R[3] * R[3] * s0 + R[4] * R[4] * s1 + R[5] * R[5] * s2;
-    c6[4] = R[3] * R[6] * s0 + R[4] * R[7] * s1 + R[5] * R[8] * s2;
-    c6[5] = R[6] * R[6] * s0 + R[7] * R[7] * s1 + R[8] * R[8] * s2;
+    const float s0 = FSGS_MUL(s[0], s[0]), s1 = FSGS_MUL(s[1], s[1]), s2 = FSGS_MUL(s[2], s[2]);
+    const float a0 = FSGS_MUL(R[0], s0), a1 = FSGS_MUL(R[1], s1), a2 = FSGS_MUL(R[2], s2);
+    const float b0 = FSGS_MUL(R[3], s0), b1 = FSGS_MUL(R[4], s1), b2 = FSGS_MUL(R[5], s2);
+    const float d0 = FSGS_MUL(R[6], s0), d1 = FSGS_MUL(R[7], s1), d2 = FSGS_MUL(R[8], s2);
+    c6[0] = dot3(R[0], a0, R[1], a1, R[2], a2);
+    c6[1] = dot3(R[3], a0, R[4], a1, R[5], a2);
+    c6[2] = dot3(R[6], a0, R[7], a1, R[8], a2);
+    c6[3] = dot3(R[3], b0, R[4], b1, R[5], b2);
+    c6[4] = dot3(R[6], b0, R[7], b1, R[8], b2);
+    c6[5] = dot3(R[6], d0, R[7], d1, R[8], d2);
 }
 
 // View-space point with the reference's +-1.3 tanfov clamp, and M = J * W3 (2x3, row-major),
@@ -90,25 +122,28 @@ FSGS_HD void ewa_M(const CamConst &cc, const float *V, const float *mean, float 
     const float txtz = t[0] / t[2], tytz = t[1] / t[2];
     xmask = (txtz < -cc.limx || txtz > cc.limx) ? 0.f : 1.f;
     ymask = (tytz < -cc.limy || tytz > cc.limy) ? 0.f : 1.f;
-    t[0] = fminf(cc.limx, fmaxf(-cc.limx, txtz)) * t[2];
-    t[1] = fminf(cc.limy, fmaxf(-cc.limy, tytz)) * t[2];
-    const float J00 = cc.fx / t[2], J02 = -(cc.fx * t[0]) / (t[2] * t[2]);
-    const float J11 = cc.fy / t[2], J12 = -(cc.fy * t[1]) / (t[2] * t[2]);
-    M[0] = J00 * V[0] + J02 * V[2]; M[1] = J00 * V[4] + J02 * V[6]; M[2] = J00 * V[8] + J02 * V[10];
-    M[3] = J11 * V[1] + J12 * V[2]; M[4] = J11 * V[5] + J12 * V[6]; M[5] = J11 * V[9] + J12 * V[10];
+    t[0] = FSGS_MUL(fminf(cc.limx, fmaxf(-cc.limx, txtz)), t[2]);
+    t[1] = FSGS_MUL(fminf(cc.limy, fmaxf(-cc.limy, tytz)), t[2]);
+    const float tz2 = FSGS_MUL(t[2], t[2]);
+    const float J00 = cc.fx / t[2], J02 = -FSGS_MUL(cc.fx, t[0]) / tz2;
+    const float J11 = cc.fy / t[2], J12 = -FSGS_MUL(cc.fy, t[1]) / tz2;
+    M[0] = FSGS_FMA(J02, V[2], FSGS_MUL(J00, V[0])); M[1] = FSGS_FMA(J02, V[6], FSGS_MUL(J00, V[4]));
+    M[2] = FSGS_FMA(J02, V[10], FSGS_MUL(J00, V[8]));
+    M[3] = FSGS_FMA(J12, V[2], FSGS_MUL(J11, V[1])); M[4] = FSGS_FMA(J12, V[6], FSGS_MUL(J11, V[5]));
+    M[5] = FSGS_FMA(J12, V[10], FSGS_MUL(J11, V[9]));
 }
 
 // (S M0, S M1) and a,b,c of M S M^T + 0.3 I.
 FSGS_HD void ewa_abc(const float *M, const float *c6, float *SM0, float *SM1, float &a, float &b, float &c) {
-    SM0[0] = c6[0] * M[0] + c6[1] * M[1] + c6[2] * M[2];
-    SM0[1] = c6[1] * M[0] + c6[3] * M[1] + c6[4] * M[2];
-    SM0[2] = c6[2] * M[0] + c6[4] * M[1] + c6[5] * M[2];
-    SM1[0] = c6[0] * M[3] + c6[1] * M[4] + c6[2] * M[5];
-    SM1[1] = c6[1] * M[3] + c6[3] * M[4] + c6[4] * M[5];
-    SM1[2] = c6[2] * M[3] + c6[4] * M[4] + c6[5] * M[5];
-    a = M[0] * SM0[0] + M[1] * SM0[1] + M[2] * SM0[2] + COV_DILATION;
-    b = M[0] * SM1[0] + M[1] * SM1[1] + M[2] * SM1[2];
-    c = M[3] * SM1[0] + M[4] * SM1[1] + M[5] * SM1[2] + COV_DILATION;
+    SM0[0] = dot3(c6[0], M[0], c6[1], M[1], c6[2], M[2]);
+    SM0[1] = dot3(c6[1], M[0], c6[3], M[1], c6[4], M[2]);
+    SM0[2] = dot3(c6[2], M[0], c6[4], M[1], c6[5], M[2]);
+    SM1[0] = dot3(c6[0], M[3], c6[1], M[4], c6[2], M[5]);
+    SM1[1] = dot3(c6[1], M[3], c6[3], M[4], c6[4], M[5]);
+    SM1[2] = dot3(c6[2], M[3], c6[4], M[4], c6[5], M[5]);
+    a = dot3p(M[0], SM0[0], M[1], SM0[1], M[2], SM0[2], COV_DILATION);
+    b = dot3(M[0], SM1[0], M[1], SM1[1], M[2], SM1[2]);
+    c = dot3p(M[3], SM1[0], M[4], SM1[1], M[5], SM1[2], COV_DILATION);
 }
 
 FSGS_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -119,22 +154,22 @@ FSGS_HD bool project_gaussian(const CamConst &cc, const float *V, const float *P
     float vx, vy, vz;
     xf43(V, mean[0], mean[1], mean[2], vx, vy, vz);
     if (vz <= NEAR_CULL) return false;
-    const float hx = PM[0] * mean[0] + PM[4] * mean[1] + PM[8] * mean[2] + PM[12];
-    const float hy = PM[1] * mean[0] + PM[5] * mean[1] + PM[9] * mean[2] + PM[13];
-    const float hw = PM[3] * mean[0] + PM[7] * mean[1] + PM[11] * mean[2] + PM[15];
-    const float pw = 1.0f / (hw + 0.0000001f);
+    const float hx = dot3p(PM[0], mean[0], PM[4], mean[1], PM[8], mean[2], PM[12]);
+    const float hy = dot3p(PM[1], mean[0], PM[5], mean[1], PM[9], mean[2], PM[13]);
+    const float hw = dot3p(PM[3], mean[0], PM[7], mean[1], PM[11], mean[2], PM[15]);
+    const float pw = 1.0f / FSGS_ADD(hw, 0.0000001f);
     float t[3], M[6], xm, ym, SM0[3], SM1[3];
     ewa_M(cc, V, mean, t, M, xm, ym);
     ewa_abc(M, c6, SM0, SM1, o.a, o.b, o.c);
-    const float det = o.a * o.c - o.b * o.b;
+    const float det = FSGS_FMA(o.a, o.c, -FSGS_MUL(o.b, o.b));
     if (det == 0.0f) return false;
     const float det_inv = 1.f / det;
-    o.conx = o.c * det_inv; o.cony = -o.b * det_inv; o.conz = o.a * det_inv;
-    const float mid = 0.5f * (o.a + o.c);
-    const float lam = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
-    const float rad = ceilf(3.f * sqrtf(lam));
-    o.px = ((hx * pw + 1.0f) * cc.W - 1.0f) * 0.5f;
-    o.py = ((hy * pw + 1.0f) * cc.H - 1.0f) * 0.5f;
+    o.conx = FSGS_MUL(o.c, det_inv); o.cony = FSGS_MUL(-o.b, det_inv); o.conz = FSGS_MUL(o.a, det_inv);
+    const float mid = FSGS_MUL(0.5f, FSGS_ADD(o.a, o.c));
+    const float lam = FSGS_ADD(mid, sqrtf(fmaxf(0.1f, FSGS_FMA(mid, mid, -det))));
+    const float rad = ceilf(FSGS_MUL(3.f, sqrtf(lam)));
+    o.px = FSGS_MUL(FSGS_FMA(FSGS_FMA(hx, pw, 1.0f), (float)cc.W, -1.0f), 0.5f);
+    o.py = FSGS_MUL(FSGS_FMA(FSGS_FMA(hy, pw, 1.0f), (float)cc.H, -1.0f), 0.5f);
     o.rminx = clampi((int)((o.px - rad) / TILE), 0, cc.gx);
     o.rminy = clampi((int)((o.py - rad) / TILE), 0, cc.gy);
     o.rmaxx = clampi((int)((o.px + rad + TILE - 1) / TILE), 0, cc.gx);
@@ -445,28 +480,66 @@ FSGS_HD float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // Fused flavour, forward: transform_to_frame + activations + projection + SH for Gaussian i.
 // pose: row-major 3x4 (first 12 floats of LearnPose.forward's output).  Returns false if skipped.
+// Pose-independent geometry of Gaussian i: Sigma_3D from the raw scale / rotation parameters.  Its inputs and outputs
+// pass through opaque register barriers on the device, so that the compiler forms the same multiply-adds here
+// whatever kernel the function is inlined into (it cannot contract across the barriers): k_preprocess_fused and
+// k_freeze_model must produce the SAME bits (the frozen-model forward is tested bit-identical).
+FSGS_HD void frozen_sigma(const CamConst &cc, const float *sc_raw, const float *rot_raw, float *c6) {
+    float s[3] = {cc.mod * expf(sc_raw[0]), cc.mod * expf(sc_raw[1]), cc.mod * expf(sc_raw[2])};
+    const float qq = FSGS_FMA(rot_raw[3], rot_raw[3], dot3(rot_raw[0], rot_raw[0], rot_raw[1], rot_raw[1], rot_raw[2], rot_raw[2]));
+    const float qn = fmaxf(sqrtf(qq), 1e-12f);
+    const float qi = 1.0f / qn;
+    float q[4] = {rot_raw[0] * qi, rot_raw[1] * qi, rot_raw[2] * qi, rot_raw[3] * qi};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) asm volatile("" : "+f"(s[k]));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) asm volatile("" : "+f"(q[k]));
+#endif
+    cov3d_from_scale_rot(s, q, c6);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) asm volatile("" : "+f"(c6[k]));
+#endif
+}
+// ... and its colour: SH view direction = WORLD position minus the frozen camera centre (reference quirk iii)
+FSGS_HD void frozen_colour(const CamConst &cc, const float *cam_center, const float *xyz, const float *dc,
+                           const float *rest, float *rgb, uint8_t &clamp) {
+    float d[3] = {xyz[0] - cam_center[0], xyz[1] - cam_center[1], xyz[2] - cam_center[2]};
+    const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    d[0] *= inv; d[1] *= inv; d[2] *= inv;
+    sh_to_rgb(cc.sh_deg, d, [&](int k, int ch) { return k == 0 ? dc[ch] : rest[3 * (k - 1) + ch]; }, rgb, clamp);
+}
+
 FSGS_HD bool fused_forward_one(const CamConst &cc, const float *V, const float *PM, const float *pose,
                                const float *cam_center, const float *xyz, const float *dc, const float *rest,
                                float op_raw, const float *sc_raw, const float *rot_raw, Splat &sp, float &opacity,
                                float *rgb, uint8_t &clamp) {
     float mean[3];
-    for (int r = 0; r < 3; ++r)
-        mean[r] = pose[4 * r] * xyz[0] + pose[4 * r + 1] * xyz[1] + pose[4 * r + 2] * xyz[2] + pose[4 * r + 3];
-    const float s[3] = {cc.mod * expf(sc_raw[0]), cc.mod * expf(sc_raw[1]), cc.mod * expf(sc_raw[2])};
-    const float qn = fmaxf(sqrtf(rot_raw[0] * rot_raw[0] + rot_raw[1] * rot_raw[1] + rot_raw[2] * rot_raw[2] +
-                                 rot_raw[3] * rot_raw[3]), 1e-12f);
-    const float qi = 1.0f / qn;
-    const float q[4] = {rot_raw[0] * qi, rot_raw[1] * qi, rot_raw[2] * qi, rot_raw[3] * qi};
+    pose_mean(pose, xyz, mean);
     float c6[6];
-    cov3d_from_scale_rot(s, q, c6);
+    frozen_sigma(cc, sc_raw, rot_raw, c6);
     if (!project_gaussian(cc, V, PM, mean, c6, sp)) return false;
     opacity = sigmoidf(op_raw);
-    // SH view direction: WORLD position minus the frozen camera centre (reference quirk iii)
-    float d[3] = {xyz[0] - cam_center[0], xyz[1] - cam_center[1], xyz[2] - cam_center[2]};
-    const float inv = 1.0f / sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    d[0] *= inv; d[1] *= inv; d[2] *= inv;
-    sh_to_rgb(cc.sh_deg, d, [&](int k, int ch) { return k == 0 ? dc[ch] : rest[3 * (k - 1) + ch]; }, rgb, clamp);
+    frozen_colour(cc, cam_center, xyz, dc, rest, rgb, clamp);
     return true;
+}
+
+// The same forward split at the pose: everything of Gaussian i that does not depend on the pose (activated
+// opacity, Sigma_3D, SH colour + clamp mask -- reference quirks ii / iii) ...
+FSGS_HD void fused_frozen_one(const CamConst &cc, const float *cam_center, const float *xyz, const float *dc,
+                              const float *rest, float op_raw, const float *sc_raw, const float *rot_raw, float *c6,
+                              float &opacity, float *rgb, uint8_t &clamp) {
+    frozen_sigma(cc, sc_raw, rot_raw, c6);
+    opacity = sigmoidf(op_raw);
+    frozen_colour(cc, cam_center, xyz, dc, rest, rgb, clamp);
+}
+// ... and the pose-dependent rest: camera-frame mean + projection.  Returns false if skipped.
+FSGS_HD bool fused_forward_frozen_one(const CamConst &cc, const float *V, const float *PM, const float *pose,
+                                      const float *xyz, const float *c6, Splat &sp) {
+    float mean[3];
+    pose_mean(pose, xyz, mean);
+    return project_gaussian(cc, V, PM, mean, c6, sp);
 }
 
 // Geometry half of the fused backward, shared by the full and the pose-only bodies: camera-frame mean,
@@ -475,8 +548,7 @@ FSGS_HD void fused_backward_geometry(const CamConst &cc, const float *V, const f
                                      const float *xyz, const float *sc_raw, const float *rot_raw, const float *acc,
                                      float *s, float *q, float &qi, float *dmean, float *dc6) {
     float mean[3];
-    for (int r = 0; r < 3; ++r)
-        mean[r] = pose[4 * r] * xyz[0] + pose[4 * r + 1] * xyz[1] + pose[4 * r + 2] * xyz[2] + pose[4 * r + 3];
+    pose_mean(pose, xyz, mean);
     s[0] = cc.mod * expf(sc_raw[0]); s[1] = cc.mod * expf(sc_raw[1]); s[2] = cc.mod * expf(sc_raw[2]);
     const float qn = fmaxf(sqrtf(rot_raw[0] * rot_raw[0] + rot_raw[1] * rot_raw[1] + rot_raw[2] * rot_raw[2] +
                                  rot_raw[3] * rot_raw[3]), 1e-12f);

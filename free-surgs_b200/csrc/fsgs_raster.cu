@@ -75,7 +75,7 @@ inline int blocks(int n) { return (n + CTA - 1) / CTA; }
 // steps) to obtain the per-launch duration of each kernel for the roofline line.
 enum KernelId { K_PRE_API = 0, K_PRE_FUSED, K_SCAN, K_SCATTER, K_SORT, K_COMP_FWD, K_COMP_BWD, K_PRE_API_BWD,
                 K_PRE_FUSED_BWD, K_MARK_VISIBLE, K_POSE_FWD, K_POSE_BWD, K_SH_EXPAND, K_PRE_POSE_BWD, K_LOSS_FWD, K_LOSS_BWD, K_PEARSON_FWD, K_PEARSON_BWD,
-                K_LOCAL_PEARSON_FWD, K_LOCAL_PEARSON_BWD, K_EXCHANGE, K_COUNT };
+                K_LOCAL_PEARSON_FWD, K_LOCAL_PEARSON_BWD, K_EXCHANGE, K_FREEZE, K_PRE_FROZEN, K_COUNT };
 struct Profiler {
     bool on = false;
     static constexpr int MAXREC = 8192;
@@ -365,7 +365,7 @@ const char *fsgs_kernel_names(void) {
     return "k_preprocess_api,k_preprocess_fused,k_tile_scan,k_scatter,k_tile_sort,k_composite_fwd,"
            "k_composite_bwd,k_preprocess_api_bwd,k_preprocess_fused_bwd,k_mark_visible,k_pose_forward,k_pose_backward,"
            "k_sh_grad_expand,k_preprocess_pose_bwd,k_rgb_loss_fwd,k_rgb_loss_bwd,k_pearson_sums,k_pearson_bwd,"
-           "k_local_pearson_sums,k_local_pearson_bwd,k_exchange_rows";
+           "k_local_pearson_sums,k_local_pearson_bwd,k_exchange_rows,k_freeze_model,k_preprocess_frozen";
 }
 
 size_t fsgs_geom_bytes(int32_t P) { return geom_layout(P).total; }
@@ -569,6 +569,75 @@ int fsgs_render_forward_ex(const fsgs_settings *st, int32_t P, const float *bg, 
         sticky_flag());
     prof_end(K_PRE_FUSED, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused");
+    return forward_tail<true>(st, cc, P, bg, B, binning_alloc, binning_user, out_planes, nullptr, num_rendered_host,
+                              num_rect_host, ex, stream);
+}
+
+// ---- frozen-model forward (tracking loops: many poses, one Gaussian model) -------------------------------
+size_t fsgs_frozen_bytes(int32_t P) { return (size_t)(P > 0 ? P : 1) * 64; }
+
+int fsgs_freeze_model(const fsgs_settings *st, int32_t P, const float *xyz, const float *features_dc,
+                      const float *features_rest, const float *opacity_raw, const float *scaling_raw,
+                      const float *rotation_raw, const float *cam_center, void *frozen, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CamConst cc;
+    int rc = make_cam(st, cc);
+    if (rc) return rc;
+    if (P < 0 || !cam_center || (P > 0 && (!xyz || !features_dc || !features_rest || !opacity_raw || !scaling_raw ||
+                                           !rotation_raw || !frozen)))
+        return FSGS_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(frozen) | reinterpret_cast<uintptr_t>(rotation_raw)) & 15u) return FSGS_E_INVALID;
+    if ((rc = check_arch())) return rc;
+    if (P == 0) return FSGS_OK;
+    cc.n_coeffs = 16;
+    prof_begin(K_FREEZE, stream);
+    k_freeze_model<<<blocks(P), CTA, 0, stream>>>(cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw,
+                                                  rotation_raw, cam_center, static_cast<float4 *>(frozen));
+    prof_end(K_FREEZE, stream);
+    FSGS_LAUNCH_OK("k_freeze_model");
+    return FSGS_OK;
+}
+
+int fsgs_render_forward_frozen(const fsgs_settings *st, int32_t P, const float *bg, const void *frozen, const float *pose,
+                               const float *viewmatrix, const float *projmatrix, fsgs_alloc_fn geom_alloc,
+                               void *geom_user, fsgs_alloc_fn binning_alloc, void *binning_user, fsgs_alloc_fn img_alloc,
+                               void *img_user, float *out_planes, int32_t *radii, int64_t *num_rendered_host,
+                               int64_t *num_rect_host, const fsgs_render_extras *extras, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    RenderExtras ex{};
+    if (extras) {
+        ex.uncertainty = extras->uncertainty; ex.presence_mask = extras->presence_mask; ex.nan_mask = extras->nan_mask;
+        ex.visibility = extras->visibility; ex.max_radii2D = extras->max_radii2D;
+    }
+    CamConst cc;
+    int rc = make_cam(st, cc);
+    if (rc) return rc;
+    if (P < 0 || !bg || !out_planes || !viewmatrix || !projmatrix || !pose || !geom_alloc || !binning_alloc || !img_alloc)
+        return FSGS_E_INVALID;
+    if (P > 0 && (!frozen || !radii || (reinterpret_cast<uintptr_t>(frozen) & 15u))) return FSGS_E_INVALID;
+    if ((rc = check_arch())) return rc;
+    if ((rc = one_time_setup())) return rc;
+    cc.n_coeffs = 16;
+    if (num_rendered_host) *num_rendered_host = 0;
+    if (num_rect_host) *num_rect_host = 0;
+    const int HW = cc.W * cc.H;
+    if (P == 0) {
+        k_fill_bg<<<blocks(HW), CTA, 0, stream>>>(HW, 6, bg, out_planes, nullptr);
+        FSGS_LAUNCH_OK("k_fill_bg");
+        k_fill_extras<<<blocks(HW), CTA, 0, stream>>>(HW, bg, ex);
+        FSGS_LAUNCH_OK("k_fill_extras");
+        return FSGS_OK;
+    }
+    Buffers B;
+    if ((rc = alloc_fixed(P, cc, geom_alloc, geom_user, img_alloc, img_user, B, stream))) return rc;
+    prof_begin(K_PRE_FROZEN, stream);
+    k_preprocess_frozen<<<blocks(P), CTA, 0, stream>>>(
+        cc, P, static_cast<const float4 *>(frozen), pose, viewmatrix, projmatrix,
+        reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped), radii,
+        reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
+        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags, ex.visibility, ex.max_radii2D);
+    prof_end(K_PRE_FROZEN, stream);
+    FSGS_LAUNCH_OK("k_preprocess_frozen");
     return forward_tail<true>(st, cc, P, bg, B, binning_alloc, binning_user, out_planes, nullptr, num_rendered_host,
                               num_rect_host, ex, stream);
 }

@@ -86,6 +86,11 @@ _SIGNATURES = {
     "fsgs_compact_grad_expand": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i32, _i32] + [_vp] * 10),
     "fsgs_exchange_rows": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _vp]),
     "fsgs_set_instance_capacity": (ctypes.c_int, [_i32, _i64]),
+    "fsgs_frozen_bytes": (ctypes.c_size_t, [_i32]),
+    "fsgs_freeze_model": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 9),
+    "fsgs_render_forward_frozen": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 5 +
+                                   [ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp] + [_vp] * 2 +
+                                   [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp, _vp]),
     "fsgs_watchdog_flag": (ctypes.c_int, [_i32, _i32]),
     "fsgs_sh_grad_expand": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 6),
     "fsgs_rgb_loss_scratch_bytes": (ctypes.c_size_t, [_i32, _i32, _i32]),

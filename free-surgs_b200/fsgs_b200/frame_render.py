@@ -46,6 +46,67 @@ def set_grad_reducer(fn, chunks: int = 1, alloc=None) -> None:
     _GRAD_REDUCER["alloc"] = alloc
 
 
+class FrozenModel:
+    """Pose-independent per-Gaussian rows of one Gaussian model (``fsgs_freeze_model``: sigmoid(opacity), Sigma_3D,
+    SH colour + clamp mask; 64 B per Gaussian) for the tracking loop, which renders the same model from 50 pose
+    estimates per frame (reference train.py:154-210).  ``rows(...)`` returns the buffer, re-evaluating it IN PLACE
+    when any of the seven source tensors was replaced or written to since (data pointer + version counter), so a
+    captured CUDA graph that reads the buffer sees the refreshed rows (``GraphedStep.replay`` calls ``refresh``)."""
+
+    def __init__(self):
+        self.key, self.buf, self.src, self.st, self.ready = None, None, None, None, None
+        self.lock = threading.Lock()
+
+    @staticmethod
+    def _key(src, st, dev):
+        return (tuple((x.data_ptr(), x._version, tuple(x.shape)) for x in src), int(st.sh_degree),
+                float(st.scale_modifier), int(st.flags) & ~_lib.FLAG_FIXED_CAPACITY, dev.index)
+
+    def rows(self, src, st, dev):
+        """src = (xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, cam_center): float32 contiguous CUDA
+        tensors.  Not called while a stream is capturing unless the rows are current."""
+        with self.lock:
+            key = self._key(src, st, dev)
+            capturing = torch.cuda.is_current_stream_capturing()
+            if key != self.key:
+                if capturing:
+                    return None                     # never evaluate inside a capture: the caller takes the plain forward
+                P = src[0].shape[0]
+                nbytes = int(_lib.lib().fsgs_frozen_bytes(P))
+                if self.buf is None or self.buf.numel() != nbytes or self.buf.device != dev:
+                    self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                stream = torch.cuda.current_stream(dev)
+                if self.ready is not None:
+                    stream.wait_event(self.ready)   # earlier readers / writers of the buffer on other streams
+                with _on_device(dev):
+                    rc = _lib.lib().fsgs_freeze_model(ctypes.byref(st), P, *[_ptr(x) for x in src], _ptr(self.buf),
+                                                      ctypes.c_void_p(stream.cuda_stream))
+                _lib.check(rc)
+                self.ready = torch.cuda.Event()
+                self.ready.record(stream)
+                self.key, self.src, self.st = key, tuple(src), st
+            elif not capturing and self.ready is not None:
+                torch.cuda.current_stream(dev).wait_event(self.ready)
+            return self.buf
+
+    def refresh(self):
+        """Re-evaluate the rows if their sources changed (eager; for captured graphs that read the buffer)."""
+        if self.src is not None:
+            self.rows(self.src, self.st, self.src[0].device)
+
+
+USE_FROZEN_MODEL = True          # tracking against a frozen model renders from FrozenModel rows (bit-identical)
+_FROZEN: Dict[int, FrozenModel] = {}
+_CAPTURED_FROZEN = []            # FrozenModel objects read by fused forwards recorded during a graph capture
+
+
+def _frozen_model(dev) -> FrozenModel:
+    fm = _FROZEN.get(dev.index)
+    if fm is None:
+        fm = _FROZEN[dev.index] = FrozenModel()
+    return fm
+
+
 def _exchange_stream(dev) -> "torch.cuda.Stream":
     s = _XCHG_STREAMS.get(dev.index)
     if s is None:
@@ -114,7 +175,8 @@ class _RenderFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, rs, cam_center,
-                active_sh_degree, gs_grad, cam_grad, max_radii2D=None, want_extras=False, stats=None):
+                active_sh_degree, gs_grad, cam_grad, max_radii2D=None, want_extras=False, stats=None,
+                use_frozen=False):
         _require_cuda(xyz)
         dev = xyz.device
         P = xyz.shape[0]
@@ -146,11 +208,24 @@ class _RenderFused(torch.autograd.Function):
             ex_ptr = ctypes.cast(ctypes.pointer(ex), ctypes.c_void_p)
             mb = masks.view(torch.bool)
             extras = (unc, mb[:H * W].view(H, W), mb[H * W:2 * H * W].view(1, H, W), mb[2 * H * W:])
+        rows = None
+        if use_frozen and P > 0:
+            # pose-independent quantities evaluated once per model state (FrozenModel), 64 B instead of 236 B per Gaussian
+            fm = _frozen_model(dev)
+            rows = fm.rows((*t[1:7], t[8]), st, dev)
+            if rows is not None and capturing:
+                _CAPTURED_FROZEN.append(fm)
         with _on_device(dev):
-            rc = _lib.lib().fsgs_render_forward_ex(
-                ctypes.byref(st), P, *[_ptr(x) for x in t], arena.callback("geom"), None, arena.callback("binning"),
-                None, arena.callback("img"), None, _ptr(planes), _ptr(radii), ctypes.byref(nr), ctypes.byref(nrect),
-                ex_ptr, ctypes.c_void_p(stream))
+            if rows is not None:
+                rc = _lib.lib().fsgs_render_forward_frozen(
+                    ctypes.byref(st), P, _ptr(t[0]), _ptr(rows), _ptr(t[7]), _ptr(t[9]), _ptr(t[10]),
+                    arena.callback("geom"), None, arena.callback("binning"), None, arena.callback("img"), None,
+                    _ptr(planes), _ptr(radii), ctypes.byref(nr), ctypes.byref(nrect), ex_ptr, ctypes.c_void_p(stream))
+            else:
+                rc = _lib.lib().fsgs_render_forward_ex(
+                    ctypes.byref(st), P, *[_ptr(x) for x in t], arena.callback("geom"), None, arena.callback("binning"),
+                    None, arena.callback("img"), None, _ptr(planes), _ptr(radii), ctypes.byref(nr), ctypes.byref(nrect),
+                    ex_ptr, ctypes.c_void_p(stream))
         _lib.check(rc)
         empty = torch.empty(0, dtype=torch.uint8, device=dev)
         keep = getattr(_TLS, "keep_geom", None)
@@ -217,7 +292,8 @@ class _RenderFused(torch.autograd.Function):
                     None, None, None, None, None, None, _ptr(g_pose), None, None, ctypes.c_void_p(stream))
             arena.finish().release()
             _lib.check(rc)
-            return (None, None, None, None, None, None, g_pose, None, None, None, None, None, None, None, None, None)
+            return (None, None, None, None, None, None, g_pose, None, None, None, None, None, None, None, None, None,
+                    None)
 
         def carve(flat, layout):
             off = 0
@@ -291,23 +367,26 @@ class _RenderFused(torch.autograd.Function):
                 if side is not None:
                     main.wait_stream(side)             # every gradient tensor is complete before autograd hands it on
         return (g["xyz"], g["f_dc"], g["f_rest"], g["opacity"], g["scaling"], g["rotation"],
-                g["pose"] if cam_grad else None, g["means2D"], None, None, None, None, None, None, None, None)
+                g["pose"] if cam_grad else None, g["means2D"], None, None, None, None, None, None, None, None, None)
 
 
 def render_planes(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D, raster_settings,
                   cam_center, active_sh_degree, gs_grad=True, cam_grad=True, max_radii2D=None, want_extras=False,
-                  densification_stats=None):
+                  densification_stats=None, frozen_model=False):
     """Tensor-level entry: -> ((rgb[3,H,W], depth[H,W], silhouette[H,W], depth_sq[H,W]), radii[P] int32,
     (instances, reference-rectangle instances)); the four images are views of one [6,H,W] buffer.
     With ``want_extras`` a 4th element: (uncertainty[1,H,W], presence_mask[H,W], nan_mask[1,H,W],
-    visibility[P], max_radii2D_updated_in_place: bool), produced by the forward kernels."""
+    visibility[P], max_radii2D_updated_in_place: bool), produced by the forward kernels.
+    ``frozen_model``: the Gaussian parameters are not being optimised (pose tracking): the forward reads the
+    pose-independent rows of ``FrozenModel`` instead of the raw parameters -- same result, bit for bit."""
     _check_identity_view(raster_settings)
     mr = max_radii2D
     fuse_mr = (want_extras and mr is not None and mr.dtype == torch.float32 and mr.is_contiguous()
                and mr.device == xyz.device and mr.numel() == xyz.shape[0])
     rgb, depth, sil, dsq, radii, *extras = _RenderFused.apply(xyz, f_dc, f_rest, opacity_raw, scaling_raw, rotation_raw, pose, means2D,
                                                 raster_settings, cam_center, active_sh_degree, gs_grad, cam_grad,
-                                                mr if fuse_mr else None, want_extras, densification_stats)
+                                                mr if fuse_mr else None, want_extras, densification_stats,
+                                                bool(frozen_model) and USE_FROZEN_MODEL)
     if want_extras:
         return (rgb, depth, sil, dsq), radii, getattr(_TLS, "last_stats", (0, 0)), (*extras, fuse_mr)
     return (rgb, depth, sil, dsq), radii, getattr(_TLS, "last_stats", (0, 0))
@@ -376,7 +455,7 @@ def render(viewpoint_camera, index, pc, gs_grad=True, cam_grad=True):
         xyz, pc.params['_features_dc'], pc.params['_features_rest'], pc.params['_opacity'], pc.params['_scaling'],
         pc.params['_rotation'], pose, means2D, pc.cam, viewpoint_camera.cam_center, pc.active_sh_degree,
         gs_grad=gs_grad, cam_grad=cam_grad, max_radii2D=pc.variables.get('max_radii2D'), want_extras=True,
-        densification_stats=_folded_stats(pc, gs_grad))
+        densification_stats=_folded_stats(pc, gs_grad), frozen_model=frozen)
     out = _pack_fused(pc, viewmatrix_cur, planes, radius, means2D, extras)
     out["num_rendered"] = stats
     return out

@@ -37,6 +37,7 @@ class GraphedStep:
         self.fn, self.warmup, self.headroom = fn, int(warmup), float(headroom)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.graph, self.outputs, self._captured, self.capacity = None, None, [], 0
+        self._frozen = []          # frame_render.FrozenModel buffers the captured forwards read
         self._capture()
 
     def _capture(self) -> None:
@@ -58,13 +59,18 @@ class GraphedStep:
         self.capacity = max(int(most * self.headroom) + 4096, int(self.capacity * self.headroom))
         _lib.check(_lib.lib().fsgs_set_instance_capacity(dev.index, self.capacity))
         del frame_render._CAPTURED[:]
+        del frame_render._CAPTURED_FROZEN[:]
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.outputs = self.fn()
         self._captured = list(frame_render._CAPTURED)
+        self._frozen = list(dict.fromkeys(frame_render._CAPTURED_FROZEN))
         del frame_render._CAPTURED[:]
+        del frame_render._CAPTURED_FROZEN[:]
 
     def replay(self):
+        for fm in self._frozen:        # tracking against a frozen model: re-evaluate the pose-independent rows (in
+            fm.refresh()               # place, eagerly) if the model was written to since -- a few version compares
         self.graph.replay()
         return self.outputs
 

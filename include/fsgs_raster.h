@@ -158,6 +158,29 @@ int fsgs_render_forward_ex(const fsgs_settings *st, int32_t P, const float *bg, 
                            int32_t *radii, int64_t *num_rendered_host, int64_t *num_rect_host,
                            const fsgs_render_extras *extras, void *stream);
 
+/* Frozen-model forward: the fused render for loops that render ONE Gaussian model from many poses -- Free-SurGS'
+ * tracking (train.py:154-210: 50 iterations per frame that only move the pose; gaussian_renderer/__init__.py:49-92 is
+ * called with the same parameters every time).  With the reference's quirks (identity rasteriser view, quaternions not
+ * rotated into the camera frame, SH view direction = world position - a frozen camera centre; pose_optimizer.py:603,
+ * gaussian_model.py:308-333) everything about a Gaussian except its camera-frame mean is independent of the pose.
+ *   fsgs_freeze_model           evaluates sigmoid(opacity), Sigma_3D = R S^2 R^T and the SH colour + clamp mask once
+ *                               into `frozen` (fsgs_frozen_bytes(P) = 64 B per Gaussian, 16-byte aligned device memory);
+ *   fsgs_render_forward_frozen  = fsgs_render_forward_ex reading 64 B instead of 236 B per Gaussian.  Same outputs, bit
+ *                               for bit; the buffers it hands out feed the same fsgs_render_backward* calls (which
+ *                               still take the raw parameters).
+ * The caller owns the invalidation: re-freeze after any change of the parameters, cam_center, st->sh_degree or
+ * st->scale_modifier. */
+size_t fsgs_frozen_bytes(int32_t P);
+int fsgs_freeze_model(const fsgs_settings *st, int32_t P, const float *xyz, const float *features_dc,
+                      const float *features_rest, const float *opacity_raw, const float *scaling_raw,
+                      const float *rotation_raw, const float *cam_center, void *frozen, void *stream);
+int fsgs_render_forward_frozen(const fsgs_settings *st, int32_t P, const float *bg, const void *frozen,
+                               const float *pose, const float *viewmatrix, const float *projmatrix,
+                               fsgs_alloc_fn geom_alloc, void *geom_user, fsgs_alloc_fn binning_alloc,
+                               void *binning_user, fsgs_alloc_fn img_alloc, void *img_user, float *out_planes,
+                               int32_t *radii, int64_t *num_rendered_host, int64_t *num_rect_host,
+                               const fsgs_render_extras *extras, void *stream);
+
 /* Backward of the fused render.  dL_dplanes[6,H,W].  Outputs (overwritten; NULL = skip):
  * dL_dxyz[P,3], dL_dfeatures_dc[P,1,3], dL_dfeatures_rest[P,15,3], dL_dopacity_raw[P,1],
  * dL_dscaling_raw[P,3], dL_drotation_raw[P,4], dL_dpose[4,4] (row 3 = 0),

@@ -283,3 +283,69 @@ def test_cuda_graph_capture_of_a_whole_step_matches_eager():
     gs.release()
     assert gs.graph is None and gs.outputs is None
     check(eager(), got, "eager after release")
+
+
+def test_frozen_model_forward_is_bit_identical_and_follows_the_model():
+    """Tracking against a frozen model renders from the pose-independent rows of fsgs_freeze_model
+    (fsgs_render_forward_frozen): the frame, radii, derived maps and the pose gradient must equal the plain forward
+    bit for bit; rows are re-evaluated when a parameter is written to; a captured step follows too."""
+    from fsgs_b200 import GraphedStep
+    render, model, sc, poses, pc = _setup(P=30000, W=640, H=512)
+    for v in pc.params.values():
+        v.requires_grad_(False)
+    G = torch.randn(3, 512, 640, generator=torch.Generator().manual_seed(11)).to(DEV)
+
+    def step():
+        # (returns detached copies only: an autograd graph kept alive here would pin the pose parameters'
+        # AccumulateGrad nodes to this stream and break the capture below)
+        poses.pose_param_net.zero_grad(set_to_none=True)
+        out = render.render(poses, 0, pc, gs_grad=False, cam_grad=True)
+        (out["render"] * G).sum().backward()
+        snap = {k: out[k].detach().clone() for k in ("render", "render_dep", "render_opacity", "uncertainty", "radii",
+                                                     "visibility_filter", "presence_mask", "nan_mask")}
+        return snap, poses.pose_param_net.r.grad.clone(), poses.pose_param_net.t.grad.clone()
+
+    def snapshot(out):
+        return list(out.values())
+
+    def same(a, b):
+        return all(torch.equal(x, y) for x, y in zip(a, b))
+
+    for trial in range(2):
+        render.USE_FROZEN_MODEL = False
+        out, gr0, gt0 = step()
+        ref = snapshot(out)
+        render.USE_FROZEN_MODEL = True
+        out, gr1, gt1 = step()                   # evaluates the rows (trial 0) / finds them stale (trial 1)
+        assert same(ref, snapshot(out)), trial
+        out, gr2, gt2 = step()                   # reuses them
+        assert same(ref, snapshot(out)), trial
+        # the pose gradient is a float sum over atomics: equal up to summation order
+        assert rel_err(gr1, gr0) < 1e-5 and rel_err(gt1, gt0) < 1e-5 and rel_err(gr2, gr0) < 1e-5
+        with torch.no_grad():                    # in-place change of the model: the rows must follow
+            pc.params["_features_dc"] += 0.05
+            pc.params["_scaling"] -= 0.02
+            pc.params["_xyz"] += 0.001
+    # a captured tracking step reads the rows' buffer: replay() refreshes it when the model was written to
+    static_G = G.clone()
+
+    def captured():
+        poses.pose_param_net.r.grad = None
+        poses.pose_param_net.t.grad = None
+        out = render.render(poses, 0, pc, gs_grad=False, cam_grad=True)
+        (out["render"] * static_G).sum().backward()
+        return out["render"].detach()
+
+    gs = GraphedStep(captured)
+    assert len(gs._frozen) == 1
+    img = gs.replay().clone()
+    render.USE_FROZEN_MODEL = False
+    out, _, _ = step()
+    assert torch.equal(img, out["render"])
+    with torch.no_grad():
+        pc.params["_opacity"] -= 0.3
+    out, _, _ = step()                            # plain forward on the changed model
+    render.USE_FROZEN_MODEL = True
+    img = gs.replay().clone()
+    assert torch.equal(img, out["render"])
+    gs.release()
