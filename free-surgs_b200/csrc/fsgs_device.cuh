@@ -227,6 +227,44 @@ __device__ __forceinline__ void warp_reduce_scatter16(float (&v)[16], int lane) 
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 
+// Shared-memory accesses by explicit 32-bit shared-window address + compile-time offset.  The backward compositor keeps
+// a handful of per-lane base addresses in registers for the whole kernel and addresses everything relative to them:
+// with C++ pointers into the dynamic shared array the compiler re-derived those bases from %tid / the shared-window
+// base inside every phase-B round (ncu source page: ~40 of 220 instructions per round were S2R / IMAD / LEA / LOP3
+// address re-materialisation under the 64-register cap).
+template <int OFF>
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int lds_u8(uint32_t a) {
+    unsigned int v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(a), "n"(OFF), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// make a kernel-constant register value opaque, so that the compiler keeps it instead of re-deriving it where used
+__device__ __forceinline__ uint32_t keep_reg(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
 // 16-byte vector reduction into global memory (sm_90+): one L2 operation, no value returned.
 // (atomicAdd(float4*) compiles to ATOMG with a discarded result; this is the plain RED form.)
 __device__ __forceinline__ void red_add_v4(float4 *addr, float4 v) {

@@ -236,15 +236,18 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
 //     There is no shared-memory accumulator: float atomics on shared memory are CAS loops
 //     (ATOMS.CAST.SPIN, ~10 wavefronts each), the L2 does them natively.
 //
-// Shared memory (dynamic, ~48 KB -> 4 CTAs/SM): records 2 x 128 x 48 B (bulk-TMA double buffer),
+// Shared memory (dynamic, ~53 KB -> 4 CTAs/SM): records 2 x 192 x 48 B (bulk-TMA ring),
 // s_pair 8 warps x 3 x 8 x 32 floats (pixel index XOR-swizzled by the slot's low bit so that both
 // the phase-A scalar stores and the phase-B 128-bit row loads are bank-conflict free), per-pixel
 // upstream gradients 8 warps x 2 x 4 x 9 float4 (row stride 9 for the same reason).
+// Record staging ring: A/B on B200 (round 2, config 2): 128 x 3 stages 0.4753 ms, 192 x 2 stages 0.4719 (fewer batches:
+// less per-batch compaction and fewer partly filled phase-B rounds; same 18 KB), 160 x 2 0.4911*, 144 x 3 0.4928*
+// (* before the phase-B address clean-up, against 0.4963 for 128 x 3).
 #ifndef FSGS_BWD_BATCH
-#define FSGS_BWD_BATCH 128
+#define FSGS_BWD_BATCH 192
 #endif
 #ifndef FSGS_BWD_STAGES
-#define FSGS_BWD_STAGES 3
+#define FSGS_BWD_STAGES 2
 #endif
 constexpr int BWD_BATCH = FSGS_BWD_BATCH;
 constexpr int PCHUNK = 8;
@@ -252,7 +255,7 @@ constexpr int PAIR_COMP = 3;
 constexpr int NWARP = CTA / 32;
 constexpr int SG_ROW = 9;   // float4 per pixel row of s_g (8 used)
 
-constexpr int BWD_STAGES = FSGS_BWD_STAGES;   // record staging ring (3 x 6 KB): warps may drift up to two batches apart
+constexpr int BWD_STAGES = FSGS_BWD_STAGES;   // record staging ring (2 x 9 KB): warps may drift one batch apart
 struct BwdSmem {
     float4 rec[BWD_STAGES][BWD_BATCH * REC_F4];
     float pair[NWARP][PAIR_COMP][PCHUNK][32];
@@ -279,8 +282,10 @@ struct BwdSmem {
 // and RGB-only screen-space columns of the accumulator row are not needed -- the pose reaches a splat only through
 // its mean (2-D mean, conic via the Jacobian, view depth) -- so their sums, the w / q_rgb planes of the pair buffer
 // (w is still needed for the depth column when a depth-side gradient is present) and the third flush are dropped.
+// Phase B addressed through C++ pointers into the shared array: the form the POSE-ONLY kernel keeps (its phase A is
+// the tighter one; with the explicit-address form below it spilled and ran 0.350 instead of 0.341 ms).
 template <bool FUSED, int LEVEL, bool POSE_ONLY>
-__device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int warp, int lane,
+__device__ __forceinline__ void bwd_phase_b_ptr(BwdSmem &sm, const float4 *sb, int warp, int lane,
                                             int cn, uint2 packed, float bx, float by, float kx, float ky,
                                             float *__restrict__ grad_acc) {
     const int e = lane >> 2, row = lane & 3;
@@ -365,12 +370,148 @@ __device__ __forceinline__ void bwd_phase_b(BwdSmem &sm, const float4 *sb, int w
     }
 }
 
+// Per-lane shared-window addresses of phase B, computed once per kernel (lane = (entry e, pixel row)):
+//   pair  : s_pair[warp][0][e][0] + the row's first 16-byte chunk, swizzled (the second chunk is pair ^ 16;
+//           components w / q_rgb at +1024 / +2048)
+//   g     : the row's upstream gradients, 8 x float4 (plane 1 -- silhouette / depth^2 -- at +4 * SG_ROW * 16)
+//   tp_st : this lane's 3 float4 of the row-combine buffer;  tp_ld : float4 `row` of the entry's first row
+//   list  : this lane's entry of a chunk, s_list[warp][e] (+ the chunk's first list position)
+struct BwdLaneAddr {
+    uint32_t pair, g, tp_st, tp_ld, list;
+};
+// KEEP: pin the addresses in registers (the general kernel); the pose-only kernel, whose phase A is the tighter one,
+// was measured faster when the compiler stays free to re-derive them (0.341 vs 0.351 ms).
+template <bool KEEP>
+__device__ __forceinline__ uint32_t keep_if(uint32_t v) { return KEEP ? keep_reg(v) : v; }
+template <bool KEEP>
+__device__ __forceinline__ BwdLaneAddr bwd_lane_addr(BwdSmem &sm, int warp, int lane) {
+    const int e = lane >> 2, row = lane & 3;
+    BwdLaneAddr a;
+    a.pair = keep_if<KEEP>(smem_u32(&sm.pair[warp][0][e][0]) + (uint32_t)(((row * 2) ^ (e & 1)) * 16));
+    a.g = keep_if<KEEP>(smem_u32(&sm.g[warp][0][row * SG_ROW]));
+    const uint32_t tp = smem_u32(&sm.pair[warp][0][0][0]);
+    a.tp_st = keep_if<KEEP>(tp + (uint32_t)(lane * 48));
+    a.tp_ld = keep_if<KEEP>(tp + (uint32_t)((e * 4 * 3 + row) * 16));
+    a.list = keep_if<KEEP>(smem_u32(&sm.list[warp][e]));
+    return a;
+}
+constexpr int PAIR_COMP_BYTES = PCHUNK * 32 * 4;          // one component plane of a warp's pair buffer
+constexpr int SG_PLANE_BYTES = 4 * SG_ROW * 16;           // one plane of a warp's upstream-gradient buffer
+
+template <bool FUSED, int LEVEL, bool POSE_ONLY>
+__device__ __forceinline__ void bwd_phase_b(const BwdLaneAddr &la, uint32_t sb_a, int lane,
+                                            int cn, int c0, float bx, float by, float kx, float ky,
+                                            float *__restrict__ grad_acc) {
+    const int e = lane >> 2, row = lane & 3;
+    // lanes of the first cn entries; they alone touch the pair buffer below, so they alone synchronise
+    const unsigned int amask = cn >= PCHUNK ? FULL : ((1u << (4 * cn)) - 1u);
+    if (e < cn) {
+        const uint32_t rec = sb_a + (uint32_t)lds_u8(la.list + (uint32_t)c0) * 48u;      // this lane's entry record
+        float4 o0, o1, o2;
+        const float4 q0 = lds128<0>(rec);
+        const float dx0 = q0.x - bx, dy = q0.y - (by + (float)row);
+        float S0 = 0.f, S1 = 0.f, S2 = 0.f, R0 = 0.f, R1 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, cz = 0.f, cz2 = 0.f;
+        const uint32_t p0 = la.pair, p1 = la.pair ^ 16u;
+        auto half = [&](const float4 qv, const float4 wv, const float4 rv, const float4 g0, const float4 g1, const float4 g2,
+                        const float4 g3, const float4 h01, const float4 h23, int hh) __attribute__((always_inline)) {
+            const float qa[4] = {qv.x, qv.y, qv.z, qv.w}, wa[4] = {wv.x, wv.y, wv.z, wv.w},
+                        ra[4] = {rv.x, rv.y, rv.z, rv.w};
+            const float4 ga[4] = {g0, g1, g2, g3};
+            const float g5[4] = {h01.x, h01.y, h23.x, h23.y};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = hh * 4 + k;
+                const float fi = (float)i, fi2 = (float)(i * i);
+                S0 += qa[k];
+                if (i > 0) { S1 = fmaf(qa[k], fi, S1); S2 = fmaf(qa[k], fi2, S2); }
+                if (POSE_ONLY) {
+                    if (LEVEL >= 1) cz = fmaf(wa[k], ga[k].w, cz);
+                } else {
+                    if (FUSED && LEVEL >= 1) { R0 += ra[k]; if (i > 0) R1 = fmaf(ra[k], fi, R1); }
+                    cr = fmaf(wa[k], ga[k].x, cr); cg = fmaf(wa[k], ga[k].y, cg); cb = fmaf(wa[k], ga[k].z, cb);
+                    if (LEVEL >= 1) cz = fmaf(wa[k], ga[k].w, cz);
+                }
+                if (FUSED && LEVEL >= 2) cz2 = fmaf(wa[k], g5[k], cz2);
+            }
+        };
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr bool NEED_W = !POSE_ONLY || LEVEL >= 1, NEED_R = FUSED && LEVEL >= 1 && !POSE_ONLY;
+        constexpr bool NEED_G = !POSE_ONLY || LEVEL >= 1, NEED_G5 = FUSED && LEVEL >= 2;
+        // (depth^2-plane gradients: .y of plane 1; two pixels per 128-bit load would need a different layout -- this
+        //  level only occurs when a caller differentiates the detached depth^2 output)
+        {
+            const float4 qv = lds128<0>(p0);
+            const float4 wv = NEED_W ? lds128<PAIR_COMP_BYTES>(p0) : z4;
+            const float4 rv = NEED_R ? lds128<2 * PAIR_COMP_BYTES>(p0) : z4;
+            const float4 g0 = NEED_G ? lds128<0>(la.g) : z4, g1 = NEED_G ? lds128<16>(la.g) : z4,
+                         g2 = NEED_G ? lds128<32>(la.g) : z4, g3 = NEED_G ? lds128<48>(la.g) : z4;
+            float4 h01 = z4, h23 = z4;
+            if (NEED_G5) {
+                h01 = make_float4(lds128<SG_PLANE_BYTES>(la.g).y, lds128<SG_PLANE_BYTES + 16>(la.g).y, 0.f, 0.f);
+                h23 = make_float4(lds128<SG_PLANE_BYTES + 32>(la.g).y, lds128<SG_PLANE_BYTES + 48>(la.g).y, 0.f, 0.f);
+            }
+            half(qv, wv, rv, g0, g1, g2, g3, h01, h23, 0);
+        }
+        {
+            const float4 qv = lds128<0>(p1);
+            const float4 wv = NEED_W ? lds128<PAIR_COMP_BYTES>(p1) : z4;
+            const float4 rv = NEED_R ? lds128<2 * PAIR_COMP_BYTES>(p1) : z4;
+            const float4 g0 = NEED_G ? lds128<64>(la.g) : z4, g1 = NEED_G ? lds128<80>(la.g) : z4,
+                         g2 = NEED_G ? lds128<96>(la.g) : z4, g3 = NEED_G ? lds128<112>(la.g) : z4;
+            float4 h01 = z4, h23 = z4;
+            if (NEED_G5) {
+                h01 = make_float4(lds128<SG_PLANE_BYTES + 64>(la.g).y, lds128<SG_PLANE_BYTES + 80>(la.g).y, 0.f, 0.f);
+                h23 = make_float4(lds128<SG_PLANE_BYTES + 96>(la.g).y, lds128<SG_PLANE_BYTES + 112>(la.g).y, 0.f, 0.f);
+            }
+            half(qv, wv, rv, g0, g1, g2, g3, h01, h23, 1);
+        }
+        if (!FUSED || LEVEL == 0) { R0 = S0; R1 = S1; }   // no depth-side gradient (or API flavour): q_rgb == q
+        const float Sx = fmaf(dx0, S0, -S1), Rx = fmaf(dx0, R0, -R1);
+        const float Sxx = fmaf(dx0, fmaf(dx0, S0, -2.f * S1), S2);
+        const float Sy = dy * S0, Sxy = dy * Sx, Syy = dy * Sy, Ry = dy * R0;
+        if (FUSED && LEVEL >= 2) cz = fmaf(2.f * lds32<36>(rec), cz2, cz);
+        // moments -> accumulator row (bwd_finalize in fsgs_math.cuh) on this row's partial sums
+        const float2 q1 = lds64<16>(rec);   // (c2, opacity)
+        float A, B, C;
+        unscale_conic(q0.z, q0.w, q1.x, A, B, C);
+        o0 = make_float4(-kx * (A * Sx + B * Sy), -ky * (C * Sy + B * Sx), -0.5f * Sxx, -0.5f * Sxy);
+        if (POSE_ONLY) {
+            o1 = make_float4(-0.5f * Syy, 0.f, 0.f, 0.f);
+            o2 = make_float4(0.f, cz, 0.f, 0.f);
+        } else {
+            o1 = make_float4(-0.5f * Syy, S0 * fast_rcp(q1.y), cr, cg);
+            o2 = make_float4(cb, cz, -kx * (A * Rx + B * Ry), -ky * (C * Ry + B * Rx));
+        }
+        __syncwarp(amask);                              // every lane is done reading the pair buffer
+    // [entry][row][3] float4 = 1536 B of 3072.  (The four-row loads below put the eight entries of a quarter-warp on two
+    // 16-byte bank groups -- ncu: 5.4 M shared-memory bank conflicts per launch.  Padding the entry stride to 13 float4
+    // removes them and was measured SLOWER, 0.511 vs 0.494 ms: the kernel is issue bound and the padded indexing costs
+    // more instructions than the conflicts cost cycles.  Round 2 A/B, tools/ab_variants.py.)
+        sts128<0>(la.tp_st, o0); sts128<16>(la.tp_st, o1);
+        if (!POSE_ONLY || LEVEL >= 1) sts128<32>(la.tp_st, o2);
+        __syncwarp(amask);
+        if (row < ((POSE_ONLY && LEVEL == 0) ? 2 : 3)) {
+            const float4 r0 = lds128<0>(la.tp_ld), r1 = lds128<48>(la.tp_ld), r2 = lds128<96>(la.tp_ld),
+                         r3 = lds128<144>(la.tp_ld);
+            float4 o;
+            o.x = (r0.x + r1.x) + (r2.x + r3.x); o.y = (r0.y + r1.y) + (r2.y + r3.y);
+            o.z = (r0.z + r1.z) + (r2.z + r3.z); o.w = (r0.w + r1.w) + (r2.w + r3.w);
+            if ((o.x != 0.f) | (o.y != 0.f) | (o.z != 0.f) | (o.w != 0.f)) {
+                const unsigned int gid = __float_as_uint(lds32<44>(rec));
+                red_add_v4(reinterpret_cast<float4 *>(grad_acc + (size_t)gid * ACC_F) + row, o);
+            }
+        }
+    }
+}
+
 // One staged batch, back to front, for one warp (phase A + embedded phase B).
 template <bool FUSED, int LEVEL, bool POSE_ONLY>
 __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int warp, int lane,
                                           int nrel, int last_rel, float pxf, float pyf, float bx, float by,
                                           float kx, float ky, const float *g, float T_final, float bgdot_rgb,
-                                          float bgdot_dep, BwdPixel &ps, float *__restrict__ grad_acc) {
+                                          float bgdot_dep, BwdPixel &ps, float *__restrict__ grad_acc,
+                                          const BwdLaneAddr &la) {
+    const uint32_t sb_a = smem_u32(sb);
     for (int c0 = ((nrel - 1) / PCHUNK) * PCHUNK; c0 >= 0; c0 -= PCHUNK) {
         const int cn = min(PCHUNK, nrel - c0);                 // this chunk: list positions c0 .. c0+cn-1
         const uint2 packed = *reinterpret_cast<const uint2 *>(&sm.list[warp][c0]);
@@ -411,7 +552,8 @@ __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int war
                 if (s < cn) slot(s);
         }
         __syncwarp();
-        bwd_phase_b<FUSED, LEVEL, POSE_ONLY>(sm, sb, warp, lane, cn, packed, bx, by, kx, ky, grad_acc);
+        if (POSE_ONLY) bwd_phase_b_ptr<FUSED, LEVEL, POSE_ONLY>(sm, sb, warp, lane, cn, packed, bx, by, kx, ky, grad_acc);
+        else bwd_phase_b<FUSED, LEVEL, POSE_ONLY>(la, sb_a, lane, cn, c0, bx, by, kx, ky, grad_acc);
         __syncwarp();
     }
 }
@@ -436,7 +578,7 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
     const int n = (int)(tile_offset[tile + 1] - start);
     if (n == 0) return;
     const bool use_tma = (flags & 1u) == 0;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = (int)keep_if<!POSE_ONLY>(threadIdx.x & 31);   // (kept: not re-read from %tid where used)
     const unsigned int warp_bit = 1u << warp;
     const TilePix pix = tile_pixel(cc, tile);
     const float pxf = (float)pix.px, pyf = (float)pix.py;
@@ -484,6 +626,7 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
         if (FUSED) sm.g[warp][1][(lane >> 3) * SG_ROW + (lane & 7)] = make_float4(g[4], g[5], 0.f, 0.f);
     }
     const float kx = 0.5f * cc.W, ky = 0.5f * cc.H;
+    const BwdLaneAddr la = bwd_lane_addr<!POSE_ONLY>(sm, warp, lane);
     // which upstream planes are non-zero anywhere in this warp's block (uniform per warp):
     // 0 = colour only (pose tracking), 1 = + depth (mapping), 2 = + silhouette / depth^2
     int level = __any_sync(FULL, g[3] != 0.f) ? 1 : 0;
@@ -504,13 +647,13 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
         if (nrel > 0) {
             if (level == 0)
                 bwd_batch<FUSED, 0, POSE_ONLY>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
-                                    T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
+                                    T_final, bgdot_rgb, bgdot_dep, ps, grad_acc, la);
             else if (!FUSED || level == 1)
                 bwd_batch<FUSED, 1, POSE_ONLY>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
-                                    T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
+                                    T_final, bgdot_rgb, bgdot_dep, ps, grad_acc, la);
             else
                 bwd_batch<FUSED, 2, POSE_ONLY>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
-                                    T_final, bgdot_rgb, bgdot_dep, ps, grad_acc);
+                                    T_final, bgdot_rgb, bgdot_dep, ps, grad_acc, la);
         }
     };
 

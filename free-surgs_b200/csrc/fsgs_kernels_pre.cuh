@@ -326,17 +326,30 @@ k_preprocess_frozen(CamConst cc, int P, const float4 *__restrict__ frozen, const
                     float4 *__restrict__ records, uint8_t *__restrict__ clamped, int *__restrict__ radii,
                     unsigned int *__restrict__ tile_count, unsigned long long *__restrict__ counters,
                     unsigned int flags, unsigned char *__restrict__ visibility, float *__restrict__ max_radii2D) {
+    // the CTA's rows are one contiguous 16 KB slice: fully coalesced 128-bit loads into shared memory (row stride
+    // 5 float4 against bank conflicts), then every thread picks up its own row
+    __shared__ float4 s_rows[CTA * 5];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    {
+        const int base = blockIdx.x * blockDim.x;
+        const int n4 = min((int)blockDim.x, P - base) * 4;
+        const float4 *src = frozen + (size_t)base * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = k * CTA + (int)threadIdx.x;
+            if (idx < n4) s_rows[(idx >> 2) * 5 + (idx & 3)] = ldg4(src + idx);
+        }
+        __syncthreads();
+    }
     unsigned int rect_tiles = 0;
     Splat sp;
     sp.px = sp.py = sp.conx = sp.cony = sp.conz = 0.f; sp.radius = 0;
     float opacity = 0.f;
     bool vis = false;
     if (i < P) {
-        const size_t n = (size_t)i;
-        const float4 f0 = ldg4(frozen + n * 4), f1 = ldg4(frozen + n * 4 + 1), f2 = ldg4(frozen + n * 4 + 2),
-                     f3 = ldg4(frozen + n * 4 + 3);
+        const float4 *row = s_rows + threadIdx.x * 5;
+        const float4 f0 = row[0], f1 = row[1], f2 = row[2], f3 = row[3];
         float V[16], PM[16], Rt[12];
         load16(viewmatrix, V);
         load16(projmatrix, PM);

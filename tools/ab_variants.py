@@ -1,6 +1,7 @@
 """A/B harness for kernel build variants (run on the GPU box).
    python tools/ab_variants.py libA.so libB.so ...   (paths relative to the repo root; '' = the default build)
-For each library: runs the bench workload (P=500k, m=2) in a fresh process and prints step ms and per-kernel ms."""
+For each library: runs the bench workload (P=500k, m=2; AB_P / AB_M override; AB_MODE=track = the tracking step
+against a frozen model) in a fresh process and prints step ms and per-kernel ms."""
 import json
 import os
 import subprocess
@@ -19,8 +20,16 @@ sc = make_scene(P, 1280, 1024, size_mult=m, seed=0)
 poses, pc = model.scene_to_device(sc, "cuda")
 G = torch.cat([sc.grads_out["G_rgb"], sc.grads_out["G_dep"][None]]).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+TRACK = os.environ.get("AB_MODE", "full") == "track"      # tracking against a frozen model (pose-only backward)
+if TRACK:
+    for v in pc.params.values():
+        v.requires_grad_(False)
 def step():
     pc.zero_grad(); poses.pose_param_net.zero_grad(set_to_none=True)
+    if TRACK:
+        out = render.render(poses, 0, pc, gs_grad=False, cam_grad=True)
+        (out["render"] * G[:3]).sum().backward()
+        return
     out = render.render(poses, 0, pc, gs_grad=True, cam_grad=True)
     ((out["render"] * G[:3]).sum() + (out["render_dep"] * G[3]).sum()).backward()
 for _ in range(5): step()
