@@ -250,9 +250,9 @@ __device__ __forceinline__ float lds32(uint32_t a) {
     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned int lds_u8(uint32_t a) {
+__device__ __forceinline__ unsigned int lds_u16(uint32_t a) {
     unsigned int v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
 template <int OFF>

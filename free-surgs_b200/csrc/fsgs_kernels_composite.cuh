@@ -76,24 +76,36 @@ __device__ __forceinline__ void stage_plain(float4 *dst, const float4 *src, int 
     for (int p = threadIdx.x; p < cnt * REC_F4; p += CTA) dst[p] = ldg4(src + p);
 }
 
-// Ballot-compact the indices j in [0, limit) of the staged batch whose block mask contains
-// `warp_bit` into `list` (ascending).  Returns the count.  One call per warp per batch.
+// Ballot-compact the entries j in [0, limit) of the staged batch whose block mask contains `warp_bit` into `list`
+// (ascending).  Returns the count.  One call per warp per batch.
+// The list holds the entries' BYTE OFFSETS inside the staged batch (j * 48, 16 bits): the compositors' inner loops
+// then address a record as [offset + batch base] straight from the unpacked list word -- with 8-bit indices every
+// visit paid a constant materialisation and an integer multiply-add for j * 48 (ncu source page, round 2: 2 of the
+// forward's 33 instructions per visit).
+typedef unsigned short list_t;
+constexpr int REC_BYTES = REC_F4 * 16;
 __device__ __forceinline__ int compact_entries(const float4 *sb, int limit, unsigned int warp_bit, int lane,
-                                               unsigned char *list) {
+                                               list_t *list) {
     int n = 0;
     for (int c = 0; c < limit; c += 32) {
         const int j = c + lane;
         const bool rel = j < limit && (__float_as_uint(sb[j * 3 + 2].z) & warp_bit) != 0;
         const unsigned int b = __ballot_sync(FULL, rel);
-        if (rel) list[n + __popc(b & ((1u << lane) - 1u))] = (unsigned char)j;
+        if (rel) list[n + __popc(b & ((1u << lane) - 1u))] = (list_t)(j * REC_BYTES);
         n += __popc(b);
     }
     __syncwarp();
     return n;
 }
 
-__device__ __forceinline__ int list_byte(uint2 packed, int s) {
-    return (int)(((s < 4 ? packed.x : packed.y) >> (8 * (s & 3))) & 0xffu);
+// entry s (0..7) of a chunk of 8 list entries loaded as one 128-bit word
+__device__ __forceinline__ int list_off(uint4 packed, int s) {
+    const unsigned int w = s < 2 ? packed.x : s < 4 ? packed.y : s < 6 ? packed.z : packed.w;
+    return (int)((s & 1) ? (w >> 16) : (w & 0xffffu));
+}
+// the record at byte offset `off` of a staged batch
+__device__ __forceinline__ const float4 *rec_at(const float4 *sb, int off) {
+    return reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(sb) + off);
 }
 
 template <bool FUSED>
@@ -105,7 +117,7 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
                 unsigned long long capacity, RenderExtras ex) {
     __shared__ __align__(128) float4 s_rec[2][BATCH * REC_F4];
     __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ __align__(8) unsigned char s_list[CTA / 32][BATCH];   // rows read 8 entries at a time
+    __shared__ __align__(16) list_t s_list[CTA / 32][BATCH];   // rows read 8 entries (16 B) at a time
     if (counters[CNT_R] > capacity) return;   // optimistic launch into a too-small buffer: the host relaunches
     const int tile = blockIdx.x;
     const unsigned int start = tile_offset[tile];
@@ -153,10 +165,11 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
         if (__all_sync(FULL, T < 0.f)) continue;                    // this warp's pixels are finished
         const float4 *sb = s_rec[buf];
         const int nrel = compact_entries(sb, cnt, warp_bit, lane, s_list[warp]);
-        int lj = -1;                                                // last contributing entry of this batch
-        auto entry = [&](int j) __attribute__((always_inline)) {
-            const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
-            const float2 q2 = *reinterpret_cast<const float2 *>(&sb[j * 3 + 2]);   // (b, depth)
+        int lj = -1;                                                // last contributing entry of this batch (byte offset)
+        auto entry = [&](int j) __attribute__((always_inline)) {    // j = byte offset of the record in the batch
+            const float4 *r = rec_at(sb, j);
+            const float4 q0 = r[0], q1 = r[1];
+            const float2 q2 = *reinterpret_cast<const float2 *>(r + 2);   // (b, depth)
             const float dx = q0.x - pxf, dy = q0.y - pyf;
             const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
             const float alpha = fminf(ALPHA_MAX, q1.y * fast_exp2(p2));
@@ -178,15 +191,15 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
         };
         for (int c0 = 0; c0 < nrel; c0 += 8) {
             if (__all_sync(FULL, T < 0.f)) break;
-            const uint2 packed = *reinterpret_cast<const uint2 *>(&s_list[warp][c0]);
+            const uint4 packed = *reinterpret_cast<const uint4 *>(&s_list[warp][c0]);
             if (c0 + 8 <= nrel) {
 #pragma unroll
-                for (int s = 0; s < 8; ++s) entry(list_byte(packed, s));
+                for (int s = 0; s < 8; ++s) entry(list_off(packed, s));
             } else {
                 for (int s = 0; s < nrel - c0; ++s) entry((int)s_list[warp][c0 + s]);
             }
         }
-        if (lj >= 0) last = (unsigned int)(k * BATCH + lj + 1);
+        if (lj >= 0) last = (unsigned int)(k * BATCH + lj / REC_BYTES + 1);
     }
     T = fabsf(T);
 
@@ -261,7 +274,7 @@ struct BwdSmem {
     float pair[NWARP][PAIR_COMP][PCHUNK][32];
     float4 g[NWARP][2][4 * SG_ROW];
     uint64_t full[BWD_STAGES];
-    unsigned char list[NWARP][BWD_BATCH];   // 8-byte aligned rows (read 8 entries at a time)
+    alignas(16) list_t list[NWARP][BWD_BATCH];   // byte offsets; 16-byte aligned rows (read 8 entries at a time)
     unsigned int done_cnt[BWD_STAGES];      // warps finished with the batch currently in each stage
     unsigned int maxlast;
 };
@@ -285,12 +298,13 @@ struct BwdSmem {
 // Phase B addressed through C++ pointers into the shared array: the form the POSE-ONLY kernel keeps (its phase A is
 // the tighter one; with the explicit-address form below it spilled and ran 0.350 instead of 0.341 ms).
 template <bool FUSED, int LEVEL, bool POSE_ONLY>
-__device__ __forceinline__ void bwd_phase_b_ptr(BwdSmem &sm, const float4 *sb, int warp, int lane,
-                                            int cn, uint2 packed, float bx, float by, float kx, float ky,
+__device__ __forceinline__ void bwd_phase_b_ptr(BwdSmem &sm, const float4 *sbatch, int warp, int lane,
+                                            int cn, uint4 packed, float bx, float by, float kx, float ky,
                                             float *__restrict__ grad_acc) {
     const int e = lane >> 2, row = lane & 3;
     const bool act = e < cn;
-    const int j = list_byte(packed, e);
+    const float4 *sb = rec_at(sbatch, list_off(packed, e));   // this lane's entry record
+    constexpr int j = 0;
     float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0;
     if (act) {
         const float4 q0 = sb[j * 3];
@@ -406,7 +420,7 @@ __device__ __forceinline__ void bwd_phase_b(const BwdLaneAddr &la, uint32_t sb_a
     // lanes of the first cn entries; they alone touch the pair buffer below, so they alone synchronise
     const unsigned int amask = cn >= PCHUNK ? FULL : ((1u << (4 * cn)) - 1u);
     if (e < cn) {
-        const uint32_t rec = sb_a + (uint32_t)lds_u8(la.list + (uint32_t)c0) * 48u;      // this lane's entry record
+        const uint32_t rec = sb_a + lds_u16(la.list + (uint32_t)(2 * c0));      // this lane's entry record
         float4 o0, o1, o2;
         const float4 q0 = lds128<0>(rec);
         const float dx0 = q0.x - bx, dy = q0.y - (by + (float)row);
@@ -504,7 +518,8 @@ __device__ __forceinline__ void bwd_phase_b(const BwdLaneAddr &la, uint32_t sb_a
     }
 }
 
-// One staged batch, back to front, for one warp (phase A + embedded phase B).
+// One staged batch, back to front, for one warp (phase A + embedded phase B).  last_rel: this pixel's contributor
+// count relative to the batch, as a byte offset (entries at offsets >= last_rel lie behind the pixel's last one).
 template <bool FUSED, int LEVEL, bool POSE_ONLY>
 __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int warp, int lane,
                                           int nrel, int last_rel, float pxf, float pyf, float bx, float by,
@@ -514,11 +529,12 @@ __device__ __forceinline__ void bwd_batch(BwdSmem &sm, const float4 *sb, int war
     const uint32_t sb_a = smem_u32(sb);
     for (int c0 = ((nrel - 1) / PCHUNK) * PCHUNK; c0 >= 0; c0 -= PCHUNK) {
         const int cn = min(PCHUNK, nrel - c0);                 // this chunk: list positions c0 .. c0+cn-1
-        const uint2 packed = *reinterpret_cast<const uint2 *>(&sm.list[warp][c0]);
+        const uint4 packed = *reinterpret_cast<const uint4 *>(&sm.list[warp][c0]);
         auto slot = [&](int s) __attribute__((always_inline)) {
-            const int j = list_byte(packed, s);
-            const float4 q0 = sb[j * 3], q1 = sb[j * 3 + 1];
-            const float2 q2 = *reinterpret_cast<const float2 *>(&sb[j * 3 + 2]);   // (b, depth)
+            const int j = list_off(packed, s);                                     // byte offset of the record
+            const float4 *r = rec_at(sb, j);
+            const float4 q0 = r[0], q1 = r[1];
+            const float2 q2 = *reinterpret_cast<const float2 *>(r + 2);            // (b, depth)
             const float dx = q0.x - pxf, dy = q0.y - pyf;
             const float p2 = gauss_power2(q0.z, q0.w, q1.x, dx, dy);
             const float G = fast_exp2(p2);
@@ -646,13 +662,13 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
         const int nrel = limit > 0 ? compact_entries(sb, limit, warp_bit, lane, sm.list[warp]) : 0;
         if (nrel > 0) {
             if (level == 0)
-                bwd_batch<FUSED, 0, POSE_ONLY>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 0, POSE_ONLY>(sm, sb, warp, lane, nrel, (last - k * BWD_BATCH) * REC_BYTES, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc, la);
             else if (!FUSED || level == 1)
-                bwd_batch<FUSED, 1, POSE_ONLY>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 1, POSE_ONLY>(sm, sb, warp, lane, nrel, (last - k * BWD_BATCH) * REC_BYTES, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc, la);
             else
-                bwd_batch<FUSED, 2, POSE_ONLY>(sm, sb, warp, lane, nrel, last - k * BWD_BATCH, pxf, pyf, bx, by, kx, ky, g,
+                bwd_batch<FUSED, 2, POSE_ONLY>(sm, sb, warp, lane, nrel, (last - k * BWD_BATCH) * REC_BYTES, pxf, pyf, bx, by, kx, ky, g,
                                     T_final, bgdot_rgb, bgdot_dep, ps, grad_acc, la);
         }
     };
