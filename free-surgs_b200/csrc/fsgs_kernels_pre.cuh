@@ -508,9 +508,15 @@ __device__ __forceinline__ void tile_sort_network(const Keys &a, int n) {
     __syncthreads();
 }
 
-constexpr int SORT_SMEM_KEYS = 8192;   // 64 KB of dynamic shared memory
-constexpr int BUCKET_MAX_KEYS = 4096;  // lists up to this length take the bucket path (48 KB of the 64 KB window)
-constexpr int BUCKET_SMEM_IN = 2048;   // ... of which lists up to this length also keep their unsorted keys in shared memory
+// Shared-memory window of k_tile_sort, in 8-byte keys, chosen per launch (`win`):
+//   SORT_SMEM_KEYS (64 KB, 3 CTAs/SM) when nothing is known about the list lengths or the longest list of the previous
+//   frame was long; SORT_SMEM_KEYS_SMALL (32 KB, 4 CTAs/SM -- then limited by registers) when the previous frame's
+//   longest list leaves 25 % headroom below win/2.  A/B on B200 (round 2, config 2): 0.093 -> 0.080 ms.
+// Lists up to win/2 take the bucket path (3/4 of the window), of which lists up to win/4 also keep their unsorted keys
+// in shared memory; lists up to win take the compare-exchange network in shared memory, longer ones in global memory --
+// so a wrong guess costs time on the affected tiles, never correctness.
+constexpr int SORT_SMEM_KEYS = 8192;
+constexpr int SORT_SMEM_KEYS_SMALL = 4096;
 constexpr int BUCKET_MAX_FILL = 24;    // fullest bucket the rank pass accepts before falling back to the network
 
 // Gather one sorted instance: per-Gaussian record -> compositor record (conic pre-scaled for the
@@ -548,13 +554,14 @@ __device__ __forceinline__ int depth_bucket(unsigned long long key, float zmin, 
 // the same total order on unique keys, hence bit-identical.  A tile whose fullest bucket exceeds
 // BUCKET_MAX_FILL (many equal depths, strongly clustered depths) returns false and the caller runs the
 // network instead.
-__device__ __forceinline__ bool tile_sort_bucket(int n, const unsigned long long *__restrict__ g,
+__device__ __forceinline__ bool tile_sort_bucket(int n, int win, const unsigned long long *__restrict__ g,
                                                  const float4 *__restrict__ records, float4 *__restrict__ dst,
                                                  int tile_x0, int tile_y0, bool no_cull) {
-    unsigned long long *s_out = fsgs_sort_smem;                                                  // [BUCKET_MAX_KEYS]
-    unsigned int *s_hist = reinterpret_cast<unsigned int *>(fsgs_sort_smem + BUCKET_MAX_KEYS);   // [nb <= BUCKET_MAX_KEYS]
-    unsigned long long *s_in = fsgs_sort_smem + BUCKET_MAX_KEYS + BUCKET_MAX_KEYS / 2;           // [BUCKET_SMEM_IN]
-    const bool in_smem = n <= BUCKET_SMEM_IN;
+    const int bucket_max = win >> 1;                                                         // n <= bucket_max here
+    unsigned long long *s_out = fsgs_sort_smem;                                              // [bucket_max]
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(fsgs_sort_smem + bucket_max);    // [nb <= bucket_max]
+    unsigned long long *s_in = fsgs_sort_smem + bucket_max + (bucket_max >> 1);              // [win / 4]
+    const bool in_smem = n <= (win >> 2);
     auto key_at = [&](int p) { return in_smem ? s_in[p] : __ldg(g + p); };
     __shared__ unsigned int s_red[3][CTA / 32];
     __shared__ unsigned int s_warp_sum[CTA / 32];
@@ -582,7 +589,7 @@ __device__ __forceinline__ bool tile_sort_bucket(int n, const unsigned long long
     __syncthreads();
 
     // exclusive scan of s_hist (thread t owns buckets [t*per, (t+1)*per)) + the fullest bucket
-    constexpr int PER_MAX = BUCKET_MAX_KEYS / CTA;
+    constexpr int PER_MAX = SORT_SMEM_KEYS / 2 / CTA;
     unsigned int cnt[PER_MAX], sum = 0, fill = 0;
 #pragma unroll
     for (int i = 0; i < PER_MAX; ++i) {
@@ -634,7 +641,7 @@ __device__ __forceinline__ bool tile_sort_bucket(int n, const unsigned long long
 __global__ void __launch_bounds__(CTA)
 k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long long *__restrict__ keys,
             const float4 *__restrict__ records, float4 *__restrict__ sorted_rec, unsigned int flags,
-            const unsigned long long *__restrict__ counters, unsigned long long capacity) {
+            const unsigned long long *__restrict__ counters, unsigned long long capacity, int win) {
     if (counters[CNT_R] > capacity) return;
     unsigned long long *s_keys = fsgs_sort_smem;
     const unsigned int start = tile_offset[blockIdx.x];
@@ -644,15 +651,15 @@ k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long 
     const bool no_cull = (flags & 2u) != 0;
     unsigned long long *g = keys + start;
     float4 *dst = sorted_rec + (size_t)start * 3;
-    if (n <= BUCKET_MAX_KEYS && !(flags & 16u)) {           // FSGS_FLAG_SORT_NETWORK forces the network (A/B, tests)
-        if (tile_sort_bucket(n, g, records, dst, tile_x0, tile_y0, no_cull)) return;
+    if (n <= (win >> 1) && !(flags & 16u)) {                // FSGS_FLAG_SORT_NETWORK forces the network (A/B, tests)
+        if (tile_sort_bucket(n, win, g, records, dst, tile_x0, tile_y0, no_cull)) return;
         __syncthreads();                                    // bucket path declined: the network, in shared memory
         for (int p = threadIdx.x; p < n; p += blockDim.x) s_keys[p] = g[p];
         __syncthreads();
         if (n > 1) tile_sort_network(SmemKeys{}, n);
         for (int p = threadIdx.x; p < n; p += blockDim.x)
             emit_sorted_record(records, (unsigned int)s_keys[p], dst + (size_t)p * 3, tile_x0, tile_y0, no_cull);
-    } else if (n <= SORT_SMEM_KEYS) {
+    } else if (n <= win) {
         for (int p = threadIdx.x; p < n; p += blockDim.x) s_keys[p] = g[p];
         __syncthreads();
         if (n > 1) tile_sort_network(SmemKeys{}, n);

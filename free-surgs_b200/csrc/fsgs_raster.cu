@@ -124,6 +124,7 @@ struct HostMailbox {
 };
 thread_local HostMailbox g_mail;
 unsigned long long g_hint[64] = {};         // last R per device (benign race: performance hint only)
+unsigned long long g_hint_maxlist[64] = {}; // longest tile list of the last frame per device (likewise; sizes k_tile_sort's window)
 // Device watchdog: one sticky 64-bit word per device (allocated once, never freed).  A bounded device-side wait that
 // gives up (mbar_wait) sets it; every forward reads it back together with the instance count -- the read-back it
 // performs anyway -- and fails with FSGS_E_WATCHDOG, so a stuck barrier is reported by the NEXT forward on that
@@ -184,8 +185,14 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
             prof_end(K_SCATTER, stream);
             FSGS_LAUNCH_OK("k_scatter");
             prof_begin(K_SORT, stream);
-            k_tile_sort<<<tiles, CTA, SORT_SMEM_KEYS * sizeof(unsigned long long), stream>>>(
-                cc.gx, tile_offset, keys, records, sorted_rec, (unsigned)st->flags, counters, capacity);
+            // shared-memory window: the small one (4 resident CTAs) when the previous frame's longest list fits its
+            // bucket path with 25 % headroom; results do not depend on the choice (fsgs_kernels_pre.cuh)
+            const unsigned long long ml = g_hint_maxlist[dev];
+            const int win = (ml > 0 && ml + ml / 4 <= (unsigned long long)(SORT_SMEM_KEYS_SMALL / 2) &&
+                             !(st->flags & FSGS_FLAG_SORT_WINDOW_LARGE))
+                                ? SORT_SMEM_KEYS_SMALL : SORT_SMEM_KEYS;
+            k_tile_sort<<<tiles, CTA, (size_t)win * sizeof(unsigned long long), stream>>>(
+                cc.gx, tile_offset, keys, records, sorted_rec, (unsigned)st->flags, counters, capacity, win);
             prof_end(K_SORT, stream);
             FSGS_LAUNCH_OK("k_tile_sort");
         }
@@ -235,6 +242,7 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
     if (num_rect_host) *num_rect_host = (int64_t)h_cnt[CNT_RECT];
     if (R >= (int64_t)1 << 32) return FSGS_E_INVALID;
     g_hint[dev] = (unsigned long long)R;
+    g_hint_maxlist[dev] = h_cnt[CNT_MAXLIST];
 
     if (!launched || (unsigned long long)R > capacity) {
         B.bl = bin_layout(R);

@@ -21,6 +21,7 @@ FLAG_NO_OPTIMISTIC = 8
 FLAG_SORT_NETWORK = 16
 FLAG_FIXED_CAPACITY = 32
 FLAG_NO_POSE_ONLY = 64
+FLAG_SORT_WINDOW_LARGE = 128
 
 
 class FsgsError(RuntimeError):

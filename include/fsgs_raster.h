@@ -75,6 +75,7 @@ typedef struct fsgs_settings {
 #define FSGS_FLAG_RESERVED_4 4u    /* (was: first backward formulation, removed; ignored)          */
 #define FSGS_FLAG_NO_OPTIMISTIC 8u /* forward: always wait for the instance count before binning   */
 #define FSGS_FLAG_SORT_NETWORK 16u /* per-tile sort: always the compare-exchange network (A/B, tests) */
+#define FSGS_FLAG_SORT_WINDOW_LARGE 128u /* per-tile sort: always the 64 KB shared-memory window (A/B, tests)  */
 #define FSGS_FLAG_NO_POSE_ONLY 64u /* fused backward: never take the pose-only specialisation (A/B, tests) */
 #define FSGS_FLAG_FIXED_CAPACITY 32u /* forward: no host read-back of the instance count (CUDA-graph capture);
                                         the binning buffer is sized by fsgs_set_instance_capacity()     */

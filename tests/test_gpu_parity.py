@@ -298,7 +298,8 @@ def test_tma_and_culling_do_not_change_results():
     try:
         for name, kw in (("default", {}), ("no_tma", dict(no_tma=True)), ("no_cull", dict(no_tile_cull=True)),
                          ("no_optimistic", dict(no_optimistic=True)),
-                         ("sort_network", dict(sort_network=True))):
+                         ("sort_network", dict(sort_network=True)),
+                         ("sort_window_large", dict(sort_window_large=True))):
             rasterizer.set_debug_flags(**kw)
             out, planes, g = _run_fused(sc, G6)
             res[name] = (planes, g, tuple(out["num_rendered"]))
@@ -310,7 +311,8 @@ def test_tma_and_culling_do_not_change_results():
     assert int(res["no_cull"][2][0]) == int(n0[1]) and int(n0[0]) < int(n0[1])
     assert torch.equal(p0, res["no_optimistic"][0])
     assert torch.equal(p0, res["sort_network"][0]), "bucket sort and compare-exchange network give the same order"
-    for name in ("no_tma", "no_cull", "no_optimistic", "sort_network"):
+    assert torch.equal(p0, res["sort_window_large"][0])
+    for name in ("no_tma", "no_cull", "no_optimistic", "sort_network", "sort_window_large"):
         tol = 2e-6                                        # float summation order (atomics) only
         for k, v in g0.items():
             if v is not None:
@@ -435,6 +437,45 @@ def test_long_tile_lists_and_depth_ties(n_stack, ties):
     check_image("depth", dep, dep_ref, aux, scale=2.0)
     for k in ("means3D", "opacities", "colors_precomp", "scales"):
         check_grad(k, gpu[k].grad, ref[k].grad, tol=2e-4)
+
+
+def test_sort_window_choice_does_not_change_results():
+    """k_tile_sort is launched with a 32 KB shared-memory window when the PREVIOUS frame's longest tile list was short
+    (4 resident CTAs instead of 3).  A frame whose lists then turn out longer -- beyond the small window's bucket
+    path (2048), beyond the window itself (4096) -- must come out bit-identical to the 64 KB-window launch."""
+    _, _, rasterizer, _ = _gpu_modules()
+    W = H = 32
+    cam = make_camera(W, H)
+    rs = _settings_to_cuda(cam, rasterizer)
+
+    def stack(P, seed):
+        g = torch.Generator().manual_seed(seed)
+        means = torch.zeros(P, 3)
+        means[:, 0] = (torch.rand(P, generator=g) - 0.5) * 0.01
+        means[:, 1] = (torch.rand(P, generator=g) - 0.5) * 0.01
+        means[:, 2] = 1.0 + torch.rand(P, generator=g)
+        return dict(means3D=means.to(DEV), opacities=(torch.full((P, 1), 0.005) + 0.007 * torch.rand(P, 1, generator=g)).to(DEV),
+                    colors_precomp=torch.rand(P, 3, generator=g).to(DEV), scales=torch.full((P, 3), 0.05, device=DEV),
+                    rotations=torch.tensor([[1.0, 0, 0, 0]]).repeat(P, 1).to(DEV), means2D=torch.zeros(P, 3, device=DEV))
+
+    def run(d):
+        c, r, dep = rasterizer.GaussianRasterizer(rs)(**d)
+        return c.clone(), dep.clone()
+
+    small, mid, long_ = stack(300, 1), stack(3000, 2), stack(9000, 3)
+    res = {}
+    try:
+        for name, kw in (("auto", {}), ("large", dict(sort_window_large=True))):
+            rasterizer.set_debug_flags(**kw)
+            out = []
+            for d in (mid, long_):
+                run(small)                      # leaves "longest list = 300" behind: the next launch takes the small window
+                out.append(run(d))
+            res[name] = out
+    finally:
+        rasterizer.set_debug_flags()
+    for (ca, da), (cl, dl) in zip(res["auto"], res["large"]):
+        assert torch.equal(ca, cl) and torch.equal(da, dl)
 
 
 def test_config4_size_runs_and_is_deterministic():
