@@ -524,14 +524,45 @@ def run_ours(args):
             return sum(a.elapsed_time(b) for a, b in tr) / args.steps
 
         t_fused = time_iter(make_iter(fsgs_losses.rgb_loss_func_fused))           # (model still frozen here)
+
+        # the tracking LOOP as train.py:166-188 runs it: 50 iterations back to back on one frame against the frozen
+        # model (render, mask, image loss, backward, Adam step on the pose), no L2 flush between iterations.  With the
+        # frozen-model forward (fsgs_freeze_model rows: 64 B instead of 236 B per Gaussian, evaluated once per model
+        # state) and without it.  Device time of the whole loop / 50.
+        def track_loop(use_rows):
+            render.USE_FROZEN_MODEL = use_rows
+            opt = torch.optim.Adam([poses.pose_param_net.r, poses.pose_param_net.t], lr=1e-5, eps=1e-15)
+            it = make_iter(fsgs_losses.rgb_loss_func_fused)
+
+            def loop():
+                for _ in range(50):
+                    it()
+                    opt.step()
+            r0, t0 = poses.pose_param_net.r.detach().clone(), poses.pose_param_net.t.detach().clone()
+            loop()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); loop(); b.record()
+            barrier()
+            with torch.no_grad():
+                poses.pose_param_net.r.copy_(r0); poses.pose_param_net.t.copy_(t0)
+            return a.elapsed_time(b) / 50
+
+        loop_rows, loop_plain = track_loop(True), track_loop(False)
+        render.USE_FROZEN_MODEL = True
         for v in pc.params.values():
             v.requires_grad_(True)
         t_ref_style = time_iter(make_iter(fsgs_losses.rgb_loss_func))
         track_iter = {"fused_loss_frozen_model": t_fused, "pytorch_loss_trainable_model": t_ref_style,
+                      "loop_of_50_frozen_model_rows": loop_rows, "loop_of_50_frozen_model_raw_parameters": loop_plain,
+                      "loop_what": "50 tracking iterations back to back on one frame (render + mask + fused L1/SSIM + "
+                                   "pose-only backward + Adam step on the pose), no L2 flush, device ms per iteration; "
+                                   "rows = forward from the 64-byte pose-independent rows (fsgs_render_forward_frozen)",
                       "what": "render(gs_grad=False, cam_grad=True) + mask + rgb_loss_func (L1 + SSIM) + backward, "
                               "issued from Python, device time per iteration"}
     except Exception as exc:  # noqa: BLE001
         track_iter = {"error": repr(exc)[:200]}
+    render.USE_FROZEN_MODEL = True
     for v in pc.params.values():
         v.requires_grad_(True)
 

@@ -638,7 +638,10 @@ __device__ __forceinline__ bool tile_sort_bucket(int n, int win, const unsigned 
     return true;
 }
 
-__global__ void __launch_bounds__(CTA)
+#ifndef FSGS_SORT_MINB
+#define FSGS_SORT_MINB 1
+#endif
+__global__ void __launch_bounds__(CTA, FSGS_SORT_MINB)
 k_tile_sort(int gx, const unsigned int *__restrict__ tile_offset, unsigned long long *__restrict__ keys,
             const float4 *__restrict__ records, float4 *__restrict__ sorted_rec, unsigned int flags,
             const unsigned long long *__restrict__ counters, unsigned long long capacity, int win) {
