@@ -66,9 +66,12 @@ __host__ inline GeomLayout geom_layout(int P) {
 }
 
 struct BinLayout {
-    size_t keys, records, total;
+    size_t keys, records, bins, total;
 };
-__host__ inline BinLayout bin_layout(int64_t R) {
+// bins (optional): tiles x bin_cap keys -- the counting pass drops every instance's (depth, id) key straight into its
+// tile's fixed-stride bin (slot = the value its counting atomic returns), so the separate scatter pass disappears;
+// bin_cap comes from the previous frame's longest tile list (forward_tail; the scatter path is the fallback).
+__host__ inline BinLayout bin_layout(int64_t R, int tiles = 0, unsigned int bin_cap = 0) {
     BinLayout L;
     const size_t n = R > 0 ? (size_t)R : 1;
     size_t o = 0;
@@ -76,6 +79,7 @@ __host__ inline BinLayout bin_layout(int64_t R) {
     // forward allocated (which may exceed the instance count, see forward_tail)
     L.records = o; o = align_up(o + n * 48, 256);
     L.keys = o; o = align_up(o + n * 8, 256);
+    L.bins = o; o = align_up(o + (size_t)tiles * bin_cap * 8, 256);
     L.total = o;
     return L;
 }

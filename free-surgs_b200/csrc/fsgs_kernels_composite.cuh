@@ -114,11 +114,12 @@ k_composite_fwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
                 const float *__restrict__ bg, float *__restrict__ out_planes, float *__restrict__ out_depth,
                 float *__restrict__ final_T, unsigned int *__restrict__ n_contrib, unsigned int flags,
                 unsigned long long *__restrict__ err, const unsigned long long *__restrict__ counters,
-                unsigned long long capacity, RenderExtras ex) {
+                unsigned long long capacity, RenderExtras ex, unsigned int bin_cap) {
     __shared__ __align__(128) float4 s_rec[2][BATCH * REC_F4];
     __shared__ __align__(8) uint64_t s_full[2];
     __shared__ __align__(16) list_t s_list[CTA / 32][BATCH];   // rows read 8 entries (16 B) at a time
-    if (counters[CNT_R] > capacity) return;   // optimistic launch into a too-small buffer: the host relaunches
+    // optimistic launch into a too-small buffer (or from incomplete bins, bin_cap > 0): the host relaunches
+    if (counters[CNT_R] > capacity || (bin_cap && counters[CNT_MAXLIST] > bin_cap)) return;
     const int tile = blockIdx.x;
     const unsigned int start = tile_offset[tile];
     const int n = (int)(tile_offset[tile + 1] - start);
@@ -581,10 +582,10 @@ k_composite_bwd(CamConst cc, const unsigned int *__restrict__ tile_offset, const
                 const unsigned int *__restrict__ n_contrib, const float *__restrict__ g_rgb,
                 const float *__restrict__ g_depth, const float *__restrict__ g_sil, const float *__restrict__ g_dsq,
                 float *__restrict__ grad_acc, unsigned int flags, unsigned long long *__restrict__ err,
-                const unsigned long long *__restrict__ counters, unsigned long long capacity) {
-    // (the forward's tail did not run if the frame had more instances than the buffer it was given: see
-    // FSGS_FLAG_FIXED_CAPACITY; err = the device's sticky watchdog word)
-    if (counters[CNT_R] > capacity) return;
+                const unsigned long long *__restrict__ counters, unsigned long long capacity, unsigned int bin_cap) {
+    // (the forward's tail did not run if the frame had more instances than the buffer it was given, or a longer tile
+    // list than the bins it was given: see FSGS_FLAG_FIXED_CAPACITY; err = the device's sticky watchdog word)
+    if (counters[CNT_R] > capacity || (bin_cap && counters[CNT_MAXLIST] > bin_cap)) return;
     // upstream gradients: g_rgb[3,H,W] and one [H,W] plane each for depth | silhouette | depth^2 (fused
     // flavour; the API flavour has the package's depth output in g_depth).  A NULL plane is all zeros.
     extern __shared__ __align__(128) unsigned char smem_raw[];

@@ -107,6 +107,8 @@ struct Buffers {
     GeomLayout gl;
     ImgLayout il;
     BinLayout bl;
+    unsigned long long capacity = 0;   // instances the binning buffer was allocated for BEFORE the projection kernel (0: not yet)
+    unsigned int bin_cap = 0;          // keys per tile bin in it (0: no bins, the scatter path)
 };
 
 // ---- instance-count read-back without idling the GPU ----------------------------------------------
@@ -124,13 +126,65 @@ struct HostMailbox {
 };
 thread_local HostMailbox g_mail;
 unsigned long long g_hint[64] = {};         // last R per device (benign race: performance hint only)
-unsigned long long g_hint_maxlist[64] = {}; // longest tile list of the last frame per device (likewise; sizes k_tile_sort's window)
+unsigned long long g_hint_maxlist[64] = {}; // longest tile list of the last frame per device (likewise; sizes k_tile_sort's window
+                                            // and the per-tile key bins) ...
+unsigned long long g_hint_maxlist2[64] = {};// ... and of the frame before it: loops that alternate between views (mapping over
+                                            // key frames, the viewer thread) size for the larger of the two
+inline unsigned long long hint_maxlist(int dev) {
+    return g_hint_maxlist[dev] > g_hint_maxlist2[dev] ? g_hint_maxlist[dev] : g_hint_maxlist2[dev];
+}
 // Device watchdog: one sticky 64-bit word per device (allocated once, never freed).  A bounded device-side wait that
 // gives up (mbar_wait) sets it; every forward reads it back together with the instance count -- the read-back it
 // performs anyway -- and fails with FSGS_E_WATCHDOG, so a stuck barrier is reported by the NEXT forward on that
 // device (like an asynchronous CUDA error), in release mode too.  fsgs_watchdog_flag() reads it on demand.
 unsigned long long *g_sticky[64] = {};
 unsigned long long g_fixed_cap[64] = {};    // FSGS_FLAG_FIXED_CAPACITY: instance capacity per device (fsgs_set_instance_capacity)
+unsigned int g_fixed_bin_cap[64] = {};      // ... and the per-tile bin capacity the last fixed-capacity forward on the device ran with
+                                            // (0 = scatter path); its backward compares the longest list with it (device guard)
+
+// Binning buffer ahead of the projection kernel.  When the device left hints (instance count and longest tile list of
+// the previous frame) -- or the capacity is fixed (graph capture) -- the buffer is allocated before the projection
+// kernel runs, with one fixed-stride bin of keys per tile, and that kernel's counting pass writes every instance's key
+// into its bin (BinSink): no scatter pass.  A frame that outgrows the bins (or the capacity) is caught by the device
+// guards of the tail kernels and relaunched through the scatter path with exact sizes.
+int prepare_binning(const fsgs_settings *st, int tiles, fsgs_alloc_fn binning_alloc, void *binning_user, Buffers &B) {
+    int dev = 0;
+    FSGS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return FSGS_E_INVALID;
+    const bool fixed = (st->flags & FSGS_FLAG_FIXED_CAPACITY) != 0;
+    unsigned long long capacity = 0;
+    if (fixed) {
+        capacity = g_fixed_cap[dev];
+        if (capacity == 0 || st->debug) return FSGS_E_INVALID;
+    } else if (g_hint[dev] > 0 && !(st->flags & FSGS_FLAG_NO_OPTIMISTIC)) {
+        capacity = g_hint[dev] + g_hint[dev] / 8 + 4096;
+    }
+    if (capacity == 0) return FSGS_OK;               // first frame on this device: the tail waits for the counts
+    unsigned int bin_cap = 0;
+    const unsigned long long ml = hint_maxlist(dev);
+    if (ml > 0 && ml < (1ull << 20) && !(st->flags & FSGS_FLAG_NO_BINS))
+        bin_cap = (unsigned int)((ml + ml / 2 + 64 + 63) / 64 * 64);
+    // (a pathological frame -- one enormous list -- would make tiles x bin_cap explode: fall back to the scatter path)
+    if ((unsigned long long)tiles * bin_cap > 4 * capacity + (1u << 20)) bin_cap = 0;
+    B.bl = bin_layout((int64_t)capacity, tiles, bin_cap);
+    B.bin = static_cast<char *>(binning_alloc(binning_user, B.bl.total));
+    if (!B.bin) return FSGS_E_ALLOC;
+    B.capacity = capacity;
+    B.bin_cap = bin_cap;
+    if (fixed) g_fixed_bin_cap[dev] = bin_cap;
+    return FSGS_OK;
+}
+// Backward of a fixed-capacity (captured) forward: the bin capacity that forward ran with, for the device guard.
+// (Outside capture the host has already checked the counts before a backward can be issued: 0 = no guard.)
+inline unsigned int fixed_bin_cap(const fsgs_settings *st) {
+    if (!(st->flags & FSGS_FLAG_FIXED_CAPACITY)) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    return g_fixed_bin_cap[dev];
+}
+inline BinSink bin_sink(const Buffers &B) {
+    return BinSink{B.bin_cap ? reinterpret_cast<unsigned long long *>(B.bin + B.bl.bins) : nullptr, B.bin_cap};
+}
 
 int mailbox(int dev, unsigned long long **pinned, cudaEvent_t *ev) {
     if (!g_mail.pinned) FSGS_CUDA(cudaHostAlloc((void **)&g_mail.pinned, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -174,25 +228,29 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
         FSGS_CUDA(cudaEventRecord(landed, stream));
     }
 
-    // launches scatter -> sort -> composite into a buffer of `capacity` instances
-    auto launch_tail = [&](unsigned long long capacity, bool have_instances) -> int {
+    // launches (scatter ->) sort -> composite into a buffer of `capacity` instances; bin_cap > 0: the keys already sit
+    // in the per-tile bins the counting pass filled
+    auto launch_tail = [&](unsigned long long capacity, bool have_instances, unsigned int bin_cap) -> int {
         unsigned long long *keys = reinterpret_cast<unsigned long long *>(B.bin + B.bl.keys);
+        unsigned long long *bins = bin_cap ? reinterpret_cast<unsigned long long *>(B.bin + B.bl.bins) : nullptr;
         float4 *sorted_rec = reinterpret_cast<float4 *>(B.bin + B.bl.records);
         if (have_instances) {
-            prof_begin(K_SCATTER, stream);
-            k_scatter<<<blocks(P), CTA, 0, stream>>>(cc, P, records, tile_offset, cursor, keys, (unsigned)st->flags,
-                                                     counters, capacity);
-            prof_end(K_SCATTER, stream);
-            FSGS_LAUNCH_OK("k_scatter");
+            if (!bins) {
+                prof_begin(K_SCATTER, stream);
+                k_scatter<<<blocks(P), CTA, 0, stream>>>(cc, P, records, tile_offset, cursor, keys, (unsigned)st->flags,
+                                                         counters, capacity);
+                prof_end(K_SCATTER, stream);
+                FSGS_LAUNCH_OK("k_scatter");
+            }
             prof_begin(K_SORT, stream);
             // shared-memory window: the small one (4 resident CTAs) when the previous frame's longest list fits its
             // bucket path with 25 % headroom; results do not depend on the choice (fsgs_kernels_pre.cuh)
-            const unsigned long long ml = g_hint_maxlist[dev];
+            const unsigned long long ml = hint_maxlist(dev);
             const int win = (ml > 0 && ml + ml / 4 <= (unsigned long long)(SORT_SMEM_KEYS_SMALL / 2) &&
                              !(st->flags & FSGS_FLAG_SORT_WINDOW_LARGE))
                                 ? SORT_SMEM_KEYS_SMALL : SORT_SMEM_KEYS;
             k_tile_sort<<<tiles, CTA, (size_t)win * sizeof(unsigned long long), stream>>>(
-                cc.gx, tile_offset, keys, records, sorted_rec, (unsigned)st->flags, counters, capacity, win);
+                cc.gx, tile_offset, keys, records, sorted_rec, (unsigned)st->flags, counters, capacity, win, bins, bin_cap);
             prof_end(K_SORT, stream);
             FSGS_LAUNCH_OK("k_tile_sort");
         }
@@ -200,7 +258,7 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
         k_composite_fwd<FUSED><<<tiles, CTA, 0, stream>>>(
             cc, tile_offset, sorted_rec, bg, out_planes, out_depth, reinterpret_cast<float *>(B.img + B.il.final_T),
             reinterpret_cast<unsigned int *>(B.img + B.il.n_contrib), (unsigned)st->flags, sticky, counters,
-            capacity, ex);
+            capacity, ex, bin_cap);
         prof_end(K_COMP_FWD, stream);
         FSGS_LAUNCH_OK("k_composite_fwd");
         return FSGS_OK;
@@ -210,25 +268,18 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
         // Stream-capture mode (CUDA graphs): nothing here may touch the host.  The binning buffer is sized for the
         // capacity the caller declared; if the frame has more instances, every tail kernel (and the backward
         // compositor) returns at once on the device-side guard and the caller finds counters[0] > capacity.
-        const unsigned long long cap = g_fixed_cap[dev];
-        if (cap == 0 || st->debug) return FSGS_E_INVALID;
-        B.bl = bin_layout((int64_t)cap);
-        B.bin = static_cast<char *>(binning_alloc(binning_user, B.bl.total));
-        if (!B.bin) return FSGS_E_ALLOC;
-        if ((rc = launch_tail(cap, true)) != FSGS_OK) return rc;
+        const unsigned long long cap = B.capacity;          // allocated by prepare_binning
+        if (cap == 0 || !B.bin) return FSGS_E_INVALID;
+        if ((rc = launch_tail(cap, true, B.bin_cap)) != FSGS_OK) return rc;
         if (num_rendered_host) *num_rendered_host = (int64_t)cap;     // an upper bound; the backward only needs > 0
         if (num_rect_host) *num_rect_host = 0;
         return FSGS_OK;
     }
-    const unsigned long long hint = g_hint[dev];
     unsigned long long capacity = 0;
     bool launched = false;
-    if (hint > 0 && !(st->flags & FSGS_FLAG_NO_OPTIMISTIC)) {
-        capacity = hint + hint / 8 + 4096;
-        B.bl = bin_layout((int64_t)capacity);
-        B.bin = static_cast<char *>(binning_alloc(binning_user, B.bl.total));
-        if (!B.bin) return FSGS_E_ALLOC;
-        if ((rc = launch_tail(capacity, true)) != FSGS_OK) return rc;
+    if (B.capacity > 0 && B.bin) {                          // prepare_binning found hints: optimistic launch
+        capacity = B.capacity;
+        if ((rc = launch_tail(capacity, true, B.bin_cap)) != FSGS_OK) return rc;
         launched = true;
     }
     FSGS_CUDA(cudaEventSynchronize(landed));
@@ -242,13 +293,17 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
     if (num_rect_host) *num_rect_host = (int64_t)h_cnt[CNT_RECT];
     if (R >= (int64_t)1 << 32) return FSGS_E_INVALID;
     g_hint[dev] = (unsigned long long)R;
+    g_hint_maxlist2[dev] = g_hint_maxlist[dev];
     g_hint_maxlist[dev] = h_cnt[CNT_MAXLIST];
 
-    if (!launched || (unsigned long long)R > capacity) {
+    if (!launched || (unsigned long long)R > capacity || (B.bin_cap && h_cnt[CNT_MAXLIST] > B.bin_cap)) {
+        // no hint, or the frame outgrew the buffer / a tile outgrew its bin (the optimistic kernels left on their
+        // device guards): exact size, scatter path
         B.bl = bin_layout(R);
         B.bin = static_cast<char *>(binning_alloc(binning_user, B.bl.total));
         if (!B.bin) return FSGS_E_ALLOC;
-        if ((rc = launch_tail((unsigned long long)(R > 0 ? R : 1), R > 0)) != FSGS_OK) return rc;
+        B.bin_cap = 0;
+        if ((rc = launch_tail((unsigned long long)(R > 0 ? R : 1), R > 0, 0)) != FSGS_OK) return rc;
     }
     if (st->debug) {
         FSGS_CUDA(cudaMemcpyAsync(h_cnt + 4, sticky, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -424,11 +479,12 @@ int fsgs_rasterize_forward(const fsgs_settings *st, int32_t P, const float *bg, 
     Buffers B;
     if ((rc = alloc_fixed(P, cc, geom_alloc, geom_user, img_alloc, img_user, B, stream))) return rc;
     prof_begin(K_PRE_API, stream);
+    if ((rc = prepare_binning(st, B.il.tiles, binning_alloc, binning_user, B))) return rc;
     k_preprocess_api<<<blocks(P), CTA, 0, stream>>>(
         cc, P, means3D, colors_precomp, shs, opacities, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, campos,
         reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped), radii,
         reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
-        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags);
+        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags, bin_sink(B));
     prof_end(K_PRE_API, stream);
     FSGS_LAUNCH_OK("k_preprocess_api");
     return forward_tail<false>(st, cc, P, bg, B, binning_alloc, binning_user, out_color, out_depth, num_rendered_host,
@@ -465,7 +521,8 @@ int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rend
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_dout_color, dL_dout_depth, nullptr, nullptr, acc, (unsigned)st->flags, sticky_flag(),
-            reinterpret_cast<const unsigned long long *>(im + il.counters), (unsigned long long)num_rendered);
+            reinterpret_cast<const unsigned long long *>(im + il.counters), (unsigned long long)num_rendered,
+            fixed_bin_cap(st));
         prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");
     }
@@ -568,13 +625,14 @@ int fsgs_render_forward_ex(const fsgs_settings *st, int32_t P, const float *bg, 
     }
     Buffers B;
     if ((rc = alloc_fixed(P, cc, geom_alloc, geom_user, img_alloc, img_user, B, stream))) return rc;
+    if ((rc = prepare_binning(st, B.il.tiles, binning_alloc, binning_user, B))) return rc;
     prof_begin(K_PRE_FUSED, stream);
     k_preprocess_fused<<<(P + PRE_CTA - 1) / PRE_CTA, PRE_CTA, 0, stream>>>(
         cc, P, xyz, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, pose, cam_center, viewmatrix,
         projmatrix, reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped),
         radii, reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
         reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags, ex.visibility, ex.max_radii2D,
-        sticky_flag());
+        sticky_flag(), bin_sink(B));
     prof_end(K_PRE_FUSED, stream);
     FSGS_LAUNCH_OK("k_preprocess_fused");
     return forward_tail<true>(st, cc, P, bg, B, binning_alloc, binning_user, out_planes, nullptr, num_rendered_host,
@@ -638,12 +696,14 @@ int fsgs_render_forward_frozen(const fsgs_settings *st, int32_t P, const float *
     }
     Buffers B;
     if ((rc = alloc_fixed(P, cc, geom_alloc, geom_user, img_alloc, img_user, B, stream))) return rc;
+    if ((rc = prepare_binning(st, B.il.tiles, binning_alloc, binning_user, B))) return rc;
     prof_begin(K_PRE_FROZEN, stream);
     k_preprocess_frozen<<<blocks(P), CTA, 0, stream>>>(
         cc, P, static_cast<const float4 *>(frozen), pose, viewmatrix, projmatrix,
         reinterpret_cast<float4 *>(B.geom + B.gl.records), reinterpret_cast<uint8_t *>(B.geom + B.gl.clamped), radii,
         reinterpret_cast<unsigned int *>(B.img + B.il.tile_count),
-        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags, ex.visibility, ex.max_radii2D);
+        reinterpret_cast<unsigned long long *>(B.img + B.il.counters), (unsigned)st->flags, ex.visibility, ex.max_radii2D,
+        bin_sink(B));
     prof_end(K_PRE_FROZEN, stream);
     FSGS_LAUNCH_OK("k_preprocess_frozen");
     return forward_tail<true>(st, cc, P, bg, B, binning_alloc, binning_user, out_planes, nullptr, num_rendered_host,
@@ -731,7 +791,8 @@ int fsgs_render_backward_v2(const fsgs_settings *st, int32_t P, int64_t num_rend
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),
             dL_drgb, dL_ddepth, dL_dsil, dL_ddepth_sq, acc, (unsigned)st->flags, sticky_flag(),
-            reinterpret_cast<const unsigned long long *>(im + il.counters), (unsigned long long)num_rendered);
+            reinterpret_cast<const unsigned long long *>(im + il.counters), (unsigned long long)num_rendered,
+            fixed_bin_cap(st));
         prof_end(K_COMP_BWD, stream);
         FSGS_LAUNCH_OK("k_composite_bwd");
     }
@@ -783,6 +844,11 @@ extern "C" int fsgs_debug_pair_stats(unsigned long long *out8) {
     return FSGS_OK;
 }
 #endif
+
+int64_t fsgs_fixed_bin_capacity(int32_t device) {
+    if (device < 0 || device >= 64) return FSGS_E_INVALID;
+    return (int64_t)g_fixed_bin_cap[device];
+}
 
 int fsgs_set_instance_capacity(int32_t device, int64_t capacity) {
     if (device < 0 || device >= 64 || capacity < 0) return FSGS_E_INVALID;

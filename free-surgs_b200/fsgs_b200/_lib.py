@@ -22,6 +22,7 @@ FLAG_SORT_NETWORK = 16
 FLAG_FIXED_CAPACITY = 32
 FLAG_NO_POSE_ONLY = 64
 FLAG_SORT_WINDOW_LARGE = 128
+FLAG_NO_BINS = 256
 
 
 class FsgsError(RuntimeError):
@@ -87,6 +88,7 @@ _SIGNATURES = {
     "fsgs_compact_grad_expand": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i32, _i32] + [_vp] * 10),
     "fsgs_exchange_rows": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _vp]),
     "fsgs_set_instance_capacity": (ctypes.c_int, [_i32, _i64]),
+    "fsgs_fixed_bin_capacity": (_i64, [_i32]),
     "fsgs_frozen_bytes": (ctypes.c_size_t, [_i32]),
     "fsgs_freeze_model": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 9),
     "fsgs_render_forward_frozen": (ctypes.c_int, [ctypes.POINTER(Settings), _i32] + [_vp] * 5 +

@@ -26,7 +26,7 @@ from .rasterizer import GaussianRasterizer, _Arena, _f32, _on_device, _ptr, _req
 
 _IDENTITY_OK: Dict[tuple, bool] = {}
 _TLS = threading.local()
-_CAPTURED = []      # (image-state buffer, capacity, W, H) of every fused forward recorded during a graph capture
+_CAPTURED = []      # (image-state buffer, capacity, W, H, bin capacity) of every fused forward recorded during a graph capture
 
 # Frame-parallel gradient exchange hook (set through fsgs_b200.dist.enable_frame_parallel): a callable that
 # sum-all-reduces a flat float32 CUDA tensor in place, ordered on the current stream; None = single GPU.
@@ -248,7 +248,9 @@ class _RenderFused(torch.autograd.Function):
                                  "Gaussian on the model's device")
             ctx.stats = (acc, den)
         if capturing:
-            _CAPTURED.append((arena.tensors["img"], int(nr.value), W, H))      # for GraphedStep.overflowed()
+            # for GraphedStep.overflowed(): image state, instance capacity, per-tile bin capacity of this forward
+            _CAPTURED.append((arena.tensors["img"], int(nr.value), W, H,
+                              int(_lib.lib().fsgs_fixed_bin_capacity(dev.index))))
             del _CAPTURED[:-64]                                                 # (bounded, whoever does the capturing)
         ctx.mark_non_differentiable(radii, *extras)
         ctx.set_materialize_grads(False)        # an output the loss does not use arrives as None, not as zeros

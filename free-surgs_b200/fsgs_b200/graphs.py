@@ -84,20 +84,28 @@ class GraphedStep:
             self.graph.reset()
         self.graph, self.outputs, self._captured = None, None, []
 
-    def instance_counts(self) -> List[int]:
-        """Instance count of every captured fused forward in the LAST replay (synchronises)."""
+    def _counters(self):
+        """(instances, longest tile list) of every captured fused forward in the LAST replay (synchronises)."""
         out = []
-        for img, _cap, W, H in self._captured:
+        for img, _cap, W, H, _bin_cap in self._captured:
             off = (ctypes.c_size_t * 6)()
             _lib.lib().fsgs_img_offsets(W, H, off)
-            out.append(int(img[off[5]:off[5] + 8].view(torch.int64).item()))
+            c = img[off[5]:off[5] + 24].view(torch.int64).tolist()
+            out.append((int(c[0]), int(c[2])))
         return out
+
+    def instance_counts(self) -> List[int]:
+        """Instance count of every captured fused forward in the LAST replay (synchronises)."""
+        return [n for n, _ in self._counters()]
 
     def overflowed(self) -> bool:
         """True if the last replay produced more instances than the captured capacity (its binning / compositing
         kernels then skipped themselves).  Also raises if the device watchdog fired (a captured forward cannot
         read that flag back itself)."""
-        over = any(n > cap for n, (_img, cap, _w, _h) in zip(self.instance_counts(), self._captured))
+        # more instances than the binning buffer holds, or a tile list longer than its bin (the counting pass drops
+        # the keys into fixed-stride per-tile bins sized from the warm-up's longest list)
+        over = any(n > cap or (bin_cap and longest > bin_cap)
+                   for (n, longest), (_img, cap, _w, _h, bin_cap) in zip(self._counters(), self._captured))
         rc = _lib.lib().fsgs_watchdog_flag(self.device.index, 1)
         if rc < 0:
             _lib.check(rc)

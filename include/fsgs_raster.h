@@ -75,6 +75,7 @@ typedef struct fsgs_settings {
 #define FSGS_FLAG_RESERVED_4 4u    /* (was: first backward formulation, removed; ignored)          */
 #define FSGS_FLAG_NO_OPTIMISTIC 8u /* forward: always wait for the instance count before binning   */
 #define FSGS_FLAG_SORT_NETWORK 16u /* per-tile sort: always the compare-exchange network (A/B, tests) */
+#define FSGS_FLAG_NO_BINS 256u     /* forward: never bin the keys in the counting pass, always the scatter pass (A/B, tests) */
 #define FSGS_FLAG_SORT_WINDOW_LARGE 128u /* per-tile sort: always the 64 KB shared-memory window (A/B, tests)  */
 #define FSGS_FLAG_NO_POSE_ONLY 64u /* fused backward: never take the pose-only specialisation (A/B, tests) */
 #define FSGS_FLAG_FIXED_CAPACITY 32u /* forward: no host read-back of the instance count (CUDA-graph capture);
@@ -267,6 +268,10 @@ int fsgs_watchdog_flag(int32_t device, int32_t reset);
  * directions return immediately (outputs undefined) and counters[0] (see fsgs_img_offsets) > capacity tells
  * the caller to re-capture with a larger capacity. */
 int fsgs_set_instance_capacity(int32_t device, int64_t capacity);
+/* Per-tile bin capacity (keys) the last FSGS_FLAG_FIXED_CAPACITY forward on the device ran with; 0 = it took the scatter
+ * path.  A replayed frame whose longest tile list (counters[2], see fsgs_img_offsets) exceeds it skipped its binning /
+ * compositing kernels exactly as when counters[0] > capacity: re-capture after an eager frame has refreshed the hints. */
+int64_t fsgs_fixed_bin_capacity(int32_t device);
 
 /* Frame-parallel gradient exchange (one frame per GPU, shared Gaussian model).
  * Every SH-coefficient gradient of a Gaussian is  basis_k(dir) * gc[ch]  with gc = the colour gradient after

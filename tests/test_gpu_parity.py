@@ -299,7 +299,8 @@ def test_tma_and_culling_do_not_change_results():
         for name, kw in (("default", {}), ("no_tma", dict(no_tma=True)), ("no_cull", dict(no_tile_cull=True)),
                          ("no_optimistic", dict(no_optimistic=True)),
                          ("sort_network", dict(sort_network=True)),
-                         ("sort_window_large", dict(sort_window_large=True))):
+                         ("sort_window_large", dict(sort_window_large=True)),
+                         ("no_bins", dict(no_bins=True))):
             rasterizer.set_debug_flags(**kw)
             out, planes, g = _run_fused(sc, G6)
             res[name] = (planes, g, tuple(out["num_rendered"]))
@@ -312,7 +313,8 @@ def test_tma_and_culling_do_not_change_results():
     assert torch.equal(p0, res["no_optimistic"][0])
     assert torch.equal(p0, res["sort_network"][0]), "bucket sort and compare-exchange network give the same order"
     assert torch.equal(p0, res["sort_window_large"][0])
-    for name in ("no_tma", "no_cull", "no_optimistic", "sort_network", "sort_window_large"):
+    assert torch.equal(p0, res["no_bins"][0]), "keys binned by the counting pass vs the scatter pass: same lists"
+    for name in ("no_tma", "no_cull", "no_optimistic", "sort_network", "sort_window_large", "no_bins"):
         tol = 2e-6                                        # float summation order (atomics) only
         for k, v in g0.items():
             if v is not None:
@@ -439,7 +441,7 @@ def test_long_tile_lists_and_depth_ties(n_stack, ties):
         check_grad(k, gpu[k].grad, ref[k].grad, tol=2e-4)
 
 
-def test_sort_window_choice_does_not_change_results():
+def test_sort_window_and_key_bins_do_not_change_results():
     """k_tile_sort is launched with a 32 KB shared-memory window when the PREVIOUS frame's longest tile list was short
     (4 resident CTAs instead of 3).  A frame whose lists then turn out longer -- beyond the small window's bucket
     path (2048), beyond the window itself (4096) -- must come out bit-identical to the 64 KB-window launch."""
@@ -465,17 +467,20 @@ def test_sort_window_choice_does_not_change_results():
     small, mid, long_ = stack(300, 1), stack(3000, 2), stack(9000, 3)
     res = {}
     try:
-        for name, kw in (("auto", {}), ("large", dict(sort_window_large=True))):
+        for name, kw in (("auto", {}), ("large", dict(sort_window_large=True)), ("no_bins", dict(no_bins=True))):
             rasterizer.set_debug_flags(**kw)
             out = []
             for d in (mid, long_):
-                run(small)                      # leaves "longest list = 300" behind: the next launch takes the small window
-                out.append(run(d))
+                run(small); run(small)          # leave "longest list = 300" behind (the library keeps the last two
+                out.append(run(d))              # frames' values): the next launch takes the small window
             res[name] = out
     finally:
         rasterizer.set_debug_flags()
-    for (ca, da), (cl, dl) in zip(res["auto"], res["large"]):
-        assert torch.equal(ca, cl) and torch.equal(da, dl)
+    # (the same sequence also makes a tile outgrow the per-tile key bin sized from the previous frame's longest list:
+    # the optimistic kernels leave on their device guard and the host relaunches the scatter path)
+    for other in ("large", "no_bins"):
+        for (ca, da), (cl, dl) in zip(res["auto"], res[other]):
+            assert torch.equal(ca, cl) and torch.equal(da, dl), other
 
 
 def test_config4_size_runs_and_is_deterministic():
