@@ -778,10 +778,10 @@ def run_ours(args):
                             "step (round 1's loop); ms_per_step_eager: that loop issuing the frame from Python.  No L2 "
                             "flush inside these loops: a step streams ~0.8 GB through the 126 MB L2 and its inputs arrive "
                             "over PCIe"},
-            # pose fwd, 5 forward kernels, 2 backward kernels, pose bwd (+ the SH-gradient expansion when N > 1)
-            # pose fwd, 5 forward kernels, compositor bwd, per-Gaussian bwd, pose bwd; N > 1: + the row exchange kernel
-            # (nvlink transport) and the expansion kernel per Gaussian range
-            "gpu_launches": (9 + (((3 if args.exchange_transport == "nvlink" else 2)
+            # pose fwd, 4 forward kernels (projection + key binning, tile scan, per-tile sort, compositor; k_scatter only
+            # runs as the fallback of the key bins), compositor bwd, per-Gaussian bwd, pose bwd; N > 1: + the row
+            # exchange kernel (nvlink transport) and the expansion kernel per Gaussian range
+            "gpu_launches": (8 + (((3 if args.exchange_transport == "nvlink" else 2)
                                    * len(render._chunk_bounds(args.P, args.exchange_chunks)) - 1)
                                   if world > 1 and args.exchange == "compact" else 0)) * args.steps,
             "clocks": clocks,
