@@ -54,6 +54,15 @@ def test_invalid_arguments_are_rejected_before_any_cuda_call():
     st = _lib.Settings(64, 64, 1.0, 1.0, 1.0, 7, 0, 0, 0)      # unsupported SH degree
     rc = L.fsgs_render_backward(ctypes.byref(st), 1, 0, *([None] * 16), 1, 1, *([None] * 9))
     assert rc == -1
+    # frozen-model forward: NULL / mis-aligned arguments are rejected before any device call
+    st_ok = _lib.Settings(64, 64, 1.0, 1.0, 1.0, 3, 16, 0, 0)
+    assert L.fsgs_frozen_bytes(1000) == 64000 and L.fsgs_frozen_bytes(0) == 64
+    assert L.fsgs_freeze_model(ctypes.byref(st_ok), 5, None, None, None, None, None, None, None, None, None) == -1
+    one_ = ctypes.c_void_p(256)
+    assert L.fsgs_freeze_model(ctypes.byref(st_ok), 5, one_, one_, one_, one_, one_, one_, one_, ctypes.c_void_p(264), None) == -1   # rows not 16-byte aligned
+    assert L.fsgs_render_forward_frozen(ctypes.byref(st_ok), 5, one_, None, one_, one_, one_, cb, None, cb, None, cb, None,
+                                        one_, one_, None, None, None, None) == -1                                     # rows NULL
+    assert L.fsgs_fixed_bin_capacity(-1) == -1 and L.fsgs_fixed_bin_capacity(0) >= 0
     # fused image loss: argument checks come before any device call
     one = ctypes.c_void_p(256)                                 # a non-NULL placeholder; never dereferenced
     assert L.fsgs_rgb_loss_forward(0, 8, 8, one, one, None, None, 0, 0.2, None, one, one, None) == -1      # C = 0
