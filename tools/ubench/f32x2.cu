@@ -4,6 +4,78 @@
 #include <cuda_runtime.h>
 
 #define ITER 4096
+// Phase-B-like mix of the backward compositor: per step 2 x LDS.128 (distinct per-lane addresses), 8 multiply-adds of the
+// loaded values into accumulators, 4 integer instructions.  MODE 0: scalar FFMA; MODE 1: packed fma.rn.f32x2 on the
+// register pairs the 128-bit loads deliver.
+template <int MODE>
+__global__ void kb(float *out, float a, int stride) {
+    __shared__ float4 sm[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sm[i] = make_float4(a + i, a * i, a - i, a);
+    __syncthreads();
+    float x0 = 0, x1 = 0, x2 = 0, x3 = 0, x4 = 0, x5 = 0, x6 = 0, x7 = 0;
+    float y0 = 0, y1 = 0, y2 = 0, y3 = 0, y4 = 0, y5 = 0, y6 = 0, y7 = 0;
+    const float c0 = a, c1 = a + 1.f, c2 = a + 2.f, c3 = a + 3.f;
+    unsigned long long p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0, k01, k23, k10, k32;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(k01) : "f"(c0), "f"(c1));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(k23) : "f"(c2), "f"(c3));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(k10) : "f"(c1), "f"(c0));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(k32) : "f"(c3), "f"(c2));
+    int idx = threadIdx.x, acc = 0;
+#pragma unroll 1
+    for (int i = 0; i < ITER; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            // 1 LDS.128 per 16 multiply-adds and 6 integer instructions: the ratio of the real phase B
+            const float4 v = sm[(idx + 32 * u) & 511];      // lane-linear: conflict-free, 4 wavefronts
+            idx += stride; acc ^= idx; acc += u; acc = (acc << 1) ^ (idx >> 2); acc += idx & 7; acc ^= acc >> 3;
+            if (MODE == 0) {
+                x0 = fmaf(v.x, c0, x0); x1 = fmaf(v.y, c1, x1); x2 = fmaf(v.z, c2, x2); x3 = fmaf(v.w, c3, x3);
+                x4 = fmaf(v.x, c1, x4); x5 = fmaf(v.y, c0, x5); x6 = fmaf(v.z, c3, x6); x7 = fmaf(v.w, c2, x7);
+                y0 = fmaf(v.x, c2, y0); y1 = fmaf(v.y, c3, y1); y2 = fmaf(v.z, c0, y2); y3 = fmaf(v.w, c1, y3);
+                y4 = fmaf(v.x, c3, y4); y5 = fmaf(v.y, c2, y5); y6 = fmaf(v.z, c1, y6); y7 = fmaf(v.w, c0, y7);
+            } else {
+                unsigned long long v01, v23;
+                asm("mov.b64 %0, {%1,%2};" : "=l"(v01) : "f"(v.x), "f"(v.y));
+                asm("mov.b64 %0, {%1,%2};" : "=l"(v23) : "f"(v.z), "f"(v.w));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p0) : "l"(v01), "l"(k01));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p1) : "l"(v23), "l"(k23));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p2) : "l"(v01), "l"(k10));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p3) : "l"(v23), "l"(k32));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p4) : "l"(v01), "l"(k23));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p5) : "l"(v23), "l"(k01));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p6) : "l"(v01), "l"(k32));
+                asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(p7) : "l"(v23), "l"(k10));
+            }
+        }
+    }
+    float z0, z1, s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 + y0 + y1 + y2 + y3 + y4 + y5 + y6 + y7 + (float)acc;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(z0), "=f"(z1) : "l"(p0)); s += z0 + z1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(z0), "=f"(z1) : "l"(p1)); s += z0 + z1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(z0), "=f"(z1) : "l"(p2)); s += z0 + z1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(z0), "=f"(z1) : "l"(p3)); s += z0 + z1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(z0), "=f"(z1) : "l"(p4)); s += z0 + z1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(z0), "=f"(z1) : "l"(p5)); s += z0 + z1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(z0), "=f"(z1) : "l"(p6)); s += z0 + z1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(z0), "=f"(z1) : "l"(p7)); s += z0 + z1;
+    if (s == 12345.678f) out[0] = s;
+}
+template <int MODE>
+void runb(const char *name) {
+    float *d; cudaMalloc(&d, 4);
+    int blocks = 148 * 4, threads = 256;
+    kb<MODE><<<blocks, threads>>>(d, 1.0001f, 1);
+    cudaDeviceSynchronize();
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    kb<MODE><<<blocks, threads>>>(d, 1.0001f, 1);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    // clocks per unrolled step per SMSP: 8 warps per SMSP resident (4 CTAs x 8 warps / 4)
+    double steps = (double)blocks * threads / 32 * ITER * 8.0;
+    printf("%-44s %8.3f ms  %6.2f clk per step per SMSP (1965 MHz)\n", name, ms, ms * 1e-3 * 1.965e9 * 148 * 4 / steps);
+    cudaFree(d);
+}
+
 template <int MODE>
 __global__ void k(float *out, float a, float b) {
     float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -115,5 +187,7 @@ int main() {
     run<11>("4 FFMA  + 2 sel + 2 add + 2 EX2", 12);
     run<8>("8x SHFL", 8);
     run<9>("4 SHFL + 4 FFMA", 8);
+    runb<0>("phase-B mix: 1 LDS.128 + 16 FFMA + 6 int");
+    runb<1>("phase-B mix: 1 LDS.128 + 8 FFMA2 + 6 int");
     return 0;
 }
