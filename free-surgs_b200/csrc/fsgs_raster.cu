@@ -11,6 +11,7 @@
 #include "fsgs_kernels_bwd.cuh"
 #include "fsgs_kernels_loss.cuh"
 #include "fsgs_kernels_composite.cuh"
+#include "fsgs_kernels_refstyle.cuh"
 #include "fsgs_kernels_pre.cuh"
 
 using namespace fsgs;
@@ -255,6 +256,15 @@ int forward_tail(const fsgs_settings *st, const CamConst &cc, int P, const float
             FSGS_LAUNCH_OK("k_tile_sort");
         }
         prof_begin(K_COMP_FWD, stream);
+        if (!FUSED && (st->flags & FSGS_FLAG_UPSTREAM_STYLE)) {
+            // baseline, not the product (fsgs_kernels_refstyle.cuh): the published rasteriser's kernel structure
+            k_composite_fwd_ref<<<tiles, CTA, 0, stream>>>(
+                cc, tile_offset, sorted_rec, bg, out_planes, out_depth, reinterpret_cast<float *>(B.img + B.il.final_T),
+                reinterpret_cast<unsigned int *>(B.img + B.il.n_contrib), counters, capacity, bin_cap);
+            prof_end(K_COMP_FWD, stream);
+            FSGS_LAUNCH_OK("k_composite_fwd_ref");
+            return FSGS_OK;
+        }
         k_composite_fwd<FUSED><<<tiles, CTA, 0, stream>>>(
             cc, tile_offset, sorted_rec, bg, out_planes, out_depth, reinterpret_cast<float *>(B.img + B.il.final_T),
             reinterpret_cast<unsigned int *>(B.img + B.il.n_contrib), (unsigned)st->flags, sticky, counters,
@@ -517,6 +527,14 @@ int fsgs_rasterize_backward(const fsgs_settings *st, int32_t P, int64_t num_rend
     FSGS_CUDA(cudaMemsetAsync(acc, 0, (size_t)P * ACC_F * 4, stream));
     if (num_rendered > 0) {
         prof_begin(K_COMP_BWD, stream);
+        if (st->flags & FSGS_FLAG_UPSTREAM_STYLE) {
+            k_composite_bwd_ref<<<il.tiles, CTA, 0, stream>>>(
+                cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset),
+                reinterpret_cast<const float4 *>(bn + bl.records), bg, reinterpret_cast<const float *>(im + il.final_T),
+                reinterpret_cast<const unsigned int *>(im + il.n_contrib), dL_dout_color, dL_dout_depth, acc,
+                reinterpret_cast<const unsigned long long *>(im + il.counters), (unsigned long long)num_rendered,
+                fixed_bin_cap(st));
+        } else
         k_composite_bwd<false><<<il.tiles, CTA, sizeof(BwdSmem), stream>>>(
             cc, reinterpret_cast<const unsigned int *>(im + il.tile_offset), reinterpret_cast<const float4 *>(bn + bl.records),
             bg, reinterpret_cast<const float *>(im + il.final_T), reinterpret_cast<const unsigned int *>(im + il.n_contrib),

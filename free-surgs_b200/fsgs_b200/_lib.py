@@ -23,6 +23,7 @@ FLAG_FIXED_CAPACITY = 32
 FLAG_NO_POSE_ONLY = 64
 FLAG_SORT_WINDOW_LARGE = 128
 FLAG_NO_BINS = 256
+FLAG_UPSTREAM_STYLE = 512
 
 
 class FsgsError(RuntimeError):

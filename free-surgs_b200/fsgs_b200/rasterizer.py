@@ -39,13 +39,16 @@ _FLAGS = {"flags": 0}
 
 def set_debug_flags(no_tma: bool = False, no_tile_cull: bool = False,
                     no_optimistic: bool = False, sort_network: bool = False, no_pose_only: bool = False,
-                    sort_window_large: bool = False, no_bins: bool = False) -> None:
+                    sort_window_large: bool = False, no_bins: bool = False, upstream_style: bool = False) -> None:
     _FLAGS["flags"] = ((_lib.FLAG_NO_TMA if no_tma else 0) | (_lib.FLAG_NO_TILE_CULL if no_tile_cull else 0)
                        | (_lib.FLAG_NO_OPTIMISTIC if no_optimistic else 0)
                        | (_lib.FLAG_SORT_NETWORK if sort_network else 0)
                        | (_lib.FLAG_NO_POSE_ONLY if no_pose_only else 0)
                        | (_lib.FLAG_SORT_WINDOW_LARGE if sort_window_large else 0)
-                       | (_lib.FLAG_NO_BINS if no_bins else 0))
+                       | (_lib.FLAG_NO_BINS if no_bins else 0)
+                       # baseline for bench.py (GaussianRasterizer path only): the published rasteriser's compositor
+                       # structure on the reference's full 3-sigma rectangles
+                       | ((_lib.FLAG_UPSTREAM_STYLE | _lib.FLAG_NO_TILE_CULL) if upstream_style else 0))
 
 
 class _WorkspacePool:

@@ -75,6 +75,9 @@ typedef struct fsgs_settings {
 #define FSGS_FLAG_RESERVED_4 4u    /* (was: first backward formulation, removed; ignored)          */
 #define FSGS_FLAG_NO_OPTIMISTIC 8u /* forward: always wait for the instance count before binning   */
 #define FSGS_FLAG_SORT_NETWORK 16u /* per-tile sort: always the compare-exchange network (A/B, tests) */
+#define FSGS_FLAG_UPSTREAM_STYLE 512u /* BASELINE for bench.py, API flavour only: compositors in the published rasteriser's
+                                         kernel structure (one thread per pixel over the whole list, per-pair scalar atomics);
+                                         set FSGS_FLAG_NO_TILE_CULL with it for the reference's full 3-sigma rectangles */
 #define FSGS_FLAG_NO_BINS 256u     /* forward: never bin the keys in the counting pass, always the scatter pass (A/B, tests) */
 #define FSGS_FLAG_SORT_WINDOW_LARGE 128u /* per-tile sort: always the 64 KB shared-memory window (A/B, tests)  */
 #define FSGS_FLAG_NO_POSE_ONLY 64u /* fused backward: never take the pose-only specialisation (A/B, tests) */

@@ -321,6 +321,32 @@ def test_tma_and_culling_do_not_change_results():
                 assert rel_err(res[name][1][k], v) < tol, (name, k)
 
 
+def test_upstream_style_baseline_compositors_agree_with_the_library():
+    """bench.py times the published rasteriser's kernel structure (one thread per pixel over the whole list, per-pair
+    scalar atomics; FSGS_FLAG_UPSTREAM_STYLE, csrc/fsgs_kernels_refstyle.cuh) beside the library's compositors.  The
+    baseline must compute the same thing: identical planes, gradients equal up to summation order."""
+    _, _, rasterizer, _ = _gpu_modules()
+    sc = make_scene(6000, 320, 256, size_mult=2.0, seed=4)
+    G6 = torch.randn(6, sc.height, sc.width, generator=torch.Generator().manual_seed(5))
+    res = {}
+    try:
+        for name, kw in (("library", {}), ("upstream_style", dict(upstream_style=True))):
+            rasterizer.set_debug_flags(**kw)
+            _lib.profile_enable(True)
+            out, planes, g = _run_fused(sc, G6, which="two_pass")
+            prof = _lib.profile_collect()
+            _lib.profile_enable(False)
+            res[name] = (planes, g, prof)
+    finally:
+        _lib.profile_enable(False)
+        rasterizer.set_debug_flags()
+    assert res["library"][2]["k_composite_fwd"][1] == 2 and res["upstream_style"][2]["k_composite_bwd"][1] == 2   # two passes
+    assert torch.equal(res["library"][0], res["upstream_style"][0])
+    for k, v in res["library"][1].items():
+        if v is not None:
+            assert rel_err(res["upstream_style"][1][k], v) < 2e-5, k
+
+
 def test_optimistic_tail_relaunches_when_the_instance_count_outgrows_the_hint():
     """The forward launches scatter/sort/composite into a buffer sized from the PREVIOUS frame's instance count
     before the host knows the current one; when the count outgrows it (densification, a new scene) the kernels
