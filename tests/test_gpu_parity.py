@@ -340,7 +340,8 @@ def test_upstream_style_baseline_compositors_agree_with_the_library():
     finally:
         _lib.profile_enable(False)
         rasterizer.set_debug_flags()
-    assert res["library"][2]["k_composite_fwd"][1] == 2 and res["upstream_style"][2]["k_composite_bwd"][1] == 2   # two passes
+    # two passes (a forward compositor may run a third time: an optimistic launch that left on its guard, then the relaunch)
+    assert res["library"][2]["k_composite_fwd"][1] >= 2 and res["upstream_style"][2]["k_composite_bwd"][1] == 2
     assert torch.equal(res["library"][0], res["upstream_style"][0])
     for k, v in res["library"][1].items():
         if v is not None:
