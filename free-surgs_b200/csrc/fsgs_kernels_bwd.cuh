@@ -242,12 +242,23 @@ k_preprocess_pose_bwd(CamConst cc, int P, const float *__restrict__ xyz, const f
 // ranks, every SH-coefficient gradient is basis_k(dir) * gc (zero beyond the active degree), with
 // dir = normalize(xyz - cam_center) identical on all ranks.  Pure write kernel: 192 B/Gaussian, staged in
 // shared memory and written with one bulk TMA store per CTA like the backward above.
+// One-shot variant of the exchange for SMALL rank counts (fsgs_compact_grad_expand_peers): the sum over the ranks is
+// folded into this kernel -- collective + the compute that consumes it in ONE kernel over peer memory.  The CTA pulls
+// its 256 rows (14 336 contiguous bytes) from every rank's buffer with coalesced 128-bit loads (the peers' through
+// NVLink peer pointers), adds them in rank order (every rank adds in the same order: bit-identical sums), parks them in
+// shared memory and continues as below.  Per rank (N - 1) x the payload crosses the links, against 2 (N - 1) / N x for
+// the two-shot kernel -- equal at N = 2, where it saves the separate exchange kernel and its launch.
+struct PeerRows {
+    const float4 *p[8];    // row buffers of ranks 0 .. world-1 (this rank's own among them), 16-byte aligned
+    int world;
+};
+
 __global__ void __launch_bounds__(CTA)
 k_sh_grad_expand(int P, int sh_deg, const float *__restrict__ xyz, const float *__restrict__ cam_center,
                  const float *__restrict__ gc, float *__restrict__ dL_dfdc, float *__restrict__ dL_dfrest, int use_tma,
                  int first, const float *__restrict__ compact, float *__restrict__ dL_dxyz,
                  float *__restrict__ dL_dopacity_raw, float *__restrict__ dL_dscaling_raw,
-                 float *__restrict__ dL_drotation_raw) {
+                 float *__restrict__ dL_drotation_raw, PeerRows peers) {
     // [first, P): the Gaussian range of this launch (first % 4 == 0).  With `compact` [P,14] (the rank-summed rows of
     // k_preprocess_fused_bwd) the colour gradient is taken from the row and the row's other 11 floats are unpacked
     // into the per-parameter gradient tensors on the way.
@@ -255,11 +266,50 @@ k_sh_grad_expand(int P, int sh_deg, const float *__restrict__ xyz, const float *
     const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
     const int base = first + blockIdx.x * blockDim.x, count = min((int)blockDim.x, P - base);
     const bool staged = (reinterpret_cast<uintptr_t>(dL_dfrest) & 15u) == 0 && use_tma;
+    if (peers.world > 1) {
+        // rows [base, base + count) of every rank, summed in rank order into the (not yet used) staging buffer
+        const int n4 = (count * 14 + 3) / 4;                       // base % 4 == 0: the slice starts on a float4
+        float4 *s_rows = reinterpret_cast<float4 *>(s_rest);
+        // 256 rows = 896 float4: up to four per thread, all of one rank's loads in flight before they are added (the
+        // peers' cross NVLink: microseconds of latency each)
+        constexpr int U = (CTA * 14 / 4 + CTA - 1) / CTA;
+        const size_t at = (size_t)base * 14 / 4;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = u * CTA + (int)threadIdx.x;
+            acc[u] = q < n4 ? peers.p[0][at + q] : zero4;
+        }
+        for (int r = 1; r < peers.world; ++r) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = u * CTA + (int)threadIdx.x;
+                v[u] = q < n4 ? peers.p[r][at + q] : zero4;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = u * CTA + (int)threadIdx.x;
+            if (q < n4) s_rows[q] = acc[u];
+        }
+        __syncthreads();
+    }
+    float2 mine[7];
+    if (peers.world > 1 && i < P) {
+        const float2 *row = reinterpret_cast<const float2 *>(s_rest) + 7 * threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) mine[k] = row[k];
+    }
+    if (peers.world > 1) __syncthreads();                          // the staging buffer is reused for the SH rows below
     if (i < P) {
         const size_t n = (size_t)i;
         float g0, g1, g2;
-        if (compact) {
-            const float2 *row = reinterpret_cast<const float2 *>(compact + 14 * n);
+        if (compact || peers.world > 1) {
+            const float2 *row = peers.world > 1 ? mine : reinterpret_cast<const float2 *>(compact + 14 * n);
             const float2 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3], r4 = row[4], r5 = row[5], r6 = row[6];
             *reinterpret_cast<float4 *>(dL_drotation_raw + 4 * n) = make_float4(r0.x, r0.y, r1.x, r1.y);
             dL_dxyz[3 * n] = r2.x; dL_dxyz[3 * n + 1] = r2.y; dL_dxyz[3 * n + 2] = r3.x;

@@ -885,7 +885,7 @@ int fsgs_sh_grad_expand(const fsgs_settings *st, int32_t P, const float *xyz, co
     prof_begin(K_SH_EXPAND, stream);
     k_sh_grad_expand<<<blocks(P), CTA, 0, stream>>>(P, st->sh_degree, xyz, cam_center, dL_dsh_rgb, dL_dfeatures_dc,
                                                     dL_dfeatures_rest, (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1, 0, nullptr,
-                                                    nullptr, nullptr, nullptr, nullptr);
+                                                    nullptr, nullptr, nullptr, nullptr, PeerRows{});
     prof_end(K_SH_EXPAND, stream);
     FSGS_LAUNCH_OK("k_sh_grad_expand");
     return FSGS_OK;
@@ -920,6 +920,36 @@ int fsgs_exchange_rows(void *multicast_ptr, void *const *peer_ptrs_host, int32_t
     return FSGS_OK;
 }
 
+int fsgs_compact_grad_expand_peers(const fsgs_settings *st, int32_t P, int32_t first, int32_t count, const float *xyz,
+                                   const float *cam_center, void *const *row_ptrs_host, int32_t world, float *dL_dxyz,
+                                   float *dL_dfeatures_dc, float *dL_dfeatures_rest, float *dL_dopacity_raw,
+                                   float *dL_dscaling_raw, float *dL_drotation_raw, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!st || st->sh_degree < 0 || st->sh_degree > 3 || P < 0 || first < 0 || (first & 255) || count < 0 ||
+        (int64_t)first + count > P || world < 2 || world > 8 || !row_ptrs_host)
+        return FSGS_E_INVALID;
+    if (count == 0) return FSGS_OK;
+    if (!xyz || !cam_center || !dL_dxyz || !dL_dfeatures_dc || !dL_dfeatures_rest || !dL_dopacity_raw ||
+        !dL_dscaling_raw || !dL_drotation_raw)
+        return FSGS_E_INVALID;
+    PeerRows pr{};
+    pr.world = world;
+    for (int r = 0; r < world; ++r) {
+        if (!row_ptrs_host[r] || (reinterpret_cast<uintptr_t>(row_ptrs_host[r]) & 15u)) return FSGS_E_INVALID;
+        pr.p[r] = static_cast<const float4 *>(row_ptrs_host[r]);
+    }
+    int rc = check_arch();
+    if (rc) return rc;
+    prof_begin(K_SH_EXPAND, stream);
+    k_sh_grad_expand<<<blocks(count), CTA, 0, stream>>>(first + count, st->sh_degree, xyz, cam_center, nullptr,
+                                                        dL_dfeatures_dc, dL_dfeatures_rest,
+                                                        (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1, first, nullptr, dL_dxyz,
+                                                        dL_dopacity_raw, dL_dscaling_raw, dL_drotation_raw, pr);
+    prof_end(K_SH_EXPAND, stream);
+    FSGS_LAUNCH_OK("k_sh_grad_expand");
+    return FSGS_OK;
+}
+
 int fsgs_compact_grad_expand(const fsgs_settings *st, int32_t P, int32_t first, int32_t count, const float *xyz,
                              const float *cam_center, const float *compact, float *dL_dxyz, float *dL_dfeatures_dc,
                              float *dL_dfeatures_rest, float *dL_dopacity_raw, float *dL_dscaling_raw,
@@ -938,7 +968,7 @@ int fsgs_compact_grad_expand(const fsgs_settings *st, int32_t P, int32_t first, 
     k_sh_grad_expand<<<blocks(count), CTA, 0, stream>>>(first + count, st->sh_degree, xyz, cam_center, nullptr,
                                                         dL_dfeatures_dc, dL_dfeatures_rest,
                                                         (st->flags & FSGS_FLAG_NO_TMA) ? 0 : 1, first, compact, dL_dxyz,
-                                                        dL_dopacity_raw, dL_dscaling_raw, dL_drotation_raw);
+                                                        dL_dopacity_raw, dL_dscaling_raw, dL_drotation_raw, PeerRows{});
     prof_end(K_SH_EXPAND, stream);
     FSGS_LAUNCH_OK("k_sh_grad_expand");
     return FSGS_OK;

@@ -134,6 +134,21 @@ class _NvlinkExchange:
                                                  self.world, self.rank, off // 4, n4, ctypes.c_void_p(stream)))
         self.hdl.barrier(channel=1)                     # every slice is summed and written back everywhere
 
+    def expand(self, st, P, first, count, xyz, cam_center, rows, grads, stream) -> None:
+        """One-shot exchange (small rank counts): ``fsgs_compact_grad_expand_peers`` pulls rows [first, first+count)
+        from every rank's buffer, adds them in rank order and expands them into ``grads`` -- collective and consumer
+        in one kernel.  Between two cross-GPU barriers: all rows written / all ranks done reading."""
+        import ctypes
+        from . import _lib
+        assert rows.data_ptr() == self.buf.data_ptr(), "the rows must start the symmetric buffer"
+        p = lambda x: ctypes.c_void_p(x.data_ptr())
+        self.hdl.barrier(channel=0)
+        _lib.check(_lib.lib().fsgs_compact_grad_expand_peers(
+            ctypes.byref(st), P, first, count, p(xyz), p(cam_center), self.peers, self.world, p(grads["xyz"]),
+            p(grads["f_dc"]), p(grads["f_rest"]), p(grads["opacity"]), p(grads["scaling"]), p(grads["rotation"]),
+            ctypes.c_void_p(stream)))
+        self.hdl.barrier(channel=1)
+
 
 def enable_frame_parallel(group=None, check_cam_center: torch.Tensor = None, chunks: int = 1,
                           exchange: str = "nccl") -> None:
@@ -161,8 +176,14 @@ def enable_frame_parallel(group=None, check_cam_center: torch.Tensor = None, chu
         if not torch.equal(c, ref):
             raise ValueError("frame-parallel SH-gradient exchange needs the same cam_center (SH view origin) on every rank")
     if exchange == "nvlink":
+        import os
         xch = _NvlinkExchange(group)
-        frame_render.set_grad_reducer(xch.reduce, chunks=chunks, alloc=xch.alloc)
+        # two ranks: the one-shot form (rank sum folded into the expansion kernel; same link traffic as the two-shot
+        # kernel at N = 2, one kernel less).  FSGS_EXCHANGE_ONE_SHOT=0/1 forces either (A/B; 1 is usable up to 8 ranks).
+        force = os.environ.get("FSGS_EXCHANGE_ONE_SHOT")
+        one_shot = (force == "1") if force is not None else (xch.world == 2)
+        frame_render.set_grad_reducer(xch.reduce, chunks=chunks if not one_shot else 1, alloc=xch.alloc,
+                                      expand=xch.expand if one_shot else None)
         _STATE["exchange"] = xch
         return
     if exchange != "nccl":

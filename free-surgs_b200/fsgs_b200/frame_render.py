@@ -30,20 +30,24 @@ _CAPTURED = []      # (image-state buffer, capacity, W, H, bin capacity) of ever
 
 # Frame-parallel gradient exchange hook (set through fsgs_b200.dist.enable_frame_parallel): a callable that
 # sum-all-reduces a flat float32 CUDA tensor in place, ordered on the current stream; None = single GPU.
-_GRAD_REDUCER = {"fn": None, "chunks": 1, "alloc": None}
+_GRAD_REDUCER = {"fn": None, "chunks": 1, "alloc": None, "expand": None}
 _XCHG_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
-def set_grad_reducer(fn, chunks: int = 1, alloc=None) -> None:
+def set_grad_reducer(fn, chunks: int = 1, alloc=None, expand=None) -> None:
     """``fn(flat)`` must SUM a flat float32 CUDA tensor over the ranks in place, ordered on the current stream.
     ``chunks`` > 1: the fused backward runs its per-Gaussian kernel in that many Gaussian ranges and hands each
     range's 56-byte rows to ``fn`` on a side stream while the next range is computed (``fn`` is then called
     ``chunks`` times per backward, each time under ``torch.cuda.stream(side)``).
     ``alloc(n_floats, device) -> flat float32 tensor``: where the rows live (the NVLink exchange keeps them in a
-    symmetric buffer mapped into every rank); default: a fresh tensor per backward."""
+    symmetric buffer mapped into every rank); default: a fresh tensor per backward.
+    ``expand(st, P, first, count, xyz, cam_center, rows, grads, stream)``: replaces ``fn`` + the library's expansion
+    by ONE call that sums the rows over the ranks and expands them (the one-shot exchange,
+    ``fsgs_compact_grad_expand_peers``); ``grads`` = the dict of gradient tensors to fill."""
     _GRAD_REDUCER["fn"] = fn
     _GRAD_REDUCER["chunks"] = max(1, int(chunks))
     _GRAD_REDUCER["alloc"] = alloc
+    _GRAD_REDUCER["expand"] = expand
 
 
 class FrozenModel:
@@ -347,6 +351,9 @@ class _RenderFused(torch.autograd.Function):
                 none6 = (None,) * 6
 
                 def exchange(a, b, on_stream):
+                    if _GRAD_REDUCER["expand"] is not None:    # one-shot: rank sum folded into the expansion kernel
+                        _GRAD_REDUCER["expand"](ctx.st, P, a, b - a, t[1], t[8], compact, g, on_stream)
+                        return
                     reducer(compact[a * 14:b * 14])            # SUM over the ranks, in place, ordered on the current stream
                     with _on_device(dev):
                         rc = L.fsgs_compact_grad_expand(

@@ -305,6 +305,17 @@ int fsgs_exchange_rows(void *multicast_ptr, void *const *peer_ptrs_host, int32_t
 /* The same for the 56-byte rows of fsgs_backward_opts.compact, one Gaussian range [first, first+count) at a time
  * (first % 4 == 0): unpacks rotation / xyz / scaling / opacity from the (rank-summed) rows into their gradient tensors
  * and expands the colour gradient into the SH-coefficient gradients. */
+/* One-shot form of the exchange for small rank counts: the rank sum is folded into the expansion kernel -- collective
+ * and consumer in one kernel over peer memory.  row_ptrs_host[world]: every rank's [P,14] row buffer as mapped into
+ * THIS process (this rank's own among them, in rank order, 16-byte aligned; e.g. the buffer_ptrs of a symmetric
+ * allocation).  Rows [first, first+count) (first % 256 == 0) of all ranks are summed in rank order -- bit-identical on
+ * every rank -- and expanded like fsgs_compact_grad_expand.  The caller orders it: all rows written (a cross-GPU
+ * barrier) before, all ranks done reading before any row buffer is written again.  Per rank (N-1) x the rows cross the
+ * links (two-shot: 2 (N-1)/N x): the better choice at N = 2. */
+int fsgs_compact_grad_expand_peers(const fsgs_settings *st, int32_t P, int32_t first, int32_t count, const float *xyz,
+                                   const float *cam_center, void *const *row_ptrs_host, int32_t world, float *dL_dxyz,
+                                   float *dL_dfeatures_dc, float *dL_dfeatures_rest, float *dL_dopacity_raw,
+                                   float *dL_dscaling_raw, float *dL_drotation_raw, void *stream);
 int fsgs_compact_grad_expand(const fsgs_settings *st, int32_t P, int32_t first, int32_t count, const float *xyz,
                              const float *cam_center, const float *compact, float *dL_dxyz, float *dL_dfeatures_dc,
                              float *dL_dfeatures_rest, float *dL_dopacity_raw, float *dL_dscaling_raw,

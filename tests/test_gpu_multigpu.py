@@ -1,6 +1,7 @@
-"""Frame-parallel exchange on real GPUs (needs >= 2 on the box; skipped otherwise): the library's own two-shot
-all-reduce over NVLink / NVSwitch (fsgs_exchange_rows, symmetric buffer) inside the fused backward must give the
-gradients ncclAllReduce gives and the sum of the frames' full gradients, bit-identical on every rank."""
+"""Frame-parallel exchange on real GPUs (needs >= 2 on the box; skipped otherwise): the library's own exchange over
+NVLink / NVSwitch on a symmetric buffer -- two-shot (fsgs_exchange_rows + expansion) and one-shot (the rank sum folded
+into the expansion kernel, fsgs_compact_grad_expand_peers) -- inside the fused backward must give the gradients
+ncclAllReduce gives and the sum of the frames' full gradients, bit-identical on every rank."""
 import json
 import os
 import subprocess
@@ -26,6 +27,7 @@ def test_nvlink_exchange_matches_nccl_and_the_local_sum(P):
     assert p.returncode == 0 and len(lines) == world, p.stdout[-1500:] + p.stderr[-3000:]
     for r in lines:
         assert r["nvlink_vs_local_sum"] < 1e-5 and r["nccl_vs_local_sum"] < 1e-5, r
-        assert r["nvlink_vs_nccl"] < 2e-6, r
+        assert r["nvlink_two_shot_vs_local_sum"] < 1e-5 and r["nvlink_one_shot_vs_local_sum"] < 1e-5, r
+        assert r["nvlink_vs_nccl"] < 1e-5, r                    # (two separate backward runs: float atomics order)
         assert r["nvlink_pose_local"] < 1e-5, r                 # pose gradients stay local
         assert r["bit_identical_across_ranks"], r
