@@ -248,9 +248,14 @@ k_preprocess_pose_bwd(CamConst cc, int P, const float *__restrict__ xyz, const f
 // NVLink peer pointers), adds them in rank order (every rank adds in the same order: bit-identical sums), parks them in
 // shared memory and continues as below.  Per rank (N - 1) x the payload crosses the links, against 2 (N - 1) / N x for
 // the two-shot kernel -- equal at N = 2, where it saves the separate exchange kernel and its launch.
+// Pull-gather variant (owner_slices, 4+ ranks): the exchange kernel stopped after the reduce-scatter -- rank g holds the
+// sums of the g-th 1/N slice, in a second region of its symmetric buffer -- and this kernel fetches every 16-byte word
+// from its owner while it writes the SH gradients: the all-gather half of the two-shot exchange rides on the expansion.
 struct PeerRows {
-    const float4 *p[8];    // row buffers of ranks 0 .. world-1 (this rank's own among them), 16-byte aligned
+    const float4 *p[8];    // row (one-shot) / sum (pull-gather) buffers of ranks 0 .. world-1, 16-byte aligned
     int world;
+    int owner_slices;      // 0: add the rows of all ranks;  1: take each word from the rank that owns its slice
+    int slice_first, slice_per;   // slice geometry of the reduce-scatter, in float4 (fsgs_exchange_rows)
 };
 
 __global__ void __launch_bounds__(CTA)
@@ -276,12 +281,22 @@ k_sh_grad_expand(int P, int sh_deg, const float *__restrict__ xyz, const float *
         const size_t at = (size_t)base * 14 / 4;
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 acc[U];
+        if (peers.owner_slices) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int q = u * CTA + (int)threadIdx.x;
-            acc[u] = q < n4 ? peers.p[0][at + q] : zero4;
+            for (int u = 0; u < U; ++u) {
+                const int q = u * CTA + (int)threadIdx.x;
+                const int w = (int)at + q;
+                const int owner = min(peers.world - 1, (w - peers.slice_first) / peers.slice_per);
+                acc[u] = q < n4 ? peers.p[owner][w] : zero4;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = u * CTA + (int)threadIdx.x;
+                acc[u] = q < n4 ? peers.p[0][at + q] : zero4;
+            }
         }
-        for (int r = 1; r < peers.world; ++r) {
+        for (int r = 1; r < (peers.owner_slices ? 1 : peers.world); ++r) {
             float4 v[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -375,7 +390,11 @@ __device__ __forceinline__ void multimem_st(float4 *mc, float4 v) {
 }
 
 __global__ void __launch_bounds__(CTA)
-k_exchange_rows(float4 *__restrict__ mc, PeerPtrs peers, int world, int rank, long long begin, long long end) {
+k_exchange_rows(float4 *__restrict__ mc, PeerPtrs peers, int world, int rank, long long begin, long long end,
+                long long scatter_off) {
+    // scatter_off == 0: all-reduce (the sums go back into every rank's rows).  scatter_off > 0: reduce-scatter only --
+    // the sums of this rank's slice go to ITS OWN buffer, scatter_off float4 behind the rows (a separate region: peers
+    // may still be pulling the previous step's sums while the next step's rows are being written).
     // [begin, end): this rank's slice, in float4 units from the start of the symmetric buffer.  Four independent
     // 16-byte words per thread and iteration: the round trip through the switch is microseconds long, the links
     // only fill up with a few MB in flight.
@@ -390,7 +409,10 @@ k_exchange_rows(float4 *__restrict__ mc, PeerPtrs peers, int world, int rank, lo
                 if (i + u * CTA < end) v[u] = multimem_ld_reduce_add(mc + i + u * CTA);
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (i + u * CTA < end) multimem_st(mc + i + u * CTA, v[u]);
+                if (i + u * CTA < end) {
+                    if (scatter_off) peers.p[rank][scatter_off + i + u * CTA] = v[u];
+                    else multimem_st(mc + i + u * CTA, v[u]);
+                }
         }
     } else {
         for (long long i = t0; i < end; i += stride) {
@@ -407,8 +429,8 @@ k_exchange_rows(float4 *__restrict__ mc, PeerPtrs peers, int world, int rank, lo
 #pragma unroll
                 for (int u = 0; u < U; ++u) { s[u].x += v[u].x; s[u].y += v[u].y; s[u].z += v[u].z; s[u].w += v[u].w; }
             }
-            for (int d = 0; d < world; ++d) {
-                float4 *dst = peers.p[(rank + d) % world];
+            for (int d = 0; d < (scatter_off ? 1 : world); ++d) {
+                float4 *dst = peers.p[(rank + d) % world] + scatter_off;
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     if (i + u * CTA < end) dst[i + u * CTA] = s[u];

@@ -893,9 +893,16 @@ int fsgs_sh_grad_expand(const fsgs_settings *st, int32_t P, const float *xyz, co
 
 int fsgs_exchange_rows(void *multicast_ptr, void *const *peer_ptrs_host, int32_t world, int32_t rank, int64_t first_vec4,
                        int64_t n_vec4, void *stream_) {
+    return fsgs_exchange_rows_scatter(multicast_ptr, peer_ptrs_host, world, rank, first_vec4, n_vec4, 0, stream_);
+}
+
+int fsgs_exchange_rows_scatter(void *multicast_ptr, void *const *peer_ptrs_host, int32_t world, int32_t rank,
+                               int64_t first_vec4, int64_t n_vec4, int64_t scatter_offset_vec4, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (world < 1 || world > 8 || rank < 0 || rank >= world || first_vec4 < 0 || n_vec4 < 0) return FSGS_E_INVALID;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || first_vec4 < 0 || n_vec4 < 0 || scatter_offset_vec4 < 0)
+        return FSGS_E_INVALID;
     if (!multicast_ptr && !peer_ptrs_host) return FSGS_E_INVALID;
+    if (scatter_offset_vec4 > 0 && !peer_ptrs_host) return FSGS_E_INVALID;      // the own buffer's address is needed
     if (n_vec4 == 0 || world == 1) return FSGS_OK;
     int rc = check_arch();
     if (rc) return rc;
@@ -914,19 +921,22 @@ int fsgs_exchange_rows(void *multicast_ptr, void *const *peer_ptrs_host, int32_t
     if (nb > 148 * 8) nb = 148 * 8;
     prof_begin(K_EXCHANGE, stream);
     k_exchange_rows<<<(int)nb, CTA, 0, stream>>>(static_cast<float4 *>(multicast_ptr), pp, world, rank, (long long)begin,
-                                                  (long long)end);
+                                                  (long long)end, (long long)scatter_offset_vec4);
     prof_end(K_EXCHANGE, stream);
     if (cudaGetLastError() != cudaSuccess) return FSGS_E_CUDA;
     return FSGS_OK;
 }
 
 int fsgs_compact_grad_expand_peers(const fsgs_settings *st, int32_t P, int32_t first, int32_t count, const float *xyz,
-                                   const float *cam_center, void *const *row_ptrs_host, int32_t world, float *dL_dxyz,
+                                   const float *cam_center, void *const *row_ptrs_host, int32_t world,
+                                   int32_t owner_slices, int64_t slice_first_vec4, int64_t slice_n_vec4, float *dL_dxyz,
                                    float *dL_dfeatures_dc, float *dL_dfeatures_rest, float *dL_dopacity_raw,
                                    float *dL_dscaling_raw, float *dL_drotation_raw, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!st || st->sh_degree < 0 || st->sh_degree > 3 || P < 0 || first < 0 || (first & 255) || count < 0 ||
         (int64_t)first + count > P || world < 2 || world > 8 || !row_ptrs_host)
+        return FSGS_E_INVALID;
+    if (owner_slices && (slice_first_vec4 < 0 || slice_n_vec4 < world || slice_first_vec4 + slice_n_vec4 >= (1ll << 31)))
         return FSGS_E_INVALID;
     if (count == 0) return FSGS_OK;
     if (!xyz || !cam_center || !dL_dxyz || !dL_dfeatures_dc || !dL_dfeatures_rest || !dL_dopacity_raw ||
@@ -934,6 +944,9 @@ int fsgs_compact_grad_expand_peers(const fsgs_settings *st, int32_t P, int32_t f
         return FSGS_E_INVALID;
     PeerRows pr{};
     pr.world = world;
+    pr.owner_slices = owner_slices ? 1 : 0;
+    pr.slice_first = (int)slice_first_vec4;
+    pr.slice_per = owner_slices ? (int)(slice_n_vec4 / world) : 1;      // the slices of fsgs_exchange_rows: equal parts, rest to the last
     for (int r = 0; r < world; ++r) {
         if (!row_ptrs_host[r] || (reinterpret_cast<uintptr_t>(row_ptrs_host[r]) & 15u)) return FSGS_E_INVALID;
         pr.p[r] = static_cast<const float4 *>(row_ptrs_host[r]);

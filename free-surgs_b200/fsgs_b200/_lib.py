@@ -88,7 +88,8 @@ _SIGNATURES = {
                                 [_i32, _i32] + [_vp] * 9 + [ctypes.POINTER(BackwardOpts), _vp]),
     "fsgs_compact_grad_expand": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i32, _i32] + [_vp] * 10),
     "fsgs_compact_grad_expand_peers": (ctypes.c_int, [ctypes.POINTER(Settings), _i32, _i32, _i32, _vp, _vp,
-                                                      ctypes.POINTER(_vp), _i32] + [_vp] * 7),
+                                                      ctypes.POINTER(_vp), _i32, _i32, _i64, _i64] + [_vp] * 7),
+    "fsgs_exchange_rows_scatter": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _i64, _vp]),
     "fsgs_exchange_rows": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), _i32, _i32, _i64, _i64, _vp]),
     "fsgs_set_instance_capacity": (ctypes.c_int, [_i32, _i64]),
     "fsgs_fixed_bin_capacity": (_i64, [_i32]),

@@ -96,14 +96,17 @@ class _NvlinkExchange:
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.buf, self.hdl, self.peers = None, None, None
         self.multicast = 0
+        self.cap = 0                 # floats per region: the buffer holds [rows | slice sums of the pull-gather form]
+        self.sum_peers = None
 
     def alloc(self, n_floats: int, device) -> torch.Tensor:
         """Collective on first use / growth (every rank reaches its first fused backward at the same point)."""
         import ctypes
         need = (int(n_floats) + 3) // 4 * 4
-        if self.buf is None or self.buf.numel() < need or self.buf.device != device:
-            cap = max(need, 0 if self.buf is None else int(self.buf.numel() * 1.5) // 4 * 4)
-            self.buf = self.symm_mem.empty(cap, dtype=torch.float32, device=device)
+        if self.buf is None or self.cap < need or self.buf.device != device:
+            cap = max(need, int(self.cap * 1.5) // 4 * 4)
+            self.cap = cap
+            self.buf = self.symm_mem.empty(2 * cap, dtype=torch.float32, device=device)
             self.buf.zero_()
             self.hdl = self.symm_mem.rendezvous(self.buf, self.group)
             self.multicast = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
@@ -119,6 +122,7 @@ class _NvlinkExchange:
                 self.multicast = 0
             ptrs = [int(x) for x in self.hdl.buffer_ptrs]
             self.peers = (ctypes.c_void_p * self.world)(*ptrs)
+            self.sum_peers = (ctypes.c_void_p * self.world)(*[p + 4 * cap for p in ptrs])
         return self.buf[:n_floats]
 
     def reduce(self, flat: torch.Tensor) -> None:
@@ -134,6 +138,25 @@ class _NvlinkExchange:
                                                  self.world, self.rank, off // 4, n4, ctypes.c_void_p(stream)))
         self.hdl.barrier(channel=1)                     # every slice is summed and written back everywhere
 
+    def expand_pull_gather(self, st, P, first, count, xyz, cam_center, rows, grads, stream) -> None:
+        """Two-shot with its second half riding on the expansion (4+ ranks): reduce-scatter of the rows into the sum
+        region of every slice's owner (``fsgs_exchange_rows_scatter``), then ``fsgs_compact_grad_expand_peers`` fetches
+        every word from its owner while it writes the SH gradients.  Two barriers, as the plain two-shot form."""
+        import ctypes
+        from . import _lib
+        assert rows.data_ptr() == self.buf.data_ptr() and first == 0 and count == P, "one Gaussian range only"
+        p = lambda x: ctypes.c_void_p(x.data_ptr())
+        n4 = (P * 14 + 3) // 4
+        self.hdl.barrier(channel=0)                     # every rank's rows are written
+        _lib.check(_lib.lib().fsgs_exchange_rows_scatter(
+            ctypes.c_void_p(self.multicast) if self.multicast else None, self.peers, self.world, self.rank, 0, n4,
+            self.cap // 4, ctypes.c_void_p(stream)))
+        self.hdl.barrier(channel=1)                     # every slice's sums sit in its owner's sum region
+        _lib.check(_lib.lib().fsgs_compact_grad_expand_peers(
+            ctypes.byref(st), P, 0, P, p(xyz), p(cam_center), self.sum_peers, self.world, 1, 0, n4, p(grads["xyz"]),
+            p(grads["f_dc"]), p(grads["f_rest"]), p(grads["opacity"]), p(grads["scaling"]), p(grads["rotation"]),
+            ctypes.c_void_p(stream)))
+
     def expand(self, st, P, first, count, xyz, cam_center, rows, grads, stream) -> None:
         """One-shot exchange (small rank counts): ``fsgs_compact_grad_expand_peers`` pulls rows [first, first+count)
         from every rank's buffer, adds them in rank order and expands them into ``grads`` -- collective and consumer
@@ -144,7 +167,7 @@ class _NvlinkExchange:
         p = lambda x: ctypes.c_void_p(x.data_ptr())
         self.hdl.barrier(channel=0)
         _lib.check(_lib.lib().fsgs_compact_grad_expand_peers(
-            ctypes.byref(st), P, first, count, p(xyz), p(cam_center), self.peers, self.world, p(grads["xyz"]),
+            ctypes.byref(st), P, first, count, p(xyz), p(cam_center), self.peers, self.world, 0, 0, 0, p(grads["xyz"]),
             p(grads["f_dc"]), p(grads["f_rest"]), p(grads["opacity"]), p(grads["scaling"]), p(grads["rotation"]),
             ctypes.c_void_p(stream)))
         self.hdl.barrier(channel=1)
@@ -180,10 +203,19 @@ def enable_frame_parallel(group=None, check_cam_center: torch.Tensor = None, chu
         xch = _NvlinkExchange(group)
         # two ranks: the one-shot form (rank sum folded into the expansion kernel; same link traffic as the two-shot
         # kernel at N = 2, one kernel less).  FSGS_EXCHANGE_ONE_SHOT=0/1 forces either (A/B; 1 is usable up to 8 ranks).
-        force = os.environ.get("FSGS_EXCHANGE_ONE_SHOT")
-        one_shot = (force == "1") if force is not None else (xch.world == 2)
-        frame_render.set_grad_reducer(xch.reduce, chunks=chunks if not one_shot else 1, alloc=xch.alloc,
-                                      expand=xch.expand if one_shot else None)
+        # four ranks and more: the two-shot kernel.  (Its variant with the all-gather half riding on the expansion kernel,
+        # "pull_gather", was measured at N = 4: exchange 0.045 + expansion 0.057 ms against 0.073 + 0.027 -- no gain, step
+        # 1.101 vs 1.083 ms; kept as an option.)  FSGS_EXCHANGE_FORM=two_shot|one_shot|pull_gather forces a form (A/B,
+        # tests); FSGS_EXCHANGE_ONE_SHOT=0/1 is the older spelling of the first two.
+        form = os.environ.get("FSGS_EXCHANGE_FORM")
+        if form is None:
+            force = os.environ.get("FSGS_EXCHANGE_ONE_SHOT")
+            form = ("one_shot" if force == "1" else "two_shot") if force is not None else \
+                   ("one_shot" if xch.world == 2 else "two_shot")
+        if form not in ("two_shot", "one_shot", "pull_gather"):
+            raise ValueError(f"FSGS_EXCHANGE_FORM must be two_shot, one_shot or pull_gather, got {form!r}")
+        fused = {"two_shot": None, "one_shot": xch.expand, "pull_gather": xch.expand_pull_gather}[form]
+        frame_render.set_grad_reducer(xch.reduce, chunks=chunks if fused is None else 1, alloc=xch.alloc, expand=fused)
         _STATE["exchange"] = xch
         return
     if exchange != "nccl":

@@ -313,9 +313,21 @@ int fsgs_exchange_rows(void *multicast_ptr, void *const *peer_ptrs_host, int32_t
  * barrier) before, all ranks done reading before any row buffer is written again.  Per rank (N-1) x the rows cross the
  * links (two-shot: 2 (N-1)/N x): the better choice at N = 2. */
 int fsgs_compact_grad_expand_peers(const fsgs_settings *st, int32_t P, int32_t first, int32_t count, const float *xyz,
-                                   const float *cam_center, void *const *row_ptrs_host, int32_t world, float *dL_dxyz,
+                                   const float *cam_center, void *const *row_ptrs_host, int32_t world,
+                                   int32_t owner_slices, int64_t slice_first_vec4, int64_t slice_n_vec4, float *dL_dxyz,
                                    float *dL_dfeatures_dc, float *dL_dfeatures_rest, float *dL_dopacity_raw,
                                    float *dL_dscaling_raw, float *dL_drotation_raw, void *stream);
+/* Pull-gather form for 4+ ranks = two-shot with its second half riding on the expansion:
+ *   fsgs_exchange_rows_scatter(..., scatter_offset_vec4 > 0)  reduce-scatter only: rank g sums the g-th 1/N slice of the
+ *       rows over all ranks and stores the sums into ITS OWN buffer, scatter_offset_vec4 float4 behind the rows
+ *       (peer_ptrs_host is required; scatter_offset_vec4 == 0 is fsgs_exchange_rows);
+ *   fsgs_compact_grad_expand_peers(..., owner_slices = 1, slice_first_vec4, slice_n_vec4) with row_ptrs_host[r] = rank
+ *       r's SUM region: every 16-byte word is fetched from the rank that owns its slice (same slice arithmetic) while
+ *       the SH gradients are written.
+ * Order: barrier (rows written) - scatter - barrier (sums written) - expand.  No trailing barrier: the next step
+ * writes rows, not sums, and reaches its own scatter only behind the next first barrier. */
+int fsgs_exchange_rows_scatter(void *multicast_ptr, void *const *peer_ptrs_host, int32_t world, int32_t rank,
+                               int64_t first_vec4, int64_t n_vec4, int64_t scatter_offset_vec4, void *stream);
 int fsgs_compact_grad_expand(const fsgs_settings *st, int32_t P, int32_t first, int32_t count, const float *xyz,
                              const float *cam_center, const float *compact, float *dL_dxyz, float *dL_dfeatures_dc,
                              float *dL_dfeatures_rest, float *dL_dopacity_raw, float *dL_dscaling_raw,

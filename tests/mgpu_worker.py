@@ -39,22 +39,24 @@ local_full = [run(f) for f in range(world)]                       # no exchange:
 want = {k: sum(local_full[f][0][k] for f in range(world)) for k in local_full[0][0]}
 got = {}
 # nvlink = the library's default choice for this rank count; the two forms of its exchange are also forced in turn:
-# two-shot (fsgs_exchange_rows + expansion) and one-shot (rank sum folded into the expansion kernel)
-for transport, one_shot in (("nccl", None), ("nvlink", None), ("nvlink_two_shot", "0"), ("nvlink_one_shot", "1")):
-    if one_shot is None:
-        os.environ.pop("FSGS_EXCHANGE_ONE_SHOT", None)
+# two-shot (fsgs_exchange_rows + expansion), one-shot (rank sum folded into the expansion kernel) and pull-gather
+# (reduce-scatter, the all-gather half riding on the expansion kernel)
+for transport, form in (("nccl", None), ("nvlink", None), ("nvlink_two_shot", "two_shot"), ("nvlink_one_shot", "one_shot"),
+                        ("nvlink_pull_gather", "pull_gather")):
+    if form is None:
+        os.environ.pop("FSGS_EXCHANGE_FORM", None)
     else:
-        os.environ["FSGS_EXCHANGE_ONE_SHOT"] = one_shot
+        os.environ["FSGS_EXCHANGE_FORM"] = form
     fd.enable_frame_parallel(check_cam_center=torch.zeros(3, device=dev), exchange=transport.split("_")[0])
     got[transport] = run(rank)
     fd.disable_frame_parallel()
     res[transport + "_vs_local_sum"] = max(rel(got[transport][0][k], want[k]) for k in want)
     res[transport + "_pose_local"] = rel(got[transport][1], local_full[rank][1])
-os.environ.pop("FSGS_EXCHANGE_ONE_SHOT", None)
+os.environ.pop("FSGS_EXCHANGE_FORM", None)
 res["nvlink_vs_nccl"] = max(rel(got["nvlink"][0][k], got["nccl"][0][k]) for k in want)
 # every rank must hold bit-identical summed gradients (replicas must not drift apart)
 res["bit_identical_across_ranks"] = True
-for transport in ("nvlink", "nvlink_two_shot", "nvlink_one_shot"):
+for transport in ("nvlink", "nvlink_two_shot", "nvlink_one_shot", "nvlink_pull_gather"):
     flat = torch.cat([got[transport][0][k].reshape(-1) for k in sorted(want)])
     ref = flat.clone()
     dist.broadcast(ref, src=0)
