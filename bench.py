@@ -781,7 +781,9 @@ def run_ours(args):
                        "tile_instances": R_inst, "tile_instances_reference_rect": R_rect,
                        "parallelism": f"frame-dp{world}" + ("" if world == 1 else
                                                              "+nccl allreduce(grads, 236 B/Gaussian)" if args.exchange == "full"
-                                                             else f"+{args.exchange_transport} allreduce(56 B/Gaussian rows, "
+                                                             else f"+{args.exchange_transport}"
+                                                                  f"{' one-shot (sum folded into the expansion kernel)' if render._GRAD_REDUCER.get('expand') is not None else ''}"
+                                                                  f" allreduce(56 B/Gaussian rows, "
                                                                   f"{args.exchange_chunks} Gaussian range(s), in backward)"),
                        # which integration level each number of this line belongs to
                        "integration_levels": {
@@ -833,7 +835,9 @@ def run_ours(args):
             # pose fwd, 4 forward kernels (projection + key binning, tile scan, per-tile sort, compositor; k_scatter only
             # runs as the fallback of the key bins), compositor bwd, per-Gaussian bwd, pose bwd; N > 1: + the row
             # exchange kernel (nvlink transport) and the expansion kernel per Gaussian range
-            "gpu_launches": (8 + (((3 if args.exchange_transport == "nvlink" else 2)
+            # (one-shot form of the NVLink exchange, two ranks: the rank sum is inside the expansion kernel -- one launch)
+            "gpu_launches": (8 + ((1 if render._GRAD_REDUCER.get("expand") is not None else
+                                   (3 if args.exchange_transport == "nvlink" else 2)
                                    * len(render._chunk_bounds(args.P, args.exchange_chunks)) - 1)
                                   if world > 1 and args.exchange == "compact" else 0)) * args.steps,
             "clocks": clocks,
