@@ -63,6 +63,19 @@ def test_invalid_arguments_are_rejected_before_any_cuda_call():
     assert L.fsgs_render_forward_frozen(ctypes.byref(st_ok), 5, one_, None, one_, one_, one_, cb, None, cb, None, cb, None,
                                         one_, one_, None, None, None, None) == -1                                     # rows NULL
     assert L.fsgs_fixed_bin_capacity(-1) == -1 and L.fsgs_fixed_bin_capacity(0) >= 0
+    # frame-parallel exchange: rank / world / pointer checks come first
+    ptrs = (ctypes.c_void_p * 2)(256, 512)
+    assert L.fsgs_exchange_rows_scatter(None, None, 2, 0, 0, 16, 0, None) == -1                  # no buffers at all
+    assert L.fsgs_exchange_rows_scatter(one_, None, 2, 0, 0, 16, 4, None) == -1                  # scatter needs peer pointers
+    assert L.fsgs_exchange_rows_scatter(None, ptrs, 2, 2, 0, 16, 0, None) == -1                  # rank outside the world
+    assert L.fsgs_exchange_rows_scatter(None, ptrs, 1, 0, 0, 16, 0, None) == 0                   # one rank: nothing to do
+    bad = (ctypes.c_void_p * 2)(256, 520)                                                        # second buffer mis-aligned
+    assert L.fsgs_compact_grad_expand_peers(ctypes.byref(st_ok), 512, 0, 512, one_, one_, bad, 2, 0, 0, 0,
+                                            one_, one_, one_, one_, one_, one_, None) == -1
+    assert L.fsgs_compact_grad_expand_peers(ctypes.byref(st_ok), 512, 100, 412, one_, one_, ptrs, 2, 0, 0, 0,
+                                            one_, one_, one_, one_, one_, one_, None) == -1      # first % 256 != 0
+    assert L.fsgs_compact_grad_expand_peers(ctypes.byref(st_ok), 512, 0, 512, one_, one_, ptrs, 1, 0, 0, 0,
+                                            one_, one_, one_, one_, one_, one_, None) == -1      # needs >= 2 ranks
     # fused image loss: argument checks come before any device call
     one = ctypes.c_void_p(256)                                 # a non-NULL placeholder; never dereferenced
     assert L.fsgs_rgb_loss_forward(0, 8, 8, one, one, None, None, 0, 0.2, None, one, one, None) == -1      # C = 0
